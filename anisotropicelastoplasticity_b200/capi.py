@@ -1,0 +1,99 @@
+"""ctypes binding of the C ABI in include/aep_b200.h (libaep_b200.so, hand-written sm_100a CUDA).
+
+No fallback of any kind: if the library is missing, `load()` raises with the build command; if there is no
+sm_100 GPU, `aep_create` fails and `check()` raises with the library's message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaep_b200.so")
+_LIB = None
+
+NUM_STAGES = 8
+STAGES = ("sort", "p2g", "forces", "grid", "g2p", "mesh", "halo", "_")
+MIGRATE_FLOATS = 44
+
+dp = C.POINTER(C.c_double)
+i64p = C.POINTER(C.c_int64)
+
+
+class Config(C.Structure):
+    """struct aep_config."""
+    _fields_ = [("device", C.c_int32), ("material", C.c_int32),
+                ("grid_min", C.c_double * 3), ("grid_max", C.c_double * 3), ("res", C.c_int32 * 3), ("_pad0", C.c_int32),
+                ("cfl", C.c_double), ("gravity", C.c_double), ("collider_friction", C.c_double), ("snow_hardening", C.c_double),
+                ("sand_h", C.c_double * 4), ("dt_rate_floor", C.c_double), ("frame_dt", C.c_double),
+                ("particle_capacity", C.c_int64), ("slab_axis", C.c_int32), ("slab_lo", C.c_int32), ("slab_hi", C.c_int32),
+                ("sort_every", C.c_int32)]
+
+
+class AepError(RuntimeError):
+    pass
+
+
+# every symbol include/aep_b200.h declares (tests check the library exports all of them)
+SYMBOLS = (
+    "aep_default_config", "aep_create", "aep_destroy", "aep_last_error", "aep_sync", "aep_upload_particles",
+    "aep_upload_mesh", "aep_set_levelset_analytic", "aep_set_levelset_samples", "aep_init", "aep_substep", "aep_run",
+    "aep_run_frames", "aep_p2g", "aep_stage_forces", "aep_stage_grid", "aep_stage_g2p", "aep_set_dt", "aep_get_clock",
+    "aep_num_particles", "aep_download_particles", "aep_download_grid", "aep_download_mesh", "aep_download_positions_f32",
+    "aep_stats", "aep_kernel_launches", "aep_stream", "aep_profile", "aep_get_timers", "aep_halo_info", "aep_halo_pack",
+    "aep_halo_recv_buffer", "aep_halo_add", "aep_vmax_device_ptr", "aep_step_forces", "aep_step_grid", "aep_step_g2p",
+    "aep_step_p2g", "aep_grid_activity", "aep_migrate_extract", "aep_migrate_recv_buffer", "aep_migrate_insert",
+)
+
+
+def load():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise AepError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       f"(nvcc -gencode arch=compute_100a,code=sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.aep_last_error.restype = C.c_char_p; L.aep_last_error.argtypes = [vp]
+    L.aep_create.argtypes = [C.POINTER(vp), C.POINTER(Config)]
+    L.aep_default_config.argtypes = [C.POINTER(Config)]
+    L.aep_num_particles.restype = C.c_int64; L.aep_num_particles.argtypes = [vp]
+    L.aep_kernel_launches.restype = C.c_int64; L.aep_kernel_launches.argtypes = [vp]
+    L.aep_stream.restype = vp; L.aep_stream.argtypes = [vp]
+    L.aep_upload_particles.argtypes = [vp, C.c_int64] + [dp] * 10 + [C.c_double] * 4
+    L.aep_upload_mesh.argtypes = [vp, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, C.POINTER(C.c_int32), dp, dp, dp, dp, dp, dp, dp] + [C.c_double] * 5
+    L.aep_set_levelset_analytic.argtypes = [vp, C.c_int, dp]
+    L.aep_set_levelset_samples.argtypes = [vp, C.POINTER(C.c_uint8), dp]
+    for name in ("aep_destroy", "aep_sync", "aep_init", "aep_substep", "aep_step_forces", "aep_step_grid", "aep_step_g2p", "aep_step_p2g"):
+        getattr(L, name).argtypes = [vp]
+    L.aep_run.argtypes = [vp, C.c_int]
+    L.aep_run_frames.argtypes = [vp, C.c_int, C.c_int, i64p]
+    L.aep_p2g.argtypes = [vp, C.c_int]
+    for name in ("aep_stage_forces", "aep_stage_grid", "aep_stage_g2p", "aep_set_dt"):
+        getattr(L, name).argtypes = [vp, C.c_double]
+    L.aep_get_clock.argtypes = [vp, dp, dp, dp, C.POINTER(C.c_int32), i64p, dp, i64p]
+    L.aep_download_particles.argtypes = [vp] + [dp] * 9
+    L.aep_download_grid.argtypes = [vp] + [dp] * 4
+    L.aep_download_mesh.argtypes = [vp] + [dp] * 7
+    L.aep_download_positions_f32.argtypes = [vp, C.POINTER(C.c_float)]
+    L.aep_stats.argtypes = [vp, dp, dp, dp, dp]
+    L.aep_profile.argtypes = [vp, C.c_int]
+    L.aep_get_timers.argtypes = [vp, dp, i64p]
+    L.aep_grid_activity.argtypes = [vp, i64p, i64p]
+    L.aep_halo_info.argtypes = [vp, C.c_int, C.c_int, i64p]
+    L.aep_halo_pack.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.aep_halo_recv_buffer.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.aep_halo_add.argtypes = [vp, C.c_int, C.c_int]
+    L.aep_vmax_device_ptr.argtypes = [vp, C.POINTER(vp)]
+    L.aep_migrate_extract.argtypes = [vp, i64p, i64p, C.POINTER(vp), C.POINTER(vp)]
+    L.aep_migrate_recv_buffer.argtypes = [vp, C.c_int, C.c_int64, C.POINTER(vp)]
+    L.aep_migrate_insert.argtypes = [vp, C.c_int64, C.c_int64]
+    _LIB = L
+    return L
+
+
+def check(rc, ctx=None):
+    if rc != 0:
+        msg = load().aep_last_error(ctx)
+        raise AepError(f"libaep_b200 error {rc}: {msg.decode() if msg else '?'}")

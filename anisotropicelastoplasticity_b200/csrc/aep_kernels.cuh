@@ -1,0 +1,659 @@
+// aep_kernels.cuh -- sm_100a kernels of the MPM substep (particles: sand / snow).
+//
+// Device data layout (all fp32, 16-byte records so every particle access is one LDG/STG.128):
+//   particle arrays (struct of float4 arrays, index = slot in cell-sorted order)
+//     X  = (fx, fy, fz, cell)     fractional position inside the cell, packed cell (i | j<<10 | k<<20)
+//     VM = (vx, vy, vz, m)
+//     C0..C2 = rows of the APIC matrix B                                   (.w unused)
+//     E0 = (FE row 0, vol)  E1 = (FE row 1, q)  E2 = (FE row 2, det F_P)
+//     Q0 = (FP row 0, id)   Q1 = (FP row 1, m)  Q2 = (FP row 2, -)
+//   grid arrays, node index = (k*ny + j)*nx + i  (RegularGrid.cpp:164-168)
+//     mp = (m, px, py, pz)   f = (fx, fy, fz, -)   vt = (v~x, v~y, v~z, s)  with v = s * v~  (s in {0,1})
+//   block flags: one byte per 8x8x8 node block, set by P2G; grid passes skip unflagged blocks.
+//
+// Scatter strategy: shared-memory float atomics are CAS loops on sm_100 (ATOMS.CAST.SPIN) while global memory
+// has native vector reductions (REDG.E.ADD.F32x4).  So a warp walks its 32 cell-sorted particles one at a time,
+// the 32 lanes own the 64 stencil nodes (2 each) and accumulate in registers over the run of particles that share
+// a cell; one REDG.F32x4 per node per run goes to L2.  No atomics in the inner loop, no shared memory.
+#pragma once
+#include <stdint.h>
+#include "aep_math.cuh"
+
+namespace aep {
+
+enum { PX = 0, PVM, PC0, PC1, PC2, PE0, PE1, PE2, PQ0, PQ1, PQ2, P_NARR };
+
+struct PartP {
+    float4* a[P_NARR];
+};
+
+struct GridP {
+    int nx, ny, nz;
+    int nbx, nby, nbz;                 // number of 8^3 node blocks per axis
+    float hx, hy, hz, ihx, ihy, ihz;
+    float mnx, mny, mnz;
+    float apic;                        // 3 / hmin^2                       HybridSolver.cpp:175-177
+    float inv_cell_vol;                // 1 / (hx hy hz)                   HybridSolver.cpp:246
+    float gravity, friction;
+    float4* mp;
+    float4* f;
+    float4* vt;
+    unsigned char* flags;
+    const unsigned char* ls_code;      // 0 outside, 1..6 axis normals (+x -x +y -y +z -z), 7 general (ls_nrm)
+    const float4* ls_nrm;
+};
+
+// simulation clock + reductions, lives in device memory so that n substeps need no host round trip
+struct SimClock {
+    double t, inner_t, frame_dt, cfl, rate_floor, hmin;
+    float dt;                          // dt used by forces / grid update (previous iteration's value, HybridSolver.cpp:873-878)
+    unsigned int vmax_bits;            // max |v_i| of the last grid update, as float bits (non-negative -> ordered as uint)
+    int frame_flag, frame_no;
+    long long substeps;
+    unsigned long long escaped;        // particles that tried to leave the grid (clamped), sticky
+    float vmax_last;
+    int pad;
+};
+
+__device__ __forceinline__ int cell_i(int c) { return c & 1023; }
+__device__ __forceinline__ int cell_j(int c) { return (c >> 10) & 1023; }
+__device__ __forceinline__ int cell_k(int c) { return (c >> 20) & 1023; }
+__device__ __forceinline__ int cell_pack(int i, int j, int k) { return i | (j << 10) | (k << 20); }
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// per-axis stencil of a thread-owned particle: weights (masked to 0 outside the grid, HybridSolver.cpp:44-46)
+// and clamped node coordinates
+struct Axis {
+    float N[4], D[4];
+    int n0;            // first node (cell - 1), may be -1
+};
+__device__ __forceinline__ bool axis_setup(Axis& a, float f, int cell, int nres, float ih) {
+    bspline4(f, a.N, a.D);
+    a.n0 = cell - 1;
+    bool complete = true;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        const int n = a.n0 + o;
+        const bool in = (n >= 0) && (n < nres);
+        complete &= in;
+        a.N[o] = in ? a.N[o] : 0.0f;
+        a.D[o] = in ? a.D[o] * ih : 0.0f;
+    }
+    return complete;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ================================================================================================ sort keys
+__global__ void k_build_keys(const float4* __restrict__ X, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals,
+                             int n, int nx, int ny) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = __float_as_int(X[i].w);
+    keys[i] = (unsigned)((cell_k(c) * ny + cell_j(c)) * nx + cell_i(c));
+    vals[i] = (unsigned)i;
+}
+
+// gather all particle arrays through the sort permutation (dst[i] = src[perm[i]])
+__global__ void __launch_bounds__(256) k_reorder(PartP src, PartP dst, const unsigned int* __restrict__ perm, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned s = perm[i];
+    float4 r[P_NARR];
+#pragma unroll
+    for (int a = 0; a < P_NARR; ++a) r[a] = ldg4(src.a[a] + s);
+#pragma unroll
+    for (int a = 0; a < P_NARR; ++a) dst.a[a][i] = r[a];
+}
+
+// ================================================================================================ grid passes
+// zero (m,p) and f of every block that the previous P2G touched, and drop its flag
+__global__ void __launch_bounds__(256) k_clear_blocks(GridP G) {
+    const int b = blockIdx.x;
+    if (!G.flags[b]) return;
+    const int bx = b % G.nbx, by = (b / G.nbx) % G.nby, bz = b / (G.nbx * G.nby);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int t = threadIdx.x + 256 * h;
+        const int i = bx * 8 + (t & 7), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t >> 6);
+        if (i < G.nx && j < G.ny && k < G.nz) {
+            const size_t n = ((size_t)k * G.ny + j) * G.nx + i;
+            G.mp[n] = z; G.f[n] = z;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) G.flags[b] = 0;
+}
+
+__device__ __forceinline__ void block_max_to_clock(float v, SimClock* clk) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __shared__ float red[8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = red[0];
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+        if (m > 0.0f) atomicMax(&clk->vmax_bits, __float_as_uint(m));
+    }
+}
+
+// max |p/m| over active nodes: RegularGrid::CFL_condition for the initial dt (HybridSolver.cpp:860)
+__global__ void __launch_bounds__(256) k_vmax_from_mp(GridP G, SimClock* clk) {
+    const int b = blockIdx.x;
+    if (!G.flags[b]) return;
+    const int bx = b % G.nbx, by = (b / G.nbx) % G.nby, bz = b / (G.nbx * G.nby);
+    float vm = 0.0f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int t = threadIdx.x + 256 * h;
+        const int i = bx * 8 + (t & 7), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t >> 6);
+        if (i < G.nx && j < G.ny && k < G.nz) {
+            const float4 mp = G.mp[((size_t)k * G.ny + j) * G.nx + i];
+            if (mp.x > 0.0f) {
+                const float im = 1.0f / mp.x;
+                const float vx = mp.y * im, vy = mp.z * im, vz = mp.w * im;
+                vm = fmaxf(vm, sqrtf(vx * vx + vy * vy + vz * vz));
+            }
+        }
+    }
+    block_max_to_clock(vm, clk);
+}
+
+// updateGridVelocities_ (HybridSolver.cpp:725-737) + gravity (:457) + max|v| (RegularGrid.cpp:188-200)
+// + gridCollisionHandling_ level-set part (:467-511), one coalesced float4 pass over the active blocks.
+__global__ void __launch_bounds__(256) k_grid_update(GridP G, SimClock* clk) {
+    const int b = blockIdx.x;
+    if (!G.flags[b]) return;                                    // uniform per CTA
+    const int bx = b % G.nbx, by = (b / G.nbx) % G.nby, bz = b / (G.nbx * G.nby);
+    const float dt = clk->dt;
+    float vm = 0.0f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int t = threadIdx.x + 256 * h;
+        const int i = bx * 8 + (t & 7), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t >> 6);
+        if (i < G.nx && j < G.ny && k < G.nz) {
+            const size_t n = ((size_t)k * G.ny + j) * G.nx + i;
+            const float4 mp = G.mp[n];
+            float vx = 0.f, vy = 0.f, vz = 0.f, s = 1.0f;
+            if (mp.x > 0.0f) {
+                const float4 f = G.f[n];
+                const float im = 1.0f / mp.x;
+                vx = fmaf(dt, f.x * im, mp.y * im);
+                vy = fmaf(dt, f.y * im, mp.z * im);
+                vz = fmaf(dt, fmaf(-G.gravity, mp.x, f.z) * im, mp.w * im);
+                vm = fmaxf(vm, sqrtf(vx * vx + vy * vy + vz * vz));
+                const int code = G.ls_code ? G.ls_code[n] : 0;
+                if (code) {
+                    float nx_, ny_, nz_;
+                    if (code == 7) { const float4 nn = G.ls_nrm[n]; nx_ = nn.x; ny_ = nn.y; nz_ = nn.z; }
+                    else {
+                        nx_ = (code == 1) ? 1.f : (code == 2 ? -1.f : 0.f);
+                        ny_ = (code == 3) ? 1.f : (code == 4 ? -1.f : 0.f);
+                        nz_ = (code == 5) ? 1.f : (code == 6 ? -1.f : 0.f);
+                    }
+                    const float vn = vx * nx_ + vy * ny_ + vz * nz_;                 // HybridSolver.cpp:486
+                    if (vn < 0.0f) {                                                 // :488 approaching
+                        vx = fmaf(-vn, nx_, vx); vy = fmaf(-vn, ny_, vy); vz = fmaf(-vn, nz_, vz);   // :490-492
+                        const float vt = sqrtf(vx * vx + vy * vy + vz * vz);
+                        // :494-502 stick test; the Coulomb reduction at :501 is a no-op expression statement
+                        s = (vt < -G.friction * vn) ? 0.0f : 1.0f;
+                    }
+                }
+            }
+            G.vt[n] = make_float4(vx, vy, vz, s);
+        }
+    }
+    block_max_to_clock(vm, clk);
+}
+
+// dt rule + frame clipping of HybridSolver.cpp:878-892, one thread, all in double like the reference
+__global__ void k_advance_clock(SimClock* clk, int fixed_dt) {
+    const float vmax = __uint_as_float(clk->vmax_bits);
+    clk->vmax_last = vmax; clk->vmax_bits = 0u;
+    if (fixed_dt) return;
+    double dt = clk->cfl / fmax(clk->rate_floor, (double)vmax / clk->hmin);
+    if (clk->inner_t + dt >= clk->frame_dt) {
+        dt = clk->frame_dt - clk->inner_t; clk->t += clk->frame_dt; clk->inner_t = 0.0; clk->frame_flag = 1; clk->frame_no += 1;
+    } else {
+        clk->inner_t += dt; clk->frame_flag = 0;
+    }
+    clk->dt = (float)dt;
+    clk->substeps += 1;
+}
+__global__ void k_initial_dt(SimClock* clk) {                      // HybridSolver.cpp:860
+    const float vmax = __uint_as_float(clk->vmax_bits);
+    clk->vmax_last = vmax; clk->vmax_bits = 0u;
+    clk->dt = (float)(clk->cfl / fmax(clk->rate_floor, (double)vmax / clk->hmin));
+}
+
+// ================================================================================================ P2G
+// particleToGrid_ (HybridSolver.cpp:113-231): m_i = sum w m ; p_i = sum w m (v + (3/h^2) B (x_i - x_p)).
+// Per particle the affine momentum is written as q0 + Qm * (oi, oj, ok) with (oi,oj,ok) the lane's node offset.
+__device__ __forceinline__ void flush_nodes(const GridP& G, float4* __restrict__ dst, int cell, int oi, int oj, int ok,
+                                            const float4& a0, const float4& a1, bool mark) {
+    const int ni = cell_i(cell) - 1 + oi, nj = cell_j(cell) - 1 + oj, nk0 = cell_k(cell) - 1 + ok, nk1 = nk0 + 2;
+    const bool inij = (ni >= 0) && (ni < G.nx) && (nj >= 0) && (nj < G.ny);
+    if (inij && nk0 >= 0 && nk0 < G.nz) {
+        atomicAdd(dst + (((size_t)nk0 * G.ny + nj) * G.nx + ni), a0);
+        if (mark) G.flags[((nk0 >> 3) * G.nby + (nj >> 3)) * G.nbx + (ni >> 3)] = 1;
+    }
+    if (inij && nk1 >= 0 && nk1 < G.nz) {
+        atomicAdd(dst + (((size_t)nk1 * G.ny + nj) * G.nx + ni), a1);
+        if (mark) G.flags[((nk1 >> 3) * G.nby + (nj >> 3)) * G.nbx + (ni >> 3)] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
+    const int lane = threadIdx.x & 31;
+    const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    if (base >= n) return;
+    const int cnt = min(32, n - base);
+    const unsigned FULL = 0xffffffffu;
+    // lane-owned particle -> broadcast payload
+    float fx = 0.f, fy = 0.f, fz = 0.f, m = 0.f; int cell = -1;
+    float q0x = 0.f, q0y = 0.f, q0z = 0.f, Q[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (lane < cnt) {
+        const float4 X = ldg4(P.a[PX] + base + lane), VM = ldg4(P.a[PVM] + base + lane);
+        const float4 c0 = ldg4(P.a[PC0] + base + lane), c1 = ldg4(P.a[PC1] + base + lane), c2 = ldg4(P.a[PC2] + base + lane);
+        fx = X.x; fy = X.y; fz = X.z; cell = __float_as_int(X.w); m = VM.w;
+        const float k = m * G.apic;
+        Q[0] = k * c0.x * G.hx; Q[1] = k * c0.y * G.hy; Q[2] = k * c0.z * G.hz;
+        Q[3] = k * c1.x * G.hx; Q[4] = k * c1.y * G.hy; Q[5] = k * c1.z * G.hz;
+        Q[6] = k * c2.x * G.hx; Q[7] = k * c2.y * G.hy; Q[8] = k * c2.z * G.hz;
+        // x_i - x_p = h * (o - (1 + f)) per axis
+        const float gx = 1.0f + fx, gy = 1.0f + fy, gz = 1.0f + fz;
+        q0x = fmaf(m, VM.x, -(Q[0] * gx + Q[1] * gy + Q[2] * gz));
+        q0y = fmaf(m, VM.y, -(Q[3] * gx + Q[4] * gy + Q[5] * gz));
+        q0z = fmaf(m, VM.z, -(Q[6] * gx + Q[7] * gy + Q[8] * gz));
+    }
+    const int oi = lane & 3, oj = (lane >> 2) & 3, ok = lane >> 4;           // node offsets owned by this lane: (oi,oj,ok), (oi,oj,ok+2)
+    const float foi = (float)oi, foj = (float)oj, fok = (float)ok;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    int cur = __shfl_sync(FULL, cell, 0);
+    for (int p = 0; p < cnt; ++p) {
+        const int c = __shfl_sync(FULL, cell, p);
+        if (c != cur) {                                                      // warp-uniform
+            flush_nodes(G, G.mp, cur, oi, oj, ok, a0, a1, true);
+            a0 = make_float4(0.f, 0.f, 0.f, 0.f); a1 = a0; cur = c;
+        }
+        const float pfx = __shfl_sync(FULL, fx, p), pfy = __shfl_sync(FULL, fy, p), pfz = __shfl_sync(FULL, fz, p);
+        const float pm = __shfl_sync(FULL, m, p);
+        const float px = __shfl_sync(FULL, q0x, p), py = __shfl_sync(FULL, q0y, p), pz = __shfl_sync(FULL, q0z, p);
+        float q[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) q[i] = __shfl_sync(FULL, Q[i], p);
+        float wx, wy, wz0, wz1, d;
+        bspline_lane(pfx, oi, wx, d); bspline_lane(pfy, oj, wy, d); bspline_lane(pfz, ok, wz0, d); bspline_lane(pfz, ok + 2, wz1, d);
+        const float wxy = wx * wy, w0 = wxy * wz0, w1 = wxy * wz1;
+        const float mx0 = fmaf(q[0], foi, fmaf(q[1], foj, fmaf(q[2], fok, px)));
+        const float my0 = fmaf(q[3], foi, fmaf(q[4], foj, fmaf(q[5], fok, py)));
+        const float mz0 = fmaf(q[6], foi, fmaf(q[7], foj, fmaf(q[8], fok, pz)));
+        a0.x = fmaf(w0, pm, a0.x); a0.y = fmaf(w0, mx0, a0.y); a0.z = fmaf(w0, my0, a0.z); a0.w = fmaf(w0, mz0, a0.w);
+        a1.x = fmaf(w1, pm, a1.x); a1.y = fmaf(w1, fmaf(2.0f, q[2], mx0), a1.y);
+        a1.z = fmaf(w1, fmaf(2.0f, q[5], my0), a1.z); a1.w = fmaf(w1, fmaf(2.0f, q[8], mz0), a1.w);
+    }
+    flush_nodes(G, G.mp, cur, oi, oj, ok, a0, a1, true);
+}
+
+// first P2G only: rho_p = sum_i w m_i / (hx hy hz), V_p = m_p / rho_p           HybridSolver.cpp:242-249
+__global__ void __launch_bounds__(256) k_init_volumes(PartP P, GridP G, int n) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float4 X = P.a[PX][p];
+    const int cell = __float_as_int(X.w);
+    Axis ax, ay, az;
+    axis_setup(ax, X.x, cell_i(cell), G.nx, G.ihx); axis_setup(ay, X.y, cell_j(cell), G.ny, G.ihy); axis_setup(az, X.z, cell_k(cell), G.nz, G.ihz);
+    float dens = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int nk = clampi(az.n0 + k, 0, G.nz - 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int nj = clampi(ay.n0 + j, 0, G.ny - 1);
+            const float wjk = ay.N[j] * az.N[k];
+            const size_t row = ((size_t)nk * G.ny + nj) * G.nx;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ni = clampi(ax.n0 + i, 0, G.nx - 1);
+                dens = fmaf(ax.N[i] * wjk, ldg4(G.mp + row + ni).x, dens);
+            }
+        }
+    }
+    dens *= G.inv_cell_vol;
+    const float m = P.a[PVM][p].w;
+    float4 e0 = P.a[PE0][p]; e0.w = m * (1.0f / dens); P.a[PE0][p] = e0;
+}
+
+// ================================================================================================ forces
+// computeGridForces_, particle part (HybridSolver.cpp:252-368).  Phase 1 (thread per particle): gather
+// grad v = sum_i v_i (grad w_i)^T with v_i = p_i / m_i, Fhat = (I + dt grad v) FE, SVD, stress, A = V_p P FE^T.
+// Phase 2 (warp cooperative, same 32 particles): f_i -= A grad w_ip, register accumulation per cell run.
+__global__ void __launch_bounds__(256) k_forces(PartP P, GridP G, MatParams mpar, const SimClock* __restrict__ clk, int n) {
+    const int lane = threadIdx.x & 31;
+    const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    if (base >= n) return;
+    const int cnt = min(32, n - base);
+    const unsigned FULL = 0xffffffffu;
+    const float dt = clk->dt;
+    float fx = 0.f, fy = 0.f, fz = 0.f; int cell = -1;
+    float A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (lane < cnt) {
+        const int p = base + lane;
+        const float4 X = ldg4(P.a[PX] + p);
+        const float4 e0 = ldg4(P.a[PE0] + p), e1 = ldg4(P.a[PE1] + p), e2 = ldg4(P.a[PE2] + p);
+        fx = X.x; fy = X.y; fz = X.z; cell = __float_as_int(X.w);
+        Axis ax, ay, az;
+        axis_setup(ax, fx, cell_i(cell), G.nx, G.ihx); axis_setup(ay, fy, cell_j(cell), G.ny, G.ihy); axis_setup(az, fz, cell_k(cell), G.nz, G.ihz);
+        float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};          // g[3r+c] = sum_i v_i[r] dw_i[c]
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int nk = clampi(az.n0 + k, 0, G.nz - 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int nj = clampi(ay.n0 + j, 0, G.ny - 1);
+                const size_t row = ((size_t)nk * G.ny + nj) * G.nx;
+                const float nn = ay.N[j] * az.N[k], dn = ay.D[j] * az.N[k], nd = ay.N[j] * az.D[k];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ni = clampi(ax.n0 + i, 0, G.nx - 1);
+                    const float4 mp = ldg4(G.mp + row + ni);
+                    const float im = mp.x > 0.0f ? 1.0f / mp.x : 0.0f;           // HybridSolver.cpp:233-240
+                    const float vx = mp.y * im, vy = mp.z * im, vz = mp.w * im;
+                    const float dwx = ax.D[i] * nn, dwy = ax.N[i] * dn, dwz = ax.N[i] * nd;
+                    g[0] = fmaf(vx, dwx, g[0]); g[1] = fmaf(vx, dwy, g[1]); g[2] = fmaf(vx, dwz, g[2]);
+                    g[3] = fmaf(vy, dwx, g[3]); g[4] = fmaf(vy, dwy, g[4]); g[5] = fmaf(vy, dwz, g[5]);
+                    g[6] = fmaf(vz, dwx, g[6]); g[7] = fmaf(vz, dwy, g[7]); g[8] = fmaf(vz, dwz, g[8]);
+                }
+            }
+        }
+        const float FE[9] = { e0.x, e0.y, e0.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z };
+        float GF[9], Fh[9];
+        mat_mul(g, FE, GF);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Fh[i] = fmaf(dt, GF[i], FE[i]);              // HybridSolver.cpp:306
+        stress_times_FEt(mpar, Fh, FE, e0.w, e2.w, A);
+    }
+    // ---- phase 2: scatter
+    const int oi = lane & 3, oj = (lane >> 2) & 3, ok = lane >> 4;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    int cur = __shfl_sync(FULL, cell, 0);
+    for (int p = 0; p < cnt; ++p) {
+        const int c = __shfl_sync(FULL, cell, p);
+        if (c != cur) {
+            flush_nodes(G, G.f, cur, oi, oj, ok, a0, a1, false);
+            a0 = make_float4(0.f, 0.f, 0.f, 0.f); a1 = a0; cur = c;
+        }
+        const float pfx = __shfl_sync(FULL, fx, p), pfy = __shfl_sync(FULL, fy, p), pfz = __shfl_sync(FULL, fz, p);
+        float a[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) a[i] = __shfl_sync(FULL, A[i], p);
+        float wx, dx, wy, dy, wz0, dz0, wz1, dz1;
+        bspline_lane(pfx, oi, wx, dx); bspline_lane(pfy, oj, wy, dy); bspline_lane(pfz, ok, wz0, dz0); bspline_lane(pfz, ok + 2, wz1, dz1);
+        dx *= G.ihx; dy *= G.ihy; dz0 *= G.ihz; dz1 *= G.ihz;
+        const float gx = dx * wy, gy = wx * dy, gz = wx * wy;
+        {   // node (oi,oj,ok)
+            const float d0 = gx * wz0, d1 = gy * wz0, d2 = gz * dz0;
+            a0.x -= fmaf(a[0], d0, fmaf(a[1], d1, a[2] * d2));                   // HybridSolver.cpp:356-366
+            a0.y -= fmaf(a[3], d0, fmaf(a[4], d1, a[5] * d2));
+            a0.z -= fmaf(a[6], d0, fmaf(a[7], d1, a[8] * d2));
+        }
+        {   // node (oi,oj,ok+2)
+            const float d0 = gx * wz1, d1 = gy * wz1, d2 = gz * dz1;
+            a1.x -= fmaf(a[0], d0, fmaf(a[1], d1, a[2] * d2));
+            a1.y -= fmaf(a[3], d0, fmaf(a[4], d1, a[5] * d2));
+            a1.z -= fmaf(a[6], d0, fmaf(a[7], d1, a[8] * d2));
+        }
+    }
+    flush_nodes(G, G.f, cur, oi, oj, ok, a0, a1, false);
+}
+
+// ================================================================================================ G2P
+// updateParticleVelocities_ (HybridSolver.cpp:739-745), updateAffineMomenta_ with damp 0 (:760-825, :908-917),
+// advection x = sum w (x_i + dt v~_i) (:942-945), updateDeformationGradient_ (:553-578), updatePlasticity_
+// (:612-681), all in registers, one thread per particle.  Writes the new sort key.
+__global__ void __launch_bounds__(128) k_g2p(PartP P, GridP G, MatParams mpar, SimClock* __restrict__ clk,
+                                             unsigned int* __restrict__ keys, unsigned int* __restrict__ vals, int n) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float dt = clk->dt;
+    const float4 X = ldg4(P.a[PX] + p);
+    const int cell = __float_as_int(X.w);
+    int ci = cell_i(cell), cj = cell_j(cell), ck = cell_k(cell);
+    Axis ax, ay, az;
+    bool complete = axis_setup(ax, X.x, ci, G.nx, G.ihx);
+    complete &= axis_setup(ay, X.y, cj, G.ny, G.ihy);
+    complete &= axis_setup(az, X.z, ck, G.nz, G.ihz);
+    // distances from the particle to the stencil nodes, per axis: h * (o - 1 - f)
+    float rx[4], ry[4], rz[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { rx[o] = G.hx * ((float)(o - 1) - X.x); ry[o] = G.hy * ((float)(o - 1) - X.y); rz[o] = G.hz * ((float)(o - 1) - X.z); }
+    float vp[3] = {0.f, 0.f, 0.f}, va[3] = {0.f, 0.f, 0.f};            // sum w v (post-collision), sum w v~ (pre-friction)
+    float B[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        // sum w v (x_i - x_p)^T
+    float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        // sum v~ (grad w)^T
+    float s0 = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;                    // sum w, sum w (x_i - x_p): only != (1, 0) for truncated stencils
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int nk = clampi(az.n0 + k, 0, G.nz - 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int nj = clampi(ay.n0 + j, 0, G.ny - 1);
+            const size_t row = ((size_t)nk * G.ny + nj) * G.nx;
+            const float nn = ay.N[j] * az.N[k], dn = ay.D[j] * az.N[k], nd = ay.N[j] * az.D[k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ni = clampi(ax.n0 + i, 0, G.nx - 1);
+                const float4 t = ldg4(G.vt + row + ni);
+                const float w = ax.N[i] * nn;
+                const float dwx = ax.D[i] * nn, dwy = ax.N[i] * dn, dwz = ax.N[i] * nd;
+                const float ws = w * t.w;
+                const float ux = ws * t.x, uy = ws * t.y, uz = ws * t.z;         // w * v_i
+                vp[0] += ux; vp[1] += uy; vp[2] += uz;
+                va[0] = fmaf(w, t.x, va[0]); va[1] = fmaf(w, t.y, va[1]); va[2] = fmaf(w, t.z, va[2]);
+                B[0] = fmaf(ux, rx[i], B[0]); B[1] = fmaf(ux, ry[j], B[1]); B[2] = fmaf(ux, rz[k], B[2]);
+                B[3] = fmaf(uy, rx[i], B[3]); B[4] = fmaf(uy, ry[j], B[4]); B[5] = fmaf(uy, rz[k], B[5]);
+                B[6] = fmaf(uz, rx[i], B[6]); B[7] = fmaf(uz, ry[j], B[7]); B[8] = fmaf(uz, rz[k], B[8]);
+                g[0] = fmaf(t.x, dwx, g[0]); g[1] = fmaf(t.x, dwy, g[1]); g[2] = fmaf(t.x, dwz, g[2]);
+                g[3] = fmaf(t.y, dwx, g[3]); g[4] = fmaf(t.y, dwy, g[4]); g[5] = fmaf(t.y, dwz, g[5]);
+                g[6] = fmaf(t.z, dwx, g[6]); g[7] = fmaf(t.z, dwy, g[7]); g[8] = fmaf(t.z, dwz, g[8]);
+                if (!complete) { s0 += w; s1x = fmaf(w, rx[i], s1x); s1y = fmaf(w, ry[j], s1y); s1z = fmaf(w, rz[k], s1z); }
+            }
+        }
+    }
+    // ---- advection (HybridSolver.cpp:944): x' = sum w (x_i + dt v~_i) = x + [sum w (x_i - x)] + (sum w - 1) x + dt sum w v~
+    float dxp = dt * va[0], dyp = dt * va[1], dzp = dt * va[2];
+    if (!complete) {
+        const float xw = fmaf((float)ci + X.x, G.hx, G.mnx), yw = fmaf((float)cj + X.y, G.hy, G.mny), zw = fmaf((float)ck + X.z, G.hz, G.mnz);
+        dxp += s1x + (s0 - 1.0f) * xw; dyp += s1y + (s0 - 1.0f) * yw; dzp += s1z + (s0 - 1.0f) * zw;
+    }
+    float nfx = fmaf(dxp, G.ihx, X.x), nfy = fmaf(dyp, G.ihy, X.y), nfz = fmaf(dzp, G.ihz, X.z);
+    {
+        const float flx = floorf(nfx), fly = floorf(nfy), flz = floorf(nfz);
+        nfx -= flx; nfy -= fly; nfz -= flz; ci += (int)flx; cj += (int)fly; ck += (int)flz;
+        nfx = fminf(nfx, 0.99999994f); nfy = fminf(nfy, 0.99999994f); nfz = fminf(nfz, 0.99999994f);
+        const int cci = clampi(ci, 0, G.nx - 1), ccj = clampi(cj, 0, G.ny - 1), cck = clampi(ck, 0, G.nz - 1);
+        if (cci != ci || ccj != cj || cck != ck || !(nfx == nfx) || !(nfy == nfy) || !(nfz == nfz)) {
+            atomicAdd(&clk->escaped, 1ull);
+            if (!(nfx == nfx)) nfx = 0.5f; if (!(nfy == nfy)) nfy = 0.5f; if (!(nfz == nfz)) nfz = 0.5f;
+        }
+        ci = cci; cj = ccj; ck = cck;
+    }
+    // ---- deformation gradient + plasticity
+    const float4 e0 = ldg4(P.a[PE0] + p), e1 = ldg4(P.a[PE1] + p), e2 = ldg4(P.a[PE2] + p);
+    const float4 q0 = ldg4(P.a[PQ0] + p), q1 = ldg4(P.a[PQ1] + p), q2 = ldg4(P.a[PQ2] + p);
+    float FE[9] = { e0.x, e0.y, e0.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z };
+    float FP[9] = { q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z };
+    float GF[9], Fh[9];
+    mat_mul(g, FE, GF);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Fh[i] = fmaf(dt, GF[i], FE[i]);                  // HybridSolver.cpp:575
+    float q = e1.w;
+    return_map(mpar, Fh, FE, FP, q);
+    const float Jp = mat_det(FP);
+    // ---- write back
+    const int ncell = cell_pack(ci, cj, ck);
+    P.a[PX][p] = make_float4(nfx, nfy, nfz, __int_as_float(ncell));
+    P.a[PVM][p] = make_float4(vp[0], vp[1], vp[2], q1.w);
+    P.a[PC0][p] = make_float4(B[0], B[1], B[2], 0.f);
+    P.a[PC1][p] = make_float4(B[3], B[4], B[5], 0.f);
+    P.a[PC2][p] = make_float4(B[6], B[7], B[8], 0.f);
+    P.a[PE0][p] = make_float4(FE[0], FE[1], FE[2], e0.w);
+    P.a[PE1][p] = make_float4(FE[3], FE[4], FE[5], q);
+    P.a[PE2][p] = make_float4(FE[6], FE[7], FE[8], Jp);
+    P.a[PQ0][p] = make_float4(FP[0], FP[1], FP[2], q0.w);
+    P.a[PQ1][p] = make_float4(FP[3], FP[4], FP[5], q1.w);
+    P.a[PQ2][p] = make_float4(FP[6], FP[7], FP[8], q2.w);
+    keys[p] = (unsigned)((ck * G.ny + cj) * G.nx + ci);
+    vals[p] = (unsigned)p;
+}
+
+// ================================================================================================ host <-> device
+// fp64 reference layouts -> packed fp32 records.  `st` is a staged chunk: columns of length cnt, in the order
+// x(3) v(3) B1(3) B2(3) B3(3) m vol q, then FE (cnt x 9, column-major per particle), FP likewise.
+__global__ void k_upload_convert(PartP P, GridP G, const double* __restrict__ st, int cnt, int dst0, long long id0,
+                                 double mnx, double mny, double mnz, double hx, double hy, double hz, SimClock* clk) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const double* c = st;
+    auto col = [&](int k) { return c[(size_t)k * cnt + i]; };
+    const double mn[3] = { mnx, mny, mnz }, h[3] = { hx, hy, hz };
+    const int nres[3] = { G.nx, G.ny, G.nz };
+    float fr[3]; int ce[3]; bool bad = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double u = (col(a) - mn[a]) / h[a];
+        int cc = (int)u;                                         // static_cast<int>, HybridSolver.cpp:34-36
+        double f = u - (double)cc;
+        if (f < 0.0) { cc -= 1; f += 1.0; }                      // negative side of the grid: keep f in [0,1)
+        if (cc < 0 || cc >= nres[a] || !(u == u)) { bad = true; cc = cc < 0 ? 0 : nres[a] - 1; f = 0.5; }
+        float ff = (float)f; if (ff >= 1.0f) ff = 0.99999994f;
+        fr[a] = ff; ce[a] = cc;
+    }
+    if (bad) atomicAdd(&clk->escaped, 1ull);
+    const int d = dst0 + i;
+    const float m = (float)col(15);
+    P.a[PX][d] = make_float4(fr[0], fr[1], fr[2], __int_as_float(cell_pack(ce[0], ce[1], ce[2])));
+    P.a[PVM][d] = make_float4((float)col(3), (float)col(4), (float)col(5), m);
+    P.a[PC0][d] = make_float4((float)col(6), (float)col(7), (float)col(8), 0.f);
+    P.a[PC1][d] = make_float4((float)col(9), (float)col(10), (float)col(11), 0.f);
+    P.a[PC2][d] = make_float4((float)col(12), (float)col(13), (float)col(14), 0.f);
+    const double* fe = st + (size_t)18 * cnt + (size_t)9 * i;    // column-major 3x3: (r,c) at 3c + r
+    const double* fp = st + (size_t)27 * cnt + (size_t)9 * i;
+    float FP[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) FP[3 * r + cc] = (float)fp[3 * cc + r];
+    P.a[PE0][d] = make_float4((float)fe[0], (float)fe[3], (float)fe[6], (float)col(16));
+    P.a[PE1][d] = make_float4((float)fe[1], (float)fe[4], (float)fe[7], (float)col(17));
+    P.a[PE2][d] = make_float4((float)fe[2], (float)fe[5], (float)fe[8], mat_det(FP));
+    P.a[PQ0][d] = make_float4(FP[0], FP[1], FP[2], __int_as_float((int)(id0 + i)));
+    P.a[PQ1][d] = make_float4(FP[3], FP[4], FP[5], m);
+    P.a[PQ2][d] = make_float4(FP[6], FP[7], FP[8], 0.f);
+}
+
+// packed records [s0, s0+cnt) -> staged fp64 chunk for original ids [id0, id0+cnt_ids): scatter by id.
+// out columns: x(3) v(3) B1(3) B2(3) B3(3) vol q, then FE, FP (9 each, column-major per particle)
+__global__ void k_download_convert(PartP P, GridP G, double* __restrict__ st, int n, long long id0, int cnt_ids,
+                                   double mnx, double mny, double mnz, double hx, double hy, double hz) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const float4 q0 = P.a[PQ0][s];
+    const long long id = (long long)__float_as_int(q0.w) - id0;
+    if (id < 0 || id >= cnt_ids) return;
+    const size_t i = (size_t)id, cnt = (size_t)cnt_ids;
+    const float4 X = P.a[PX][s], VM = P.a[PVM][s], c0 = P.a[PC0][s], c1 = P.a[PC1][s], c2 = P.a[PC2][s];
+    const float4 e0 = P.a[PE0][s], e1 = P.a[PE1][s], e2 = P.a[PE2][s], q1 = P.a[PQ1][s], q2 = P.a[PQ2][s];
+    const int cell = __float_as_int(X.w);
+    st[0 * cnt + i] = mnx + ((double)cell_i(cell) + (double)X.x) * hx;
+    st[1 * cnt + i] = mny + ((double)cell_j(cell) + (double)X.y) * hy;
+    st[2 * cnt + i] = mnz + ((double)cell_k(cell) + (double)X.z) * hz;
+    st[3 * cnt + i] = VM.x; st[4 * cnt + i] = VM.y; st[5 * cnt + i] = VM.z;
+    st[6 * cnt + i] = c0.x; st[7 * cnt + i] = c0.y; st[8 * cnt + i] = c0.z;
+    st[9 * cnt + i] = c1.x; st[10 * cnt + i] = c1.y; st[11 * cnt + i] = c1.z;
+    st[12 * cnt + i] = c2.x; st[13 * cnt + i] = c2.y; st[14 * cnt + i] = c2.z;
+    st[15 * cnt + i] = e0.w; st[16 * cnt + i] = e1.w;
+    double* fe = st + 17 * cnt + 9 * i; double* fp = st + 26 * cnt + 9 * i;
+    fe[0] = e0.x; fe[3] = e0.y; fe[6] = e0.z; fe[1] = e1.x; fe[4] = e1.y; fe[7] = e1.z; fe[2] = e2.x; fe[5] = e2.y; fe[8] = e2.z;
+    fp[0] = q0.x; fp[3] = q0.y; fp[6] = q0.z; fp[1] = q1.x; fp[4] = q1.y; fp[7] = q1.z; fp[2] = q2.x; fp[5] = q2.y; fp[8] = q2.z;
+}
+
+__global__ void k_download_positions_f32(PartP P, GridP G, float* __restrict__ out, int n) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const float4 X = P.a[PX][s];
+    const int id = __float_as_int(P.a[PQ0][s].w);
+    const int cell = __float_as_int(X.w);
+    out[3 * (size_t)id + 0] = fmaf((float)cell_i(cell) + X.x, G.hx, G.mnx);
+    out[3 * (size_t)id + 1] = fmaf((float)cell_j(cell) + X.y, G.hy, G.mny);
+    out[3 * (size_t)id + 2] = fmaf((float)cell_k(cell) + X.z, G.hz, G.mnz);
+}
+
+// grid -> fp64 reference layout (Ng x 3 column-major).  mode 0: after P2G (v = p/m); mode 1: after grid update
+// (v = s v~, vt = v~).  Forces get the gravity term the reference folds in at HybridSolver.cpp:457.
+__global__ void k_download_grid(GridP G, double* __restrict__ m, double* __restrict__ v, double* __restrict__ f,
+                                double* __restrict__ vt, long long n0, long long cnt, long long Ng, int mode) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const size_t n = (size_t)(n0 + i);
+    const float4 mp = G.mp[n], ff = G.f[n];
+    if (m) m[i] = mp.x;
+    if (f) { f[i] = ff.x; f[cnt + i] = ff.y; f[2 * cnt + i] = (double)ff.z - (double)G.gravity * (double)mp.x; }
+    const int b = (((int)(n / ((size_t)G.nx * G.ny)) >> 3) * G.nby + ((int)((n / G.nx) % G.ny) >> 3)) * G.nbx + ((int)(n % G.nx) >> 3);
+    const bool act = G.flags[b] != 0;
+    if (mode == 0) {
+        if (v) {
+            const double im = mp.x > 0.0f ? 1.0 / (double)mp.x : 0.0;
+            v[i] = mp.y * im; v[cnt + i] = mp.z * im; v[2 * cnt + i] = mp.w * im;
+        }
+    } else {
+        const float4 t = act ? G.vt[n] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v) { v[i] = t.w * t.x; v[cnt + i] = t.w * t.y; v[2 * cnt + i] = t.w * t.z; }
+        if (vt) { vt[i] = t.x; vt[cnt + i] = t.y; vt[2 * cnt + i] = t.z; }
+    }
+}
+
+// active blocks / nodes with mass (roofline accounting)
+__global__ void __launch_bounds__(256) k_count_active(GridP G, unsigned long long* __restrict__ out2) {
+    const int b = blockIdx.x;
+    if (!G.flags[b]) return;
+    const int bx = b % G.nbx, by = (b / G.nbx) % G.nby, bz = b / (G.nbx * G.nby);
+    int cnt = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int t = threadIdx.x + 256 * h;
+        const int i = bx * 8 + (t & 7), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t >> 6);
+        if (i < G.nx && j < G.ny && k < G.nz) cnt += G.mp[((size_t)k * G.ny + j) * G.nx + i].x > 0.0f;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out2 + 1, (unsigned long long)cnt);
+    if (threadIdx.x == 0) atomicAdd(out2, 1ull);
+}
+
+// bulk statistics (double accumulation): sum m x (3), sum 0.5 m v^2, sum det FP, sum m
+__global__ void __launch_bounds__(256) k_stats(PartP P, GridP G, double* __restrict__ out6, int n) {
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const float4 X = P.a[PX][s], VM = P.a[PVM][s];
+        const int cell = __float_as_int(X.w);
+        const double m = VM.w;
+        acc[0] += m * ((double)G.mnx + ((double)cell_i(cell) + X.x) * (double)G.hx);
+        acc[1] += m * ((double)G.mny + ((double)cell_j(cell) + X.y) * (double)G.hy);
+        acc[2] += m * ((double)G.mnz + ((double)cell_k(cell) + X.z) * (double)G.hz);
+        acc[3] += 0.5 * m * ((double)VM.x * VM.x + (double)VM.y * VM.y + (double)VM.z * VM.z);
+        acc[4] += (double)P.a[PE2][s].w;
+        acc[5] += m;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(out6 + k, v);
+    }
+}
+
+}  // namespace aep

@@ -1,0 +1,264 @@
+// aep_math.cuh -- register-resident math for the MPM substep kernels (sm_100a, fp32).
+//
+// Restates, in a GPU-friendly form, the scalar kernels of the reference:
+//   cubic_B_spline / Dcubic_B_spline      interpolation.cpp:9-33
+//   Eigen::JacobiSVD<Matrix3d> contract   HybridSolver.cpp:308,620   (s >= 0; uses are order/sign invariant)
+//   snow / sand stress                    HybridSolver.cpp:281-339
+//   snow / sand return mapping            HybridSolver.cpp:626-677
+//   Gram-Schmidt QR                       geometry.cpp:31-62
+// All matrices are row-major float[9]: M[3*r + c].
+#pragma once
+#ifndef AEP_HOST_MATH_TEST   // tests/cpu_math_harness.cpp compiles this header for the host with shims
+#include <cuda_runtime.h>
+#endif
+
+namespace aep {
+
+// ------------------------------------------------------------------------------------------------ B-splines
+// A particle sits in cell c with fractional offset f in [0,1).  Its four stencil nodes per axis are
+// c-1+o, o = 0..3, at signed distance u = f + 1 - o (in cells).  With g = 1 - f:
+//   N:  g^3/6 | f^3/2 - f^2 + 2/3 | g^3/2 - g^2 + 2/3 | f^3/6          (interpolation.cpp:9-16, |u| form)
+//   N': -g^2/2 | 3f^2/2 - 2f | -3g^2/2 + 2g | f^2/2                    (interpolation.cpp:18-33)
+// Nodes with weight <= 0 are dropped by the reference (HybridSolver.cpp:60); they contribute 0 here.
+__device__ __forceinline__ void bspline4(float f, float (&N)[4], float (&D)[4]) {
+    const float g = 1.0f - f;
+    const float f2 = f * f, g2 = g * g;
+    N[0] = g2 * g * (1.0f / 6.0f);
+    N[1] = fmaf(f2, fmaf(0.5f, f, -1.0f), 2.0f / 3.0f);
+    N[2] = fmaf(g2, fmaf(0.5f, g, -1.0f), 2.0f / 3.0f);
+    N[3] = f2 * f * (1.0f / 6.0f);
+    D[0] = -0.5f * g2;
+    D[1] = f * fmaf(1.5f, f, -2.0f);
+    D[2] = -g * fmaf(1.5f, g, -2.0f);
+    D[3] = 0.5f * f2;
+}
+
+// One lane's node offset o (0..3): value and derivative of the weight of a particle at fraction f.
+__device__ __forceinline__ void bspline_lane(float f, int o, float& N, float& D) {
+    const bool lo = (o < 2);                 // o = 0,1 use f ; o = 2,3 use the mirrored variable
+    const bool inner = (o == 1) || (o == 2);
+    // a = |u| folded to [0,1): inner nodes a = f (o=1) or 1-f (o=2); outer nodes: t = 2-|u| = 1-f (o=0) or f (o=3)
+    const float a = (o == 1 || o == 3) ? f : 1.0f - f;
+    const float a2 = a * a;
+    const float n_in = fmaf(a2, fmaf(0.5f, a, -1.0f), 2.0f / 3.0f);
+    const float n_out = a2 * a * (1.0f / 6.0f);
+    const float d_in = a * fmaf(1.5f, a, -2.0f);          // derivative w.r.t. a
+    const float d_out = 0.5f * a2;                        // derivative w.r.t. t
+    N = inner ? n_in : n_out;
+    // du/da: o=1: +1, o=2: -1 ; d/du of outer: o=0: u=2-t -> -d_out ; o=3: u=t-2 -> +d_out
+    const float d = inner ? d_in : d_out;
+    D = (o == 1 || o == 3) ? d : -d;
+    (void)lo;
+}
+
+// ------------------------------------------------------------------------------------------------ 3x3 helpers
+__device__ __forceinline__ void mat_mul(const float (&A)[9], const float (&B)[9], float (&C)[9]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            C[3 * r + c] = fmaf(A[3 * r], B[c], fmaf(A[3 * r + 1], B[3 + c], A[3 * r + 2] * B[6 + c]));
+}
+// C = A * B^T
+__device__ __forceinline__ void mat_mul_nt(const float (&A)[9], const float (&B)[9], float (&C)[9]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            C[3 * r + c] = fmaf(A[3 * r], B[3 * c], fmaf(A[3 * r + 1], B[3 * c + 1], A[3 * r + 2] * B[3 * c + 2]));
+}
+// C = A^T * B
+__device__ __forceinline__ void mat_mul_tn(const float (&A)[9], const float (&B)[9], float (&C)[9]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            C[3 * r + c] = fmaf(A[r], B[c], fmaf(A[3 + r], B[3 + c], A[6 + r] * B[6 + c]));
+}
+__device__ __forceinline__ float mat_det(const float (&A)[9]) {
+    return A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+}
+// cofactor matrix: cof(A) = det(A) * A^{-T}
+__device__ __forceinline__ void mat_cof(const float (&A)[9], float (&C)[9]) {
+    C[0] = A[4] * A[8] - A[5] * A[7]; C[1] = A[5] * A[6] - A[3] * A[8]; C[2] = A[3] * A[7] - A[4] * A[6];
+    C[3] = A[2] * A[7] - A[1] * A[8]; C[4] = A[0] * A[8] - A[2] * A[6]; C[5] = A[1] * A[6] - A[0] * A[7];
+    C[6] = A[1] * A[5] - A[2] * A[4]; C[7] = A[2] * A[3] - A[0] * A[5]; C[8] = A[0] * A[4] - A[1] * A[3];
+}
+
+// ------------------------------------------------------------------------------------------------ SVD
+// One-sided (Hestenes) Jacobi: rotate the columns of A = F V until orthogonal; s_c = |a_c|, u_c = a_c / s_c.
+// Meets Eigen::JacobiSVD's contract up to ordering (s >= 0, U and V orthogonal, F = U diag(s) V^T); every use on
+// the hot path is a symmetric function of (s, U, V) so ordering is irrelevant.  The rotation angle may be
+// approximate (fast division / rsqrt): the iteration self-corrects, only c^2 + s^2 = 1 must hold to rounding,
+// which one Newton step on rsqrt guarantees.  High relative accuracy of s near 1 (no F^T F squaring).
+struct Svd3 {
+    float U[9], S[3], V[9];
+};
+
+template <int P, int Q>
+__device__ __forceinline__ bool jacobi_rot(float (&A)[3][3], float (&W)[3][3]) {
+    const float al = fmaf(A[P][0], A[P][0], fmaf(A[P][1], A[P][1], A[P][2] * A[P][2]));
+    const float be = fmaf(A[Q][0], A[Q][0], fmaf(A[Q][1], A[Q][1], A[Q][2] * A[Q][2]));
+    const float ga = fmaf(A[P][0], A[Q][0], fmaf(A[P][1], A[Q][1], A[P][2] * A[Q][2]));
+    const bool act = ga * ga > 1e-14f * al * be;
+    const float zeta = __fdividef(be - al, act ? 2.0f * ga : 1.0f);
+    const float az = fabsf(zeta);
+    const float rt = fmaf(zeta, zeta, 1.0f);
+    float t = __fdividef(1.0f, az + rt * rsqrtf(rt));
+    t = act ? copysignf(t, zeta) : 0.0f;
+    t = (t == t) ? t : 0.0f;                            // overflow of zeta^2 -> inf * 0: no rotation needed
+    const float tt = fmaf(t, t, 1.0f);
+    float c = rsqrtf(tt);
+    c = c * fmaf(-0.5f * tt, c * c, 1.5f);              // Newton step: c^2 (1 + t^2) = 1 to rounding
+    const float s = c * t;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float ap = A[P][r], aq = A[Q][r];
+        A[P][r] = fmaf(c, ap, -s * aq); A[Q][r] = fmaf(s, ap, c * aq);
+        const float wp = W[P][r], wq = W[Q][r];
+        W[P][r] = fmaf(c, wp, -s * wq); W[Q][r] = fmaf(s, wp, c * wq);
+    }
+    return act;
+}
+
+__device__ __forceinline__ void svd3(const float (&F)[9], Svd3& o) {
+    float A[3][3], W[3][3];                             // [column][row]
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { A[c][r] = F[3 * r + c]; W[c][r] = (r == c) ? 1.0f : 0.0f; }
+#pragma unroll 1
+    for (int sweep = 0; sweep < 8; ++sweep) {
+        bool any = jacobi_rot<0, 1>(A, W);
+        any |= jacobi_rot<0, 2>(A, W);
+        any |= jacobi_rot<1, 2>(A, W);
+        if (!any) break;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float n2 = fmaf(A[c][0], A[c][0], fmaf(A[c][1], A[c][1], A[c][2] * A[c][2]));
+        const float s = sqrtf(n2);
+        const float inv = 1.0f / fmaxf(s, 1e-30f);
+        o.S[c] = s;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { o.U[3 * r + c] = A[c][r] * inv; o.V[3 * r + c] = W[c][r]; }
+    }
+}
+
+// M = U diag(d) V^T
+__device__ __forceinline__ void usvt(const float (&U)[9], const float (&d)[3], const float (&V)[9], float (&M)[9]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            M[3 * r + c] = fmaf(U[3 * r] * d[0], V[3 * c], fmaf(U[3 * r + 1] * d[1], V[3 * c + 1], U[3 * r + 2] * d[2] * V[3 * c + 2]));
+}
+
+// ------------------------------------------------------------------------------------------------ materials
+struct MatParams {
+    float lambda0, mu0;        // Lame from E, nu                        HybridSolver.cpp:264-265
+    float xi;                  // snow hardening                         HybridSolver.cpp:267
+    float lo, hi;              // 1 - theta_c, 1 + theta_s               HybridSolver.cpp:628-630
+    float h0, h1, h2, h3;      // sand friction-angle hardening          HybridSolver.cpp:641-644
+    float k_vol;               // (3 lambda + 2 mu) / (2 mu)             HybridSolver.cpp:655
+    int material;              // 0 snow, 1 sand
+};
+
+// First Piola stress times F_E^T times volume:  A = V_p * P(Fhat) * FE^T       HybridSolver.cpp:314-339
+__device__ __forceinline__ void stress_times_FEt(const MatParams& mp, const float (&Fh)[9], const float (&FE)[9],
+                                                 float vol, float Jp, float (&A)[9]) {
+    Svd3 sv; svd3(Fh, sv);
+    float P[9];
+    if (mp.material == 0) {
+        // snow, fixed corotated with hardening e^{xi (1 - Jp)}:  P = 2 mu (F - R) + lambda (J - 1) J F^{-T}
+        const float hard = expf(mp.xi * (1.0f - Jp));
+        const float mu = mp.mu0 * hard, la = mp.lambda0 * hard;
+        // F - R = U (S - I) V^T, evaluated in that form (no cancellation between O(1) matrices)
+        const float d[3] = { 2.0f * mu * (sv.S[0] - 1.0f), 2.0f * mu * (sv.S[1] - 1.0f), 2.0f * mu * (sv.S[2] - 1.0f) };
+        usvt(sv.U, d, sv.V, P);
+        float cof[9]; mat_cof(Fh, cof);
+        const float J = mat_det(Fh);
+        const float k = la * (J - 1.0f);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) P[i] = fmaf(k, cof[i], P[i]);
+    } else {
+        // sand, Hencky strain:  P = U diag(2 mu ln s / s + lambda tr(ln s) / s) V^T
+        const float l0 = logf(sv.S[0]), l1 = logf(sv.S[1]), l2 = logf(sv.S[2]);
+        const float tr = l0 + l1 + l2;
+        const float d[3] = { (2.0f * mp.mu0 * l0 + mp.lambda0 * tr) / sv.S[0], (2.0f * mp.mu0 * l1 + mp.lambda0 * tr) / sv.S[1],
+                             (2.0f * mp.mu0 * l2 + mp.lambda0 * tr) / sv.S[2] };
+        usvt(sv.U, d, sv.V, P);
+    }
+    float T[9]; mat_mul_nt(P, FE, T);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A[i] = vol * T[i];
+}
+
+// Plastic return mapping on the candidate Fhat (in: Fh, FP, q; out: FE, FP, q).      HybridSolver.cpp:612-681
+// When the projection leaves the singular values untouched the reference's U S V^T / V S^-1 U^T Ftot round trip
+// is the identity in exact arithmetic, so FE = Fhat and FP is left alone (closest to the fp64 reference).
+__device__ __forceinline__ void return_map(const MatParams& mp, const float (&Fh)[9], float (&FE)[9], float (&FP)[9], float& q) {
+    Svd3 sv; svd3(Fh, sv);
+    float sn[3] = { sv.S[0], sv.S[1], sv.S[2] };
+    bool changed = false;
+    if (mp.material == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {                                                // HybridSolver.cpp:626-631
+            const float c = fminf(fmaxf(sn[i], mp.lo), mp.hi);
+            changed |= (c != sn[i]); sn[i] = c;
+        }
+    } else {
+        const float PI_F = 3.14159265358979323846f;
+        const float phi = (mp.h0 + (mp.h1 * q - mp.h3) * expf(-mp.h2 * q)) * (PI_F / 180.0f);      // HybridSolver.cpp:646-647
+        const float sp = sinf(phi);
+        const float alpha = 0.81649658092772603f * 2.0f * sp / (3.0f - sp);                          // sqrt(2/3), :649-650
+        const float l0 = logf(sn[0]), l1 = logf(sn[1]), l2 = logf(sn[2]);
+        const float tr = l0 + l1 + l2;
+        const float m3 = tr * (1.0f / 3.0f);
+        const float d0 = l0 - m3, d1 = l1 - m3, d2 = l2 - m3;
+        const float dn = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
+        const float dg = dn + mp.k_vol * tr * alpha;                                                 // :654-656
+        if (dg <= 0.0f) {
+        } else if (dn == 0.0f || tr > 0.0f) {                                                        // :662-666
+            q += sqrtf(fmaf(l0, l0, fmaf(l1, l1, l2 * l2)));
+            sn[0] = sn[1] = sn[2] = 1.0f; changed = true;
+        } else {                                                                                     // :667-673
+            const float k = dg / dn;
+            sn[0] = expf(l0 - k * d0); sn[1] = expf(l1 - k * d1); sn[2] = expf(l2 - k * d2);
+            q += dg; changed = true;
+        }
+    }
+    if (!changed) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) FE[i] = Fh[i];
+        return;
+    }
+    float Ftot[9]; mat_mul(Fh, FP, Ftot);                                            // :618-619
+    usvt(sv.U, sn, sv.V, FE);                                                        // :675
+    const float inv[3] = { 1.0f / sn[0], 1.0f / sn[1], 1.0f / sn[2] };
+    float Mi[9]; usvt(sv.V, inv, sv.U, Mi);                                          // V S^-1 U^T
+    mat_mul(Mi, Ftot, FP);                                                           // :676-677
+}
+
+// ------------------------------------------------------------------------------------------------ QR (cloth)
+// classical Gram-Schmidt on columns (d1 d2 d3), geometry.cpp:31-62.  Q, R row-major.
+__device__ __forceinline__ void gram_schmidt(const float (&d1)[3], const float (&d2)[3], const float (&d3)[3],
+                                             float (&Q)[9], float (&R)[9]) {
+    const float r11 = sqrtf(d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2]);
+    const float i11 = 1.0f / r11;
+    const float q1[3] = { d1[0] * i11, d1[1] * i11, d1[2] * i11 };
+    const float r12 = d2[0] * q1[0] + d2[1] * q1[1] + d2[2] * q1[2];
+    float q2[3] = { d2[0] - r12 * q1[0], d2[1] - r12 * q1[1], d2[2] - r12 * q1[2] };
+    const float r22 = sqrtf(q2[0] * q2[0] + q2[1] * q2[1] + q2[2] * q2[2]);
+    const float i22 = 1.0f / r22; q2[0] *= i22; q2[1] *= i22; q2[2] *= i22;
+    const float r13 = d3[0] * q1[0] + d3[1] * q1[1] + d3[2] * q1[2];
+    const float r23 = d3[0] * q2[0] + d3[1] * q2[1] + d3[2] * q2[2];
+    float q3[3] = { d3[0] - r13 * q1[0] - r23 * q2[0], d3[1] - r13 * q1[1] - r23 * q2[1], d3[2] - r13 * q1[2] - r23 * q2[2] };
+    const float r33 = sqrtf(q3[0] * q3[0] + q3[1] * q3[1] + q3[2] * q3[2]);
+    const float i33 = 1.0f / r33; q3[0] *= i33; q3[1] *= i33; q3[2] *= i33;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { Q[3 * r] = q1[r]; Q[3 * r + 1] = q2[r]; Q[3 * r + 2] = q3[r]; }
+    R[0] = r11; R[1] = r12; R[2] = r13; R[3] = 0.f; R[4] = r22; R[5] = r23; R[6] = 0.f; R[7] = 0.f; R[8] = r33;
+}
+
+}  // namespace aep

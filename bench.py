@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- particle-substeps/s of the full MPM substep (HybridSolver.cpp:867-1032) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            # this engine (libaep_b200.so through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port; the reference
+                                                           # itself cannot be built here: Eigen/libigl/GLFW absent)
+
+Workload (config.workload): BASELINE.json configs[4], the synthetic 64M-particle sand dam break on a 512^3 grid --
+the configuration the headline target is quoted on; it fits one B200 (~33 GB), so it is also the N=1 workload and
+the N>1 runs are STRONG scaling of the same scene split into y-slabs.  `--res R` shrinks it (particles ~ R^3).
+
+A "step" is one substep over all particles.  `value` = particles * K / (device time of K substeps, max over ranks),
+state resident in HBM.  `e2e` = the same through the host-facing call sequence of HybridSolver::solve: upload of the
+fp64 host state (reference layouts, pinned), K substeps, float32 position download (the per-frame OBJ payload).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from anisotropicelastoplasticity_b200 import scenes as sc  # noqa: E402
+
+METRIC = "particle_substeps_per_sec"
+UNIT = "particle-substeps/s"
+# algorithmic bytes, SURVEY.md 8(d): per particle-substep 340 B (sand) / 376 B (snow); per active grid node 172 B
+BYTES_PARTICLE = {sc.SAND: 340.0, sc.SNOW: 376.0}
+BYTES_NODE = 172.0
+# per-stage split of the same model (sand; snow adds 36 B to forces)
+STAGE_BYTES = {"forces": (52.0, 24.0), "g2p": (224.0, 24.0), "p2g": (64.0, 44.0), "grid": (0.0, 52.0), "sort": (0.0, 0.0)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(device)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            busy = [s for s in sm if s >= 0.5 * max(sm)]
+            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def dam_break_positions(res, seed=5, y_range=None):
+    """C5 positions only (memory-lean): the column of scenes.c5_dam_break, optionally restricted to y in [y0, y1)."""
+    rng = np.random.default_rng(seed)
+    h = 1.0 / res
+    lo = np.array([2 * h, 2 * h, 2 * h]); hi = np.array([0.25, 1.0 - 2 * h, 0.25])
+    keep = None
+    if y_range is not None:
+        keep = lambda p: (p[:, 1] >= y_range[0]) & (p[:, 1] < y_range[1])
+    return sc.jittered_lattice(lo, hi, np.array([h, h, h]), rng, keep=keep)
+
+
+def packed_rest_state(x, mass, pinned=False):
+    """Host arrays in the reference's layouts for particles at rest (F = I, v = B = 0), built without (N,3,3) temporaries."""
+    import torch
+    n = x.shape[0]
+
+    def buf(shape, fill=0.0):
+        t = torch.empty(shape, dtype=torch.float64, pin_memory=pinned)
+        a = t.numpy(); a[...] = fill
+        return t, a
+    keep = []
+    xs_t, xs = buf((3, n)); xs[...] = x.T
+    v_t, v = buf((3, n)); b1_t, b1 = buf((3, n)); b2_t, b2 = buf((3, n)); b3_t, b3 = buf((3, n))
+    fe_t, fe = buf((n, 9)); fe[:, 0] = 1.0; fe[:, 4] = 1.0; fe[:, 8] = 1.0
+    fp_t, fp = buf((n, 9)); fp[...] = fe
+    m_t, m = buf((n,), mass); vol_t, vol = buf((n,), 1.0); q_t, q = buf((n,))
+    keep = [xs_t, v_t, b1_t, b2_t, b3_t, fe_t, fp_t, m_t, vol_t, q_t]
+    return [xs, v, b1, b2, b3, fe, fp, m, vol, q], keep
+
+
+def make_shell_scene(res):
+    """Grid + level set of C5 without particles."""
+    g = sc.GridSpec(np.zeros(3), np.ones(3), np.array([res] * 3))
+    h = g.h; e = 1e-4 * h[0]
+    ls = sc.LevelSetSpec(sc.LS_BOX, np.array([2 * h[0] - e, 2 * h[1] - e, 2 * h[2] - e, 1 - 2 * h[0] + e, 1 - 2 * h[1] + e, 1 - 2 * h[2] + e, 0, 0.0]))
+    return sc.Scene("C5_dam_break", g, sc.SAND, None, None, ls)
+
+
+def cpu_baseline(threads, seconds_budget=20.0, res=64):
+    """The oracle (CPU restatement of the reference's path) on a bounded sample of the same workload: the C5 dam break at
+    res^3 (same particles per cell, same material, same collider), 2 warm-up + timed substeps."""
+    from oracle.oracle_py import Oracle
+    scene = sc.c5_dam_break(res=res)
+    o = Oracle(scene, threads=threads); o.init()
+    used = o.L.orc_get_threads(o.h)
+    for _ in range(2):
+        o.substep()
+    n = 0; t0 = time.perf_counter()
+    while True:
+        o.substep(); n += 1
+        el = time.perf_counter() - t0
+        if el > seconds_budget or n >= 200:
+            break
+    return {"value": scene.particles.n * n / el, "unit": UNIT, "cores": int(used), "kind": "port",
+            "sample": f"C5 dam break at {res}^3 grid, {scene.particles.n} particles, {n} substeps in {el:.1f} s (fp64 oracle, oracle/mpm_oracle.cpp)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The reference cannot be
+    compiled here (needs Eigen + libigl + GLFW + GLEW), so this times the oracle port with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle_py import Oracle
+    res = args.ref_res
+    scene = sc.c5_dam_break(res=res)
+    o = Oracle(scene, threads=0); o.init()
+    used = o.L.orc_get_threads(o.h)
+    for _ in range(args.warmup):
+        o.substep()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.substep()
+    el = time.perf_counter() - t0
+    val = scene.particles.n * args.steps / el
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args, res_override=res, note="bounded sample of the workload: same scene at a smaller grid"),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": int(used), "kind": "port",
+                             "sample": f"C5 dam break at {res}^3 grid, {scene.particles.n} particles, {args.steps} substeps"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, res_override=None, note=None, n_particles=None):
+    res = res_override or args.res
+    cfg = {"workload": f"C5 synthetic sand dam break (Drucker-Prager), 8 particles/cell, {res}^3 grid", "grid": [res] * 3,
+           "material": "sand", "collider": "box level set", "timestep": "reference rule dt = 0.3 / max(300, vmax/h), on device",
+           "l2": "inputs (particle state >> 126 MB L2) larger than L2; no explicit flush"}
+    if n_particles is not None:
+        cfg["particles"] = int(n_particles)
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+def run_engine(args):
+    import torch
+    from anisotropicelastoplasticity_b200.engine import Engine
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 or args.gpus > 1:
+        from anisotropicelastoplasticity_b200 import distributed as dist_mod
+        return dist_mod.bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, UNIT)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    res = args.res
+    t_gen = time.perf_counter()
+    x = dam_break_positions(res)
+    n = x.shape[0]
+    mass = sc.SAND_RHO * (1.0 / res) ** 3 / 8.0
+    arrs, keep = packed_rest_state(x, mass, pinned=True)
+    del x
+    t_gen = time.perf_counter() - t_gen
+    shell = make_shell_scene(res)
+    eng = Engine(shell, device=local)
+    eng.upload_packed(n, arrs, sc.SAND_E, sc.SAND_NU, 2.5e-2, 7.5e-3)
+    eng.init()
+    stream = torch.cuda.ExternalStream(eng.stream, device=local)
+    # ---- warm-up
+    eng.run(args.warmup); eng.sync()
+    # ---- timed region: K substeps, device events on the engine's stream
+    sampler = ClockSampler(local)
+    launches0 = eng.kernel_launches
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); ev0.record(stream)
+    eng.run(args.steps)
+    ev1.record(stream); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = eng.kernel_launches - launches0
+    clk = eng.clock()
+    value = n * args.steps / (ms * 1e-3)
+    # ---- per-stage device time (separate pass with 2 events per stage) -> dominant kernel roofline
+    blocks, nodes = eng.grid_activity()
+    eng.profile(True); eng.run(max(3, min(args.steps, 10))); eng.sync(); tm = eng.timers(); eng.profile(False)
+    peak, peak_kind = measured_peak_gbs()
+    stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in tm.items()}
+    dom = max(("forces", "g2p", "p2g", "grid", "sort"), key=lambda k: stage_ms.get(k, 0.0))
+    bp, bn = STAGE_BYTES[dom]
+    dom_bytes = bp * n + bn * nodes
+    achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+    sub_bytes = BYTES_PARTICLE[sc.SAND] * n + BYTES_NODE * nodes
+    sub_gbs = sub_bytes / (ms * 1e-3 / args.steps) / 1e9
+    roofline = {"bound": "hbm", "kernel": {"forces": "k_forces", "g2p": "k_g2p", "p2g": "k_p2g", "grid": "k_grid_update", "sort": "cub radix sort + k_reorder"}[dom],
+                "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth, MEASURED_PEAKS.json", "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom],
+                "stage_ms": stage_ms,
+                "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes, "active_blocks": blocks}}
+    # ---- e2e: host fp64 state -> device, K substeps, f32 positions back (HybridSolver::solve's host-visible traffic)
+    eng.close(); del eng
+    eng2 = Engine(shell, device=local)
+    out_t = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
+    import ctypes as C
+    from anisotropicelastoplasticity_b200 import capi
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    eng2.upload_packed(n, arrs, sc.SAND_E, sc.SAND_NU, 2.5e-2, 7.5e-3)
+    eng2.init()
+    eng2.run(args.steps)
+    capi.check(eng2.L.aep_download_positions_f32(eng2.h, C.cast(out_t.data_ptr(), C.POINTER(C.c_float))), eng2.h)
+    t_e2e = time.perf_counter() - t0
+    h2d = 36 * 8 * n; d2h = 12 * n
+    e2e = {"value": n * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+           "seconds": t_e2e, "what": "aep_upload_particles(fp64 host, pinned) + aep_init + K substeps + aep_download_positions_f32"}
+    assert np.isfinite(out_t.numpy()).all()
+    eng2.close()
+    cpu = cpu_baseline(threads=1) if not args.no_cpu else None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, n_particles=n), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "sim": {"dt": clk["dt"], "t": clk["t"] + clk["inner_t"], "escaped": clk["escaped"], "vmax": clk["vmax"]},
+            "setup_s": {"generate": t_gen}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--res", type=int, default=512, help="grid resolution of the C5 dam break (512 = 64M particles)")
+    ap.add_argument("--ref-res", type=int, default=64, help="grid resolution of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,192 @@
+/* ============================================================================================
+ * aep_b200.h -- C ABI of the B200-native MPM substep engine (libaep_b200.so).
+ *
+ * Drop-in boundary for the hot path of 2iw31Zhv/AnisotropicElastoplasticity:
+ *   HybridSolver::solve's loop body, AnisotropicElastoplasticity/HybridSolver.cpp:867-1032
+ *   ("HS:" below), and the functions it calls.  The reference has no FFI of its own; its boundary
+ *   is the C++ class surface HybridSolver / ParticleSystem / RegularGrid / LagrangianMesh
+ *   (HybridSolver.h:27-95).  include/aep/ *.h re-creates those classes on top of this ABI and
+ *   INTEGRATION.md shows the few lines a maintainer changes in the reference to bind to it.
+ *
+ * Conventions
+ *   - plain C: opaque handle, POD config struct, raw pointers + sizes, int return codes
+ *     (0 = AEP_OK, negative = error; message via aep_last_error).  No exceptions cross the ABI.
+ *   - host arrays use the reference's memory layouts:
+ *       N x 3 matrix            column-major, leading dimension N      (Eigen::MatrixX3d)
+ *       N 3x3 tensors           9 doubles each, column-major per item  (std::vector<Eigen::Matrix3d>)
+ *       grid node index         k*nx*ny + j*nx + i                     (RegularGrid.cpp:164-168)
+ *     fp64 at the boundary, fp32 on the device; conversion happens on the GPU at upload/download.
+ *   - one aep_ctx is single-threaded (caller serialises).  All stepping calls are asynchronous on the
+ *     context's CUDA stream; downloads and aep_sync synchronise.
+ *   - there is NO CPU fallback: aep_create fails with AEP_ERR_CUDA when no sm_100 device is usable.
+ * ============================================================================================ */
+#ifndef AEP_B200_H
+#define AEP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AEP_API __attribute__((visibility("default")))
+#else
+#define AEP_API
+#endif
+
+#define AEP_OK 0
+#define AEP_ERR_INVALID (-1)   /* bad argument / call order            */
+#define AEP_ERR_CUDA (-2)      /* CUDA runtime error (see last_error)  */
+#define AEP_ERR_ALLOC (-3)     /* out of device / host memory          */
+#define AEP_ERR_STATE (-4)     /* particles left the grid, NaN, ...    */
+
+/* MaterialType, HybridSolver.h:21-25 */
+#define AEP_SNOW 0
+#define AEP_SAND 1
+
+/* Level-set primitives.  1,2 = LevelSet.cpp:8-42; 3,4 are new (BASELINE configs C2/C3/C5 need a sphere / a box);
+ * 5 = arbitrary std::function sampled at the grid nodes by the host (HS:473-482 only ever evaluates phi there). */
+#define AEP_LS_NONE 0
+#define AEP_LS_GROUND 1         /* params: groundZ                                  */
+#define AEP_LS_WALL2GROUND 2    /* params: wallX, wallY, groundZ                    */
+#define AEP_LS_SPHERE_GROUND 3  /* params: cx, cy, cz, radius, groundZ              */
+#define AEP_LS_BOX 4            /* params: x0, y0, z0, x1, y1, z1 (inside is free)  */
+#define AEP_LS_SAMPLED 5
+
+typedef struct aep_ctx aep_ctx;
+
+/* Every literal the reference hard-codes on the hot path, with its default (SURVEY.md section 5 "Config / flags"). */
+typedef struct aep_config {
+    int32_t device;            /* CUDA device ordinal                                                        */
+    int32_t material;          /* AEP_SAND: literal at HS:873,955,959                                        */
+    double grid_min[3];        /* RegularGrid ctor, RegularGrid.cpp:117-162                                  */
+    double grid_max[3];
+    int32_t res[3];
+    int32_t _pad0;
+    double cfl;                /* 0.3, main.cpp:27                                                           */
+    double gravity;            /* 9.8 along -z, HS:457                                                       */
+    double collider_friction;  /* 0.2, HS:465                                                                */
+    double snow_hardening;     /* 10, HS:267                                                                 */
+    double sand_h[4];          /* 35, 9, 0.2, 10, HS:641-644                                                 */
+    double dt_rate_floor;      /* 300, HS:860,878   dt = cfl / max(rate_floor, vmax/hmin)                    */
+    double frame_dt;           /* 1/60, HS:880-884                                                           */
+    int64_t particle_capacity; /* 0 = exactly what aep_upload_particles is given; >0 reserves room for
+                                  particles migrating in from neighbouring ranks                             */
+    /* spatial slab owned by this context (multi-GPU).  Cells [slab_lo, slab_hi) along slab_axis.
+     * slab_axis < 0: the context owns the whole grid.                                                        */
+    int32_t slab_axis;
+    int32_t slab_lo;
+    int32_t slab_hi;
+    int32_t sort_every;        /* physical re-sort period in substeps (1 = every substep)                    */
+} aep_config;
+
+AEP_API int aep_default_config(aep_config* cfg);
+AEP_API int aep_create(aep_ctx** out, const aep_config* cfg);
+AEP_API int aep_destroy(aep_ctx* ctx);
+/* ctx may be NULL: returns the message of the last failed aep_create on this thread. */
+AEP_API const char* aep_last_error(aep_ctx* ctx);
+AEP_API int aep_sync(aep_ctx* ctx);
+
+/* ---- state upload ---------------------------------------------------------------------------------------
+ * ParticleSystem public members (ParticleSystem.h:22-41).  B1,B2,B3 = affineMomenta_{1,2,3} (rows of B).
+ * E, nu, theta_c, theta_s = youngsModulus, poissonRatio, criticalCompression, criticalStretch.              */
+AEP_API int aep_upload_particles(aep_ctx* ctx, int64_t n, const double* x, const double* v, const double* B1,
+                                 const double* B2, const double* B3, const double* FE, const double* FP,
+                                 const double* m, const double* vol, const double* q, double E, double nu,
+                                 double theta_c, double theta_s);
+
+/* LagrangianMesh public members (LagrangianMesh.h:38-74).  vB/eB: three consecutive N x 3 blocks (rows of B);
+ * ed/eD: elementDirections_{1,2,3} / rest directions as three consecutive nf x 3 blocks; faces nf x 3
+ * column-major int32; fixedv: nv doubles (bindConstraints, LagrangianMesh.cpp:354-363) or NULL.            */
+AEP_API int aep_upload_mesh(aep_ctx* ctx, int64_t nv, int64_t nf, const double* vx, const double* vv,
+                            const double* vm, const double* vvol, const double* vB, const int32_t* faces,
+                            const double* ev, const double* em, const double* evol, const double* eB,
+                            const double* ed, const double* eD, const double* fixedv, double mu, double lambda,
+                            double shear_stiffness, double stiffness, double friction_coeff);
+
+/* HybridSolver::setLevelSet (HybridSolver.h:89).  Colliders are static (HS:484) and only sampled at nodes.  */
+AEP_API int aep_set_levelset_analytic(aep_ctx* ctx, int kind, const double* params8);
+AEP_API int aep_set_levelset_samples(aep_ctx* ctx, const uint8_t* inside /*Ng*/, const double* normal /*Ng x 3*/);
+
+/* ---- stepping ------------------------------------------------------------------------------------------- */
+/* HS:830-860: bin particles, first particleToGrid_ (computes volumes, HS:242-249), initial dt.             */
+AEP_API int aep_init(aep_ctx* ctx);
+/* One iteration of the while loop HS:867-1032 with the reference's dt rule evaluated on the device.        */
+AEP_API int aep_substep(aep_ctx* ctx);
+/* n iterations back to back, no host synchronisation in between.                                           */
+AEP_API int aep_run(aep_ctx* ctx, int n_substeps);
+/* Run until `n_frames` more 1/60 s frames have completed (HS:880-892); returns the substeps taken.         */
+AEP_API int aep_run_frames(aep_ctx* ctx, int n_frames, int max_substeps, int64_t* substeps_done);
+
+/* Stage-level entry points for the parity tests; same split as the reference's private methods.            */
+AEP_API int aep_p2g(aep_ctx* ctx, int first);                 /* re-bin + particleToGrid_      HS:113-250, 18-97 */
+AEP_API int aep_stage_forces(aep_ctx* ctx, double dt);        /* computeGridForces_            HS:252-458        */
+AEP_API int aep_stage_grid(aep_ctx* ctx, double dt);          /* updateGridVelocities_ + max|v| + gridCollisionHandling_  HS:725-737, 460-551 */
+AEP_API int aep_stage_g2p(aep_ctx* ctx, double dt);           /* HS:739-825, 940-951, 553-609, 612-723           */
+
+AEP_API int aep_set_dt(aep_ctx* ctx, double dt);
+/* dt, simulated time t, time inside the current frame, frames completed, substeps done, max |v_i| of the last
+ * grid update, number of particles that tried to leave the grid (sticky).  Any pointer may be NULL.        */
+AEP_API int aep_get_clock(aep_ctx* ctx, double* dt, double* t, double* inner_t, int32_t* frame_no,
+                          int64_t* substeps, double* vmax, int64_t* escaped);
+
+/* ---- state download (original particle order, reference layouts; any pointer may be NULL) --------------- */
+AEP_API int64_t aep_num_particles(aep_ctx* ctx);
+AEP_API int aep_download_particles(aep_ctx* ctx, double* x, double* v, double* B1, double* B2, double* B3,
+                                   double* FE, double* FP, double* vol, double* q);
+/* RegularGrid::masses / velocities / forces (RegularGrid.h:36-41) and gridVelocitiesBeforeFriction (HS:460-463).
+ * After aep_p2g: v = p/m.  After aep_stage_grid: v = post-collision, vt = pre-friction.                     */
+AEP_API int aep_download_grid(aep_ctx* ctx, double* m, double* v, double* f, double* vt);
+AEP_API int aep_download_mesh(aep_ctx* ctx, double* vx, double* vv, double* vB, double* ex, double* ev,
+                              double* eB, double* ed);
+/* positions only, float32 x,y,z interleaved, original order: the per-frame OBJ payload of HS:991-1007.     */
+AEP_API int aep_download_positions_f32(aep_ctx* ctx, float* xyz);
+/* bulk statistics on the device: centre of mass (3), kinetic energy, mean det F_P, total mass.             */
+AEP_API int aep_stats(aep_ctx* ctx, double* com3, double* kinetic, double* mean_jp, double* mass);
+
+/* ---- instrumentation ------------------------------------------------------------------------------------ */
+/* 8x8x8-node blocks touched by the last P2G and nodes with m_i > 0 (the "active nodes" of the roofline model).  */
+AEP_API int aep_grid_activity(aep_ctx* ctx, int64_t* active_blocks, int64_t* active_nodes);
+/* Number of kernels this library launched since aep_create (its own kernels and the cub sort passes).      */
+AEP_API int64_t aep_kernel_launches(aep_ctx* ctx);
+/* The CUDA stream all work is enqueued on (cudaStream_t as void*), for event timing by the caller.          */
+AEP_API void* aep_stream(aep_ctx* ctx);
+/* Per-stage device time accumulated since the last reset when profiling is enabled (costs 2 events/stage).  */
+AEP_API int aep_profile(aep_ctx* ctx, int enable);
+AEP_API int aep_get_timers(aep_ctx* ctx, double* ms /*AEP_NUM_STAGES*/, int64_t* calls /*AEP_NUM_STAGES*/);
+#define AEP_STAGE_SORT 0
+#define AEP_STAGE_P2G 1
+#define AEP_STAGE_FORCES 2
+#define AEP_STAGE_GRID 3
+#define AEP_STAGE_G2P 4
+#define AEP_STAGE_MESH 5
+#define AEP_STAGE_HALO 6
+#define AEP_NUM_STAGES 8
+
+/* ---- multi-GPU slab decomposition -------------------------------------------------------------
+ * The context owns cells [slab_lo, slab_hi) along slab_axis.  Ghost node planes: 1 below, 2 above (cubic support).
+ * The exchange itself (NCCL send/recv or peer copies) is driven by the caller on buffers this library packs:
+ *   side 0 = low neighbour, 1 = high neighbour; what 0 = (m, p) after P2G, 1 = f after the force pass.
+ * halo buffers are device pointers of `*n_floats` float32 laid out [plane][node-in-plane][channel].          */
+AEP_API int aep_halo_info(aep_ctx* ctx, int what, int side, int64_t* n_floats);
+AEP_API int aep_halo_pack(aep_ctx* ctx, int what, int side, void** dev_send);
+AEP_API int aep_halo_recv_buffer(aep_ctx* ctx, int what, int side, void** dev_recv);
+AEP_API int aep_halo_add(aep_ctx* ctx, int what, int side);
+/* local max |v_i| lives on the device; the caller all-reduces (max) this one float in place before aep_stage_g2p */
+AEP_API int aep_vmax_device_ptr(aep_ctx* ctx, void** dev_float);
+/* split stepping for the multi-GPU driver: forces | grid | finish_dt | g2p+rebin | p2g */
+AEP_API int aep_step_forces(aep_ctx* ctx);
+AEP_API int aep_step_grid(aep_ctx* ctx);
+AEP_API int aep_step_g2p(aep_ctx* ctx);
+AEP_API int aep_step_p2g(aep_ctx* ctx);
+/* particle migration: records are AEP_MIGRATE_FLOATS float32 per particle */
+#define AEP_MIGRATE_FLOATS 44
+AEP_API int aep_migrate_extract(aep_ctx* ctx, int64_t* n_low, int64_t* n_high, void** dev_low, void** dev_high);
+AEP_API int aep_migrate_recv_buffer(aep_ctx* ctx, int side, int64_t n, void** dev_recv);
+AEP_API int aep_migrate_insert(aep_ctx* ctx, int64_t n_from_low, int64_t n_from_high);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AEP_B200_H */

@@ -425,6 +425,28 @@ void cloth_in_plane(const Sim& S, std::vector<double>& vf, std::vector<double>& 
     }
 }
 
+// HS:277-352 body of the particle loop: stress = V_p * P(Fhat) * FE^T
+M3 particle_stress(const Sim& S, const M3& Fh, const M3& FE, const M3& FP, double vol, double lambda0, double mu0) {
+    double lambda = lambda0, mu = mu0;
+    if (S.material == 0) {                                         // SNOW HS:281-287
+        double Jp = det(FP);
+        lambda = lambda0 * std::exp(S.snow_xi * (1 - Jp)); mu = mu0 * std::exp(S.snow_xi * (1 - Jp));
+    }
+    M3 U, V; double sg[3]; svd3(Fh, U, sg, V);                     // HS:308
+    if (S.material == 0) {                                         // HS:314-325
+        M3 Rm = mul(U, transpose(V));
+        double J = det(Fh);
+        M3 P = add(scale(sub(Fh, Rm), 2.0 * mu), scale(inverse(transpose(Fh)), lambda * (J - 1.0) * J));
+        return scale(mul(P, transpose(FE)), vol);
+    }
+    double ls[3] = { std::log(sg[0]), std::log(sg[1]), std::log(sg[2]) };   // SAND HS:326-339
+    double tr = ls[0] + ls[1] + ls[2];
+    M3 Dg = diag3(2 * mu * (1.0 / sg[0]) * ls[0] + lambda * tr * (1.0 / sg[0]),
+                  2 * mu * (1.0 / sg[1]) * ls[1] + lambda * tr * (1.0 / sg[1]),
+                  2 * mu * (1.0 / sg[2]) * ls[2] + lambda * tr * (1.0 / sg[2]));
+    return scale(mul(mul(mul(U, Dg), transpose(V)), transpose(FE)), vol);
+}
+
 // HS:252-458 computeGridForces_
 void compute_grid_forces(Sim& S, double Dt) {
     std::fill(S.gf.begin(), S.gf.end(), 0.0);
@@ -433,29 +455,10 @@ void compute_grid_forces(Sim& S, double Dt) {
         double lambda0 = S.E * S.nu / (1.0 + S.nu) / (1.0 - 2.0 * S.nu), mu0 = S.E / 2.0 / (1.0 + S.nu);   // HS:264-265
 #pragma omp parallel for schedule(static) num_threads(S.nthreads)
         for (long p = 0; p < S.Np; ++p) {
-            double lambda = lambda0, mu = mu0;
             M3 FE = load_m3(S.FE, p);
-            if (S.material == 0) {                                         // SNOW HS:281-287
-                double Jp = det(load_m3(S.FP, p));
-                lambda = lambda0 * std::exp(S.snow_xi * (1 - Jp)); mu = mu0 * std::exp(S.snow_xi * (1 - Jp));
-            }
             M3 Mod = scale(grad_field(S, S.sp, p, S.gv), Dt);              // HS:269-271
             M3 Fh = add(FE, mul(Mod, FE));                                 // HS:306
-            M3 U, V; double sg[3]; svd3(Fh, U, sg, V);                     // HS:308
-            M3 stress;
-            if (S.material == 0) {                                         // HS:314-325
-                M3 Rm = mul(U, transpose(V));
-                double J = det(Fh);
-                M3 P = add(scale(sub(Fh, Rm), 2.0 * mu), scale(inverse(transpose(Fh)), lambda * (J - 1.0) * J));
-                stress = scale(mul(P, transpose(FE)), S.vol[p]);
-            } else {                                                       // SAND HS:326-339
-                double ls[3] = { std::log(sg[0]), std::log(sg[1]), std::log(sg[2]) };
-                double tr = ls[0] + ls[1] + ls[2];
-                M3 Dg = diag3(2 * mu * (1.0 / sg[0]) * ls[0] + lambda * tr * (1.0 / sg[0]),
-                              2 * mu * (1.0 / sg[1]) * ls[1] + lambda * tr * (1.0 / sg[1]),
-                              2 * mu * (1.0 / sg[2]) * ls[2] + lambda * tr * (1.0 / sg[2]));
-                stress = scale(mul(mul(mul(U, Dg), transpose(V)), transpose(FE)), S.vol[p]);
-            }
+            M3 stress = particle_stress(S, Fh, FE, load_m3(S.FP, p), S.vol[p], lambda0, mu0);
             scatter_stress(S, S.sp, p, stress, par);
         }
     }
@@ -653,38 +656,43 @@ void update_deformation_gradient(Sim& S, double Dt) {
     }
 }
 
+// HS:616-679 body of the particle loop
+void particle_return_map(const Sim& S, const M3& Fc, M3& FE_out, M3& FP, double& q) {
+    const double PI = 3.14159265358979323846;                              // igl::PI
+    M3 Ftot = mul(Fc, FP);                                                 // HS:618-619
+    M3 U, V; double sg[3]; svd3(Fc, U, sg, V);                             // HS:620
+    if (S.material == 0) {                                                 // HS:626-631
+        for (int i = 0; i < 3; ++i) sg[i] = clampd(sg[i], 1.0 - S.thetaC, 1.0 + S.thetaS);
+    } else {                                                               // HS:632-674
+        double lambda = S.E * S.nu / (1.0 + S.nu) / (1.0 - 2.0 * S.nu), mu = S.E / 2.0 / (1.0 + S.nu);
+        double phi = (S.sand_h[0] + (S.sand_h[1] * q - S.sand_h[3]) * std::exp(-S.sand_h[2] * q)) * PI / 180.0;   // HS:646-647
+        double alpha = std::sqrt(2.0 / 3.0) * 2.0 * std::sin(phi) / (3.0 - std::sin(phi));                         // HS:649-650
+        double ls[3] = { std::log(sg[0]), std::log(sg[1]), std::log(sg[2]) };
+        double tr = ls[0] + ls[1] + ls[2];
+        double dv[3] = { ls[0] - tr / 3.0 * 1.0, ls[1] - tr / 3.0 * 1.0, ls[2] - tr / 3.0 * 1.0 };
+        double dvn = std::sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]);
+        double dg = dvn + (3.0 * lambda + 2.0 * mu) / 2.0 / mu * tr * alpha;                                        // HS:654-656
+        if (dg <= 0.0) {
+        } else if (dvn == 0.0 || tr > 0.0) {                               // HS:662-666
+            q += std::sqrt(ls[0] * ls[0] + ls[1] * ls[1] + ls[2] * ls[2]);
+            sg[0] = sg[1] = sg[2] = 1.0;
+        } else {                                                           // HS:667-673
+            for (int i = 0; i < 3; ++i) sg[i] = std::exp(ls[i] - dg * dv[i] / dvn);
+            q += dg;
+        }
+    }
+    FE_out = mul(mul(U, diag3(sg[0], sg[1], sg[2])), transpose(V));                                                  // HS:675
+    FP = mul(mul(mul(V, diag3(1.0 / sg[0], 1.0 / sg[1], 1.0 / sg[2])), transpose(U)), Ftot);                         // HS:676-677
+}
+
 // HS:612-723 updatePlasticity_
 void update_plasticity(Sim& S) {
     if (S.Np) {
-        const double PI = 3.14159265358979323846;                          // igl::PI
 #pragma omp parallel for schedule(static) num_threads(S.nthreads)
         for (long p = 0; p < S.Np; ++p) {
-            M3 Fc = load_m3(S.cand, p), FP = load_m3(S.FP, p);
-            M3 Ftot = mul(Fc, FP);                                         // HS:618-619
-            M3 U, V; double sg[3]; svd3(Fc, U, sg, V);                     // HS:620
-            if (S.material == 0) {                                         // HS:626-631
-                for (int i = 0; i < 3; ++i) sg[i] = clampd(sg[i], 1.0 - S.thetaC, 1.0 + S.thetaS);
-            } else {                                                       // HS:632-674
-                double lambda = S.E * S.nu / (1.0 + S.nu) / (1.0 - 2.0 * S.nu), mu = S.E / 2.0 / (1.0 + S.nu);
-                double qp = S.q[p];
-                double phi = (S.sand_h[0] + (S.sand_h[1] * qp - S.sand_h[3]) * std::exp(-S.sand_h[2] * qp)) * PI / 180.0;   // HS:646-647
-                double alpha = std::sqrt(2.0 / 3.0) * 2.0 * std::sin(phi) / (3.0 - std::sin(phi));                           // HS:649-650
-                double ls[3] = { std::log(sg[0]), std::log(sg[1]), std::log(sg[2]) };
-                double tr = ls[0] + ls[1] + ls[2];
-                double dv[3] = { ls[0] - tr / 3.0 * 1.0, ls[1] - tr / 3.0 * 1.0, ls[2] - tr / 3.0 * 1.0 };
-                double dvn = std::sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]);
-                double dg = dvn + (3.0 * lambda + 2.0 * mu) / 2.0 / mu * tr * alpha;                                          // HS:654-656
-                if (dg <= 0.0) {
-                } else if (dvn == 0.0 || tr > 0.0) {                       // HS:662-666
-                    S.q[p] += std::sqrt(ls[0] * ls[0] + ls[1] * ls[1] + ls[2] * ls[2]);
-                    sg[0] = sg[1] = sg[2] = 1.0;
-                } else {                                                   // HS:667-673
-                    for (int i = 0; i < 3; ++i) sg[i] = std::exp(ls[i] - dg * dv[i] / dvn);
-                    S.q[p] += dg;
-                }
-            }
-            store_m3(S.FE, p, mul(mul(U, diag3(sg[0], sg[1], sg[2])), transpose(V)));                                         // HS:675
-            store_m3(S.FP, p, mul(mul(mul(V, diag3(1.0 / sg[0], 1.0 / sg[1], 1.0 / sg[2])), transpose(U)), Ftot));            // HS:676-677
+            M3 FE, FP = load_m3(S.FP, p); double qp = S.q[p];
+            particle_return_map(S, load_m3(S.cand, p), FE, FP, qp);
+            store_m3(S.FE, p, FE); store_m3(S.FP, p, FP); S.q[p] = qp;
         }
     }
     if (S.Nv) {                                                            // HS:684-722
@@ -877,6 +885,21 @@ void orc_svd3(const double* F9, double* U9, double* s3, double* V9) {
 void orc_svd2(const double* A4, double* U4, double* s2, double* V4) { svd2(A4, U4, s2, V4); }
 void orc_gram_schmidt(const double* A9, double* Q9, double* R9) {
     M3 A, Q, R; std::memcpy(A.a, A9, 72); gram_schmidt(Q, R, A); std::memcpy(Q9, Q.a, 72); std::memcpy(R9, R.a, 72);
+}
+
+// single-particle hooks: same code path as the loops above (used to pin the fp32 device math)
+void orc_particle_stress(int material, double E, double nu, double snow_xi, const double* Fh9, const double* FE9, const double* FP9,
+                         double vol, double* A9) {
+    Sim S; S.material = material; S.snow_xi = snow_xi;
+    double lambda0 = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu), mu0 = E / 2.0 / (1.0 + nu);
+    M3 Fh, FE, FP; std::memcpy(Fh.a, Fh9, 72); std::memcpy(FE.a, FE9, 72); std::memcpy(FP.a, FP9, 72);
+    M3 A = particle_stress(S, Fh, FE, FP, vol, lambda0, mu0); std::memcpy(A9, A.a, 72);
+}
+void orc_particle_return_map(int material, double E, double nu, double thetaC, double thetaS, const double* Fc9, double* FE9,
+                             double* FP9, double* q) {
+    Sim S; S.material = material; S.E = E; S.nu = nu; S.thetaC = thetaC; S.thetaS = thetaS;
+    M3 Fc, FE, FP; std::memcpy(Fc.a, Fc9, 72); std::memcpy(FP.a, FP9, 72);
+    particle_return_map(S, Fc, FE, FP, *q); std::memcpy(FE9, FE.a, 72); std::memcpy(FP9, FP.a, 72);
 }
 double orc_ls_phi(int kind, const double* P, const double* x) { return ls_phi(kind, P, x); }
 void orc_ls_normal(int kind, const double* P, const double* x, double* n) { ls_normal(kind, P, x, n); }

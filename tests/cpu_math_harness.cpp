@@ -1,0 +1,43 @@
+// tests/cpu_math_harness.cpp -- TEST-ONLY: compiles the device math header (csrc/aep_math.cuh) for the host so that the
+// fp32 B-spline / SVD / stress / return-mapping code can be checked against the fp64 oracle without a GPU.
+// Not part of the product; nothing in the package loads it.
+#include <cmath>
+#include <cstring>
+#define AEP_HOST_MATH_TEST
+#define __device__
+#define __host__
+#define __forceinline__ inline
+static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+static inline float __fdividef(float a, float b) { return a / b; }
+#include "../anisotropicelastoplasticity_b200/csrc/aep_math.cuh"
+
+using namespace aep;
+extern "C" {
+void h_bspline4(float f, float* N, float* D) { float n[4], d[4]; bspline4(f, n, d); std::memcpy(N, n, 16); std::memcpy(D, d, 16); }
+void h_bspline_lane(float f, int o, float* N, float* D) { bspline_lane(f, o, *N, *D); }
+void h_svd3(const float* F, float* U, float* S, float* V) {
+    float f[9]; std::memcpy(f, F, 36); Svd3 sv; svd3(f, sv);
+    std::memcpy(U, sv.U, 36); std::memcpy(S, sv.S, 12); std::memcpy(V, sv.V, 36);
+}
+static MatParams mk(int material, double E, double nu, double thetaC, double thetaS) {
+    MatParams M; const double la = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu), mu = E / 2.0 / (1.0 + nu);
+    M.lambda0 = (float)la; M.mu0 = (float)mu; M.xi = 10.f; M.lo = (float)(1.0 - thetaC); M.hi = (float)(1.0 + thetaS);
+    M.h0 = 35.f; M.h1 = 9.f; M.h2 = 0.2f; M.h3 = 10.f; M.k_vol = (float)((3.0 * la + 2.0 * mu) / 2.0 / mu); M.material = material;
+    return M;
+}
+// row-major float[9] in/out
+void h_stress(int material, double E, double nu, const float* Fh, const float* FE, float vol, float Jp, float* A) {
+    MatParams M = mk(material, E, nu, 2.5e-2, 7.5e-3);
+    float fh[9], fe[9], a[9]; std::memcpy(fh, Fh, 36); std::memcpy(fe, FE, 36);
+    stress_times_FEt(M, fh, fe, vol, Jp, a); std::memcpy(A, a, 36);
+}
+void h_return_map(int material, double E, double nu, double thetaC, double thetaS, const float* Fh, float* FE, float* FP, float* q) {
+    MatParams M = mk(material, E, nu, thetaC, thetaS);
+    float fh[9], fe[9], fp[9]; std::memcpy(fh, Fh, 36); std::memcpy(fp, FP, 36);
+    return_map(M, fh, fe, fp, *q); std::memcpy(FE, fe, 36); std::memcpy(FP, fp, 36);
+}
+void h_gram_schmidt(const float* d1, const float* d2, const float* d3, float* Q, float* R) {
+    float a[3], b[3], c[3], q[9], r[9]; std::memcpy(a, d1, 12); std::memcpy(b, d2, 12); std::memcpy(c, d3, 12);
+    gram_schmidt(a, b, c, q, r); std::memcpy(Q, q, 36); std::memcpy(R, r, 36);
+}
+}

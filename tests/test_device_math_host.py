@@ -1,0 +1,91 @@
+"""fp32 device math (csrc/aep_math.cuh) compiled for the HOST through tests/cpu_math_harness.cpp and checked against
+the fp64 oracle.  CPU only; pins B-spline, SVD, stress and return-mapping numerics before any GPU time is spent.
+The harness is test infrastructure: the product never loads it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as op
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+fp = C.POINTER(C.c_float); dp = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def H(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("harness") / "libmath_host.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, os.path.join(HERE, "cpu_math_harness.cpp")])
+    h = C.CDLL(so)
+    h.h_bspline4.argtypes = [C.c_float, fp, fp]; h.h_bspline_lane.argtypes = [C.c_float, C.c_int, fp, fp]
+    h.h_stress.argtypes = [C.c_int, C.c_double, C.c_double, fp, fp, C.c_float, C.c_float, fp]
+    h.h_return_map.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, fp, fp, fp, fp]
+    return h
+
+
+def P(a): return a.ctypes.data_as(fp)
+def D(a): return a.ctypes.data_as(dp)
+def f32(a): return np.ascontiguousarray(a, np.float32)
+
+
+def test_bspline_forms_match_reference(H):
+    """thread form (4 nodes) and lane form (one node) both equal interpolation.cpp:9-33 at u = f + 1 - o."""
+    rng = np.random.default_rng(0)
+    for f in list(rng.random(300)) + [0.0, 0.99999994, 0.5, 1e-7]:
+        N = np.zeros(4, np.float32); Dv = np.zeros(4, np.float32); H.h_bspline4(C.c_float(f), P(N), P(Dv))
+        for o in range(4):
+            u = float(np.float32(f)) + 1 - o
+            n1 = C.c_float(); d1 = C.c_float(); H.h_bspline_lane(C.c_float(f), o, C.byref(n1), C.byref(d1))
+            assert abs(N[o] - op.cubic_bspline(u)) < 2e-7 and abs(Dv[o] - op.dcubic_bspline(u)) < 3e-7
+            assert abs(n1.value - N[o]) < 1e-7 and abs(d1.value - Dv[o]) < 1e-7
+
+
+def test_svd3_fp32(H):
+    rng = np.random.default_rng(1)
+    for k in range(4000):
+        kind = k % 4
+        if kind == 0: F = np.eye(3) + 1e-3 * rng.standard_normal((3, 3))
+        elif kind == 1: F = np.eye(3) + 0.3 * rng.standard_normal((3, 3))
+        elif kind == 2: F = rng.standard_normal((3, 3))
+        else:
+            Q, _ = np.linalg.qr(rng.standard_normal((3, 3))); F = Q @ np.diag([1.0, 1.0 + 1e-6, 1.0 - 1e-6]) @ Q.T
+        F32 = f32(F); U = np.zeros(9, np.float32); S = np.zeros(3, np.float32); V = np.zeros(9, np.float32)
+        H.h_svd3(P(F32.ravel()), P(U), P(S), P(V))
+        U = U.reshape(3, 3).astype(np.float64); V = V.reshape(3, 3).astype(np.float64); S = S.astype(np.float64)
+        scale = max(1.0, np.abs(F32).max())
+        assert (S >= 0).all()                                             # Eigen contract: non-negative singular values
+        assert np.abs(U @ np.diag(S) @ V.T - F32).max() < 2e-6 * scale
+        assert np.abs(U.T @ U - np.eye(3)).max() < 2e-6 and np.abs(V.T @ V - np.eye(3)).max() < 2e-6
+        assert np.abs(np.sort(S)[::-1] - np.linalg.svd(F32.astype(np.float64), compute_uv=False)).max() < 1e-6 * scale
+
+
+@pytest.mark.parametrize("mat,E,nu", [(1, 3.537e5, 0.3), (0, 1.4e5, 0.2)])
+def test_stress_and_return_map_vs_oracle(H, mat, E, nu):
+    """fp32 stress error is bounded by eps_fp32 / strain (F is stored in fp32); return mapping to ~1e-6 absolute."""
+    L = op.lib()
+    L.orc_particle_stress.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, dp, dp, dp, C.c_double, dp]
+    L.orc_particle_return_map.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp, dp, dp]
+    rng = np.random.default_rng(2)
+    cm = lambda M: np.ascontiguousarray(M.T).ravel()
+    for strain in (1e-3, 1e-2, 5e-2, 0.2):
+        worst = 0.0; amax = 0.0
+        for _ in range(300):
+            FE = f32(np.eye(3) + strain * rng.standard_normal((3, 3))); Fh = f32(FE + 0.3 * strain * rng.standard_normal((3, 3)))
+            FPm = f32(np.eye(3) + 0.02 * rng.standard_normal((3, 3))); vol = 1e-6; q0 = float(np.float32(abs(rng.standard_normal()) * 0.3))
+            Jp = np.float32(np.linalg.det(FPm.astype(np.float64)))
+            A = np.zeros(9, np.float32); H.h_stress(mat, E, nu, P(Fh.ravel()), P(FE.ravel()), C.c_float(vol), C.c_float(Jp), P(A))
+            A64 = np.zeros(9)
+            L.orc_particle_stress(mat, E, nu, 10.0, D(cm(Fh.astype(np.float64))), D(cm(FE.astype(np.float64))), D(cm(FPm.astype(np.float64))), vol, D(A64))
+            A64 = A64.reshape(3, 3).T
+            worst = max(worst, np.abs(A.reshape(3, 3) - A64).max()); amax = max(amax, np.abs(A64).max())
+            FEo = np.zeros(9, np.float32); FPo = FPm.copy().ravel(); q = C.c_float(q0)
+            H.h_return_map(mat, E, nu, 2.5e-2, 7.5e-3, P(Fh.ravel()), P(FEo), P(FPo), C.byref(q))
+            FE9 = np.zeros(9); FP9 = cm(FPm.astype(np.float64)).copy(); q64 = C.c_double(q0)
+            L.orc_particle_return_map(mat, E, nu, 2.5e-2, 7.5e-3, D(cm(Fh.astype(np.float64))), D(FE9), D(FP9), C.byref(q64))
+            assert np.abs(FEo.reshape(3, 3) - FE9.reshape(3, 3).T).max() < 3e-6
+            assert np.abs(FPo.reshape(3, 3) - FP9.reshape(3, 3).T).max() < 3e-6
+            assert abs(q.value - q64.value) < 3e-6
+        assert worst / amax < 3e-7 / strain + 1e-6, (strain, worst / amax)
