@@ -38,7 +38,7 @@ class AepError(RuntimeError):
 SYMBOLS = (
     "aep_default_config", "aep_create", "aep_destroy", "aep_last_error", "aep_sync", "aep_upload_particles",
     "aep_upload_mesh", "aep_set_levelset_analytic", "aep_set_levelset_samples", "aep_init", "aep_substep", "aep_run",
-    "aep_run_frames", "aep_p2g", "aep_stage_forces", "aep_stage_grid", "aep_stage_g2p", "aep_set_dt", "aep_get_clock",
+    "aep_run_frames", "aep_p2g", "aep_stage_forces", "aep_stage_grid", "aep_stage_g2p", "aep_set_dt", "aep_set_fixed_dt", "aep_get_clock",
     "aep_num_particles", "aep_download_particles", "aep_download_grid", "aep_download_mesh", "aep_download_positions_f32",
     "aep_stats", "aep_kernel_launches", "aep_stream", "aep_profile", "aep_get_timers", "aep_halo_info", "aep_halo_pack",
     "aep_halo_recv_buffer", "aep_halo_add", "aep_vmax_device_ptr", "aep_step_forces", "aep_step_grid", "aep_step_g2p",
@@ -70,7 +70,7 @@ def load():
     L.aep_run.argtypes = [vp, C.c_int]
     L.aep_run_frames.argtypes = [vp, C.c_int, C.c_int, i64p]
     L.aep_p2g.argtypes = [vp, C.c_int]
-    for name in ("aep_stage_forces", "aep_stage_grid", "aep_stage_g2p", "aep_set_dt"):
+    for name in ("aep_stage_forces", "aep_stage_grid", "aep_stage_g2p", "aep_set_dt", "aep_set_fixed_dt"):
         getattr(L, name).argtypes = [vp, C.c_double]
     L.aep_get_clock.argtypes = [vp, dp, dp, dp, C.POINTER(C.c_int32), i64p, dp, i64p]
     L.aep_download_particles.argtypes = [vp] + [dp] * 9

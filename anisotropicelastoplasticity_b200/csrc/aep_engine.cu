@@ -533,11 +533,17 @@ int aep_set_dt(aep_ctx* c, double dt) {
     CU(cudaStreamSynchronize(c->stream));
     return AEP_OK;
 }
+int aep_set_fixed_dt(aep_ctx* c, double dt) {
+    if (!c) return AEP_ERR_INVALID;
+    if (dt > 0.0) { c->fixed_dt = 1; return aep_set_dt(c, dt); }
+    c->fixed_dt = 0;
+    return AEP_OK;
+}
 int aep_stage_forces(aep_ctx* c, double dt) { int r = require_init(c); if (r) return r; if ((r = aep_set_dt(c, dt))) return r; return do_forces(c); }
 int aep_stage_grid(aep_ctx* c, double dt) {
     int r = require_init(c); if (r) return r; if ((r = aep_set_dt(c, dt))) return r;
     if ((r = do_grid(c))) return r;
-    k_advance_clock<<<1, 1, 0, c->stream>>>(c->d_clk, 1); LAUNCH_OK("k_advance_clock");   // latch vmax, keep dt
+    k_advance_clock<<<1, 1, 0, c->stream>>>(c->d_clk, 2); LAUNCH_OK("k_advance_clock");   // latch vmax, keep dt
     return AEP_OK;
 }
 int aep_stage_g2p(aep_ctx* c, double dt) { int r = require_init(c); if (r) return r; if ((r = aep_set_dt(c, dt))) return r; return do_g2p(c); }

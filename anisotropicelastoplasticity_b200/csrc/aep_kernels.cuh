@@ -213,7 +213,13 @@ __global__ void __launch_bounds__(256) k_grid_update(GridP G, SimClock* clk) {
 __global__ void k_advance_clock(SimClock* clk, int fixed_dt) {
     const float vmax = __uint_as_float(clk->vmax_bits);
     clk->vmax_last = vmax; clk->vmax_bits = 0u;
-    if (fixed_dt) return;
+    if (fixed_dt == 2) return;                                   // stage-level API: only latch max|v|
+    if (fixed_dt == 1) {                                         // pinned dt (aep_set_fixed_dt): plain time accumulation
+        clk->inner_t += (double)clk->dt; clk->frame_flag = 0;
+        if (clk->inner_t >= clk->frame_dt) { clk->inner_t -= clk->frame_dt; clk->t += clk->frame_dt; clk->frame_flag = 1; clk->frame_no += 1; }
+        clk->substeps += 1;
+        return;
+    }
     double dt = clk->cfl / fmax(clk->rate_floor, (double)vmax / clk->hmin);
     if (clk->inner_t + dt >= clk->frame_dt) {
         dt = clk->frame_dt - clk->inner_t; clk->t += clk->frame_dt; clk->inner_t = 0.0; clk->frame_flag = 1; clk->frame_no += 1;

@@ -1,18 +1,472 @@
-// aep_mesh.cuh -- LagrangianMesh (cloth) path.  PLACEHOLDER until the particle path is verified on hardware.
+// aep_mesh.cuh -- LagrangianMesh (cloth) path of the hybrid solver on the GPU.
+//
+// Mesh vertices and element centroids are transferred to / from the grid exactly like particles (HybridSolver.cpp:
+// 121-125,137-141,216-230,748-756,918-935,946-950); the cloth constitutive model works per face:
+//   in-plane fixed-corotated stress on the QR factors       LagrangianMesh.cpp:382-460
+//   normal / shear stress from R's third column             HybridSolver.cpp:389-455
+//   d1,d2 from advected vertices, d3 by grad v~             HybridSolver.cpp:581-608
+//   cone return mapping on (r13, r23, r33)                  HybridSolver.cpp:684-722
+//   pinned vertices zero 3x3x3 node blocks                  HybridSolver.cpp:513-550
+// Mesh points are few (<= ~1e6) and cannot be re-sorted (topology), so they reuse the warp-cooperative scatter of the
+// particle kernels with run length 1 and otherwise use one thread per point.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <cmath>
+#include <vector>
+
 #include "aep_kernels.cuh"
 
 namespace aep {
-struct MeshState { long long nv = 0, nf = 0; int n_fixed = 0; };
-inline void mesh_free(MeshState&) {}
-inline int mesh_upload(MeshState&, const GridP&, const double*, const double*, int64_t, int64_t, const double*, const double*, const double*,
-                       const double*, const double*, const int32_t*, const double*, const double*, const double*, const double*, const double*,
-                       const double*, const double*, double, double, double, double, double, cudaStream_t) { return -1; }
-inline int mesh_p2g(MeshState&, const GridP&, cudaStream_t, long long*) { return 0; }
-inline int mesh_forces(MeshState&, const GridP&, cudaStream_t, long long*) { return 0; }
-inline int mesh_pin(MeshState&, const GridP&, cudaStream_t, long long*) { return 0; }
-inline int mesh_g2p(MeshState&, const GridP&, SimClock*, cudaStream_t, long long*) { return 0; }
-inline int mesh_download(MeshState&, double*, double*, double*, double*, double*, double*, double*, cudaStream_t) { return 0; }
+
+struct MeshDev {
+    // vertices
+    float4 *VX, *VVM, *VC0, *VC1, *VC2, *VF;       // VF: in-plane force accumulator
+    // elements (one per face)
+    float4 *EX, *EVM, *EC0, *EC1, *EC2;
+    float4 *ED1, *ED2, *ED3;                       // current directions; ED3.w = element volume
+    float4 *RD1, *RD2, *RD3;                       // rest directions
+    float4* PK;                                    // (pk00, pk01, pk11, -) = invRest * P   LagrangianMesh.cpp:446
+    int4* faces;
+    int* fixed_ids;
+    float mu, lambda, gamma, kstiff, cf;
+};
+
+struct MeshState {
+    long long nv = 0, nf = 0;
+    int n_fixed = 0;
+    MeshDev d{};
+    std::vector<void*> allocs;
+    double mn[3]{}, h[3]{};
+};
+
+// ------------------------------------------------------------------------------------------------ device helpers
+// position difference b - a in world units from packed (cell, frac) records
+__device__ __forceinline__ void pos_diff(const GridP& G, const float4& a, const float4& b, float (&d)[3]) {
+    const int ca = __float_as_int(a.w), cb = __float_as_int(b.w);
+    d[0] = ((float)(cell_i(cb) - cell_i(ca)) + (b.x - a.x)) * G.hx;
+    d[1] = ((float)(cell_j(cb) - cell_j(ca)) + (b.y - a.y)) * G.hy;
+    d[2] = ((float)(cell_k(cb) - cell_k(ca)) + (b.z - a.z)) * G.hz;
+}
+// a + delta (world units) -> packed record, clamped to the grid
+__device__ __forceinline__ float4 pos_offset(const GridP& G, const float4& a, float dx, float dy, float dz) {
+    const int c = __float_as_int(a.w);
+    float fx = fmaf(dx, G.ihx, a.x), fy = fmaf(dy, G.ihy, a.y), fz = fmaf(dz, G.ihz, a.z);
+    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    fx = fminf(fx - flx, 0.99999994f); fy = fminf(fy - fly, 0.99999994f); fz = fminf(fz - flz, 0.99999994f);
+    const int ci = clampi(cell_i(c) + (int)flx, 0, G.nx - 1), cj = clampi(cell_j(c) + (int)fly, 0, G.ny - 1), ck = clampi(cell_k(c) + (int)flz, 0, G.nz - 1);
+    return make_float4(fx, fy, fz, __int_as_float(cell_pack(ci, cj, ck)));
+}
+
+// common G2P gather for a mesh point: v = sum w v_i, va = sum w v~_i, B = sum w v_i (x_i-x_p)^T, g = sum v~_i grad w^T,
+// plus the truncated-stencil position correction (see k_g2p)
+struct PointGather {
+    float vp[3], va[3], B[9], g[9], corr[3];
+};
+__device__ __forceinline__ void point_gather(const GridP& G, const float4& X, PointGather& o) {
+    const int cell = __float_as_int(X.w);
+    const int ci = cell_i(cell), cj = cell_j(cell), ck = cell_k(cell);
+    Axis ax, ay, az;
+    bool complete = axis_setup(ax, X.x, ci, G.nx, G.ihx);
+    complete &= axis_setup(ay, X.y, cj, G.ny, G.ihy);
+    complete &= axis_setup(az, X.z, ck, G.nz, G.ihz);
+    float rx[4], ry[4], rz[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { rx[q] = G.hx * ((float)(q - 1) - X.x); ry[q] = G.hy * ((float)(q - 1) - X.y); rz[q] = G.hz * ((float)(q - 1) - X.z); }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { o.vp[i] = 0.f; o.va[i] = 0.f; o.corr[i] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { o.B[i] = 0.f; o.g[i] = 0.f; }
+    float s0 = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int nk = clampi(az.n0 + k, 0, G.nz - 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int nj = clampi(ay.n0 + j, 0, G.ny - 1);
+            const size_t row = ((size_t)nk * G.ny + nj) * G.nx;
+            const float nn = ay.N[j] * az.N[k], dn = ay.D[j] * az.N[k], nd = ay.N[j] * az.D[k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ni = clampi(ax.n0 + i, 0, G.nx - 1);
+                const float w = ax.N[i] * nn;
+                const float4 t = ldg4(G.vt + row + ni);
+                const float dwx = ax.D[i] * nn, dwy = ax.N[i] * dn, dwz = ax.N[i] * nd;
+                const float ws = w * t.w;
+                const float ux = ws * t.x, uy = ws * t.y, uz = ws * t.z;
+                o.vp[0] += ux; o.vp[1] += uy; o.vp[2] += uz;
+                o.va[0] = fmaf(w, t.x, o.va[0]); o.va[1] = fmaf(w, t.y, o.va[1]); o.va[2] = fmaf(w, t.z, o.va[2]);
+                o.B[0] = fmaf(ux, rx[i], o.B[0]); o.B[1] = fmaf(ux, ry[j], o.B[1]); o.B[2] = fmaf(ux, rz[k], o.B[2]);
+                o.B[3] = fmaf(uy, rx[i], o.B[3]); o.B[4] = fmaf(uy, ry[j], o.B[4]); o.B[5] = fmaf(uy, rz[k], o.B[5]);
+                o.B[6] = fmaf(uz, rx[i], o.B[6]); o.B[7] = fmaf(uz, ry[j], o.B[7]); o.B[8] = fmaf(uz, rz[k], o.B[8]);
+                o.g[0] = fmaf(t.x, dwx, o.g[0]); o.g[1] = fmaf(t.x, dwy, o.g[1]); o.g[2] = fmaf(t.x, dwz, o.g[2]);
+                o.g[3] = fmaf(t.y, dwx, o.g[3]); o.g[4] = fmaf(t.y, dwy, o.g[4]); o.g[5] = fmaf(t.y, dwz, o.g[5]);
+                o.g[6] = fmaf(t.z, dwx, o.g[6]); o.g[7] = fmaf(t.z, dwy, o.g[7]); o.g[8] = fmaf(t.z, dwz, o.g[8]);
+                if (!complete) { s0 += w; s1x = fmaf(w, rx[i], s1x); s1y = fmaf(w, ry[j], s1y); s1z = fmaf(w, rz[k], s1z); }
+            }
+        }
+    }
+    if (!complete) {
+        const float xw = fmaf((float)ci + X.x, G.hx, G.mnx), yw = fmaf((float)cj + X.y, G.hy, G.mny), zw = fmaf((float)ck + X.z, G.hz, G.mnz);
+        o.corr[0] = s1x + (s0 - 1.0f) * xw; o.corr[1] = s1y + (s0 - 1.0f) * yw; o.corr[2] = s1z + (s0 - 1.0f) * zw;
+    }
+}
+// C = skew(B) + (1 - damp) sym(B), damp = 1 for the mesh (HybridSolver.cpp:808-824, 920-933)
+__device__ __forceinline__ void skew_part(float (&B)[9]) {
+    const float a01 = 0.5f * (B[1] - B[3]), a02 = 0.5f * (B[2] - B[6]), a12 = 0.5f * (B[5] - B[7]);
+    B[0] = 0.f; B[1] = a01; B[2] = a02; B[3] = -a01; B[4] = 0.f; B[5] = a12; B[6] = -a02; B[7] = -a12; B[8] = 0.f;
+}
+
+// warp-cooperative stress scatter shared with the particle force kernel's phase 2 (run length 1 for mesh points):
+// f_i -= A grad w_ie    HybridSolver.cpp:444-454
+__device__ __forceinline__ void warp_scatter_stress(const GridP& G, float fx, float fy, float fz, int cell, const float (&A)[9], int cnt, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    const int oi = lane & 3, oj = (lane >> 2) & 3, ok = lane >> 4;
+    for (int p = 0; p < cnt; ++p) {
+        const int c = __shfl_sync(FULL, cell, p);
+        const float pfx = __shfl_sync(FULL, fx, p), pfy = __shfl_sync(FULL, fy, p), pfz = __shfl_sync(FULL, fz, p);
+        float a[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) a[i] = __shfl_sync(FULL, A[i], p);
+        float wx, dx, wy, dy, wz0, dz0, wz1, dz1;
+        bspline_lane(pfx, oi, wx, dx); bspline_lane(pfy, oj, wy, dy); bspline_lane(pfz, ok, wz0, dz0); bspline_lane(pfz, ok + 2, wz1, dz1);
+        dx *= G.ihx; dy *= G.ihy; dz0 *= G.ihz; dz1 *= G.ihz;
+        const float gx = dx * wy, gy = wx * dy, gz = wx * wy;
+        float4 a0, a1;
+        { const float d0 = gx * wz0, d1 = gy * wz0, d2 = gz * dz0;
+          a0 = make_float4(-fmaf(a[0], d0, fmaf(a[1], d1, a[2] * d2)), -fmaf(a[3], d0, fmaf(a[4], d1, a[5] * d2)), -fmaf(a[6], d0, fmaf(a[7], d1, a[8] * d2)), 0.f); }
+        { const float d0 = gx * wz1, d1 = gy * wz1, d2 = gz * dz1;
+          a1 = make_float4(-fmaf(a[0], d0, fmaf(a[1], d1, a[2] * d2)), -fmaf(a[3], d0, fmaf(a[4], d1, a[5] * d2)), -fmaf(a[6], d0, fmaf(a[7], d1, a[8] * d2)), 0.f); }
+        flush_nodes(G, G.f, c, oi, oj, ok, a0, a1, false);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+// LagrangianMesh::computeVertexInPlaneForces (LagrangianMesh.cpp:382-460), one thread per face
+__global__ void __launch_bounds__(128) k_cloth_inplane(MeshDev M, int nf) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const float4 e1 = M.ED1[f], e2 = M.ED2[f], e3 = M.ED3[f], r1 = M.RD1[f], r2 = M.RD2[f], r3 = M.RD3[f];
+    const float d1[3] = { e1.x, e1.y, e1.z }, d2[3] = { e2.x, e2.y, e2.z }, d3[3] = { e3.x, e3.y, e3.z };
+    const float D1[3] = { r1.x, r1.y, r1.z }, D2[3] = { r2.x, r2.y, r2.z }, D3[3] = { r3.x, r3.y, r3.z };
+    float Q[9], R[9], Q0[9], R0[9];
+    gram_schmidt(d1, d2, d3, Q, R); gram_schmidt(D1, D2, D3, Q0, R0);
+    const float i11 = 1.0f / R0[0], i12 = -R0[1] / R0[0] / R0[4], i22 = 1.0f / R0[4];          // geometry.cpp:67-73
+    const float r00 = i11 * R[0], r01 = fmaf(i11, R[1], i12 * R[4]), r11 = i22 * R[4];         // invRest * inPlaneR (:431)
+    // polar rotation of the 2x2 upper-triangular [[r00 r01],[0 r11]] (det > 0): (A + cof A) / |.|  == U V^T of its SVD (:437-438)
+    const float tr = r00 + r11;
+    const float inv = rsqrtf(fmaf(tr, tr, r01 * r01));
+    const float rot00 = tr * inv, rot01 = r01 * inv, rot10 = -r01 * inv, rot11 = tr * inv;
+    const float J = r00 * r11;                                                                   // :441
+    const float lj = M.lambda * (J - 1.0f), m2 = 2.0f * M.mu;
+    const float P00 = fmaf(m2, r00 - rot00, lj * r11);                                           // :443-444 with invRefMulDet^T
+    const float P01 = m2 * (r01 - rot01);
+    const float P10 = fmaf(m2, -rot10, lj * (-r01));
+    const float P11 = fmaf(m2, r11 - rot11, lj * r00);
+    M.PK[f] = make_float4(fmaf(i11, P00, i12 * P10), fmaf(i11, P01, i12 * P11), i22 * P11, i22 * P10);   // :446
+    const float c2 = -(P00 * i11 + P01 * i12);                                                   // :452
+    const float c3a = -P01 * i22, c3b = -P11 * i22;                                              // :453
+    const int4 fa = M.faces[f];
+    float f2[3], f3[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { f2[r] = c2 * Q[3 * r]; f3[r] = fmaf(c3a, Q[3 * r], c3b * Q[3 * r + 1]); }
+    float* va = reinterpret_cast<float*>(M.VF + fa.x); float* vb = reinterpret_cast<float*>(M.VF + fa.y); float* vc = reinterpret_cast<float*>(M.VF + fa.z);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { atomicAdd(va + r, -(f2[r] + f3[r])); atomicAdd(vb + r, f2[r]); atomicAdd(vc + r, f3[r]); }   // :454-458
+}
+
+// forces += vertexOmegas^T * vertexInPlaneForces  (HybridSolver.cpp:378), warp-cooperative, run length 1
+__global__ void __launch_bounds__(256) k_vertex_force_scatter(MeshDev M, GridP G, int nv) {
+    const int lane = threadIdx.x & 31;
+    const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    if (base >= nv) return;
+    const int cnt = min(32, nv - base);
+    const unsigned FULL = 0xffffffffu;
+    float fx = 0.f, fy = 0.f, fz = 0.f, Fx = 0.f, Fy = 0.f, Fz = 0.f; int cell = 0;
+    if (lane < cnt) {
+        const float4 X = M.VX[base + lane], F = M.VF[base + lane];
+        fx = X.x; fy = X.y; fz = X.z; cell = __float_as_int(X.w); Fx = F.x; Fy = F.y; Fz = F.z;
+    }
+    const int oi = lane & 3, oj = (lane >> 2) & 3, ok = lane >> 4;
+    for (int p = 0; p < cnt; ++p) {
+        const int c = __shfl_sync(FULL, cell, p);
+        const float pfx = __shfl_sync(FULL, fx, p), pfy = __shfl_sync(FULL, fy, p), pfz = __shfl_sync(FULL, fz, p);
+        const float ax = __shfl_sync(FULL, Fx, p), ay = __shfl_sync(FULL, Fy, p), az = __shfl_sync(FULL, Fz, p);
+        float wx, wy, wz0, wz1, d;
+        bspline_lane(pfx, oi, wx, d); bspline_lane(pfy, oj, wy, d); bspline_lane(pfz, ok, wz0, d); bspline_lane(pfz, ok + 2, wz1, d);
+        const float w0 = wx * wy * wz0, w1 = wx * wy * wz1;
+        flush_nodes(G, G.f, c, oi, oj, ok, make_float4(w0 * ax, w0 * ay, w0 * az, 0.f), make_float4(w1 * ax, w1 * ay, w1 * az, 0.f), false);
+    }
+}
+
+// normal / shear part of computeGridForces_ (HybridSolver.cpp:389-455)
+__global__ void __launch_bounds__(128) k_cloth_normal(MeshDev M, GridP G, int nf) {
+    const int lane = threadIdx.x & 31;
+    const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    if (base >= nf) return;
+    const int cnt = min(32, nf - base);
+    float fx = 0.f, fy = 0.f, fz = 0.f; int cell = 0;
+    float A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (lane < cnt) {
+        const int f = base + lane;
+        const float4 X = M.EX[f]; fx = X.x; fy = X.y; fz = X.z; cell = __float_as_int(X.w);
+        const float4 e1 = M.ED1[f], e2 = M.ED2[f], e3 = M.ED3[f], pk = M.PK[f];
+        const float d1[3] = { e1.x, e1.y, e1.z }, d2[3] = { e2.x, e2.y, e2.z }, d3[3] = { e3.x, e3.y, e3.z };
+        float Q[9], R[9]; gram_schmidt(d1, d2, d3, Q, R);                                        // :401-402
+        float dR[9] = { pk.x, pk.y, M.gamma * R[2], 0.f, pk.z, M.gamma * R[5], 0.f, 0.f, 0.f };  // :406-420
+        const float om = 1.0f - R[8];
+        dR[8] = R[8] > 1.0f ? 0.0f : -M.kstiff * om * om;                                        // :414-415
+        float K[9]; mat_mul_nt(dR, R, K);                                                        // K = dR R^T  :423
+        float Sy[9];                                                                             // strictUpper(K) + upper(K)^T  :425-426
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Sy[3 * r + c] = (c > r) ? K[3 * r + c] : K[3 * c + r];
+        // R^{-T}: R upper triangular -> closed-form inverse
+        const float i00 = 1.0f / R[0], i11 = 1.0f / R[4], i22 = 1.0f / R[8];
+        const float i01 = -R[1] * i00 * i11, i12 = -R[5] * i11 * i22, i02 = (R[1] * R[5] - R[2] * R[4]) * i00 * i11 * i22;
+        const float RinvT[9] = { i00, 0.f, 0.f, i01, i11, 0.f, i02, i12, i22 };
+        float QS[9], T[9]; mat_mul(Q, Sy, QS); mat_mul(QS, RinvT, T);
+        const float4 r1 = M.RD1[f], r2 = M.RD2[f], r3 = M.RD3[f];
+        const float rc[3] = { r1.z, r2.z, r3.z };                                                // (rest^T).col(2)  :427
+        const float vol = e3.w;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float dF3 = fmaf(T[3 * r], rc[0], fmaf(T[3 * r + 1], rc[1], T[3 * r + 2] * rc[2]));
+            A[3 * r] = vol * dF3 * d3[0]; A[3 * r + 1] = vol * dF3 * d3[1]; A[3 * r + 2] = vol * dF3 * d3[2];      // :429
+        }
+    }
+    warp_scatter_stress(G, fx, fy, fz, cell, A, cnt, lane);
+}
+
+// pinned vertices: zero v and v~ in the 3x3x3 node block around every stencil node (HybridSolver.cpp:513-550).
+// Per-axis indices are NOT range checked, only the flat index (:538-539) -- reproduced, including the row wrap.
+__global__ void k_mesh_pin(MeshDev M, GridP G, int n_fixed) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_fixed * 64) return;
+    const int v = M.fixed_ids[t >> 6], e = t & 63;
+    const float4 X = M.VX[v];
+    const int cell = __float_as_int(X.w);
+    const int oi = e & 3, oj = (e >> 2) & 3, ok = e >> 4;
+    float wx, wy, wz, d;
+    bspline_lane(X.x, oi, wx, d); bspline_lane(X.y, oj, wy, d); bspline_lane(X.z, ok, wz, d);
+    const int ri = cell_i(cell) - 1 + oi, rj = cell_j(cell) - 1 + oj, rk = cell_k(cell) - 1 + ok;
+    if (!(wx > 0.f && wy > 0.f && wz > 0.f)) return;                                             // not a nonzero of vertexOmegas_
+    if (ri < 0 || ri >= G.nx || rj < 0 || rj >= G.ny || rk < 0 || rk >= G.nz) return;
+    const long long Ng = (long long)G.nx * G.ny * G.nz;
+    for (int i = ri - 1; i <= ri + 1; ++i) for (int j = rj - 1; j <= rj + 1; ++j) for (int k = rk - 1; k <= rk + 1; ++k) {
+        const long long index = ((long long)k * G.ny + j) * G.nx + i;
+        if (index >= 0 && index < Ng) G.vt[index] = make_float4(0.f, 0.f, 0.f, 1.f);
+    }
+}
+
+// vertices: velocity, affine (damp 1), advection        HybridSolver.cpp:748, 920-926, 948
+__global__ void __launch_bounds__(128) k_vertex_g2p(MeshDev M, GridP G, const SimClock* __restrict__ clk, int nv) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const float dt = clk->dt;
+    const float4 X = M.VX[v];
+    PointGather pg; point_gather(G, X, pg);
+    skew_part(pg.B);
+    M.VVM[v] = make_float4(pg.vp[0], pg.vp[1], pg.vp[2], M.VVM[v].w);
+    M.VC0[v] = make_float4(pg.B[0], pg.B[1], pg.B[2], 0.f); M.VC1[v] = make_float4(pg.B[3], pg.B[4], pg.B[5], 0.f); M.VC2[v] = make_float4(pg.B[6], pg.B[7], pg.B[8], 0.f);
+    M.VX[v] = pos_offset(G, X, fmaf(dt, pg.va[0], pg.corr[0]), fmaf(dt, pg.va[1], pg.corr[1]), fmaf(dt, pg.va[2], pg.corr[2]));
+}
+
+// elements: mean vertex velocity (:749-756), affine at the OLD centroid (:927-933), d1/d2 from advected vertices and
+// d3 += dt grad v~ d3 (:584-606), cone return mapping (:684-722), new centroid (LagrangianMesh.cpp:371-380)
+__global__ void __launch_bounds__(128) k_element_g2p(MeshDev M, GridP G, const SimClock* __restrict__ clk, int nf) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const float dt = clk->dt;
+    const float4 X = M.EX[f];
+    PointGather pg; point_gather(G, X, pg);
+    skew_part(pg.B);
+    const int4 fa = M.faces[f];
+    const float4 va = M.VVM[fa.x], vb = M.VVM[fa.y], vc = M.VVM[fa.z];
+    M.EVM[f] = make_float4((va.x + vb.x + vc.x) / 3.0f, (va.y + vb.y + vc.y) / 3.0f, (va.z + vb.z + vc.z) / 3.0f, M.EVM[f].w);
+    M.EC0[f] = make_float4(pg.B[0], pg.B[1], pg.B[2], 0.f); M.EC1[f] = make_float4(pg.B[3], pg.B[4], pg.B[5], 0.f); M.EC2[f] = make_float4(pg.B[6], pg.B[7], pg.B[8], 0.f);
+    const float4 xa = M.VX[fa.x], xb = M.VX[fa.y], xc = M.VX[fa.z];
+    float d1[3], d2[3]; pos_diff(G, xa, xb, d1); pos_diff(G, xa, xc, d2);                        // :591-594
+    const float4 e3 = M.ED3[f];
+    float d3[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) d3[r] = fmaf(dt, fmaf(pg.g[3 * r], e3.x, fmaf(pg.g[3 * r + 1], e3.y, pg.g[3 * r + 2] * e3.z)), (r == 0 ? e3.x : (r == 1 ? e3.y : e3.z)));   // :601-602
+    float Q[9], R[9]; gram_schmidt(d1, d2, d3, Q, R);                                            // :694-695
+    float r13 = R[2], r23 = R[5], r33 = R[8];
+    if (r33 > 1.0f) { r33 = 1.0f; r13 = 0.f; r23 = 0.f; }                                        // :699-703
+    else {
+        const float fn = M.kstiff * (r33 - 1.0f) * (r33 - 1.0f);
+        const float fs = M.gamma * sqrtf(r13 * r13 + r23 * r23);
+        if (fs > M.cf * fn) { const float sc = M.cf * fn / fs; r13 *= sc; r23 *= sc; }           // :711-715
+    }
+    M.ED1[f] = make_float4(d1[0], d1[1], d1[2], 0.f); M.ED2[f] = make_float4(d2[0], d2[1], d2[2], 0.f);
+    M.ED3[f] = make_float4(fmaf(Q[0], r13, fmaf(Q[1], r23, Q[2] * r33)), fmaf(Q[3], r13, fmaf(Q[4], r23, Q[5] * r33)),
+                           fmaf(Q[6], r13, fmaf(Q[7], r23, Q[8] * r33)), e3.w);                  // :718-719
+    M.EX[f] = pos_offset(G, xa, (d1[0] + d2[0]) / 3.0f, (d1[1] + d2[1]) / 3.0f, (d1[2] + d2[2]) / 3.0f);
+}
+
+// packed -> fp64 staging for download: per point x(3) v(3) B rows(9) [ + d1 d2 d3 (9) for elements ]
+__global__ void k_mesh_download(const float4* X, const float4* VM, const float4* C0, const float4* C1, const float4* C2,
+                                const float4* D1, const float4* D2, const float4* D3, double* out, int n,
+                                double mnx, double mny, double mnz, double hx, double hy, double hz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t N = (size_t)n;
+    const float4 x = X[i], v = VM[i], c0 = C0[i], c1 = C1[i], c2 = C2[i];
+    const int cell = __float_as_int(x.w);
+    out[0 * N + i] = mnx + ((double)cell_i(cell) + (double)x.x) * hx;
+    out[1 * N + i] = mny + ((double)cell_j(cell) + (double)x.y) * hy;
+    out[2 * N + i] = mnz + ((double)cell_k(cell) + (double)x.z) * hz;
+    out[3 * N + i] = v.x; out[4 * N + i] = v.y; out[5 * N + i] = v.z;
+    out[6 * N + i] = c0.x; out[7 * N + i] = c0.y; out[8 * N + i] = c0.z;
+    out[9 * N + i] = c1.x; out[10 * N + i] = c1.y; out[11 * N + i] = c1.z;
+    out[12 * N + i] = c2.x; out[13 * N + i] = c2.y; out[14 * N + i] = c2.z;
+    if (D1) {
+        const float4 a = D1[i], b = D2[i], c = D3[i];
+        out[15 * N + i] = a.x; out[16 * N + i] = a.y; out[17 * N + i] = a.z;
+        out[18 * N + i] = b.x; out[19 * N + i] = b.y; out[20 * N + i] = b.z;
+        out[21 * N + i] = c.x; out[22 * N + i] = c.y; out[23 * N + i] = c.z;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+inline void mesh_free(MeshState& m) {
+    for (void* p : m.allocs) cudaFree(p);
+    m.allocs.clear(); m.nv = m.nf = 0; m.n_fixed = 0;
+}
+
+template <typename T>
+inline cudaError_t mesh_alloc_copy(MeshState& m, T** dst, const std::vector<T>& src, cudaStream_t s) {
+    cudaError_t e = cudaMalloc((void**)dst, std::max<size_t>(src.size(), 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    m.allocs.push_back(*dst);
+    if (!src.empty()) e = cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    return e;
+}
+
+inline float4 host_pack_pos(const MeshState& m, const GridP& G, double x, double y, double z) {
+    const double p[3] = { x, y, z }; const int nres[3] = { G.nx, G.ny, G.nz };
+    float fr[3]; int ce[3];
+    for (int a = 0; a < 3; ++a) {
+        const double u = (p[a] - m.mn[a]) / m.h[a];
+        int c = (int)u; double f = u - (double)c;
+        if (f < 0.0) { c -= 1; f += 1.0; }
+        if (c < 0) { c = 0; f = 0.0; }
+        if (c >= nres[a]) { c = nres[a] - 1; f = 0.99999994; }
+        float ff = (float)f; if (ff >= 1.0f) ff = 0.99999994f;
+        fr[a] = ff; ce[a] = c;
+    }
+    const int packed = ce[0] | (ce[1] << 10) | (ce[2] << 20);
+    float w; std::memcpy(&w, &packed, 4);
+    return make_float4(fr[0], fr[1], fr[2], w);
+}
+
+inline int mesh_upload(MeshState& m, const GridP& G, const double* mn, const double* h, int64_t nv, int64_t nf, const double* vx,
+                       const double* vv, const double* vm, const double* vvol, const double* vB, const int32_t* faces,
+                       const double* ev, const double* em, const double* evol, const double* eB, const double* ed, const double* eD,
+                       const double* fixedv, double mu, double lambda, double shear, double stiff, double fric, cudaStream_t s) {
+    (void)vvol;
+    if (nv <= 0 || nf <= 0 || !vx || !vv || !vm || !vB || !faces || !ev || !em || !evol || !eB || !ed || !eD) return -1;
+    mesh_free(m);
+    for (int a = 0; a < 3; ++a) { m.mn[a] = mn[a]; m.h[a] = h[a]; }
+    const size_t NV = (size_t)nv, NF = (size_t)nf;
+    std::vector<float4> VX(NV), VVM(NV), VC0(NV), VC1(NV), VC2(NV), VF(NV, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (size_t i = 0; i < NV; ++i) {
+        VX[i] = host_pack_pos(m, G, vx[i], vx[NV + i], vx[2 * NV + i]);
+        VVM[i] = make_float4((float)vv[i], (float)vv[NV + i], (float)vv[2 * NV + i], (float)vm[i]);
+        VC0[i] = make_float4((float)vB[i], (float)vB[NV + i], (float)vB[2 * NV + i], 0.f);
+        VC1[i] = make_float4((float)vB[3 * NV + i], (float)vB[4 * NV + i], (float)vB[5 * NV + i], 0.f);
+        VC2[i] = make_float4((float)vB[6 * NV + i], (float)vB[7 * NV + i], (float)vB[8 * NV + i], 0.f);
+    }
+    std::vector<float4> EX(NF), EVM(NF), EC0(NF), EC1(NF), EC2(NF), ED1(NF), ED2(NF), ED3(NF), RD1(NF), RD2(NF), RD3(NF), PK(NF, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<int4> FA(NF);
+    for (size_t f = 0; f < NF; ++f) {
+        const int a = faces[f], b = faces[NF + f], c = faces[2 * NF + f];
+        if (a < 0 || b < 0 || c < 0 || a >= nv || b >= nv || c >= nv) return -1;
+        FA[f] = make_int4(a, b, c, 0);
+        // element centroid = mean of its vertices (LagrangianMesh.cpp:371-380, called from the ctor :185)
+        EX[f] = host_pack_pos(m, G, (vx[a] + vx[b] + vx[c]) / 3.0, (vx[NV + a] + vx[NV + b] + vx[NV + c]) / 3.0, (vx[2 * NV + a] + vx[2 * NV + b] + vx[2 * NV + c]) / 3.0);
+        EVM[f] = make_float4((float)ev[f], (float)ev[NF + f], (float)ev[2 * NF + f], (float)em[f]);
+        EC0[f] = make_float4((float)eB[f], (float)eB[NF + f], (float)eB[2 * NF + f], 0.f);
+        EC1[f] = make_float4((float)eB[3 * NF + f], (float)eB[4 * NF + f], (float)eB[5 * NF + f], 0.f);
+        EC2[f] = make_float4((float)eB[6 * NF + f], (float)eB[7 * NF + f], (float)eB[8 * NF + f], 0.f);
+        ED1[f] = make_float4((float)ed[f], (float)ed[NF + f], (float)ed[2 * NF + f], 0.f);
+        ED2[f] = make_float4((float)ed[3 * NF + f], (float)ed[4 * NF + f], (float)ed[5 * NF + f], 0.f);
+        ED3[f] = make_float4((float)ed[6 * NF + f], (float)ed[7 * NF + f], (float)ed[8 * NF + f], (float)evol[f]);
+        RD1[f] = make_float4((float)eD[f], (float)eD[NF + f], (float)eD[2 * NF + f], 0.f);
+        RD2[f] = make_float4((float)eD[3 * NF + f], (float)eD[4 * NF + f], (float)eD[5 * NF + f], 0.f);
+        RD3[f] = make_float4((float)eD[6 * NF + f], (float)eD[7 * NF + f], (float)eD[8 * NF + f], 0.f);
+    }
+    std::vector<int> fixed;
+    if (fixedv) for (size_t i = 0; i < NV; ++i) if (fixedv[i] != 0.0) fixed.push_back((int)i);      // LagrangianMesh.cpp:462-481
+    MeshDev& d = m.d;
+#define MC(field, vec) if (mesh_alloc_copy(m, &d.field, vec, s) != cudaSuccess) return -2
+    MC(VX, VX); MC(VVM, VVM); MC(VC0, VC0); MC(VC1, VC1); MC(VC2, VC2); MC(VF, VF);
+    MC(EX, EX); MC(EVM, EVM); MC(EC0, EC0); MC(EC1, EC1); MC(EC2, EC2); MC(ED1, ED1); MC(ED2, ED2); MC(ED3, ED3);
+    MC(RD1, RD1); MC(RD2, RD2); MC(RD3, RD3); MC(PK, PK); MC(faces, FA); MC(fixed_ids, fixed);
+#undef MC
+    d.mu = (float)mu; d.lambda = (float)lambda; d.gamma = (float)shear; d.kstiff = (float)stiff; d.cf = (float)fric;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return -2;
+    m.nv = nv; m.nf = nf; m.n_fixed = (int)fixed.size();
+    return 0;
+}
+
+inline int mesh_p2g(MeshState& m, const GridP& G, cudaStream_t s, long long* launches) {
+    PartP pv{}, pe{};
+    pv.a[PX] = m.d.VX; pv.a[PVM] = m.d.VVM; pv.a[PC0] = m.d.VC0; pv.a[PC1] = m.d.VC1; pv.a[PC2] = m.d.VC2;
+    pe.a[PX] = m.d.EX; pe.a[PVM] = m.d.EVM; pe.a[PC0] = m.d.EC0; pe.a[PC1] = m.d.EC1; pe.a[PC2] = m.d.EC2;
+    k_p2g<<<(int)((m.nv + 255) / 256), 256, 0, s>>>(pv, G, (int)m.nv);
+    k_p2g<<<(int)((m.nf + 255) / 256), 256, 0, s>>>(pe, G, (int)m.nf);
+    *launches += 2;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+inline int mesh_forces(MeshState& m, const GridP& G, cudaStream_t s, long long* launches) {
+    cudaMemsetAsync(m.d.VF, 0, (size_t)m.nv * sizeof(float4), s);
+    k_cloth_inplane<<<(int)((m.nf + 127) / 128), 128, 0, s>>>(m.d, (int)m.nf);
+    k_vertex_force_scatter<<<(int)((m.nv + 255) / 256), 256, 0, s>>>(m.d, G, (int)m.nv);
+    k_cloth_normal<<<(int)((m.nf + 127) / 128), 128, 0, s>>>(m.d, G, (int)m.nf);
+    *launches += 3;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+inline int mesh_pin(MeshState& m, const GridP& G, cudaStream_t s, long long* launches) {
+    const int n = m.n_fixed * 64;
+    k_mesh_pin<<<(n + 127) / 128, 128, 0, s>>>(m.d, G, m.n_fixed);
+    *launches += 1;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+inline int mesh_g2p(MeshState& m, const GridP& G, SimClock* clk, cudaStream_t s, long long* launches) {
+    k_vertex_g2p<<<(int)((m.nv + 127) / 128), 128, 0, s>>>(m.d, G, clk, (int)m.nv);
+    k_element_g2p<<<(int)((m.nf + 127) / 128), 128, 0, s>>>(m.d, G, clk, (int)m.nf);
+    *launches += 2;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+inline int mesh_download(MeshState& m, double* vx, double* vv, double* vB, double* ex, double* ev, double* eB, double* ed, cudaStream_t s) {
+    if (!m.nv) return 0;
+    const size_t NV = (size_t)m.nv, NF = (size_t)m.nf;
+    double* st = nullptr;
+    if (cudaMalloc((void**)&st, std::max(NV * 15, NF * 24) * sizeof(double)) != cudaSuccess) return -3;
+    int rc = 0;
+    k_mesh_download<<<(int)((NV + 255) / 256), 256, 0, s>>>(m.d.VX, m.d.VVM, m.d.VC0, m.d.VC1, m.d.VC2, nullptr, nullptr, nullptr, st, (int)NV,
+                                                          m.mn[0], m.mn[1], m.mn[2], m.h[0], m.h[1], m.h[2]);
+    if (vx) cudaMemcpyAsync(vx, st, 3 * NV * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (vv) cudaMemcpyAsync(vv, st + 3 * NV, 3 * NV * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (vB) cudaMemcpyAsync(vB, st + 6 * NV, 9 * NV * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) rc = -2;
+    k_mesh_download<<<(int)((NF + 255) / 256), 256, 0, s>>>(m.d.EX, m.d.EVM, m.d.EC0, m.d.EC1, m.d.EC2, m.d.ED1, m.d.ED2, m.d.ED3, st, (int)NF,
+                                                          m.mn[0], m.mn[1], m.mn[2], m.h[0], m.h[1], m.h[2]);
+    if (ex) cudaMemcpyAsync(ex, st, 3 * NF * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (ev) cudaMemcpyAsync(ev, st + 3 * NF, 3 * NF * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (eB) cudaMemcpyAsync(eB, st + 6 * NF, 9 * NF * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (ed) cudaMemcpyAsync(ed, st + 15 * NF, 9 * NF * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) rc = -2;
+    cudaFree(st);
+    return rc;
+}
+
 }  // namespace aep

@@ -20,7 +20,7 @@ def _p(a):
 
 
 class Engine:
-    def __init__(self, scene: Scene, device: int = 0, particle_capacity: int = 0, slab=None, pinned_upload=None):
+    def __init__(self, scene: Scene, device: int = 0, particle_capacity: int = 0, slab=None, dt_rate_floor=None):
         self.L = capi.load()
         cfg = capi.Config(); capi.check(self.L.aep_default_config(C.byref(cfg)))
         g = scene.grid
@@ -28,6 +28,8 @@ class Engine:
         for a in range(3):
             cfg.grid_min[a] = float(g.mn[a]); cfg.grid_max[a] = float(g.mx[a]); cfg.res[a] = int(g.res[a])
         cfg.particle_capacity = particle_capacity
+        if dt_rate_floor is not None:
+            cfg.dt_rate_floor = float(dt_rate_floor)
         if slab is not None:
             cfg.slab_axis, cfg.slab_lo, cfg.slab_hi = slab
         self.cfg = cfg
@@ -102,6 +104,7 @@ class Engine:
     def stage_grid(self, dt): capi.check(self.L.aep_stage_grid(self.h, float(dt)), self.h)
     def stage_g2p(self, dt): capi.check(self.L.aep_stage_g2p(self.h, float(dt)), self.h)
     def set_dt(self, dt): capi.check(self.L.aep_set_dt(self.h, float(dt)), self.h)
+    def set_fixed_dt(self, dt): capi.check(self.L.aep_set_fixed_dt(self.h, float(dt)), self.h)
 
     def clock(self):
         dt = C.c_double(); t = C.c_double(); it = C.c_double(); fr = C.c_int32(); ss = C.c_int64(); vm = C.c_double(); esc = C.c_int64()

@@ -126,6 +126,9 @@ AEP_API int aep_stage_grid(aep_ctx* ctx, double dt);          /* updateGridVeloc
 AEP_API int aep_stage_g2p(aep_ctx* ctx, double dt);           /* HS:739-825, 940-951, 553-609, 612-723           */
 
 AEP_API int aep_set_dt(aep_ctx* ctx, double dt);
+/* dt > 0: pin the time step (the adaptive rule of HS:878-892 is bypassed; frames are still counted every frame_dt).
+ * dt <= 0: back to the reference rule.  Not a reference feature: used for well-conditioned long-run parity tests. */
+AEP_API int aep_set_fixed_dt(aep_ctx* ctx, double dt);
 /* dt, simulated time t, time inside the current frame, frames completed, substeps done, max |v_i| of the last
  * grid update, number of particles that tried to leave the grid (sticky).  Any pointer may be NULL.        */
 AEP_API int aep_get_clock(aep_ctx* ctx, double* dt, double* t, double* inner_t, int32_t* frame_no,

@@ -43,7 +43,26 @@ def multistep(name, scene, n):
           f" | com {st['com']} vs {com} ke {st['ke']:.6e} vs {ke:.6e} jp {st['jp']:.8f} vs {jp:.8f} | t {c['t']+c['inner_t']:.6f} vs {o.time:.6f} frame {c['frame']} vs {o.frame} escaped {c['escaped']} dt {c['dt']:.6e} vs {o.dt:.6e}", flush=True)
     e.close()
 
+def cloth_report():
+    from oracle.make_golden import scene_from_dict
+    d = dict(np.load(os.path.join(ROOT, "tests", "golden", "cloth_sand.npz"))); scene = scene_from_dict(d, "cloth_sand")
+    e = Engine(scene); o = Oracle(scene); e.init(); o.init()
+    ge, go = e.grid(), o.grid()
+    print(f"== cloth_sand init: grid m {rel(ge['m'], go['m']):.2e} mom {rel(mom(ge), mom(go)):.2e} dt {e.dt:.8e} vs {o.dt:.8e}")
+    dt0 = o.dt; e.stage_forces(dt0); o.stage_forces(dt0); ge, go = e.grid(), o.grid()
+    print(f" force: f {rel(ge['f'], go['f']):.2e} max abs {np.abs(ge['f']-go['f']).max():.3e} of {np.abs(go['f']).max():.3e}")
+    e.stage_grid(dt0); o.stage_grid_update(dt0); vmax_o = o.cfl_condition() * scene.grid.h.min(); o.stage_collide()
+    ge, go = e.grid(), o.grid(); act = go["m"] > 1e-12 * go["m"].max()
+    print(f" grid : v {rel(ge['v'][act], go['v'][act]):.2e} vt {rel(ge['vt'][act], go['vt'][act]):.2e}")
+    dt1 = 0.3 / max(300.0, vmax_o / scene.grid.h.min()); e.stage_g2p(dt1); o.stage_g2p(dt1)
+    me, mo = e.mesh(), o.mesh()
+    print(" mesh : " + " ".join(f"{k} {rel(me[k], mo[k]):.2e}" for k in ("vx", "vv", "vB", "ex", "ev", "eB", "ed")))
+    e.close()
+
+
 if __name__ == "__main__":
+    try: cloth_report()
+    except Exception: traceback.print_exc()
     rng = np.random.default_rng(3)
     cases = {
         "sand_small": sc.small_block(material=sc.SAND, res=16, cells=3, seed=7),
