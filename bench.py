@@ -123,6 +123,14 @@ def packed_rest_state(x, mass, pinned=False):
     return [xs, v, b1, b2, b3, fe, fp, m, vol, q], keep
 
 
+def rate_floor_for(res):
+    """dt = cfl / max(rate_floor, vmax/h) (HybridSolver.cpp:860,878).  The reference's literal 300 (dt <= 1e-3 s) is tuned to its
+    own coarse grid (h = 0.044, main.cpp:53-69): with sand's p-wave speed ~19 m/s it gives c dt / h = 0.43 there, but 9.8 on a
+    512^3 unit box, where the explicit update blows up.  The floor is a config value of the ABI (aep_config.dt_rate_floor);
+    the bench scales it with resolution so that c dt / h stays at 0.61 (the value of the 32^3 parity scenes)."""
+    return 300.0 * res / 32.0
+
+
 def make_shell_scene(res):
     """Grid + level set of C5 without particles."""
     g = sc.GridSpec(np.zeros(3), np.ones(3), np.array([res] * 3))
@@ -180,7 +188,7 @@ def run_reference(args):
 def workload_config(args, res_override=None, note=None, n_particles=None):
     res = res_override or args.res
     cfg = {"workload": f"C5 synthetic sand dam break (Drucker-Prager), 8 particles/cell, {res}^3 grid", "grid": [res] * 3,
-           "material": "sand", "collider": "box level set", "timestep": "reference rule dt = 0.3 / max(300, vmax/h), on device",
+           "material": "sand", "collider": "box level set", "timestep": f"reference rule dt = 0.3 / max(rate_floor, vmax/h) on device, rate_floor = {rate_floor_for(res):g} (300 scaled by res/32 for stability)",
            "l2": "inputs (particle state >> 126 MB L2) larger than L2; no explicit flush"}
     if n_particles is not None:
         cfg["particles"] = int(n_particles)
@@ -208,7 +216,8 @@ def run_engine(args):
     del x
     t_gen = time.perf_counter() - t_gen
     shell = make_shell_scene(res)
-    eng = Engine(shell, device=local)
+    rate_floor = rate_floor_for(res)
+    eng = Engine(shell, device=local, dt_rate_floor=rate_floor)
     eng.upload_packed(n, arrs, sc.SAND_E, sc.SAND_NU, 2.5e-2, 7.5e-3)
     eng.init()
     stream = torch.cuda.ExternalStream(eng.stream, device=local)
@@ -245,7 +254,7 @@ def run_engine(args):
                 "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes, "active_blocks": blocks}}
     # ---- e2e: host fp64 state -> device, K substeps, f32 positions back (HybridSolver::solve's host-visible traffic)
     eng.close(); del eng
-    eng2 = Engine(shell, device=local)
+    eng2 = Engine(shell, device=local, dt_rate_floor=rate_floor)
     out_t = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
     import ctypes as C
     from anisotropicelastoplasticity_b200 import capi
