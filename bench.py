@@ -144,7 +144,7 @@ def cpu_baseline(threads, seconds_budget=20.0, res=64):
     res^3 (same particles per cell, same material, same collider), 2 warm-up + timed substeps."""
     from oracle.oracle_py import Oracle
     scene = sc.c5_dam_break(res=res)
-    o = Oracle(scene, threads=threads); o.init()
+    o = Oracle(scene, threads=threads, rate_floor=rate_floor_for(res)); o.init()
     used = o.L.orc_get_threads(o.h)
     for _ in range(2):
         o.substep()
@@ -167,7 +167,7 @@ def run_reference(args):
     from oracle.oracle_py import Oracle
     res = args.ref_res
     scene = sc.c5_dam_break(res=res)
-    o = Oracle(scene, threads=0); o.init()
+    o = Oracle(scene, threads=0, rate_floor=rate_floor_for(res)); o.init()
     used = o.L.orc_get_threads(o.h)
     for _ in range(args.warmup):
         o.substep()

@@ -49,7 +49,7 @@ def _p(a):
 class Oracle:
     """One simulation on the CPU oracle; method names mirror the C ABI of the engine (include/aep_b200.h)."""
 
-    def __init__(self, scene: Scene, threads: int = 1):
+    def __init__(self, scene: Scene, threads: int = 1, rate_floor: float = 3e2):
         L = lib(); self.L = L
         g = scene.grid
         mn = np.asarray(g.mn, np.float64); mx = np.asarray(g.mx, np.float64); res = np.asarray(g.res, np.int32)
@@ -57,7 +57,7 @@ class Oracle:
         self.ng = g.n_nodes; self.np = 0; self.nv = 0; self.nf = 0
         sand_h = np.array([35.0, 9.0, 0.2, 10.0])
         L.orc_set_params(self.h, C.c_int(scene.material), C.c_double(scene.cfl), C.c_double(9.8), C.c_double(0.2),
-                         C.c_double(10.0), _p(sand_h), C.c_double(3e2), C.c_double(1.0 / 60.0))
+                         C.c_double(10.0), _p(sand_h), C.c_double(rate_floor), C.c_double(1.0 / 60.0))
         L.orc_set_threads(self.h, C.c_int(threads))
         if scene.particles is not None:
             p = scene.particles; self.np = p.n
