@@ -37,12 +37,12 @@ class AepError(RuntimeError):
 # every symbol include/aep_b200.h declares (tests check the library exports all of them)
 SYMBOLS = (
     "aep_default_config", "aep_create", "aep_destroy", "aep_last_error", "aep_sync", "aep_upload_particles",
-    "aep_upload_mesh", "aep_set_levelset_analytic", "aep_set_levelset_samples", "aep_init", "aep_substep", "aep_run",
+    "aep_upload_mesh", "aep_set_levelset_analytic", "aep_set_levelset_samples", "aep_init", "aep_init_begin", "aep_init_volumes", "aep_init_dt", "aep_substep", "aep_run",
     "aep_run_frames", "aep_p2g", "aep_stage_forces", "aep_stage_grid", "aep_stage_g2p", "aep_set_dt", "aep_set_fixed_dt", "aep_get_clock",
     "aep_num_particles", "aep_download_particles", "aep_download_grid", "aep_download_mesh", "aep_download_positions_f32",
-    "aep_stats", "aep_kernel_launches", "aep_stream", "aep_profile", "aep_get_timers", "aep_halo_info", "aep_halo_pack",
-    "aep_halo_recv_buffer", "aep_halo_add", "aep_vmax_device_ptr", "aep_step_forces", "aep_step_grid", "aep_step_g2p",
-    "aep_step_p2g", "aep_grid_activity", "aep_migrate_extract", "aep_migrate_recv_buffer", "aep_migrate_insert",
+    "aep_stats", "aep_kernel_launches", "aep_stream", "aep_profile", "aep_get_timers", "aep_grid_activity", "aep_halo_info",
+    "aep_halo_pack", "aep_halo_add", "aep_vmax_get", "aep_vmax_set", "aep_step_forces", "aep_step_grid", "aep_step_g2p",
+    "aep_step_p2g", "aep_migrate_extract", "aep_migrate_insert", "aep_set_particle_id_base", "aep_download_particles_local",
 )
 
 
@@ -65,7 +65,7 @@ def load():
     L.aep_upload_mesh.argtypes = [vp, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, C.POINTER(C.c_int32), dp, dp, dp, dp, dp, dp, dp] + [C.c_double] * 5
     L.aep_set_levelset_analytic.argtypes = [vp, C.c_int, dp]
     L.aep_set_levelset_samples.argtypes = [vp, C.POINTER(C.c_uint8), dp]
-    for name in ("aep_destroy", "aep_sync", "aep_init", "aep_substep", "aep_step_forces", "aep_step_grid", "aep_step_g2p", "aep_step_p2g"):
+    for name in ("aep_destroy", "aep_sync", "aep_init", "aep_init_begin", "aep_init_volumes", "aep_init_dt", "aep_init_begin", "aep_init_volumes", "aep_init_dt", "aep_substep", "aep_step_forces", "aep_step_grid", "aep_step_g2p", "aep_step_p2g"):
         getattr(L, name).argtypes = [vp]
     L.aep_run.argtypes = [vp, C.c_int]
     L.aep_run_frames.argtypes = [vp, C.c_int, C.c_int, i64p]
@@ -82,13 +82,13 @@ def load():
     L.aep_get_timers.argtypes = [vp, dp, i64p]
     L.aep_grid_activity.argtypes = [vp, i64p, i64p]
     L.aep_halo_info.argtypes = [vp, C.c_int, C.c_int, i64p]
-    L.aep_halo_pack.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
-    L.aep_halo_recv_buffer.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
-    L.aep_halo_add.argtypes = [vp, C.c_int, C.c_int]
-    L.aep_vmax_device_ptr.argtypes = [vp, C.POINTER(vp)]
-    L.aep_migrate_extract.argtypes = [vp, i64p, i64p, C.POINTER(vp), C.POINTER(vp)]
-    L.aep_migrate_recv_buffer.argtypes = [vp, C.c_int, C.c_int64, C.POINTER(vp)]
-    L.aep_migrate_insert.argtypes = [vp, C.c_int64, C.c_int64]
+    L.aep_halo_pack.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.aep_halo_add.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.aep_vmax_get.argtypes = [vp, vp]; L.aep_vmax_set.argtypes = [vp, vp]
+    L.aep_migrate_extract.argtypes = [vp, vp, vp, C.c_int64, i64p, i64p]
+    L.aep_migrate_insert.argtypes = [vp, vp, C.c_int64, vp, C.c_int64]
+    L.aep_set_particle_id_base.argtypes = [vp, C.c_int64]
+    L.aep_download_particles_local.argtypes = [vp, i64p] + [dp] * 9
     _LIB = L
     return L
 

@@ -17,6 +17,7 @@
 
 #include "../../include/aep_b200.h"
 #include "aep_kernels.cuh"
+#include "aep_halo.cuh"
 #include "aep_mesh.cuh"
 
 using namespace aep;
@@ -56,6 +57,8 @@ struct aep_ctx {
     int key_bits = 0;
     MatParams mat{};
     bool keys_valid = false;
+    long long pending_leave = 0;                // particles extracted for migration, dropped at the next re-bin
+    long long id_base = 0;
 
     // mesh
     MeshState mesh;
@@ -194,18 +197,26 @@ int do_sort(aep_ctx* c, bool build_keys) {
     StageTimer T(c, AEP_STAGE_SORT);
     const int n = (int)c->n;
     if (n == 0) return AEP_OK;
-    if (build_keys) {
+    const bool slab = c->cfg.slab_axis >= 0;
+    int end_bit = c->key_bits;
+    if (build_keys && slab) {
+        k_build_keys_slab<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur].a[PX], c->d_keys[0], c->d_vals[0], n, c->G.nx, c->G.ny,
+                                                              c->cfg.slab_axis, c->cfg.slab_lo, c->cfg.slab_hi, c->key_bits);
+        LAUNCH_OK("k_build_keys_slab");
+        end_bit = c->key_bits + 1;
+    } else if (build_keys) {
         k_build_keys<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur].a[PX], c->d_keys[0], c->d_vals[0], n, c->G.nx, c->G.ny);
         LAUNCH_OK("k_build_keys");
     }
     size_t tmp = c->sort_tmp_bytes;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, tmp, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1],
-                                                    n, 0, c->key_bits, c->stream);
+                                                    n, 0, end_bit, c->stream);
     if (e != cudaSuccess) return fail(c, AEP_ERR_CUDA, "cub radix sort failed: %s", cudaGetErrorString(e));
-    c->launches += 1 + (c->key_bits + 7) / 8 * 2;     // upsweep/scan + one onesweep pass per 8 bits (cub internal; counted approximately)
+    c->launches += 1 + (end_bit + 7) / 8 * 2;     // cub internal kernels (histogram + one onesweep pass per 8 bits), counted approximately
     k_reorder<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur], c->P[c->cur ^ 1], c->d_vals[1], n);
     LAUNCH_OK("k_reorder");
     c->cur ^= 1;
+    if (slab && build_keys && c->pending_leave) { c->n -= c->pending_leave; c->pending_leave = 0; }   // leavers were sorted to the tail
     return AEP_OK;
 }
 
@@ -401,7 +412,7 @@ int aep_upload_particles(aep_ctx* c, int64_t n, const double* x, const double* v
             for (int a = 0; a < P_NARR; ++a) CU(dalloc(c, &c->P[b].a[a], (size_t)cap));
         for (int b = 0; b < 2; ++b) { CU(dalloc(c, &c->d_keys[b], (size_t)cap)); CU(dalloc(c, &c->d_vals[b], (size_t)cap)); }
         size_t tmp = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], (int)cap, 0, c->key_bits, c->stream);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], (int)cap, 0, c->key_bits + 1, c->stream);
         CU(cudaMalloc(&c->d_sort_tmp, tmp)); c->sort_tmp_bytes = tmp;
         c->cap = cap;
     }
@@ -428,7 +439,7 @@ int aep_upload_particles(aep_ctx* c, int64_t n, const double* x, const double* v
         CU(cudaMemcpyAsync(st + (size_t)17 * cnt, q + p0, cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(st + (size_t)18 * cnt, FE + (size_t)9 * p0, 9 * cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(st + (size_t)27 * cnt, FP + (size_t)9 * p0, 9 * cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        k_upload_convert<<<cdiv(cnt, 256), 256, 0, c->stream>>>(c->P[0], c->G, st, (int)cnt, (int)p0, p0, c->cfg.grid_min[0], c->cfg.grid_min[1],
+        k_upload_convert<<<cdiv(cnt, 256), 256, 0, c->stream>>>(c->P[0], c->G, st, (int)cnt, (int)p0, c->id_base + p0, c->cfg.grid_min[0], c->cfg.grid_min[1],
                                                                c->cfg.grid_min[2], c->h[0], c->h[1], c->h[2], c->d_clk);
         LAUNCH_OK("k_upload_convert");
         CU(cudaStreamSynchronize(c->stream));
@@ -483,18 +494,32 @@ int aep_set_levelset_samples(aep_ctx* c, const uint8_t* inside, const double* no
     return upload_levelset(c, code, &nrm);
 }
 
-int aep_init(aep_ctx* c) {
+int aep_init_begin(aep_ctx* c) {
     if (!c) return AEP_ERR_INVALID;
-    if (c->n == 0 && c->mesh.nv == 0) return fail(c, AEP_ERR_INVALID, "nothing to simulate: upload particles and/or a mesh first");
+    if (c->n == 0 && c->mesh.nv == 0 && c->cfg.slab_axis < 0) return fail(c, AEP_ERR_INVALID, "nothing to simulate: upload particles and/or a mesh first");
     cudaSetDevice(c->device);
-    c->inited = true;
+    c->inited = true; c->pending_leave = 0;
     int r;
     if ((r = do_sort(c, true))) return r;
-    if ((r = do_p2g(c, true))) return r;                                    // HS:854
+    return do_p2g(c, false);                                                // HS:854 (mass / momentum part)
+}
+int aep_init_volumes(aep_ctx* c) {
+    int r = require_init(c); if (r) return r;
+    if (c->n) { k_init_volumes<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->P[c->cur], c->G, (int)c->n); LAUNCH_OK("k_init_volumes"); }   // HS:242-249
     k_vmax_from_mp<<<c->nblocks, 256, 0, c->stream>>>(c->G, c->d_clk); LAUNCH_OK("k_vmax_from_mp");
-    k_initial_dt<<<1, 1, 0, c->stream>>>(c->d_clk); LAUNCH_OK("k_initial_dt"); // HS:860
+    return AEP_OK;
+}
+int aep_init_dt(aep_ctx* c) {
+    int r = require_init(c); if (r) return r;
+    k_initial_dt<<<1, 1, 0, c->stream>>>(c->d_clk); LAUNCH_OK("k_initial_dt");  // HS:860
     CU(cudaStreamSynchronize(c->stream));
     return AEP_OK;
+}
+int aep_init(aep_ctx* c) {
+    int r;
+    if ((r = aep_init_begin(c))) return r;
+    if ((r = aep_init_volumes(c))) return r;
+    return aep_init_dt(c);
 }
 
 int aep_substep(aep_ctx* c) { int r = require_init(c); if (r) return r; return do_substep(c); }
@@ -590,7 +615,7 @@ int aep_download_positions_f32(aep_ctx* c, float* xyz) {
     cudaSetDevice(c->device);
     const long long n = c->n; if (n == 0) return AEP_OK;
     int r = ensure_stage(c, (size_t)n * 3 * sizeof(float)); if (r) return r;
-    k_download_positions_f32<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur], c->G, (float*)c->d_stage, (int)n);
+    k_download_positions_f32<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur], c->G, (float*)c->d_stage, (int)n, c->cfg.slab_axis >= 0 ? 1 : 0);
     LAUNCH_OK("k_download_positions_f32");
     CU(cudaMemcpyAsync(xyz, c->d_stage, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -684,13 +709,7 @@ int aep_step_p2g(aep_ctx* c) {
     if ((r = do_sort(c, true))) return r;
     return do_p2g(c, false);
 }
-int aep_vmax_device_ptr(aep_ctx* c, void** dev_float) {
-    if (!c || !dev_float) return AEP_ERR_INVALID;
-    *dev_float = (void*)&c->d_clk->vmax_bits;
-    return AEP_OK;
-}
-
-// halo / migration: implemented in aep_halo.cuh (multi-GPU milestone)
+// halo exchange / migration entry points
 #include "aep_halo.inl"
 
 }  // extern "C"

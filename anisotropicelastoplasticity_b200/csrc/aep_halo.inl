@@ -1,8 +1,134 @@
-// aep_halo.inl -- slab halo exchange + particle migration entry points.  PLACEHOLDER (multi-GPU milestone).
-int aep_halo_info(aep_ctx* c, int, int, int64_t*) { return fail(c, AEP_ERR_INVALID, "halo exchange not built yet"); }
-int aep_halo_pack(aep_ctx* c, int, int, void**) { return fail(c, AEP_ERR_INVALID, "halo exchange not built yet"); }
-int aep_halo_recv_buffer(aep_ctx* c, int, int, void**) { return fail(c, AEP_ERR_INVALID, "halo exchange not built yet"); }
-int aep_halo_add(aep_ctx* c, int, int) { return fail(c, AEP_ERR_INVALID, "halo exchange not built yet"); }
-int aep_migrate_extract(aep_ctx* c, int64_t*, int64_t*, void**, void**) { return fail(c, AEP_ERR_INVALID, "migration not built yet"); }
-int aep_migrate_recv_buffer(aep_ctx* c, int, int64_t, void**) { return fail(c, AEP_ERR_INVALID, "migration not built yet"); }
-int aep_migrate_insert(aep_ctx* c, int64_t, int64_t) { return fail(c, AEP_ERR_INVALID, "migration not built yet"); }
+// aep_halo.inl -- C ABI of the slab decomposition (included inside extern "C" of aep_engine.cu).
+static int slab_check(aep_ctx* c, int side, bool* has) {
+    if (!c) return AEP_ERR_INVALID;
+    if (c->cfg.slab_axis < 0 || c->cfg.slab_axis > 2) return fail(c, AEP_ERR_INVALID, "context has no slab (cfg.slab_axis < 0)");
+    if (side != 0 && side != 1) return fail(c, AEP_ERR_INVALID, "side must be 0 (low) or 1 (high)");
+    const int nres = c->cfg.res[c->cfg.slab_axis];
+    *has = side == 0 ? (c->cfg.slab_lo > 0) : (c->cfg.slab_hi < nres);
+    cudaSetDevice(c->device);
+    return AEP_OK;
+}
+static PlaneMap plane_map(aep_ctx* c, int side) {
+    PlaneMap M; M.axis = c->cfg.slab_axis; M.nplanes = 3;
+    M.plane0 = (side == 0 ? c->cfg.slab_lo : c->cfg.slab_hi) - 1;
+    if (M.axis == 0) { M.nu = c->G.ny; M.nv = c->G.nz; } else if (M.axis == 1) { M.nu = c->G.nx; M.nv = c->G.nz; } else { M.nu = c->G.nx; M.nv = c->G.ny; }
+    return M;
+}
+
+int aep_halo_info(aep_ctx* c, int what, int side, int64_t* n_floats) {
+    bool has; int r = slab_check(c, side, &has); if (r) return r;
+    if (what != 0 && what != 1) return fail(c, AEP_ERR_INVALID, "what must be 0 (m,p) or 1 (f)");
+    const PlaneMap M = plane_map(c, side);
+    if (n_floats) *n_floats = has ? (int64_t)M.nplanes * M.nu * M.nv * 4 : 0;
+    return AEP_OK;
+}
+
+int aep_halo_pack(aep_ctx* c, int what, int side, void* dev_send) {
+    bool has; int r = slab_check(c, side, &has); if (r) return r;
+    if (!has) return AEP_OK;
+    if (!dev_send) return fail(c, AEP_ERR_INVALID, "null halo buffer");
+    StageTimer T(c, AEP_STAGE_HALO);
+    const PlaneMap M = plane_map(c, side);
+    const long long n = (long long)M.nplanes * M.nu * M.nv;
+    k_halo_pack<<<cdiv(n, 256), 256, 0, c->stream>>>(what == 0 ? c->G.mp : c->G.f, (float4*)dev_send, c->G, M);
+    LAUNCH_OK("k_halo_pack");
+    return AEP_OK;
+}
+
+int aep_halo_add(aep_ctx* c, int what, int side, const void* dev_recv) {
+    bool has; int r = slab_check(c, side, &has); if (r) return r;
+    if (!has) return AEP_OK;
+    if (!dev_recv) return fail(c, AEP_ERR_INVALID, "null halo buffer");
+    StageTimer T(c, AEP_STAGE_HALO);
+    const PlaneMap M = plane_map(c, side);
+    const long long n = (long long)M.nplanes * M.nu * M.nv;
+    k_halo_add<<<cdiv(n, 256), 256, 0, c->stream>>>(what == 0 ? c->G.mp : c->G.f, (const float4*)dev_recv, c->G, M);
+    LAUNCH_OK("k_halo_add");
+    return AEP_OK;
+}
+
+int aep_vmax_get(aep_ctx* c, void* dev_float) {
+    if (!c || !dev_float) return AEP_ERR_INVALID;
+    cudaSetDevice(c->device);
+    CU(cudaMemcpyAsync(dev_float, &c->d_clk->vmax_bits, 4, cudaMemcpyDeviceToDevice, c->stream));
+    return AEP_OK;
+}
+int aep_vmax_set(aep_ctx* c, const void* dev_float) {
+    if (!c || !dev_float) return AEP_ERR_INVALID;
+    cudaSetDevice(c->device);
+    CU(cudaMemcpyAsync(&c->d_clk->vmax_bits, dev_float, 4, cudaMemcpyDeviceToDevice, c->stream));
+    return AEP_OK;
+}
+
+int aep_migrate_extract(aep_ctx* c, void* dev_to_low, void* dev_to_high, int64_t capacity, int64_t* n_low, int64_t* n_high) {
+    int r = require_init(c); if (r) return r;
+    if (c->cfg.slab_axis < 0) return fail(c, AEP_ERR_INVALID, "context has no slab");
+    if (n_low) *n_low = 0; if (n_high) *n_high = 0;
+    c->pending_leave = 0;
+    if (c->n == 0) return AEP_OK;
+    if (!dev_to_low || !dev_to_high || capacity < 0) return fail(c, AEP_ERR_INVALID, "null migration buffer");
+    StageTimer T(c, AEP_STAGE_HALO);
+    unsigned long long* cnt = (unsigned long long*)c->d_stats;
+    CU(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), c->stream));
+    k_migrate_extract<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->P[c->cur], (int)c->n, c->cfg.slab_axis, c->cfg.slab_lo, c->cfg.slab_hi,
+                                                              (float4*)dev_to_low, (float4*)dev_to_high, capacity, cnt);
+    LAUNCH_OK("k_migrate_extract");
+    unsigned long long h[2];
+    CU(cudaMemcpyAsync(h, cnt, sizeof h, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
+    if ((int64_t)h[0] > capacity || (int64_t)h[1] > capacity)
+        return fail(c, AEP_ERR_STATE, "migration buffer too small: %llu / %llu particles leave, capacity %lld", h[0], h[1], (long long)capacity);
+    if (n_low) *n_low = (int64_t)h[0]; if (n_high) *n_high = (int64_t)h[1];
+    c->pending_leave = (long long)(h[0] + h[1]);
+    return AEP_OK;
+}
+
+int aep_migrate_insert(aep_ctx* c, const void* dev_from_low, int64_t n_from_low, const void* dev_from_high, int64_t n_from_high) {
+    int r = require_init(c); if (r) return r;
+    if (n_from_low < 0 || n_from_high < 0) return fail(c, AEP_ERR_INVALID, "negative count");
+    if (c->n + n_from_low + n_from_high > c->cap)
+        return fail(c, AEP_ERR_ALLOC, "particle capacity %lld exceeded by migration (%lld + %lld + %lld); raise aep_config.particle_capacity",
+                    c->cap, c->n, (long long)n_from_low, (long long)n_from_high);
+    StageTimer T(c, AEP_STAGE_HALO);
+    if (n_from_low) {
+        k_migrate_insert<<<cdiv(n_from_low, 256), 256, 0, c->stream>>>(c->P[c->cur], (int)c->n, (const float4*)dev_from_low, (int)n_from_low);
+        LAUNCH_OK("k_migrate_insert"); c->n += n_from_low;
+    }
+    if (n_from_high) {
+        k_migrate_insert<<<cdiv(n_from_high, 256), 256, 0, c->stream>>>(c->P[c->cur], (int)c->n, (const float4*)dev_from_high, (int)n_from_high);
+        LAUNCH_OK("k_migrate_insert"); c->n += n_from_high;
+    }
+    return AEP_OK;
+}
+
+int aep_set_particle_id_base(aep_ctx* c, int64_t id_base) {
+    if (!c || id_base < 0) return AEP_ERR_INVALID;
+    c->id_base = id_base;
+    return AEP_OK;
+}
+
+int aep_download_particles_local(aep_ctx* c, int64_t* ids, double* x, double* v, double* B1, double* B2, double* B3, double* FE, double* FP,
+                                 double* vol, double* q) {
+    if (!c) return AEP_ERR_INVALID;
+    cudaSetDevice(c->device);
+    const long long n = c->n; if (n == 0) return AEP_OK;
+    const long long CH = 1 << 22;
+    int r = ensure_stage(c, (size_t)std::min(n, CH) * 37 * sizeof(double)); if (r) return r;
+    for (long long p0 = 0; p0 < n; p0 += CH) {
+        const long long cnt = std::min(CH, n - p0);
+        double* st = c->d_stage; long long* dids = (long long*)(st + (size_t)35 * cnt);
+        k_download_local<<<cdiv(cnt, 256), 256, 0, c->stream>>>(c->P[c->cur], c->G, st, dids, (int)p0, (int)cnt, c->cfg.grid_min[0], c->cfg.grid_min[1],
+                                                               c->cfg.grid_min[2], c->h[0], c->h[1], c->h[2]);
+        LAUNCH_OK("k_download_local");
+        double* mats[5] = { x, v, B1, B2, B3 };
+        for (int k = 0; k < 5; ++k) if (mats[k])
+            for (int a = 0; a < 3; ++a)
+                CU(cudaMemcpyAsync(mats[k] + (size_t)a * n + p0, st + (size_t)(3 * k + a) * cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (vol) CU(cudaMemcpyAsync(vol + p0, st + (size_t)15 * cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (q) CU(cudaMemcpyAsync(q + p0, st + (size_t)16 * cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (FE) CU(cudaMemcpyAsync(FE + (size_t)9 * p0, st + (size_t)17 * cnt, 9 * cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (FP) CU(cudaMemcpyAsync(FP + (size_t)9 * p0, st + (size_t)26 * cnt, 9 * cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (ids) CU(cudaMemcpyAsync(ids + p0, dids, cnt * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return AEP_OK;
+}

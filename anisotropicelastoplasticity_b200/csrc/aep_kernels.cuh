@@ -586,11 +586,11 @@ __global__ void k_download_convert(PartP P, GridP G, double* __restrict__ st, in
     fp[0] = q0.x; fp[3] = q0.y; fp[6] = q0.z; fp[1] = q1.x; fp[4] = q1.y; fp[7] = q1.z; fp[2] = q2.x; fp[5] = q2.y; fp[8] = q2.z;
 }
 
-__global__ void k_download_positions_f32(PartP P, GridP G, float* __restrict__ out, int n) {
+__global__ void k_download_positions_f32(PartP P, GridP G, float* __restrict__ out, int n, int by_slot) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const float4 X = P.a[PX][s];
-    const int id = __float_as_int(P.a[PQ0][s].w);
+    const int id = by_slot ? s : __float_as_int(P.a[PQ0][s].w);
     const int cell = __float_as_int(X.w);
     out[3 * (size_t)id + 0] = fmaf((float)cell_i(cell) + X.x, G.hx, G.mnx);
     out[3 * (size_t)id + 1] = fmaf((float)cell_j(cell) + X.y, G.hy, G.mny);

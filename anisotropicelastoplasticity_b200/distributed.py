@@ -1,0 +1,414 @@
+"""Multi-GPU slab decomposition of the MPM substep: one process per GPU, `torch.distributed` (NCCL over
+NVLink / NVSwitch on GPUs, gloo on CPU for the host-logic tests) moves the bytes, the C ABI does everything else.
+
+The reference is single-process (no MPI/NCCL anywhere), so this layer is new.  Per substep and per neighbour pair:
+
+    forces | halo(f) | grid update | all-reduce(max |v|) | dt rule, G2P | migrate particles | re-bin, P2G | halo(m,p)
+
+* halo = the 3 node planes around a slab boundary that both neighbours scatter into; one symmetric exchange of partial
+  sums per scatter, each side adds what it receives (identical totals on both ranks, shared planes updated redundantly).
+* the only global scalar is max|v_i| for the dt rule (HybridSolver.cpp:878) -> one 4-byte all-reduce(max).
+* particles whose new cell left the slab travel to the neighbour as 44-float records with their global id.
+
+`SlabSolver` is backend-agnostic: `GpuSlabBackend` drives libaep_b200.so; tests/ provides a CPU backend on the oracle so the
+same driver runs under gloo with world_size 2.  `LocalSlabGroup` steps several backends of ONE process in lockstep with direct
+buffer swaps (several slabs on one GPU: decomposition-invariance test without NCCL).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+MIGRATE_FLOATS = 44
+
+
+# ------------------------------------------------------------------------------------------------ partition
+class SlabPlan:
+    """Cells [bounds[r], bounds[r+1]) along `axis` belong to rank r."""
+
+    def __init__(self, axis: int, bounds: Sequence[int]):
+        self.axis = int(axis); self.bounds = [int(b) for b in bounds]
+        self.world = len(self.bounds) - 1
+        for r in range(self.world):
+            if self.bounds[r + 1] - self.bounds[r] < 4 and self.world > 1:
+                raise ValueError(f"slab {r} is {self.bounds[r + 1] - self.bounds[r]} cells wide; need >= 4 (cubic support spans 3 node planes)")
+
+    @staticmethod
+    def uniform(res_axis: int, world: int, axis: int = 1) -> "SlabPlan":
+        return SlabPlan(axis, [round(r * res_axis / world) for r in range(world + 1)])
+
+    @staticmethod
+    def balanced(cells_axis: np.ndarray, res_axis: int, world: int, axis: int = 1, min_width: int = 4) -> "SlabPlan":
+        """Boundaries at particle-count quantiles (dam break: particles are not uniform in space)."""
+        hist = np.bincount(np.asarray(cells_axis, np.int64), minlength=res_axis).astype(np.float64)
+        cum = np.concatenate([[0.0], np.cumsum(hist)])
+        bounds = [0]
+        for r in range(1, world):
+            b = int(np.searchsorted(cum, cum[-1] * r / world))
+            b = max(b, bounds[-1] + min_width); b = min(b, res_axis - min_width * (world - r))
+            bounds.append(b)
+        bounds.append(res_axis)
+        return SlabPlan(axis, bounds)
+
+    def slab(self, rank):
+        return self.axis, self.bounds[rank], self.bounds[rank + 1]
+
+    def owner_of_cells(self, cells_axis):
+        return np.clip(np.searchsorted(np.asarray(self.bounds), cells_axis, side="right") - 1, 0, self.world - 1)
+
+
+# ------------------------------------------------------------------------------------------------ GPU backend
+class GpuSlabBackend:
+    """One slab on one GPU through the C ABI; communication buffers are torch CUDA tensors owned here."""
+
+    def __init__(self, engine, migrate_capacity: int = 1 << 16):
+        import torch
+        from . import capi
+        self.torch = torch; self.capi = capi
+        self.e = engine; self.L = engine.L; self.h = engine.h
+        self.device = torch.device("cuda", engine.cfg.device)
+        self.stream = torch.cuda.ExternalStream(engine.stream, device=self.device)
+        self.halo_send = {}; self.halo_recv = {}
+        for what in (0, 1):
+            for side in (0, 1):
+                n = C.c_int64(0)
+                capi.check(self.L.aep_halo_info(self.h, what, side, C.byref(n)), self.h)
+                self.halo_send[(what, side)] = torch.zeros(n.value, dtype=torch.float32, device=self.device)
+                self.halo_recv[(what, side)] = torch.zeros(n.value, dtype=torch.float32, device=self.device)
+        self.mig_cap = int(migrate_capacity)
+        self.mig_send = [torch.zeros((self.mig_cap, MIGRATE_FLOATS), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.mig_recv = [torch.zeros((self.mig_cap, MIGRATE_FLOATS), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.vmax = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.count_dtype = torch.int64
+
+    def _ck(self, rc): self.capi.check(rc, self.h)
+    # stepping
+    def init_begin(self): self._ck(self.L.aep_init_begin(self.h))
+    def init_volumes(self): self._ck(self.L.aep_init_volumes(self.h))
+    def init_dt(self): self._ck(self.L.aep_init_dt(self.h))
+    def step_forces(self): self._ck(self.L.aep_step_forces(self.h))
+    def step_grid(self): self._ck(self.L.aep_step_grid(self.h))
+    def step_g2p(self): self._ck(self.L.aep_step_g2p(self.h))
+    def step_p2g(self): self._ck(self.L.aep_step_p2g(self.h))
+    # halo
+    def halo_pack(self, what, side):
+        t = self.halo_send[(what, side)]
+        self._ck(self.L.aep_halo_pack(self.h, what, side, C.c_void_p(t.data_ptr())))
+        return t
+    def halo_recv_buffer(self, what, side): return self.halo_recv[(what, side)]
+    def halo_add(self, what, side, t): self._ck(self.L.aep_halo_add(self.h, what, side, C.c_void_p(t.data_ptr())))
+    # vmax
+    def vmax_get(self):
+        self._ck(self.L.aep_vmax_get(self.h, C.c_void_p(self.vmax.data_ptr()))); return self.vmax
+    def vmax_set(self, t): self._ck(self.L.aep_vmax_set(self.h, C.c_void_p(t.data_ptr())))
+    # migration
+    def migrate_extract(self):
+        nl = C.c_int64(0); nh = C.c_int64(0)
+        self._ck(self.L.aep_migrate_extract(self.h, C.c_void_p(self.mig_send[0].data_ptr()), C.c_void_p(self.mig_send[1].data_ptr()),
+                                            self.mig_cap, C.byref(nl), C.byref(nh)))
+        return self.mig_send[0][:nl.value], self.mig_send[1][:nh.value]
+    def migrate_recv_buffer(self, side, n):
+        if n > self.mig_cap:
+            raise RuntimeError(f"migration receive capacity {self.mig_cap} < {n}")
+        return self.mig_recv[side][:n]
+    def migrate_insert(self, from_low, from_high):
+        self._ck(self.L.aep_migrate_insert(self.h, C.c_void_p(from_low.data_ptr()) if from_low.numel() else None, from_low.shape[0],
+                                           C.c_void_p(from_high.data_ptr()) if from_high.numel() else None, from_high.shape[0]))
+    def sync(self): self.e.sync()
+
+    def particles_local(self):
+        from .scenes import from_colmajor, mats_from_colmajor
+        n = self.e.n_particles
+        ids = np.empty(n, np.int64); b = {k: np.empty(3 * n) for k in ("x", "v", "B1", "B2", "B3")}
+        FE = np.empty(9 * n); FP = np.empty(9 * n); vol = np.empty(n); q = np.empty(n)
+        dp = self.capi.dp
+        P = lambda a: a.ctypes.data_as(dp)
+        self._ck(self.L.aep_download_particles_local(self.h, ids.ctypes.data_as(self.capi.i64p), P(b["x"]), P(b["v"]), P(b["B1"]), P(b["B2"]), P(b["B3"]),
+                                                     P(FE), P(FP), P(vol), P(q)))
+        B = np.stack([from_colmajor(b["B1"], n), from_colmajor(b["B2"], n), from_colmajor(b["B3"], n)], axis=1)
+        return dict(ids=ids, x=from_colmajor(b["x"], n), v=from_colmajor(b["v"], n), B=B, FE=mats_from_colmajor(FE, n), FP=mats_from_colmajor(FP, n), vol=vol, q=q)
+
+
+# ------------------------------------------------------------------------------------------------ per-rank driver
+class SlabSolver:
+    """One rank of the decomposition over torch.distributed (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, backend, plan: SlabPlan, rank: int, group=None):
+        import torch.distributed as dist
+        self.dist = dist; self.b = backend; self.plan = plan; self.rank = rank; self.group = group
+        self.world = plan.world
+        self.nb = {0: rank - 1 if rank > 0 else None, 1: rank + 1 if rank < self.world - 1 else None}
+        self.stats = {"halo_bytes": 0, "migrated": 0}
+
+    def _batch(self, ops):
+        if not ops:
+            return
+        for w in self.dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def halo(self, what):
+        dist = self.dist; ops = []; recv = {}
+        for side in (0, 1):
+            nb = self.nb[side]
+            if nb is None:
+                continue
+            send = self.b.halo_pack(what, side); recv[side] = self.b.halo_recv_buffer(what, side)
+            ops.append(dist.P2POp(dist.isend, send, nb, group=self.group)); ops.append(dist.P2POp(dist.irecv, recv[side], nb, group=self.group))
+            self.stats["halo_bytes"] += send.numel() * send.element_size()
+        self._batch(ops)
+        for side, t in recv.items():
+            self.b.halo_add(what, side, t)
+
+    def allreduce_vmax(self):
+        t = self.b.vmax_get()
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        self.b.vmax_set(t)
+
+    def migrate(self):
+        import torch
+        dist = self.dist
+        out = self.b.migrate_extract()                      # (to_low, to_high) record tensors
+        dev = out[0].device
+        n_send = {s: torch.tensor([out[s].shape[0]], dtype=torch.int64, device=dev) for s in (0, 1)}
+        n_recv = {s: torch.zeros(1, dtype=torch.int64, device=dev) for s in (0, 1)}
+        ops = []
+        for side in (0, 1):
+            nb = self.nb[side]
+            if nb is None:
+                if out[side].shape[0]:
+                    raise RuntimeError(f"rank {self.rank}: {out[side].shape[0]} particles left the domain through side {side}")
+                continue
+            ops.append(dist.P2POp(dist.isend, n_send[side], nb, group=self.group)); ops.append(dist.P2POp(dist.irecv, n_recv[side], nb, group=self.group))
+        self._batch(ops)
+        counts = {s: int(n_recv[s].item()) for s in (0, 1)}
+        ops = []; bufs = {}
+        for side in (0, 1):
+            nb = self.nb[side]
+            bufs[side] = self.b.migrate_recv_buffer(side, counts[side])
+            if nb is None:
+                continue
+            if out[side].shape[0]:
+                ops.append(dist.P2POp(dist.isend, out[side], nb, group=self.group))
+            if counts[side]:
+                ops.append(dist.P2POp(dist.irecv, bufs[side], nb, group=self.group))
+        self._batch(ops)
+        self.b.migrate_insert(bufs[0], bufs[1])
+        self.stats["migrated"] += out[0].shape[0] + out[1].shape[0]
+
+    def init(self):
+        self.b.init_begin(); self.halo(0); self.b.init_volumes(); self.allreduce_vmax(); self.b.init_dt()
+
+    def substep(self):
+        b = self.b
+        b.step_forces(); self.halo(1)
+        b.step_grid(); self.allreduce_vmax()
+        b.step_g2p(); self.migrate()
+        b.step_p2g(); self.halo(0)
+
+    def run(self, n):
+        for _ in range(n):
+            self.substep()
+
+
+# ------------------------------------------------------------------------------------------------ in-process group
+class LocalSlabGroup:
+    """Several slabs stepped in lockstep inside one process (all on one GPU, or on the CPU test backend): the exchange is a
+    direct buffer copy.  Same backend calls, same order as SlabSolver."""
+
+    def __init__(self, backends: List, plan: SlabPlan):
+        self.bs = backends; self.plan = plan; self.world = plan.world
+
+    def _halo(self, what):
+        sends = {}
+        for r, b in enumerate(self.bs):
+            for side in (0, 1):
+                nb = r - 1 if side == 0 else r + 1
+                if 0 <= nb < self.world:
+                    sends[(r, side)] = b.halo_pack(what, side).clone()
+        for r, b in enumerate(self.bs):
+            for side in (0, 1):
+                nb = r - 1 if side == 0 else r + 1
+                if 0 <= nb < self.world:
+                    buf = b.halo_recv_buffer(what, side); buf.copy_(sends[(nb, 1 - side)]); b.halo_add(what, side, buf)
+
+    def _vmax(self):
+        import torch
+        ts = [b.vmax_get().clone() for b in self.bs]
+        m = torch.stack([t.cpu() for t in ts]).max(dim=0).values
+        for b in self.bs:
+            t = b.vmax_get(); t.copy_(m.to(t.device)); b.vmax_set(t)
+
+    def _migrate(self):
+        outs = [tuple(t.clone() for t in b.migrate_extract()) for b in self.bs]
+        for r, b in enumerate(self.bs):
+            parts = []
+            for side in (0, 1):
+                nb = r - 1 if side == 0 else r + 1
+                if 0 <= nb < self.world:
+                    src = outs[nb][1 - side]
+                    buf = b.migrate_recv_buffer(side, src.shape[0]); buf.copy_(src)
+                else:
+                    buf = b.migrate_recv_buffer(side, 0)
+                parts.append(buf)
+            b.migrate_insert(parts[0], parts[1])
+
+    def init(self):
+        for b in self.bs: b.init_begin()
+        self._halo(0)
+        for b in self.bs: b.init_volumes()
+        self._vmax()
+        for b in self.bs: b.init_dt()
+
+    def substep(self):
+        for b in self.bs: b.step_forces()
+        self._halo(1)
+        for b in self.bs: b.step_grid()
+        self._vmax()
+        for b in self.bs: b.step_g2p()
+        self._migrate()
+        for b in self.bs: b.step_p2g()
+        self._halo(0)
+
+    def run(self, n):
+        for _ in range(n):
+            self.substep()
+
+    def gather_particles(self):
+        """All particles of all slabs, ordered by global id."""
+        parts = [b.particles_local() for b in self.bs]
+        ids = np.concatenate([p["ids"] for p in parts]); order = np.argsort(ids)
+        out = {k: np.concatenate([p[k] for p in parts], axis=0)[order] for k in parts[0] if k != "ids"}
+        out["ids"] = ids[order]
+        return out
+
+
+def split_scene_particles(scene, plan: SlabPlan, rank: int):
+    """Indices (global ids) of the particles of `scene` that start in `rank`'s slab."""
+    g = scene.grid; p = scene.particles
+    a = plan.axis
+    cells = np.floor((p.x[:, a] - g.mn[a]) / g.h[a]).astype(np.int64)
+    return np.nonzero(plan.owner_of_cells(cells) == rank)[0]
+
+
+def make_gpu_slab_engine(scene, plan: SlabPlan, rank: int, device: int, capacity_factor: float = 1.3, dt_rate_floor=None, ids=None):
+    """Engine holding only `rank`'s particles of `scene` (global ids preserved when the slab is a contiguous id range or ids given)."""
+    import copy
+    from .engine import Engine
+    from .scenes import Particles
+    idx = split_scene_particles(scene, plan, rank) if ids is None else ids
+    p = scene.particles
+    local = Particles(x=p.x[idx], v=p.v[idx], B=p.B[idx], FE=p.FE[idx], FP=p.FP[idx], m=p.m[idx], vol=p.vol[idx], q=p.q[idx],
+                      E=p.E, nu=p.nu, thetaC=p.thetaC, thetaS=p.thetaS)
+    shell = copy.copy(scene); shell.particles = None
+    cap = int(max(1024, capacity_factor * len(idx) + 4096))
+    eng = Engine(shell, device=device, particle_capacity=cap, slab=plan.slab(rank), dt_rate_floor=dt_rate_floor)
+    return eng, local, idx
+
+
+# ------------------------------------------------------------------------------------------------ bench (N > 1)
+def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, UNIT):
+    """Strong scaling of the C5 dam break over `world` GPUs (one process per GPU, launched by torchrun)."""
+    import torch
+    import torch.distributed as dist
+    import bench as B
+    from . import scenes as sc
+    from .engine import Engine
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"bench.py --gpus {args.gpus} must be launched with torchrun --nproc-per-node {args.gpus} (WORLD_SIZE={world})")
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    res = args.res
+    # dam break column spans y in [2h, 1-2h] uniformly -> uniform y-slabs are balanced for all time
+    lo_c, hi_c = 2, res - 2
+    bounds = [0] + [lo_c + round(r * (hi_c - lo_c) / world) for r in range(1, world)] + [res]
+    plan = SlabPlan(1, bounds)
+    h = 1.0 / res
+    y0, y1 = plan.bounds[rank] * h, plan.bounds[rank + 1] * h
+    t_gen = time.perf_counter()
+    x = B.dam_break_positions(res, seed=5 + 1000 * rank, y_range=(y0, y1))
+    n_local = x.shape[0]
+    counts = torch.zeros(world, dtype=torch.int64, device="cuda"); counts[rank] = n_local
+    dist.all_reduce(counts); counts = counts.cpu().numpy(); n_total = int(counts.sum()); id_base = int(counts[:rank].sum())
+    mass = sc.SAND_RHO * h ** 3 / 8.0
+    arrs, keep = B.packed_rest_state(x, mass, pinned=True); del x
+    t_gen = time.perf_counter() - t_gen
+    shell = B.make_shell_scene(res)
+    rate_floor = B.rate_floor_for(res)
+
+    def build():
+        eng = Engine(shell, device=local, particle_capacity=int(1.25 * n_local + 65536), slab=plan.slab(rank), dt_rate_floor=rate_floor)
+        from . import capi
+        capi.check(eng.L.aep_set_particle_id_base(eng.h, id_base), eng.h)
+        eng.upload_packed(n_local, arrs, sc.SAND_E, sc.SAND_NU, 2.5e-2, 7.5e-3)
+        be = GpuSlabBackend(eng, migrate_capacity=max(1 << 16, n_local // 50))
+        return eng, be, SlabSolver(be, plan, rank)
+
+    eng, be, solver = build()
+    with torch.cuda.stream(be.stream):
+        solver.init()
+        solver.run(args.warmup)
+        be.sync(); dist.barrier(); torch.cuda.synchronize()
+        sampler = ClockSampler(local) if rank == 0 else None
+        l0 = eng.kernel_launches
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record(be.stream)
+        solver.run(args.steps)
+        ev1.record(be.stream); torch.cuda.synchronize()
+        ms_local = ev0.elapsed_time(ev1)
+        dist.barrier()
+    t = torch.tensor([ms_local], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    launches = eng.kernel_launches - l0
+    nodes_t = torch.tensor([eng.grid_activity()[1]], dtype=torch.int64, device="cuda"); dist.all_reduce(nodes_t); nodes = int(nodes_t.item())
+    nloc_t = torch.tensor([eng.n_particles], dtype=torch.int64, device="cuda"); dist.all_reduce(nloc_t)
+    assert int(nloc_t.item()) == n_total, "particles were lost in migration"
+    clk = eng.clock()
+    value = n_total * args.steps / (ms * 1e-3)
+    # per-stage time on this rank (profiled pass)
+    with torch.cuda.stream(be.stream):
+        eng.profile(True); solver.run(3); be.sync(); tm = eng.timers(); eng.profile(False)
+    stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in tm.items()}
+    peak, peak_kind = measured_peak_gbs()
+    dom = max(("forces", "g2p", "p2g", "grid", "sort"), key=lambda k: stage_ms.get(k, 0.0))
+    bp, bn = B.STAGE_BYTES[dom]
+    dom_bytes = bp * eng.n_particles + bn * eng.grid_activity()[1]
+    achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+    sub_bytes = B.BYTES_PARTICLE[sc.SAND] * n_total + B.BYTES_NODE * nodes
+    sub_gbs = sub_bytes / (ms * 1e-3 / args.steps) / 1e9 / world
+    roofline = {"bound": "hbm", "kernel": {"forces": "k_forces", "g2p": "k_g2p", "p2g": "k_p2g", "grid": "k_grid_update", "sort": "cub radix sort + k_reorder"}[dom],
+                "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth, MEASURED_PEAKS.json", "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom], "stage_ms": stage_ms, "rank": 0,
+                "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs_per_gpu": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes}}
+    halo_bytes = solver.stats["halo_bytes"]; migrated = solver.stats["migrated"]
+    # e2e: fresh contexts, upload from pinned host memory + init + K substeps + f32 positions back, wall clock max over ranks
+    eng.close(); del eng, be, solver
+    out_t = torch.empty((int(1.25 * n_local + 65536), 3), dtype=torch.float32, pin_memory=True)
+    dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    eng, be, solver = build()
+    with torch.cuda.stream(be.stream):
+        solver.init(); solver.run(args.steps)
+    from . import capi
+    capi.check(eng.L.aep_download_positions_f32(eng.h, C.cast(out_t.data_ptr(), C.POINTER(C.c_float))), eng.h)
+    torch.cuda.synchronize(); dist.barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda"); dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e = {"value": n_total * args.steps / float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": 36 * 8 * n_total / args.steps,
+           "d2h_bytes_per_step": 12 * n_total / args.steps, "seconds": float(t_e2e.item()),
+           "what": "per rank: aep_create + aep_upload_particles(fp64 host, pinned) + init + K substeps (halo/migration over NCCL) + f32 positions"}
+    eng.close()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(workload_config(args, n_particles=n_total), decomposition=f"{world} y-slabs, bounds {plan.bounds}",
+                               exchange="NCCL send/recv: 2 halo exchanges (3 node planes per side) + 1 four-byte all-reduce(max) + particle migration per substep"),
+                "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "comm": {"halo_bytes_per_step_per_rank": halo_bytes / max(1, args.steps + args.warmup + 3 + 1), "migrated_particles_rank0": migrated},
+                "sim": {"dt": clk["dt"], "t": clk["t"] + clk["inner_t"], "escaped": clk["escaped"], "vmax": clk["vmax"]}, "setup_s": {"generate": t_gen}}
+        print(json.dumps(line))
+    dist.destroy_process_group()

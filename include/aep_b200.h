@@ -112,6 +112,10 @@ AEP_API int aep_set_levelset_samples(aep_ctx* ctx, const uint8_t* inside /*Ng*/,
 /* ---- stepping ------------------------------------------------------------------------------------------- */
 /* HS:830-860: bin particles, first particleToGrid_ (computes volumes, HS:242-249), initial dt.             */
 AEP_API int aep_init(aep_ctx* ctx);
+/* the same in three parts for the multi-GPU driver: begin (re-bin + P2G) | halo(m,p) | volumes (+ local max|v|) | all-reduce | dt */
+AEP_API int aep_init_begin(aep_ctx* ctx);
+AEP_API int aep_init_volumes(aep_ctx* ctx);
+AEP_API int aep_init_dt(aep_ctx* ctx);
 /* One iteration of the while loop HS:867-1032 with the reference's dt rule evaluated on the device.        */
 AEP_API int aep_substep(aep_ctx* ctx);
 /* n iterations back to back, no host synchronisation in between.                                           */
@@ -143,7 +147,8 @@ AEP_API int aep_download_particles(aep_ctx* ctx, double* x, double* v, double* B
 AEP_API int aep_download_grid(aep_ctx* ctx, double* m, double* v, double* f, double* vt);
 AEP_API int aep_download_mesh(aep_ctx* ctx, double* vx, double* vv, double* vB, double* ex, double* ev,
                               double* eB, double* ed);
-/* positions only, float32 x,y,z interleaved, original order: the per-frame OBJ payload of HS:991-1007.     */
+/* positions only, float32 x,y,z interleaved: the per-frame OBJ payload of HS:991-1007.  Original particle order; for a slab
+ * context (ids are global there) the context's current order, aep_num_particles entries.                    */
 AEP_API int aep_download_positions_f32(aep_ctx* ctx, float* xyz);
 /* bulk statistics on the device: centre of mass (3), kinetic energy, mean det F_P, total mass.             */
 AEP_API int aep_stats(aep_ctx* ctx, double* com3, double* kinetic, double* mean_jp, double* mass);
@@ -168,26 +173,37 @@ AEP_API int aep_get_timers(aep_ctx* ctx, double* ms /*AEP_NUM_STAGES*/, int64_t*
 #define AEP_NUM_STAGES 8
 
 /* ---- multi-GPU slab decomposition -------------------------------------------------------------
- * The context owns cells [slab_lo, slab_hi) along slab_axis.  Ghost node planes: 1 below, 2 above (cubic support).
- * The exchange itself (NCCL send/recv or peer copies) is driven by the caller on buffers this library packs:
- *   side 0 = low neighbour, 1 = high neighbour; what 0 = (m, p) after P2G, 1 = f after the force pass.
- * halo buffers are device pointers of `*n_floats` float32 laid out [plane][node-in-plane][channel].          */
+ * The context owns the particles whose cell index along cfg.slab_axis lies in [slab_lo, slab_hi).  Their cubic
+ * stencils reach node planes slab_lo-1 .. slab_hi+1, so two neighbouring slabs both scatter into the 3 node planes
+ * b-1, b, b+1 around their common boundary b.  One symmetric exchange per scatter completes them: each side packs
+ * its partial sums of those planes, the caller swaps the buffers (NCCL send/recv, peer copy, ...), each side adds
+ * what it received (a+b == b+a bitwise, so both ranks hold identical totals and update the shared planes redundantly).
+ *   side 0 = low neighbour, 1 = high neighbour;   what 0 = (m, px, py, pz) after P2G, 1 = (fx, fy, fz, -) after forces.
+ * Communication buffers are DEVICE memory OWNED BY THE CALLER (e.g. torch tensors), float32,
+ * layout [plane 0..2][node in plane, fastest remaining axis first][4].                                          */
 AEP_API int aep_halo_info(aep_ctx* ctx, int what, int side, int64_t* n_floats);
-AEP_API int aep_halo_pack(aep_ctx* ctx, int what, int side, void** dev_send);
-AEP_API int aep_halo_recv_buffer(aep_ctx* ctx, int what, int side, void** dev_recv);
-AEP_API int aep_halo_add(aep_ctx* ctx, int what, int side);
-/* local max |v_i| lives on the device; the caller all-reduces (max) this one float in place before aep_stage_g2p */
-AEP_API int aep_vmax_device_ptr(aep_ctx* ctx, void** dev_float);
-/* split stepping for the multi-GPU driver: forces | grid | finish_dt | g2p+rebin | p2g */
+AEP_API int aep_halo_pack(aep_ctx* ctx, int what, int side, void* dev_send);
+AEP_API int aep_halo_add(aep_ctx* ctx, int what, int side, const void* dev_recv);
+/* max |v_i| of the last grid update as one float32 in caller-owned device memory: get -> all-reduce(max) -> set,
+ * between aep_step_grid and aep_step_g2p (the dt rule needs the global maximum, HS:878).                         */
+AEP_API int aep_vmax_get(aep_ctx* ctx, void* dev_float);
+AEP_API int aep_vmax_set(aep_ctx* ctx, const void* dev_float);
+/* split stepping for the multi-GPU driver:  forces | halo(f) | grid | vmax | g2p | migrate | p2g | halo(m,p)      */
 AEP_API int aep_step_forces(aep_ctx* ctx);
 AEP_API int aep_step_grid(aep_ctx* ctx);
-AEP_API int aep_step_g2p(aep_ctx* ctx);
-AEP_API int aep_step_p2g(aep_ctx* ctx);
-/* particle migration: records are AEP_MIGRATE_FLOATS float32 per particle */
+AEP_API int aep_step_g2p(aep_ctx* ctx);   /* advances the clock (dt rule) then G2P / advection / plasticity          */
+AEP_API int aep_step_p2g(aep_ctx* ctx);   /* re-bin (drops particles that left the slab) + P2G                       */
+/* particle migration after aep_step_g2p: records of AEP_MIGRATE_FLOATS float32 (the 11 float4 of a particle).
+ * extract copies the particles whose new cell left the slab into the caller's device buffers (capacity in records)
+ * and returns the counts (synchronises); insert appends received records.  Global particle ids travel with them.  */
 #define AEP_MIGRATE_FLOATS 44
-AEP_API int aep_migrate_extract(aep_ctx* ctx, int64_t* n_low, int64_t* n_high, void** dev_low, void** dev_high);
-AEP_API int aep_migrate_recv_buffer(aep_ctx* ctx, int side, int64_t n, void** dev_recv);
-AEP_API int aep_migrate_insert(aep_ctx* ctx, int64_t n_from_low, int64_t n_from_high);
+AEP_API int aep_migrate_extract(aep_ctx* ctx, void* dev_to_low, void* dev_to_high, int64_t capacity, int64_t* n_low, int64_t* n_high);
+AEP_API int aep_migrate_insert(aep_ctx* ctx, const void* dev_from_low, int64_t n_from_low, const void* dev_from_high, int64_t n_from_high);
+/* ids of uploaded particles are id_base + index (default 0); set before aep_upload_particles on each rank.      */
+AEP_API int aep_set_particle_id_base(aep_ctx* ctx, int64_t id_base);
+/* download in the context's current (cell-sorted) order together with the global ids; arrays sized aep_num_particles */
+AEP_API int aep_download_particles_local(aep_ctx* ctx, int64_t* ids, double* x, double* v, double* B1, double* B2, double* B3,
+                                         double* FE, double* FP, double* vol, double* q);
 
 #ifdef __cplusplus
 }
