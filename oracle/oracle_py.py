@@ -127,6 +127,22 @@ class Oracle:
         self.L.orc_get_grid(self.h, _p(m), _p(v), _p(f), _p(vt))
         return dict(m=m, v=from_colmajor(v, ng), f=from_colmajor(f, ng), vt=from_colmajor(vt, ng))
 
+    def set_grid(self, m=None, v=None, f=None):
+        cm = lambda a: None if a is None else colmajor(a)
+        mm = None if m is None else np.ascontiguousarray(m, np.float64); vv = cm(v); ff = cm(f)
+        self.L.orc_set_grid(self.h, _p(mm), _p(vv), _p(ff))
+
+    def compute_volumes(self): self.L.orc_compute_volumes(self.h)
+
+    def set_particles(self, p):
+        """Replace the particle set (scenes.Particles)."""
+        self.np = p.n
+        arrs = [colmajor(p.x), colmajor(p.v), colmajor(p.B[:, 0, :]), colmajor(p.B[:, 1, :]), colmajor(p.B[:, 2, :]),
+                mats_colmajor(p.FE), mats_colmajor(p.FP), np.ascontiguousarray(p.m, np.float64),
+                np.ascontiguousarray(p.vol, np.float64), np.ascontiguousarray(p.q, np.float64)]
+        self.L.orc_set_particles(self.h, C.c_long(p.n), *[_p(a) for a in arrs], C.c_double(p.E), C.c_double(p.nu),
+                                 C.c_double(p.thetaC), C.c_double(p.thetaS))
+
     def mesh(self):
         nv, nf = self.nv, self.nf
         vx = np.empty(3 * nv); vv = np.empty(3 * nv); vB = np.empty(9 * nv)
