@@ -57,6 +57,7 @@ struct aep_ctx {
     int key_bits = 0;
     MatParams mat{};
     bool keys_valid = false;
+    int steps_since_sort = 0;
     long long pending_leave = 0;                // particles extracted for migration, dropped at the next re-bin
     long long id_base = 0;
 
@@ -243,6 +244,11 @@ int do_p2g(aep_ctx* c, bool first) {
 }
 
 int do_forces(aep_ctx* c) {
+    {   // v_i = p_i / m_i on the active blocks (also feeds the cloth-free case: cheap, <1% of a substep)
+        StageTimer T(c, AEP_STAGE_GRID);
+        k_grid_normalise<<<c->nblocks, 256, 0, c->stream>>>(c->G);
+        LAUNCH_OK("k_grid_normalise");
+    }
     if (c->n) {
         StageTimer T(c, AEP_STAGE_FORCES);
         k_forces<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->P[c->cur], c->G, c->mat, c->d_clk, (int)c->n);
@@ -291,7 +297,10 @@ int do_substep(aep_ctx* c) {
     if ((r = do_grid(c))) return r;         // HS:877, 899
     if ((r = do_clock(c))) return r;        // HS:878-892
     if ((r = do_g2p(c))) return r;          // HS:903-959
-    if ((r = do_sort(c, false))) return r;  // HS:963-983 (weights at the new positions == re-binning)
+    // HS:963-983: weights at the new positions == re-binning.  Correctness never depends on the order (runs end on a cell
+    // change, reductions are atomic); sorting only keeps runs long and gathers local, so it may be done every k-th substep.
+    c->steps_since_sort += 1;
+    if (c->cfg.sort_every <= 1 || c->steps_since_sort >= c->cfg.sort_every) { if ((r = do_sort(c, false))) return r; c->steps_since_sort = 0; }
     if ((r = do_p2g(c, false))) return r;   // HS:987
     return AEP_OK;
 }

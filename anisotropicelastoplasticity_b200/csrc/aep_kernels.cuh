@@ -235,9 +235,29 @@ __global__ void k_initial_dt(SimClock* clk) {                      // HybridSolv
     clk->dt = (float)(clk->cfl / fmax(clk->rate_floor, (double)vmax / clk->hmin));
 }
 
-// ================================================================================================ P2G
-// particleToGrid_ (HybridSolver.cpp:113-231): m_i = sum w m ; p_i = sum w m (v + (3/h^2) B (x_i - x_p)).
-// Per particle the affine momentum is written as q0 + Qm * (oi, oj, ok) with (oi,oj,ok) the lane's node offset.
+// ================================================================================================ scatter machinery
+// Both scatters (P2G, force) run in two phases per warp of 32 cell-sorted particles:
+//   phase A  thread-per-particle: everything that depends on the particle only (1-D weights, affine / stress matrices)
+//            goes to a per-warp shared-memory record;
+//   phase B  one HALF-WARP per particle, 16 lanes = the 16 (j,k) rows of the 4x4x4 stencil, each lane owns the 4 nodes
+//            along x of its row and accumulates in registers over the run of particles that share a cell; a run ends with
+//            4 REDG.E.ADD.F32x4 per lane (64 B contiguous per row).  No atomics and no shuffles in the inner loop.
+__device__ __forceinline__ void flush_row(const GridP& G, float4* __restrict__ dst, int cell, int j, int k, const float4 (&acc)[4], bool mark) {
+    const int ni0 = cell_i(cell) - 1, nj = cell_j(cell) - 1 + j, nk = cell_k(cell) - 1 + k;
+    if (nj < 0 || nj >= G.ny || nk < 0 || nk >= G.nz) return;
+    float4* row = dst + ((size_t)nk * G.ny + nj) * G.nx;
+    unsigned char* frow = G.flags + ((nk >> 3) * G.nby + (nj >> 3)) * G.nbx;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ni = ni0 + i;
+        if (ni >= 0 && ni < G.nx) {
+            atomicAdd(row + ni, acc[i]);
+            if (mark && (i == 0 || i == 3 || ni == 0)) frow[ni >> 3] = 1;
+        }
+    }
+}
+
+// warp-cooperative v1 mapping (2 nodes per lane), still used by the cloth kernels where runs have length 1
 __device__ __forceinline__ void flush_nodes(const GridP& G, float4* __restrict__ dst, int cell, int oi, int oj, int ok,
                                             const float4& a0, const float4& a1, bool mark) {
     const int ni = cell_i(cell) - 1 + oi, nj = cell_j(cell) - 1 + oj, nk0 = cell_k(cell) - 1 + ok, nk1 = nk0 + 2;
@@ -252,56 +272,72 @@ __device__ __forceinline__ void flush_nodes(const GridP& G, float4* __restrict__
     }
 }
 
+__device__ __forceinline__ float sel4(const float (&a)[4], int k) { return k == 0 ? a[0] : (k == 1 ? a[1] : (k == 2 ? a[2] : a[3])); }
+__device__ __forceinline__ float f4c(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+// ================================================================================================ P2G
+// particleToGrid_ (HybridSolver.cpp:113-231): m_i = sum w m ; p_i = sum w m (v + (3/h^2) B (x_i - x_p)).
+// Per particle the momentum of node offset (i,j,k) is q0 + Qm (i,j,k)^T with Qm = m (3/h^2) B diag(h), q0 = m v - Qm (1+f).
+#define P2G_REC 7
 __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
-    const int lane = threadIdx.x & 31;
+    __shared__ float4 stage[8][32][P2G_REC];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
-    if (base >= n) return;
+    if (base >= n) return;                                                   // warp-uniform; no block-level barrier below
     const int cnt = min(32, n - base);
-    const unsigned FULL = 0xffffffffu;
-    // lane-owned particle -> broadcast payload
-    float fx = 0.f, fy = 0.f, fz = 0.f, m = 0.f; int cell = -1;
-    float q0x = 0.f, q0y = 0.f, q0z = 0.f, Q[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (lane < cnt) {
-        const float4 X = ldg4(P.a[PX] + base + lane), VM = ldg4(P.a[PVM] + base + lane);
-        const float4 c0 = ldg4(P.a[PC0] + base + lane), c1 = ldg4(P.a[PC1] + base + lane), c2 = ldg4(P.a[PC2] + base + lane);
-        fx = X.x; fy = X.y; fz = X.z; cell = __float_as_int(X.w); m = VM.w;
+    {   // ---- phase A
+        const int p = base + min(lane, cnt - 1);
+        const float4 X = ldg4(P.a[PX] + p), VM = ldg4(P.a[PVM] + p);
+        const float4 c0 = ldg4(P.a[PC0] + p), c1 = ldg4(P.a[PC1] + p), c2 = ldg4(P.a[PC2] + p);
+        float Nx[4], Ny[4], Nz[4], D[4];
+        bspline4(X.x, Nx, D); bspline4(X.y, Ny, D); bspline4(X.z, Nz, D);
+        const float m = (lane < cnt) ? VM.w : 0.0f;                          // padding lanes repeat the last particle with zero mass
         const float k = m * G.apic;
-        Q[0] = k * c0.x * G.hx; Q[1] = k * c0.y * G.hy; Q[2] = k * c0.z * G.hz;
-        Q[3] = k * c1.x * G.hx; Q[4] = k * c1.y * G.hy; Q[5] = k * c1.z * G.hz;
-        Q[6] = k * c2.x * G.hx; Q[7] = k * c2.y * G.hy; Q[8] = k * c2.z * G.hz;
-        // x_i - x_p = h * (o - (1 + f)) per axis
-        const float gx = 1.0f + fx, gy = 1.0f + fy, gz = 1.0f + fz;
-        q0x = fmaf(m, VM.x, -(Q[0] * gx + Q[1] * gy + Q[2] * gz));
-        q0y = fmaf(m, VM.y, -(Q[3] * gx + Q[4] * gy + Q[5] * gz));
-        q0z = fmaf(m, VM.z, -(Q[6] * gx + Q[7] * gy + Q[8] * gz));
+        float Q[9] = { k * c0.x * G.hx, k * c0.y * G.hy, k * c0.z * G.hz, k * c1.x * G.hx, k * c1.y * G.hy, k * c1.z * G.hz,
+                       k * c2.x * G.hx, k * c2.y * G.hy, k * c2.z * G.hz };
+        const float gx = 1.0f + X.x, gy = 1.0f + X.y, gz = 1.0f + X.z;       // x_i - x_p = h (o - (1 + f))
+        const float q0x = fmaf(m, VM.x, -(Q[0] * gx + Q[1] * gy + Q[2] * gz));
+        const float q0y = fmaf(m, VM.y, -(Q[3] * gx + Q[4] * gy + Q[5] * gz));
+        const float q0z = fmaf(m, VM.z, -(Q[6] * gx + Q[7] * gy + Q[8] * gz));
+        float4* rec = stage[wib][lane];
+        rec[0] = make_float4(Nx[0], Nx[1], Nx[2], Nx[3]); rec[1] = make_float4(Ny[0], Ny[1], Ny[2], Ny[3]); rec[2] = make_float4(Nz[0], Nz[1], Nz[2], Nz[3]);
+        rec[3] = make_float4(m, q0x, q0y, q0z);
+        rec[4] = make_float4(Q[0], Q[1], Q[2], Q[3]); rec[5] = make_float4(Q[4], Q[5], Q[6], Q[7]); rec[6] = make_float4(Q[8], 0.f, 0.f, X.w);
     }
-    const int oi = lane & 3, oj = (lane >> 2) & 3, ok = lane >> 4;           // node offsets owned by this lane: (oi,oj,ok), (oi,oj,ok+2)
-    const float foi = (float)oi, foj = (float)oj, fok = (float)ok;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-    int cur = __shfl_sync(FULL, cell, 0);
-    for (int p = 0; p < cnt; ++p) {
-        const int c = __shfl_sync(FULL, cell, p);
-        if (c != cur) {                                                      // warp-uniform
-            flush_nodes(G, G.mp, cur, oi, oj, ok, a0, a1, true);
-            a0 = make_float4(0.f, 0.f, 0.f, 0.f); a1 = a0; cur = c;
+    __syncwarp();
+    // ---- phase B
+    const int hw = lane >> 4, s = lane & 15, j = s & 3, k = s >> 2;
+    const float fj = (float)j, fk = (float)k;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc[4] = { zero, zero, zero, zero };
+    const float4* recs = &stage[wib][hw * 16][0];
+    int cur = __float_as_int(recs[6].w);
+#pragma unroll 1
+    for (int it = 0; it < 16; ++it) {
+        const float4* r = recs + it * P2G_REC;
+        const float4 r6 = r[6];
+        const int c = __float_as_int(r6.w);
+        if (c != cur) {
+            flush_row(G, G.mp, cur, j, k, acc, true);
+            acc[0] = zero; acc[1] = zero; acc[2] = zero; acc[3] = zero; cur = c;
         }
-        const float pfx = __shfl_sync(FULL, fx, p), pfy = __shfl_sync(FULL, fy, p), pfz = __shfl_sync(FULL, fz, p);
-        const float pm = __shfl_sync(FULL, m, p);
-        const float px = __shfl_sync(FULL, q0x, p), py = __shfl_sync(FULL, q0y, p), pz = __shfl_sync(FULL, q0z, p);
-        float q[9];
+        const float4 nx = r[0], mq = r[3], qa = r[4], qb = r[5];
+        const float wy = reinterpret_cast<const float*>(r + 1)[j], wz = reinterpret_cast<const float*>(r + 2)[k];
+        const float wyz = wy * wz;
+        const float bx = fmaf(qa.y, fj, fmaf(qa.z, fk, mq.y));              // q0 + Q[:,1] j + Q[:,2] k
+        const float by = fmaf(qb.x, fj, fmaf(qb.y, fk, mq.z));
+        const float bz = fmaf(qb.w, fj, fmaf(r6.x, fk, mq.w));
 #pragma unroll
-        for (int i = 0; i < 9; ++i) q[i] = __shfl_sync(FULL, Q[i], p);
-        float wx, wy, wz0, wz1, d;
-        bspline_lane(pfx, oi, wx, d); bspline_lane(pfy, oj, wy, d); bspline_lane(pfz, ok, wz0, d); bspline_lane(pfz, ok + 2, wz1, d);
-        const float wxy = wx * wy, w0 = wxy * wz0, w1 = wxy * wz1;
-        const float mx0 = fmaf(q[0], foi, fmaf(q[1], foj, fmaf(q[2], fok, px)));
-        const float my0 = fmaf(q[3], foi, fmaf(q[4], foj, fmaf(q[5], fok, py)));
-        const float mz0 = fmaf(q[6], foi, fmaf(q[7], foj, fmaf(q[8], fok, pz)));
-        a0.x = fmaf(w0, pm, a0.x); a0.y = fmaf(w0, mx0, a0.y); a0.z = fmaf(w0, my0, a0.z); a0.w = fmaf(w0, mz0, a0.w);
-        a1.x = fmaf(w1, pm, a1.x); a1.y = fmaf(w1, fmaf(2.0f, q[2], mx0), a1.y);
-        a1.z = fmaf(w1, fmaf(2.0f, q[5], my0), a1.z); a1.w = fmaf(w1, fmaf(2.0f, q[8], mz0), a1.w);
+        for (int i = 0; i < 4; ++i) {
+            const float w = f4c(nx, i) * wyz;
+            const float fi = (float)i;
+            acc[i].x = fmaf(w, mq.x, acc[i].x);
+            acc[i].y = fmaf(w, fmaf(qa.x, fi, bx), acc[i].y);
+            acc[i].z = fmaf(w, fmaf(qa.w, fi, by), acc[i].z);
+            acc[i].w = fmaf(w, fmaf(qb.z, fi, bz), acc[i].w);
+        }
     }
-    flush_nodes(G, G.mp, cur, oi, oj, ok, a0, a1, true);
+    flush_row(G, G.mp, cur, j, k, acc, true);
 }
 
 // first P2G only: rho_p = sum_i w m_i / (hx hy hz), V_p = m_p / rho_p           HybridSolver.cpp:242-249
@@ -333,93 +369,115 @@ __global__ void __launch_bounds__(256) k_init_volumes(PartP P, GridP G, int n) {
     float4 e0 = P.a[PE0][p]; e0.w = m * (1.0f / dens); P.a[PE0][p] = e0;
 }
 
+// v_i = p_i / m_i where m_i > 0 (HybridSolver.cpp:233-240) for every active node, into the vt array (free between P2G and
+// the grid update), so that the force gather below does 64 loads and no divisions per particle.
+__global__ void __launch_bounds__(256) k_grid_normalise(GridP G) {
+    const int b = blockIdx.x;
+    if (!G.flags[b]) return;
+    const int bx = b % G.nbx, by = (b / G.nbx) % G.nby, bz = b / (G.nbx * G.nby);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int t = threadIdx.x + 256 * h;
+        const int i = bx * 8 + (t & 7), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t >> 6);
+        if (i < G.nx && j < G.ny && k < G.nz) {
+            const size_t n = ((size_t)k * G.ny + j) * G.nx + i;
+            const float4 mp = G.mp[n];
+            const float im = mp.x > 0.0f ? 1.0f / mp.x : 0.0f;
+            G.vt[n] = make_float4(mp.y * im, mp.z * im, mp.w * im, 1.0f);
+        }
+    }
+}
+
 // ================================================================================================ forces
-// computeGridForces_, particle part (HybridSolver.cpp:252-368).  Phase 1 (thread per particle): gather
-// grad v = sum_i v_i (grad w_i)^T with v_i = p_i / m_i, Fhat = (I + dt grad v) FE, SVD, stress, A = V_p P FE^T.
-// Phase 2 (warp cooperative, same 32 particles): f_i -= A grad w_ip, register accumulation per cell run.
+// computeGridForces_, particle part (HybridSolver.cpp:252-368).  Phase A (thread per particle): gather
+// grad v = sum_i v_i (grad w_i)^T (x-direction summed first: 6 FMA per node + 9 per row), Fhat = (I + dt grad v) FE, SVD,
+// stress, A = V_p P FE^T.  Phase B (half-warp per particle): f_i -= A grad w_ip.
+#define FRC_REC 9
 __global__ void __launch_bounds__(256) k_forces(PartP P, GridP G, MatParams mpar, const SimClock* __restrict__ clk, int n) {
-    const int lane = threadIdx.x & 31;
+    __shared__ float4 stage[8][32][FRC_REC];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
     if (base >= n) return;
     const int cnt = min(32, n - base);
-    const unsigned FULL = 0xffffffffu;
     const float dt = clk->dt;
-    float fx = 0.f, fy = 0.f, fz = 0.f; int cell = -1;
-    float A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (lane < cnt) {
-        const int p = base + lane;
+    {   // ---- phase A
+        const int p = base + min(lane, cnt - 1);
         const float4 X = ldg4(P.a[PX] + p);
         const float4 e0 = ldg4(P.a[PE0] + p), e1 = ldg4(P.a[PE1] + p), e2 = ldg4(P.a[PE2] + p);
-        fx = X.x; fy = X.y; fz = X.z; cell = __float_as_int(X.w);
+        const int cell = __float_as_int(X.w);
         Axis ax, ay, az;
-        axis_setup(ax, fx, cell_i(cell), G.nx, G.ihx); axis_setup(ay, fy, cell_j(cell), G.ny, G.ihy); axis_setup(az, fz, cell_k(cell), G.nz, G.ihz);
-        float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};          // g[3r+c] = sum_i v_i[r] dw_i[c]
+        axis_setup(ax, X.x, cell_i(cell), G.nx, G.ihx); axis_setup(ay, X.y, cell_j(cell), G.ny, G.ihy); axis_setup(az, X.z, cell_k(cell), G.nz, G.ihz);
+        int ni[4], nj[4];
 #pragma unroll
+        for (int o = 0; o < 4; ++o) { ni[o] = clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = clampi(ay.n0 + o, 0, G.ny - 1); }
+        float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};          // g[3r+c] = sum_i v_i[r] dw_i[c]
+#pragma unroll 1
         for (int k = 0; k < 4; ++k) {
             const int nk = clampi(az.n0 + k, 0, G.nz - 1);
+            const float nzk = sel4(az.N, k), dzk = sel4(az.D, k);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int nj = clampi(ay.n0 + j, 0, G.ny - 1);
-                const size_t row = ((size_t)nk * G.ny + nj) * G.nx;
-                const float nn = ay.N[j] * az.N[k], dn = ay.D[j] * az.N[k], nd = ay.N[j] * az.D[k];
+                const float4* row = G.vt + ((size_t)nk * G.ny + nj[j]) * G.nx;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int ni = clampi(ax.n0 + i, 0, G.nx - 1);
-                    const float4 mp = ldg4(G.mp + row + ni);
-                    const float im = mp.x > 0.0f ? 1.0f / mp.x : 0.0f;           // HybridSolver.cpp:233-240
-                    const float vx = mp.y * im, vy = mp.z * im, vz = mp.w * im;
-                    const float dwx = ax.D[i] * nn, dwy = ax.N[i] * dn, dwz = ax.N[i] * nd;
-                    g[0] = fmaf(vx, dwx, g[0]); g[1] = fmaf(vx, dwy, g[1]); g[2] = fmaf(vx, dwz, g[2]);
-                    g[3] = fmaf(vy, dwx, g[3]); g[4] = fmaf(vy, dwy, g[4]); g[5] = fmaf(vy, dwz, g[5]);
-                    g[6] = fmaf(vz, dwx, g[6]); g[7] = fmaf(vz, dwy, g[7]); g[8] = fmaf(vz, dwz, g[8]);
+                    const float4 v = ldg4(row + ni[i]);
+                    a0 = fmaf(v.x, ax.N[i], a0); a1 = fmaf(v.y, ax.N[i], a1); a2 = fmaf(v.z, ax.N[i], a2);
+                    b0 = fmaf(v.x, ax.D[i], b0); b1 = fmaf(v.y, ax.D[i], b1); b2 = fmaf(v.z, ax.D[i], b2);
                 }
+                const float nn = ay.N[j] * nzk, dn = ay.D[j] * nzk, nd = ay.N[j] * dzk;
+                g[0] = fmaf(b0, nn, g[0]); g[1] = fmaf(a0, dn, g[1]); g[2] = fmaf(a0, nd, g[2]);
+                g[3] = fmaf(b1, nn, g[3]); g[4] = fmaf(a1, dn, g[4]); g[5] = fmaf(a1, nd, g[5]);
+                g[6] = fmaf(b2, nn, g[6]); g[7] = fmaf(a2, dn, g[7]); g[8] = fmaf(a2, nd, g[8]);
             }
         }
         const float FE[9] = { e0.x, e0.y, e0.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z };
-        float GF[9], Fh[9];
+        float GF[9], Fh[9], A[9];
         mat_mul(g, FE, GF);
 #pragma unroll
         for (int i = 0; i < 9; ++i) Fh[i] = fmaf(dt, GF[i], FE[i]);              // HybridSolver.cpp:306
-        stress_times_FEt(mpar, Fh, FE, e0.w, e2.w, A);
+        stress_times_FEt(mpar, Fh, FE, (lane < cnt) ? e0.w : 0.0f, e2.w, A);     // padding lanes: zero volume -> zero stress
+        float4* rec = stage[wib][lane];
+        rec[0] = make_float4(ax.N[0], ax.N[1], ax.N[2], ax.N[3]); rec[1] = make_float4(ax.D[0], ax.D[1], ax.D[2], ax.D[3]);
+        rec[2] = make_float4(ay.N[0], ay.D[0], ay.N[1], ay.D[1]); rec[3] = make_float4(ay.N[2], ay.D[2], ay.N[3], ay.D[3]);
+        rec[4] = make_float4(az.N[0], az.D[0], az.N[1], az.D[1]); rec[5] = make_float4(az.N[2], az.D[2], az.N[3], az.D[3]);
+        rec[6] = make_float4(A[0], A[1], A[2], A[3]); rec[7] = make_float4(A[4], A[5], A[6], A[7]); rec[8] = make_float4(A[8], 0.f, 0.f, X.w);
     }
-    // ---- phase 2: scatter
-    const int oi = lane & 3, oj = (lane >> 2) & 3, ok = lane >> 4;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-    int cur = __shfl_sync(FULL, cell, 0);
-    for (int p = 0; p < cnt; ++p) {
-        const int c = __shfl_sync(FULL, cell, p);
+    __syncwarp();
+    // ---- phase B: f_i[r] -= sum_c A(r,c) d_c w   with d_x w = Dx Ny Nz, d_y w = Nx Dy Nz, d_z w = Nx Ny Dz   (HybridSolver.cpp:356-366)
+    const int hw = lane >> 4, s = lane & 15, j = s & 3, k = s >> 2;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc[4] = { zero, zero, zero, zero };
+    const float4* recs = &stage[wib][hw * 16][0];
+    int cur = __float_as_int(recs[8].w);
+#pragma unroll 1
+    for (int it = 0; it < 16; ++it) {
+        const float4* r = recs + it * FRC_REC;
+        const float4 r8 = r[8];
+        const int c = __float_as_int(r8.w);
         if (c != cur) {
-            flush_nodes(G, G.f, cur, oi, oj, ok, a0, a1, false);
-            a0 = make_float4(0.f, 0.f, 0.f, 0.f); a1 = a0; cur = c;
+            flush_row(G, G.f, cur, j, k, acc, false);
+            acc[0] = zero; acc[1] = zero; acc[2] = zero; acc[3] = zero; cur = c;
         }
-        const float pfx = __shfl_sync(FULL, fx, p), pfy = __shfl_sync(FULL, fy, p), pfz = __shfl_sync(FULL, fz, p);
-        float a[9];
+        const float4 nx = r[0], dx = r[1], A0 = r[6], A1 = r[7];
+        const float2 yj = reinterpret_cast<const float2*>(r + 2)[j], zk = reinterpret_cast<const float2*>(r + 4)[k];
+        const float a = yj.x * zk.x, b = yj.y * zk.x, cc = yj.x * zk.y;          // Ny Nz, Dy Nz, Ny Dz
+        const float ux = A0.x * a, uy = A0.w * a, uz = A1.z * a;                 // A[:,0] Ny Nz         (times Dx_i)
+        const float vx = fmaf(A0.y, b, A0.z * cc), vy = fmaf(A1.x, b, A1.y * cc), vz = fmaf(A1.w, b, r8.x * cc);   // (times Nx_i)
 #pragma unroll
-        for (int i = 0; i < 9; ++i) a[i] = __shfl_sync(FULL, A[i], p);
-        float wx, dx, wy, dy, wz0, dz0, wz1, dz1;
-        bspline_lane(pfx, oi, wx, dx); bspline_lane(pfy, oj, wy, dy); bspline_lane(pfz, ok, wz0, dz0); bspline_lane(pfz, ok + 2, wz1, dz1);
-        dx *= G.ihx; dy *= G.ihy; dz0 *= G.ihz; dz1 *= G.ihz;
-        const float gx = dx * wy, gy = wx * dy, gz = wx * wy;
-        {   // node (oi,oj,ok)
-            const float d0 = gx * wz0, d1 = gy * wz0, d2 = gz * dz0;
-            a0.x -= fmaf(a[0], d0, fmaf(a[1], d1, a[2] * d2));                   // HybridSolver.cpp:356-366
-            a0.y -= fmaf(a[3], d0, fmaf(a[4], d1, a[5] * d2));
-            a0.z -= fmaf(a[6], d0, fmaf(a[7], d1, a[8] * d2));
-        }
-        {   // node (oi,oj,ok+2)
-            const float d0 = gx * wz1, d1 = gy * wz1, d2 = gz * dz1;
-            a1.x -= fmaf(a[0], d0, fmaf(a[1], d1, a[2] * d2));
-            a1.y -= fmaf(a[3], d0, fmaf(a[4], d1, a[5] * d2));
-            a1.z -= fmaf(a[6], d0, fmaf(a[7], d1, a[8] * d2));
+        for (int i = 0; i < 4; ++i) {
+            const float d = f4c(dx, i), w = f4c(nx, i);
+            acc[i].x -= fmaf(ux, d, vx * w); acc[i].y -= fmaf(uy, d, vy * w); acc[i].z -= fmaf(uz, d, vz * w);
         }
     }
-    flush_nodes(G, G.f, cur, oi, oj, ok, a0, a1, false);
+    flush_row(G, G.f, cur, j, k, acc, false);
 }
 
 // ================================================================================================ G2P
 // updateParticleVelocities_ (HybridSolver.cpp:739-745), updateAffineMomenta_ with damp 0 (:760-825, :908-917),
 // advection x = sum w (x_i + dt v~_i) (:942-945), updateDeformationGradient_ (:553-578), updatePlasticity_
-// (:612-681), all in registers, one thread per particle.  Writes the new sort key.
+// (:612-681), all in registers, one thread per particle.  The 64-node gather sums along x first (per (j,k) row:
+// a = sum v~ Nx, b = sum v~ Dx, c = sum s v~ Nx, d = sum s v~ Nx rx), then combines rows.  Writes the new sort key.
 __global__ void __launch_bounds__(128) k_g2p(PartP P, GridP G, MatParams mpar, SimClock* __restrict__ clk,
                                              unsigned int* __restrict__ keys, unsigned int* __restrict__ vals, int n) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -432,47 +490,59 @@ __global__ void __launch_bounds__(128) k_g2p(PartP P, GridP G, MatParams mpar, S
     bool complete = axis_setup(ax, X.x, ci, G.nx, G.ihx);
     complete &= axis_setup(ay, X.y, cj, G.ny, G.ihy);
     complete &= axis_setup(az, X.z, ck, G.nz, G.ihz);
-    // distances from the particle to the stencil nodes, per axis: h * (o - 1 - f)
-    float rx[4], ry[4], rz[4];
+    float rx[4], ry[4], rz[4];                                              // x_i - x_p per axis: h (o - 1 - f)
+    int ni[4], nj[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) { rx[o] = G.hx * ((float)(o - 1) - X.x); ry[o] = G.hy * ((float)(o - 1) - X.y); rz[o] = G.hz * ((float)(o - 1) - X.z); }
+    for (int o = 0; o < 4; ++o) {
+        rx[o] = G.hx * ((float)(o - 1) - X.x); ry[o] = G.hy * ((float)(o - 1) - X.y); rz[o] = G.hz * ((float)(o - 1) - X.z);
+        ni[o] = clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = clampi(ay.n0 + o, 0, G.ny - 1);
+    }
+    float nrx[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) nrx[o] = ax.N[o] * rx[o];
     float vp[3] = {0.f, 0.f, 0.f}, va[3] = {0.f, 0.f, 0.f};            // sum w v (post-collision), sum w v~ (pre-friction)
     float B[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        // sum w v (x_i - x_p)^T
     float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        // sum v~ (grad w)^T
-    float s0 = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;                    // sum w, sum w (x_i - x_p): only != (1, 0) for truncated stencils
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 4; ++k) {
         const int nk = clampi(az.n0 + k, 0, G.nz - 1);
+        const float nzk = sel4(az.N, k), dzk = sel4(az.D, k), rzk = sel4(rz, k);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int nj = clampi(ay.n0 + j, 0, G.ny - 1);
-            const size_t row = ((size_t)nk * G.ny + nj) * G.nx;
-            const float nn = ay.N[j] * az.N[k], dn = ay.D[j] * az.N[k], nd = ay.N[j] * az.D[k];
+            const float4* row = G.vt + ((size_t)nk * G.ny + nj[j]) * G.nx;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int ni = clampi(ax.n0 + i, 0, G.nx - 1);
-                const float4 t = ldg4(G.vt + row + ni);
-                const float w = ax.N[i] * nn;
-                const float dwx = ax.D[i] * nn, dwy = ax.N[i] * dn, dwz = ax.N[i] * nd;
-                const float ws = w * t.w;
-                const float ux = ws * t.x, uy = ws * t.y, uz = ws * t.z;         // w * v_i
-                vp[0] += ux; vp[1] += uy; vp[2] += uz;
-                va[0] = fmaf(w, t.x, va[0]); va[1] = fmaf(w, t.y, va[1]); va[2] = fmaf(w, t.z, va[2]);
-                B[0] = fmaf(ux, rx[i], B[0]); B[1] = fmaf(ux, ry[j], B[1]); B[2] = fmaf(ux, rz[k], B[2]);
-                B[3] = fmaf(uy, rx[i], B[3]); B[4] = fmaf(uy, ry[j], B[4]); B[5] = fmaf(uy, rz[k], B[5]);
-                B[6] = fmaf(uz, rx[i], B[6]); B[7] = fmaf(uz, ry[j], B[7]); B[8] = fmaf(uz, rz[k], B[8]);
-                g[0] = fmaf(t.x, dwx, g[0]); g[1] = fmaf(t.x, dwy, g[1]); g[2] = fmaf(t.x, dwz, g[2]);
-                g[3] = fmaf(t.y, dwx, g[3]); g[4] = fmaf(t.y, dwy, g[4]); g[5] = fmaf(t.y, dwz, g[5]);
-                g[6] = fmaf(t.z, dwx, g[6]); g[7] = fmaf(t.z, dwy, g[7]); g[8] = fmaf(t.z, dwz, g[8]);
-                if (!complete) { s0 += w; s1x = fmaf(w, rx[i], s1x); s1y = fmaf(w, ry[j], s1y); s1z = fmaf(w, rz[k], s1z); }
+                const float4 t = ldg4(row + ni[i]);
+                const float sn = t.w * ax.N[i], snr = t.w * nrx[i];
+                a0 = fmaf(t.x, ax.N[i], a0); a1 = fmaf(t.y, ax.N[i], a1); a2 = fmaf(t.z, ax.N[i], a2);
+                b0 = fmaf(t.x, ax.D[i], b0); b1 = fmaf(t.y, ax.D[i], b1); b2 = fmaf(t.z, ax.D[i], b2);
+                c0 = fmaf(t.x, sn, c0); c1 = fmaf(t.y, sn, c1); c2 = fmaf(t.z, sn, c2);
+                d0 = fmaf(t.x, snr, d0); d1 = fmaf(t.y, snr, d1); d2 = fmaf(t.z, snr, d2);
             }
+            const float nn = ay.N[j] * nzk, dn = ay.D[j] * nzk, nd = ay.N[j] * dzk;
+            va[0] = fmaf(a0, nn, va[0]); va[1] = fmaf(a1, nn, va[1]); va[2] = fmaf(a2, nn, va[2]);
+            g[0] = fmaf(b0, nn, g[0]); g[1] = fmaf(a0, dn, g[1]); g[2] = fmaf(a0, nd, g[2]);
+            g[3] = fmaf(b1, nn, g[3]); g[4] = fmaf(a1, dn, g[4]); g[5] = fmaf(a1, nd, g[5]);
+            g[6] = fmaf(b2, nn, g[6]); g[7] = fmaf(a2, dn, g[7]); g[8] = fmaf(a2, nd, g[8]);
+            const float u0 = c0 * nn, u1 = c1 * nn, u2 = c2 * nn;            // sum_i w v_i over the row
+            vp[0] += u0; vp[1] += u1; vp[2] += u2;
+            B[0] = fmaf(d0, nn, B[0]); B[1] = fmaf(u0, ry[j], B[1]); B[2] = fmaf(u0, rzk, B[2]);
+            B[3] = fmaf(d1, nn, B[3]); B[4] = fmaf(u1, ry[j], B[4]); B[5] = fmaf(u1, rzk, B[5]);
+            B[6] = fmaf(d2, nn, B[6]); B[7] = fmaf(u2, ry[j], B[7]); B[8] = fmaf(u2, rzk, B[8]);
         }
     }
     // ---- advection (HybridSolver.cpp:944): x' = sum w (x_i + dt v~_i) = x + [sum w (x_i - x)] + (sum w - 1) x + dt sum w v~
+    // the bracket and (sum w - 1) vanish unless the stencil is truncated by the domain boundary (:44-46); both are separable.
     float dxp = dt * va[0], dyp = dt * va[1], dzp = dt * va[2];
     if (!complete) {
+        const float sx = ax.N[0] + ax.N[1] + ax.N[2] + ax.N[3], sy = ay.N[0] + ay.N[1] + ay.N[2] + ay.N[3], sz = az.N[0] + az.N[1] + az.N[2] + az.N[3];
+        const float mx = nrx[0] + nrx[1] + nrx[2] + nrx[3];
+        const float my = ay.N[0] * ry[0] + ay.N[1] * ry[1] + ay.N[2] * ry[2] + ay.N[3] * ry[3];
+        const float mz = az.N[0] * rz[0] + az.N[1] * rz[1] + az.N[2] * rz[2] + az.N[3] * rz[3];
+        const float s0 = sx * sy * sz;
         const float xw = fmaf((float)ci + X.x, G.hx, G.mnx), yw = fmaf((float)cj + X.y, G.hy, G.mny), zw = fmaf((float)ck + X.z, G.hz, G.mnz);
-        dxp += s1x + (s0 - 1.0f) * xw; dyp += s1y + (s0 - 1.0f) * yw; dzp += s1z + (s0 - 1.0f) * zw;
+        dxp += mx * sy * sz + (s0 - 1.0f) * xw; dyp += sx * my * sz + (s0 - 1.0f) * yw; dzp += sx * sy * mz + (s0 - 1.0f) * zw;
     }
     float nfx = fmaf(dxp, G.ihx, X.x), nfy = fmaf(dyp, G.ihy, X.y), nfz = fmaf(dzp, G.ihz, X.z);
     {
@@ -480,9 +550,12 @@ __global__ void __launch_bounds__(128) k_g2p(PartP P, GridP G, MatParams mpar, S
         nfx -= flx; nfy -= fly; nfz -= flz; ci += (int)flx; cj += (int)fly; ck += (int)flz;
         nfx = fminf(nfx, 0.99999994f); nfy = fminf(nfy, 0.99999994f); nfz = fminf(nfz, 0.99999994f);
         const int cci = clampi(ci, 0, G.nx - 1), ccj = clampi(cj, 0, G.ny - 1), cck = clampi(ck, 0, G.nz - 1);
-        if (cci != ci || ccj != cj || cck != ck || !(nfx == nfx) || !(nfy == nfy) || !(nfz == nfz)) {
+        const bool nan = !(nfx == nfx) || !(nfy == nfy) || !(nfz == nfz);
+        if (cci != ci || ccj != cj || cck != ck || nan) {
             atomicAdd(&clk->escaped, 1ull);
-            if (!(nfx == nfx)) nfx = 0.5f; if (!(nfy == nfy)) nfy = 0.5f; if (!(nfz == nfz)) nfz = 0.5f;
+            if (!(nfx == nfx)) nfx = 0.5f;
+            if (!(nfy == nfy)) nfy = 0.5f;
+            if (!(nfz == nfz)) nfz = 0.5f;
         }
         ci = cci; cj = ccj; ck = cck;
     }

@@ -20,7 +20,7 @@ def _p(a):
 
 
 class Engine:
-    def __init__(self, scene: Scene, device: int = 0, particle_capacity: int = 0, slab=None, dt_rate_floor=None):
+    def __init__(self, scene: Scene, device: int = 0, particle_capacity: int = 0, slab=None, dt_rate_floor=None, sort_every=None):
         self.L = capi.load()
         cfg = capi.Config(); capi.check(self.L.aep_default_config(C.byref(cfg)))
         g = scene.grid
@@ -30,6 +30,8 @@ class Engine:
         cfg.particle_capacity = particle_capacity
         if dt_rate_floor is not None:
             cfg.dt_rate_floor = float(dt_rate_floor)
+        if sort_every is not None:
+            cfg.sort_every = int(sort_every)
         if slab is not None:
             cfg.slab_axis, cfg.slab_lo, cfg.slab_hi = slab
         self.cfg = cfg

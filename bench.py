@@ -188,7 +188,7 @@ def run_reference(args):
 def workload_config(args, res_override=None, note=None, n_particles=None):
     res = res_override or args.res
     cfg = {"workload": f"C5 synthetic sand dam break (Drucker-Prager), 8 particles/cell, {res}^3 grid", "grid": [res] * 3,
-           "material": "sand", "collider": "box level set", "timestep": f"reference rule dt = 0.3 / max(rate_floor, vmax/h) on device, rate_floor = {rate_floor_for(res):g} (300 scaled by res/32 for stability)",
+           "material": "sand", "collider": "box level set", "sort_every": args.sort_every, "timestep": f"reference rule dt = 0.3 / max(rate_floor, vmax/h) on device, rate_floor = {rate_floor_for(res):g} (300 scaled by res/32 for stability)",
            "l2": "inputs (particle state >> 126 MB L2) larger than L2; no explicit flush"}
     if n_particles is not None:
         cfg["particles"] = int(n_particles)
@@ -217,7 +217,7 @@ def run_engine(args):
     t_gen = time.perf_counter() - t_gen
     shell = make_shell_scene(res)
     rate_floor = rate_floor_for(res)
-    eng = Engine(shell, device=local, dt_rate_floor=rate_floor)
+    eng = Engine(shell, device=local, dt_rate_floor=rate_floor, sort_every=args.sort_every)
     eng.upload_packed(n, arrs, sc.SAND_E, sc.SAND_NU, 2.5e-2, 7.5e-3)
     eng.init()
     stream = torch.cuda.ExternalStream(eng.stream, device=local)
@@ -252,9 +252,13 @@ def run_engine(args):
                 "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom],
                 "stage_ms": stage_ms,
                 "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes, "active_blocks": blocks}}
+    if args.quick:
+        print(json.dumps({"metric": METRIC, "value": value, "ms_per_step": ms / args.steps, "sort_every": args.sort_every, "stage_ms": stage_ms,
+                          "gpu_launches": int(launches), "sim": clk, "active_nodes": nodes, "particles": n}))
+        return
     # ---- e2e: host fp64 state -> device, K substeps, f32 positions back (HybridSolver::solve's host-visible traffic)
     eng.close(); del eng
-    eng2 = Engine(shell, device=local, dt_rate_floor=rate_floor)
+    eng2 = Engine(shell, device=local, dt_rate_floor=rate_floor, sort_every=args.sort_every)
     out_t = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
     import ctypes as C
     from anisotropicelastoplasticity_b200 import capi
@@ -287,6 +291,8 @@ def main():
     ap.add_argument("--res", type=int, default=512, help="grid resolution of the C5 dam break (512 = 64M particles)")
     ap.add_argument("--ref-res", type=int, default=64, help="grid resolution of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="development: skip the e2e and cpu_baseline legs")
+    ap.add_argument("--sort-every", type=int, default=1, help="physical re-sort period in substeps (aep_config.sort_every)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

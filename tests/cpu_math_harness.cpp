@@ -36,6 +36,7 @@ void h_return_map(int material, double E, double nu, double thetaC, double theta
     float fh[9], fe[9], fp[9]; std::memcpy(fh, Fh, 36); std::memcpy(fp, FP, 36);
     return_map(M, fh, fe, fp, *q); std::memcpy(FE, fe, 36); std::memcpy(FP, fp, 36);
 }
+long h_svd_sweeps() { return g_svd_sweeps; }
 void h_gram_schmidt(const float* d1, const float* d2, const float* d3, float* Q, float* R) {
     float a[3], b[3], c[3], q[9], r[9]; std::memcpy(a, d1, 12); std::memcpy(b, d2, 12); std::memcpy(c, d3, 12);
     gram_schmidt(a, b, c, q, r); std::memcpy(Q, q, 36); std::memcpy(R, r, 36);
