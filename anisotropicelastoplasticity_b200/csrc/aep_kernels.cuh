@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
     float4 acc[4] = { zero, zero, zero, zero };
     const float4* recs = &stage[wib][hw * 16][0];
     int cur = __float_as_int(recs[6].w);
-#pragma unroll 1
+#pragma unroll 2
     for (int it = 0; it < 16; ++it) {
         const float4* r = recs + it * P2G_REC;
         const float4 r6 = r[6];
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(256) k_forces(PartP P, GridP G, MatParams mpar
     float4 acc[4] = { zero, zero, zero, zero };
     const float4* recs = &stage[wib][hw * 16][0];
     int cur = __float_as_int(recs[8].w);
-#pragma unroll 1
+#pragma unroll 2
     for (int it = 0; it < 16; ++it) {
         const float4* r = recs + it * FRC_REC;
         const float4 r8 = r[8];
