@@ -252,7 +252,7 @@ __device__ __forceinline__ void flush_row(const GridP& G, float4* __restrict__ d
         const int ni = ni0 + i;
         if (ni >= 0 && ni < G.nx) {
             atomicAdd(row + ni, acc[i]);
-            if (mark && (i == 0 || i == 3 || ni == 0)) frow[ni >> 3] = 1;
+            if (mark && (i == 0 || i == 3 || ni == 0 || ni == G.nx - 1)) frow[ni >> 3] = 1;
         }
     }
 }

@@ -224,28 +224,51 @@ class LocalSlabGroup:
     def __init__(self, backends: List, plan: SlabPlan):
         self.bs = backends; self.plan = plan; self.world = plan.world
 
+    def _fence(self):
+        """Every backend enqueues on its own non-blocking stream while the buffer swaps below run on torch's current stream:
+        order them with full synchronisation (this group is a single-process test vehicle, not the fast path)."""
+        for b in self.bs:
+            b.sync()
+        dev = getattr(self.bs[0], "device", None)
+        if dev is not None and getattr(dev, "type", "cpu") == "cuda":
+            self.bs[0].torch.cuda.synchronize()
+
     def _halo(self, what):
         sends = {}
         for r, b in enumerate(self.bs):
             for side in (0, 1):
                 nb = r - 1 if side == 0 else r + 1
                 if 0 <= nb < self.world:
-                    sends[(r, side)] = b.halo_pack(what, side).clone()
+                    sends[(r, side)] = b.halo_pack(what, side)
+        self._fence()
+        sends = {k: t.clone() for k, t in sends.items()}
+        self._fence()
+        recvs = {}
         for r, b in enumerate(self.bs):
             for side in (0, 1):
                 nb = r - 1 if side == 0 else r + 1
                 if 0 <= nb < self.world:
-                    buf = b.halo_recv_buffer(what, side); buf.copy_(sends[(nb, 1 - side)]); b.halo_add(what, side, buf)
+                    buf = b.halo_recv_buffer(what, side); buf.copy_(sends[(nb, 1 - side)]); recvs[(r, side)] = buf
+        self._fence()
+        for (r, side), buf in recvs.items():
+            self.bs[r].halo_add(what, side, buf)
 
     def _vmax(self):
         import torch
-        ts = [b.vmax_get().clone() for b in self.bs]
-        m = torch.stack([t.cpu() for t in ts]).max(dim=0).values
-        for b in self.bs:
-            t = b.vmax_get(); t.copy_(m.to(t.device)); b.vmax_set(t)
+        ts = [b.vmax_get() for b in self.bs]
+        self._fence()
+        m = torch.stack([t.detach().cpu() for t in ts]).max(dim=0).values
+        for t in ts:
+            t.copy_(m.to(t.device))
+        self._fence()
+        for b, t in zip(self.bs, ts):
+            b.vmax_set(t)
 
     def _migrate(self):
-        outs = [tuple(t.clone() for t in b.migrate_extract()) for b in self.bs]
+        outs = [b.migrate_extract() for b in self.bs]          # synchronises each context (counts come back to the host)
+        self._fence()
+        outs = [tuple(t.clone() for t in o) for o in outs]
+        self._fence()
         for r, b in enumerate(self.bs):
             parts = []
             for side in (0, 1):
@@ -256,6 +279,7 @@ class LocalSlabGroup:
                 else:
                     buf = b.migrate_recv_buffer(side, 0)
                 parts.append(buf)
+            self._fence()
             b.migrate_insert(parts[0], parts[1])
 
     def init(self):

@@ -1,0 +1,183 @@
+"""The reference-shaped C++ host layer (include/aep/*.h -> libaep_host.so): HybridSolver / ParticleSystem / RegularGrid /
+LagrangianMesh / LevelSet driving libaep_b200.so through the C ABI.
+
+CPU part: the library and the driver build with plain g++, host-only behaviour (containers, factories, OBJ loader, level sets).
+GPU part: tests/host_driver.cpp runs HybridSolver on scenes written by this file; results are compared with the oracle and
+with the Python binding of the same C ABI."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, relerr
+
+PKG = os.path.join(ROOT, "anisotropicelastoplasticity_b200")
+DRIVER = os.path.join(ROOT, "tests", "_bin", "host_driver")
+
+
+def _build():
+    import __graft_entry__ as g
+    g.build_host()
+    assert os.path.exists(os.path.join(PKG, "libaep_host.so")) and os.path.exists(DRIVER)
+
+
+def write_blob(path, arrays):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<i", len(arrays)))
+        for name, a in arrays.items():
+            a = np.ascontiguousarray(a)
+            dt = 0 if a.dtype == np.float64 else 1
+            assert a.dtype in (np.float64, np.int32), (name, a.dtype)
+            f.write(name.encode().ljust(32, b"\0")); f.write(struct.pack("<iq", dt, a.size)); f.write(a.tobytes())
+
+
+def read_blob(path):
+    out = {}
+    with open(path, "rb") as f:
+        (cnt,) = struct.unpack("<i", f.read(4))
+        for _ in range(cnt):
+            name = f.read(32).split(b"\0")[0].decode(); dt, n = struct.unpack("<iq", f.read(12))
+            out[name] = np.frombuffer(f.read(n * (8 if dt == 0 else 4)), dtype=np.float64 if dt == 0 else np.int32).copy()
+    return out
+
+
+def scene_blob(scene, ls_mode=0, rate_floor=0.0):
+    """Scene -> the reference's host layouts (column-major N x 3, 9 doubles per 3x3 column-major)."""
+    from anisotropicelastoplasticity_b200.scenes import colmajor, mats_colmajor
+    g = scene.grid
+    a = {"grid": np.concatenate([g.mn, g.mx]).astype(np.float64), "res": np.asarray(g.res, np.int32),
+         "scalars": np.array([scene.material, scene.cfl, scene.levelset.kind, ls_mode, rate_floor], np.float64),
+         "ls_params": np.asarray(scene.levelset.params, np.float64)}
+    p = scene.particles
+    if p is not None:
+        a.update(x=colmajor(p.x), v=colmajor(p.v), B1=colmajor(p.B[:, 0, :]), B2=colmajor(p.B[:, 1, :]), B3=colmajor(p.B[:, 2, :]),
+                 FE=mats_colmajor(p.FE), FP=mats_colmajor(p.FP), m=p.m.astype(np.float64), vol=p.vol.astype(np.float64), q=p.q.astype(np.float64),
+                 material=np.array([p.E, p.nu, p.thetaC, p.thetaS]))
+    m = scene.mesh
+    if m is not None:
+        a.update(mesh_vx=colmajor(m.vx), mesh_vv=colmajor(m.vv), mesh_ev=colmajor(m.ev), mesh_vm=m.vm.astype(np.float64), mesh_vvol=m.vvol.astype(np.float64),
+                 mesh_em=m.em.astype(np.float64), mesh_evol=m.evol.astype(np.float64), mesh_faces=np.ascontiguousarray(m.faces.T.astype(np.int32)),
+                 mesh_params=np.array([m.mu, m.lam, m.shear, m.stiff, m.fric]))
+        for k in range(3):
+            a[f"mesh_d{k + 1}"] = colmajor(m.ed[k]); a[f"mesh_D{k + 1}"] = colmajor(m.eD[k])
+        if m.fixed is not None:
+            a["mesh_fixed"] = np.asarray(m.fixed, np.float64)
+    return a
+
+
+def run_driver(tmp_path, scene, mode, n, ls_mode=0, tag="a"):
+    from anisotropicelastoplasticity_b200.scenes import from_colmajor, mats_from_colmajor
+    if not os.path.exists(DRIVER):
+        _build()
+    sin = str(tmp_path / f"scene_{tag}.bin"); sout = str(tmp_path / f"out_{tag}.bin"); outdir = str(tmp_path / f"frames_{tag}")
+    write_blob(sin, scene_blob(scene, ls_mode))
+    r = subprocess.run([DRIVER, "run", sin, sout, mode, str(n), outdir], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    o = read_blob(sout)
+    res = {"info": o["info"], "outdir": outdir, "grid_m": o["grid_m"], "grid_v": from_colmajor(o["grid_v"], o["grid_m"].size)}
+    if "x" in o:
+        n_p = o["vol"].size
+        res.update(x=from_colmajor(o["x"], n_p), v=from_colmajor(o["v"], n_p), FE=mats_from_colmajor(o["FE"], n_p), FP=mats_from_colmajor(o["FP"], n_p),
+                   vol=o["vol"], q=o["q"])
+    for k in ("mesh_vx", "mesh_vv", "mesh_ex", "mesh_d3"):
+        if k in o:
+            res[k] = from_colmajor(o[k], o[k].size // 3)
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ CPU
+def test_host_library_builds_and_unit_checks(tmp_path):
+    _build()
+    r = subprocess.run([DRIVER, "unit", str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "host unit OK" in r.stdout, r.stderr
+
+
+def test_host_library_exports_reference_surface():
+    """Every public method of the reference's four classes + level-set functions is an exported symbol of libaep_host.so."""
+    _build()
+    out = subprocess.run(["nm", "-DC", "--defined-only", os.path.join(PKG, "libaep_host.so")], capture_output=True, text=True).stdout
+    for sym in ("HybridSolver::solve(double, double, double)", "HybridSolver::bindViewer", "HybridSolver::updateViewer()", "HybridSolver::HybridSolver(ParticleSystem*, RegularGrid*)",
+                "ParticleSystem::SnowBall", "ParticleSystem::SandBall", "ParticleSystem::SandBlock", "ParticleSystem::SandCylinder", "ParticleSystem::ParticleSystem(",
+                "RegularGrid::RegularGrid(", "RegularGrid::toIndex(int, int, int) const", "RegularGrid::toCoordinate(int) const", "RegularGrid::max_velocity() const",
+                "LagrangianMesh::LagrangianMesh(", "LagrangianMesh::ObjMesh(", "LagrangianMesh::bindConstraints(", "LagrangianMesh::updateElementPositions()",
+                "LagrangianMesh::vertexIsFixed(int) const", "groundLevelSet(", "DgroundLevelSet(", "wall2groundLevelSet(", "Dwall2groundLevelSet("):
+        assert sym in out, sym
+
+
+def test_host_driver_fails_loudly_without_gpu(tmp_path):
+    """No CPU fallback: on a box without a B200 HybridSolver::begin throws with the library's message."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    _build()
+    from anisotropicelastoplasticity_b200 import scenes as sc
+    scene = sc.small_block(material=sc.SAND, res=16, cells=3, seed=7)
+    sin = str(tmp_path / "s.bin"); write_blob(sin, scene_blob(scene))
+    r = subprocess.run([DRIVER, "run", sin, str(tmp_path / "o.bin"), "substeps", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3 and "aep_create failed" in r.stderr and "no CPU fallback" in r.stderr
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sand", "snow"])
+def test_hybrid_solver_substeps_match_oracle(tmp_path, name):
+    """HybridSolver::begin + advance(3) + finish through the C++ classes == 3 iterations of the oracle's loop body."""
+    from anisotropicelastoplasticity_b200 import scenes as sc
+    from oracle.oracle_py import Oracle
+    mk = (lambda: sc.c1_sand_block(res=32)) if name == "sand" else (lambda: sc.c2_snow_sphere(res=32))
+    scene = mk()
+    got = run_driver(tmp_path, scene, "substeps", 3)
+    o = Oracle(mk(), threads=0); o.init()
+    for _ in range(3):
+        o.substep()
+    po = o.particles(); go = o.grid()
+    assert got["info"][3] == 3 and got["info"][0] == pytest.approx(o.dt, rel=1e-4)
+    for k, tol in (("x", 1e-5), ("v", 5e-5), ("FE", 1e-5), ("FP", 1e-5), ("vol", 1e-5)):
+        assert relerr(got[k], po[k]) < tol, k
+    assert relerr(got["grid_m"], go["m"]) < 1e-5                                             # RegularGrid::masses mirror
+    assert relerr(got["grid_m"][:, None] * got["grid_v"], go["m"][:, None] * go["v"]) < 5e-5
+
+
+@pytest.mark.gpu
+def test_hybrid_solver_std_function_levelset_equals_analytic(tmp_path):
+    """setLevelSet(std::bind(wall2groundLevelSet, ...)) as main.cpp:86-91 does (sampled at the nodes on the host) gives the same
+    state as the analytic device primitive."""
+    from anisotropicelastoplasticity_b200 import scenes as sc
+    scene = sc.c1_sand_block(res=32)
+    assert scene.levelset.kind == sc.LS_WALL2GROUND
+    scene.particles.v[:, 2] -= 2.0                                                            # make the ground matter within 4 substeps
+    scene.particles.x[:, 2] -= 0.04
+    a = run_driver(tmp_path, scene, "substeps", 4, ls_mode=0, tag="an")
+    b = run_driver(tmp_path, scene, "substeps", 4, ls_mode=1, tag="fn")
+    for k in ("x", "v", "FE"):
+        assert relerr(b[k], a[k]) < 1e-6, k
+
+
+@pytest.mark.gpu
+def test_hybrid_solver_cloth_coupling(tmp_path):
+    """LagrangianMesh + ParticleSystem through the C++ classes against the committed golden vectors (3 substeps)."""
+    d, scene = load_golden("cloth_sand")
+    got = run_driver(tmp_path, scene, "substeps", int(d["nsteps"]))
+    assert relerr(got["x"], d["o_x"]) < 1e-5 and relerr(got["FE"], d["o_FE"]) < 1e-5
+    assert relerr(got["mesh_vx"], d["o_vx"]) < 1e-5 and relerr(got["mesh_ex"], d["o_ex"]) < 1e-5 and relerr(got["mesh_vv"], d["o_vv"]) < 1e-4
+    assert relerr(got["mesh_d3"], d["o_ed"][2]) < 2e-5
+
+
+@pytest.mark.gpu
+def test_hybrid_solver_solve_writes_reference_frames(tmp_path):
+    """solve(CFL, maxt, alpha): one particle_N.obj per 1/60 s frame with 'v x y z' lines (HybridSolver.cpp:991-1007), and the
+    containers hold the final state (== the Python binding stepping the same number of frames)."""
+    from anisotropicelastoplasticity_b200 import scenes as sc
+    from anisotropicelastoplasticity_b200.engine import Engine
+    scene = sc.small_block(material=sc.SAND, res=16, cells=3, seed=7)
+    got = run_driver(tmp_path, scene, "solve", 2)
+    files = sorted(os.listdir(os.path.join(got["outdir"], "particle")))
+    assert files == ["particle_0.obj", "particle_1.obj"]
+    last = np.loadtxt(os.path.join(got["outdir"], "particle", "particle_1.obj"), usecols=(1, 2, 3))
+    with open(os.path.join(got["outdir"], "particle", "particle_1.obj")) as f:
+        assert f.readline().startswith("v ")
+    assert last.shape == got["x"].shape and np.abs(last - got["x"]).max() < 2e-6 * np.abs(got["x"]).max() + 1e-6     # %g prints 6 digits
+    e = Engine(scene); e.init(); e.run_frames(2); pe = e.particles()
+    assert relerr(got["x"], pe["x"]) < 1e-6 and relerr(got["v"], pe["v"]) < 1e-4
