@@ -201,12 +201,12 @@ int do_sort(aep_ctx* c, bool build_keys) {
     const bool slab = c->cfg.slab_axis >= 0;
     int end_bit = c->key_bits;
     if (build_keys && slab) {
-        k_build_keys_slab<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur].a[PX], c->d_keys[0], c->d_vals[0], n, c->G.nx, c->G.ny,
+        k_build_keys_slab<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur].a[PX], c->d_keys[0], c->d_vals[0], n, c->G.nqx, c->G.nqy,
                                                               c->cfg.slab_axis, c->cfg.slab_lo, c->cfg.slab_hi, c->key_bits);
         LAUNCH_OK("k_build_keys_slab");
         end_bit = c->key_bits + 1;
     } else if (build_keys) {
-        k_build_keys<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur].a[PX], c->d_keys[0], c->d_vals[0], n, c->G.nx, c->G.ny);
+        k_build_keys<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur].a[PX], c->d_keys[0], c->d_vals[0], n, c->G.nqx, c->G.nqy);
         LAUNCH_OK("k_build_keys");
     }
     size_t tmp = c->sort_tmp_bytes;
@@ -356,6 +356,7 @@ int aep_create(aep_ctx** out, const aep_config* cfg) {
     GridP& G = ctx->G;
     G.nx = cfg->res[0]; G.ny = cfg->res[1]; G.nz = cfg->res[2];
     G.nbx = (G.nx + 7) / 8; G.nby = (G.ny + 7) / 8; G.nbz = (G.nz + 7) / 8;
+    G.nqx = (G.nx + 3) / 4; G.nqy = (G.ny + 3) / 4;
     ctx->nblocks = G.nbx * G.nby * G.nbz;
     ctx->Ng = (size_t)G.nx * G.ny * G.nz;
     for (int a = 0; a < 3; ++a) ctx->h[a] = (cfg->grid_max[a] - cfg->grid_min[a]) / cfg->res[a];      // RegularGrid.cpp:137-139
@@ -377,7 +378,10 @@ int aep_create(aep_ctx** out, const aep_config* cfg) {
     SimClock clk{}; clk.frame_dt = cfg->frame_dt; clk.cfl = cfg->cfl; clk.rate_floor = cfg->dt_rate_floor; clk.hmin = ctx->hmin;
     CUC(cudaMemcpyAsync(ctx->d_clk, &clk, sizeof clk, cudaMemcpyHostToDevice, ctx->stream));
     CUC(cudaEventCreate(&ctx->tm.ev[0])); CUC(cudaEventCreate(&ctx->tm.ev[1]));
-    ctx->key_bits = 1; while (((size_t)1 << ctx->key_bits) < ctx->Ng) ctx->key_bits++;
+    {   // sort keys: (brick << 6) | cell-in-brick, see sort_key()
+        const size_t nkeys = (size_t)G.nqx * G.nqy * ((G.nz + 3) / 4) * 64;
+        ctx->key_bits = 1; while (((size_t)1 << ctx->key_bits) < nkeys) ctx->key_bits++;
+    }
     CUC(cudaStreamSynchronize(ctx->stream));
 #undef CUC
     *out = ctx;

@@ -30,6 +30,7 @@ struct PartP {
 struct GridP {
     int nx, ny, nz;
     int nbx, nby, nbz;                 // number of 8^3 node blocks per axis
+    int nqx, nqy;                      // number of 4^3 cell bricks along x, y (sort order)
     float hx, hy, hz, ihx, ihy, ihz;
     float mnx, mny, mnz;
     float apic;                        // 3 / hmin^2                       HybridSolver.cpp:175-177
@@ -85,12 +86,20 @@ __device__ __forceinline__ bool axis_setup(Axis& a, float f, int cell, int nres,
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // ================================================================================================ sort keys
+// Particles are ordered by 4x4x4-cell brick (x fastest), then by cell inside the brick (x fastest).  A CTA of 256 consecutive
+// particles at 8 per cell is then a 4x4x2 slab of cells whose stencils share a 7x7x5 node box (245 nodes, 3.9 KB) instead of the
+// 35x4x4 = 560 nodes of 32 cells in a row: the grid gathers of one CTA hit in L1 instead of going to L2.  The scatters only
+// need particles of one cell to be adjacent, which any cell-granular order provides.
+__device__ __forceinline__ unsigned sort_key(int ci, int cj, int ck, int nqx, int nqy) {
+    const unsigned brick = (unsigned)(((ck >> 2) * nqy + (cj >> 2)) * nqx + (ci >> 2));
+    return (brick << 6) | (unsigned)(((ck & 3) << 4) | ((cj & 3) << 2) | (ci & 3));
+}
 __global__ void k_build_keys(const float4* __restrict__ X, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals,
-                             int n, int nx, int ny) {
+                             int n, int nqx, int nqy) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int c = __float_as_int(X[i].w);
-    keys[i] = (unsigned)((cell_k(c) * ny + cell_j(c)) * nx + cell_i(c));
+    keys[i] = sort_key(cell_i(c), cell_j(c), cell_k(c), nqx, nqy);
     vals[i] = (unsigned)i;
 }
 
@@ -280,7 +289,7 @@ __device__ __forceinline__ float f4c(const float4& v, int i) { return i == 0 ? v
 // Per particle the momentum of node offset (i,j,k) is q0 + Qm (i,j,k)^T with Qm = m (3/h^2) B diag(h), q0 = m v - Qm (1+f).
 #define P2G_REC 7
 __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
-    __shared__ float4 stage[8][32][P2G_REC];
+    __shared__ float4 stage[8][2][16 * P2G_REC + 1];                         // +1: the two half-warps read different banks in phase B
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
     if (base >= n) return;                                                   // warp-uniform; no block-level barrier below
@@ -299,7 +308,7 @@ __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
         const float q0x = fmaf(m, VM.x, -(Q[0] * gx + Q[1] * gy + Q[2] * gz));
         const float q0y = fmaf(m, VM.y, -(Q[3] * gx + Q[4] * gy + Q[5] * gz));
         const float q0z = fmaf(m, VM.z, -(Q[6] * gx + Q[7] * gy + Q[8] * gz));
-        float4* rec = stage[wib][lane];
+        float4* rec = &stage[wib][lane >> 4][(lane & 15) * P2G_REC];
         rec[0] = make_float4(Nx[0], Nx[1], Nx[2], Nx[3]); rec[1] = make_float4(Ny[0], Ny[1], Ny[2], Ny[3]); rec[2] = make_float4(Nz[0], Nz[1], Nz[2], Nz[3]);
         rec[3] = make_float4(m, q0x, q0y, q0z);
         rec[4] = make_float4(Q[0], Q[1], Q[2], Q[3]); rec[5] = make_float4(Q[4], Q[5], Q[6], Q[7]); rec[6] = make_float4(Q[8], 0.f, 0.f, X.w);
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
     const float fj = (float)j, fk = (float)k;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 acc[4] = { zero, zero, zero, zero };
-    const float4* recs = &stage[wib][hw * 16][0];
+    const float4* recs = &stage[wib][hw][0];
     int cur = __float_as_int(recs[6].w);
 #pragma unroll 2
     for (int it = 0; it < 16; ++it) {
@@ -393,8 +402,42 @@ __global__ void __launch_bounds__(256) k_grid_normalise(GridP G) {
 // grad v = sum_i v_i (grad w_i)^T (x-direction summed first: 6 FMA per node + 9 per row), Fhat = (I + dt grad v) FE, SVD,
 // stress, A = V_p P FE^T.  Phase B (half-warp per particle): f_i -= A grad w_ip.
 #define FRC_REC 9
-__global__ void __launch_bounds__(256) k_forces(PartP P, GridP G, MatParams mpar, const SimClock* __restrict__ clk, int n) {
-    __shared__ float4 stage[8][32][FRC_REC];
+// g[3r+c] = sum_i v_i[r] d_c w_i over the 4x4x4 stencil, x summed first.  INTERIOR: every stencil node is inside the grid, so the
+// four nodes of a row are 64 contiguous bytes at a fixed offset from the row pointer (no clamping, immediate-offset loads).
+template <bool INTERIOR>
+__device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, const Axis& ay, const Axis& az, float (&g)[9]) {
+    int ni[4], nj[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { ni[o] = INTERIOR ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = INTERIOR ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
+    const float4* base = G.vt + (INTERIOR ? ax.n0 : 0);
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const int nk = INTERIOR ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
+        const float nzk = sel4(az.N, k), dzk = sel4(az.D, k);
+        const float4* plane = base + (size_t)nk * G.ny * G.nx;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4* row = plane + nj[j] * G.nx;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = ldg4(row + ni[i]);
+                a0 = fmaf(v.x, ax.N[i], a0); a1 = fmaf(v.y, ax.N[i], a1); a2 = fmaf(v.z, ax.N[i], a2);
+                b0 = fmaf(v.x, ax.D[i], b0); b1 = fmaf(v.y, ax.D[i], b1); b2 = fmaf(v.z, ax.D[i], b2);
+            }
+            const float nn = ay.N[j] * nzk, dn = ay.D[j] * nzk, nd = ay.N[j] * dzk;
+            g[0] = fmaf(b0, nn, g[0]); g[1] = fmaf(a0, dn, g[1]); g[2] = fmaf(a0, nd, g[2]);
+            g[3] = fmaf(b1, nn, g[3]); g[4] = fmaf(a1, dn, g[4]); g[5] = fmaf(a1, nd, g[5]);
+            g[6] = fmaf(b2, nn, g[6]); g[7] = fmaf(a2, dn, g[7]); g[8] = fmaf(a2, nd, g[8]);
+        }
+    }
+}
+
+// computeGridForces_, particle part (HybridSolver.cpp:252-368).  Phase A (thread per particle): gather
+// grad v = sum_i v_i (grad w_i)^T, Fhat = (I + dt grad v) FE, SVD, stress, A = V_p P FE^T.  Phase B (half-warp per particle):
+// f_i -= A grad w_ip.
+__global__ void __launch_bounds__(256, 3) k_forces(PartP P, GridP G, MatParams mpar, const SimClock* __restrict__ clk, int n) {
+    __shared__ float4 stage[8][2][16 * FRC_REC + 1];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
     if (base >= n) return;
@@ -406,49 +449,30 @@ __global__ void __launch_bounds__(256) k_forces(PartP P, GridP G, MatParams mpar
         const float4 e0 = ldg4(P.a[PE0] + p), e1 = ldg4(P.a[PE1] + p), e2 = ldg4(P.a[PE2] + p);
         const int cell = __float_as_int(X.w);
         Axis ax, ay, az;
-        axis_setup(ax, X.x, cell_i(cell), G.nx, G.ihx); axis_setup(ay, X.y, cell_j(cell), G.ny, G.ihy); axis_setup(az, X.z, cell_k(cell), G.nz, G.ihz);
-        int ni[4], nj[4];
-#pragma unroll
-        for (int o = 0; o < 4; ++o) { ni[o] = clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = clampi(ay.n0 + o, 0, G.ny - 1); }
-        float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};          // g[3r+c] = sum_i v_i[r] dw_i[c]
-#pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-            const int nk = clampi(az.n0 + k, 0, G.nz - 1);
-            const float nzk = sel4(az.N, k), dzk = sel4(az.D, k);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4* row = G.vt + ((size_t)nk * G.ny + nj[j]) * G.nx;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 v = ldg4(row + ni[i]);
-                    a0 = fmaf(v.x, ax.N[i], a0); a1 = fmaf(v.y, ax.N[i], a1); a2 = fmaf(v.z, ax.N[i], a2);
-                    b0 = fmaf(v.x, ax.D[i], b0); b1 = fmaf(v.y, ax.D[i], b1); b2 = fmaf(v.z, ax.D[i], b2);
-                }
-                const float nn = ay.N[j] * nzk, dn = ay.D[j] * nzk, nd = ay.N[j] * dzk;
-                g[0] = fmaf(b0, nn, g[0]); g[1] = fmaf(a0, dn, g[1]); g[2] = fmaf(a0, nd, g[2]);
-                g[3] = fmaf(b1, nn, g[3]); g[4] = fmaf(a1, dn, g[4]); g[5] = fmaf(a1, nd, g[5]);
-                g[6] = fmaf(b2, nn, g[6]); g[7] = fmaf(a2, dn, g[7]); g[8] = fmaf(a2, nd, g[8]);
-            }
-        }
+        bool complete = axis_setup(ax, X.x, cell_i(cell), G.nx, G.ihx);
+        complete &= axis_setup(ay, X.y, cell_j(cell), G.ny, G.ihy);
+        complete &= axis_setup(az, X.z, cell_k(cell), G.nz, G.ihz);
+        float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (__all_sync(0xffffffffu, complete)) gather_grad<true>(G, ax, ay, az, g);
+        else gather_grad<false>(G, ax, ay, az, g);
         const float FE[9] = { e0.x, e0.y, e0.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z };
         float GF[9], Fh[9], A[9];
         mat_mul(g, FE, GF);
 #pragma unroll
         for (int i = 0; i < 9; ++i) Fh[i] = fmaf(dt, GF[i], FE[i]);              // HybridSolver.cpp:306
-        stress_times_FEt(mpar, Fh, FE, (lane < cnt) ? e0.w : 0.0f, e2.w, A);     // padding lanes: zero volume -> zero stress
-        float4* rec = stage[wib][lane];
+        stress_times_FEt(mpar, Fh, FE, (lane < cnt) ? -e0.w : 0.0f, e2.w, A);    // A := -V_p P FE^T (sign of :356-366 folded in); padding lanes: zero volume
+        float4* rec = &stage[wib][lane >> 4][(lane & 15) * FRC_REC];
         rec[0] = make_float4(ax.N[0], ax.N[1], ax.N[2], ax.N[3]); rec[1] = make_float4(ax.D[0], ax.D[1], ax.D[2], ax.D[3]);
         rec[2] = make_float4(ay.N[0], ay.D[0], ay.N[1], ay.D[1]); rec[3] = make_float4(ay.N[2], ay.D[2], ay.N[3], ay.D[3]);
         rec[4] = make_float4(az.N[0], az.D[0], az.N[1], az.D[1]); rec[5] = make_float4(az.N[2], az.D[2], az.N[3], az.D[3]);
         rec[6] = make_float4(A[0], A[1], A[2], A[3]); rec[7] = make_float4(A[4], A[5], A[6], A[7]); rec[8] = make_float4(A[8], 0.f, 0.f, X.w);
     }
     __syncwarp();
-    // ---- phase B: f_i[r] -= sum_c A(r,c) d_c w   with d_x w = Dx Ny Nz, d_y w = Nx Dy Nz, d_z w = Nx Ny Dz   (HybridSolver.cpp:356-366)
+    // ---- phase B: f_i[r] += sum_c A(r,c) d_c w   with d_x w = Dx Ny Nz, d_y w = Nx Dy Nz, d_z w = Nx Ny Dz   (HybridSolver.cpp:356-366)
     const int hw = lane >> 4, s = lane & 15, j = s & 3, k = s >> 2;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 acc[4] = { zero, zero, zero, zero };
-    const float4* recs = &stage[wib][hw * 16][0];
+    const float4* recs = &stage[wib][hw][0];
     int cur = __float_as_int(recs[8].w);
 #pragma unroll 2
     for (int it = 0; it < 16; ++it) {
@@ -467,21 +491,81 @@ __global__ void __launch_bounds__(256) k_forces(PartP P, GridP G, MatParams mpar
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float d = f4c(dx, i), w = f4c(nx, i);
-            acc[i].x -= fmaf(ux, d, vx * w); acc[i].y -= fmaf(uy, d, vy * w); acc[i].z -= fmaf(uz, d, vz * w);
+            acc[i].x = fmaf(ux, d, fmaf(vx, w, acc[i].x)); acc[i].y = fmaf(uy, d, fmaf(vy, w, acc[i].y)); acc[i].z = fmaf(uz, d, fmaf(vz, w, acc[i].z));
         }
     }
     flush_row(G, G.f, cur, j, k, acc, false);
 }
 
 // ================================================================================================ G2P
+// The 64-node gather of G2P.  Per (j,k) row the x direction is summed first over v~ only:
+//   a = sum v~ Nx, b = sum v~ Dx, d = sum v~ Nx rx           (9 FMA per node)
+// then the rows are combined into  va = sum w v~,  g = sum v~ (grad w)^T,  B~ = sum w v~ (x_i - x_p)^T.
+// The post-friction velocity is v = s v~ with s in {0,1} and s = 0 only on sticking collider nodes (k_grid_update), so
+//   v_p = va - sum_{s=0} w v~   and   B = B~ - sum_{s=0} w v~ (x_i - x_p)^T;
+// the correction branch runs only for rows that contain a sticking node.
+struct G2PSums {
+    float va[3], vc[3], B[9], g[9];
+};
+template <bool INTERIOR>
+__device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const Axis& ay, const Axis& az, const float (&nrx)[4],
+                                           const float (&rx)[4], const float (&ry)[4], const float (&rz)[4], G2PSums& S) {
+    int ni[4], nj[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { ni[o] = INTERIOR ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = INTERIOR ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
+    const float4* base = G.vt + (INTERIOR ? ax.n0 : 0);
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const int nk = INTERIOR ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
+        const float nzk = sel4(az.N, k), dzk = sel4(az.D, k), rzk = sel4(rz, k);
+        const float4* plane = base + (size_t)nk * G.ny * G.nx;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4* row = plane + nj[j] * G.nx;
+            float4 t[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t[i] = ldg4(row + ni[i]);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a0 = fmaf(t[i].x, ax.N[i], a0); a1 = fmaf(t[i].y, ax.N[i], a1); a2 = fmaf(t[i].z, ax.N[i], a2);
+                b0 = fmaf(t[i].x, ax.D[i], b0); b1 = fmaf(t[i].y, ax.D[i], b1); b2 = fmaf(t[i].z, ax.D[i], b2);
+                d0 = fmaf(t[i].x, nrx[i], d0); d1 = fmaf(t[i].y, nrx[i], d1); d2 = fmaf(t[i].z, nrx[i], d2);
+            }
+            const float nn = ay.N[j] * nzk, dn = ay.D[j] * nzk, nd = ay.N[j] * dzk;
+            const float u0 = a0 * nn, u1 = a1 * nn, u2 = a2 * nn;            // sum_i w v~_i over the row
+            S.va[0] += u0; S.va[1] += u1; S.va[2] += u2;
+            S.g[0] = fmaf(b0, nn, S.g[0]); S.g[1] = fmaf(a0, dn, S.g[1]); S.g[2] = fmaf(a0, nd, S.g[2]);
+            S.g[3] = fmaf(b1, nn, S.g[3]); S.g[4] = fmaf(a1, dn, S.g[4]); S.g[5] = fmaf(a1, nd, S.g[5]);
+            S.g[6] = fmaf(b2, nn, S.g[6]); S.g[7] = fmaf(a2, dn, S.g[7]); S.g[8] = fmaf(a2, nd, S.g[8]);
+            S.B[0] = fmaf(d0, nn, S.B[0]); S.B[1] = fmaf(u0, ry[j], S.B[1]); S.B[2] = fmaf(u0, rzk, S.B[2]);
+            S.B[3] = fmaf(d1, nn, S.B[3]); S.B[4] = fmaf(u1, ry[j], S.B[4]); S.B[5] = fmaf(u1, rzk, S.B[5]);
+            S.B[6] = fmaf(d2, nn, S.B[6]); S.B[7] = fmaf(u2, ry[j], S.B[7]); S.B[8] = fmaf(u2, rzk, S.B[8]);
+            if (t[0].w * t[1].w * t[2].w * t[3].w == 0.0f) {                 // a sticking node in this row (rare)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float w = (t[i].w == 0.0f) ? -ax.N[i] * nn : 0.0f;
+                    const float cx = w * t[i].x, cy = w * t[i].y, cz = w * t[i].z;
+                    S.vc[0] += cx; S.vc[1] += cy; S.vc[2] += cz;
+                    S.B[0] = fmaf(cx, rx[i], S.B[0]); S.B[1] = fmaf(cx, ry[j], S.B[1]); S.B[2] = fmaf(cx, rzk, S.B[2]);
+                    S.B[3] = fmaf(cy, rx[i], S.B[3]); S.B[4] = fmaf(cy, ry[j], S.B[4]); S.B[5] = fmaf(cy, rzk, S.B[5]);
+                    S.B[6] = fmaf(cz, rx[i], S.B[6]); S.B[7] = fmaf(cz, ry[j], S.B[7]); S.B[8] = fmaf(cz, rzk, S.B[8]);
+                }
+            }
+        }
+    }
+}
+
 // updateParticleVelocities_ (HybridSolver.cpp:739-745), updateAffineMomenta_ with damp 0 (:760-825, :908-917),
 // advection x = sum w (x_i + dt v~_i) (:942-945), updateDeformationGradient_ (:553-578), updatePlasticity_
 // (:612-681), all in registers, one thread per particle.  The 64-node gather sums along x first (per (j,k) row:
 // a = sum v~ Nx, b = sum v~ Dx, c = sum s v~ Nx, d = sum s v~ Nx rx), then combines rows.  Writes the new sort key.
-__global__ void __launch_bounds__(128) k_g2p(PartP P, GridP G, MatParams mpar, SimClock* __restrict__ clk,
+__global__ void __launch_bounds__(128, 4) k_g2p(PartP P, GridP G, MatParams mpar, SimClock* __restrict__ clk,
                                              unsigned int* __restrict__ keys, unsigned int* __restrict__ vals, int n) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
+    const int p_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((p_raw & ~31) >= n) return;                                         // whole warp past the end
+    const bool live = p_raw < n;                                            // tail lanes recompute the last particle and write nothing:
+    const int p = live ? p_raw : n - 1;                                     // the warp stays converged for the vote below
     const float dt = clk->dt;
     const float4 X = ldg4(P.a[PX] + p);
     const int cell = __float_as_int(X.w);
@@ -491,47 +575,20 @@ __global__ void __launch_bounds__(128) k_g2p(PartP P, GridP G, MatParams mpar, S
     complete &= axis_setup(ay, X.y, cj, G.ny, G.ihy);
     complete &= axis_setup(az, X.z, ck, G.nz, G.ihz);
     float rx[4], ry[4], rz[4];                                              // x_i - x_p per axis: h (o - 1 - f)
-    int ni[4], nj[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-        rx[o] = G.hx * ((float)(o - 1) - X.x); ry[o] = G.hy * ((float)(o - 1) - X.y); rz[o] = G.hz * ((float)(o - 1) - X.z);
-        ni[o] = clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = clampi(ay.n0 + o, 0, G.ny - 1);
-    }
+    for (int o = 0; o < 4; ++o) { rx[o] = G.hx * ((float)(o - 1) - X.x); ry[o] = G.hy * ((float)(o - 1) - X.y); rz[o] = G.hz * ((float)(o - 1) - X.z); }
     float nrx[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) nrx[o] = ax.N[o] * rx[o];
-    float vp[3] = {0.f, 0.f, 0.f}, va[3] = {0.f, 0.f, 0.f};            // sum w v (post-collision), sum w v~ (pre-friction)
-    float B[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        // sum w v (x_i - x_p)^T
-    float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        // sum v~ (grad w)^T
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-        const int nk = clampi(az.n0 + k, 0, G.nz - 1);
-        const float nzk = sel4(az.N, k), dzk = sel4(az.D, k), rzk = sel4(rz, k);
+    G2PSums S;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4* row = G.vt + ((size_t)nk * G.ny + nj[j]) * G.nx;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    for (int i = 0; i < 3; ++i) { S.vc[i] = 0.f; S.va[i] = 0.f; }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 t = ldg4(row + ni[i]);
-                const float sn = t.w * ax.N[i], snr = t.w * nrx[i];
-                a0 = fmaf(t.x, ax.N[i], a0); a1 = fmaf(t.y, ax.N[i], a1); a2 = fmaf(t.z, ax.N[i], a2);
-                b0 = fmaf(t.x, ax.D[i], b0); b1 = fmaf(t.y, ax.D[i], b1); b2 = fmaf(t.z, ax.D[i], b2);
-                c0 = fmaf(t.x, sn, c0); c1 = fmaf(t.y, sn, c1); c2 = fmaf(t.z, sn, c2);
-                d0 = fmaf(t.x, snr, d0); d1 = fmaf(t.y, snr, d1); d2 = fmaf(t.z, snr, d2);
-            }
-            const float nn = ay.N[j] * nzk, dn = ay.D[j] * nzk, nd = ay.N[j] * dzk;
-            va[0] = fmaf(a0, nn, va[0]); va[1] = fmaf(a1, nn, va[1]); va[2] = fmaf(a2, nn, va[2]);
-            g[0] = fmaf(b0, nn, g[0]); g[1] = fmaf(a0, dn, g[1]); g[2] = fmaf(a0, nd, g[2]);
-            g[3] = fmaf(b1, nn, g[3]); g[4] = fmaf(a1, dn, g[4]); g[5] = fmaf(a1, nd, g[5]);
-            g[6] = fmaf(b2, nn, g[6]); g[7] = fmaf(a2, dn, g[7]); g[8] = fmaf(a2, nd, g[8]);
-            const float u0 = c0 * nn, u1 = c1 * nn, u2 = c2 * nn;            // sum_i w v_i over the row
-            vp[0] += u0; vp[1] += u1; vp[2] += u2;
-            B[0] = fmaf(d0, nn, B[0]); B[1] = fmaf(u0, ry[j], B[1]); B[2] = fmaf(u0, rzk, B[2]);
-            B[3] = fmaf(d1, nn, B[3]); B[4] = fmaf(u1, ry[j], B[4]); B[5] = fmaf(u1, rzk, B[5]);
-            B[6] = fmaf(d2, nn, B[6]); B[7] = fmaf(u2, ry[j], B[7]); B[8] = fmaf(u2, rzk, B[8]);
-        }
-    }
+    for (int i = 0; i < 9; ++i) { S.B[i] = 0.f; S.g[i] = 0.f; }
+    if (__all_sync(0xffffffffu, complete)) g2p_gather<true>(G, ax, ay, az, nrx, rx, ry, rz, S);
+    else g2p_gather<false>(G, ax, ay, az, nrx, rx, ry, rz, S);
+    float (&va)[3] = S.va; float (&B)[9] = S.B; float (&g)[9] = S.g;
+    const float vp[3] = { S.va[0] + S.vc[0], S.va[1] + S.vc[1], S.va[2] + S.vc[2] };       // sum w s v~ = sum w v~ - sum_{s=0} w v~
     // ---- advection (HybridSolver.cpp:944): x' = sum w (x_i + dt v~_i) = x + [sum w (x_i - x)] + (sum w - 1) x + dt sum w v~
     // the bracket and (sum w - 1) vanish unless the stencil is truncated by the domain boundary (:44-46); both are separable.
     float dxp = dt * va[0], dyp = dt * va[1], dzp = dt * va[2];
@@ -552,7 +609,7 @@ __global__ void __launch_bounds__(128) k_g2p(PartP P, GridP G, MatParams mpar, S
         const int cci = clampi(ci, 0, G.nx - 1), ccj = clampi(cj, 0, G.ny - 1), cck = clampi(ck, 0, G.nz - 1);
         const bool nan = !(nfx == nfx) || !(nfy == nfy) || !(nfz == nfz);
         if (cci != ci || ccj != cj || cck != ck || nan) {
-            atomicAdd(&clk->escaped, 1ull);
+            if (live) atomicAdd(&clk->escaped, 1ull);
             if (!(nfx == nfx)) nfx = 0.5f;
             if (!(nfy == nfy)) nfy = 0.5f;
             if (!(nfz == nfz)) nfz = 0.5f;
@@ -572,6 +629,7 @@ __global__ void __launch_bounds__(128) k_g2p(PartP P, GridP G, MatParams mpar, S
     return_map(mpar, Fh, FE, FP, q);
     const float Jp = mat_det(FP);
     // ---- write back
+    if (!live) return;
     const int ncell = cell_pack(ci, cj, ck);
     P.a[PX][p] = make_float4(nfx, nfy, nfz, __int_as_float(ncell));
     P.a[PVM][p] = make_float4(vp[0], vp[1], vp[2], q1.w);
@@ -584,7 +642,7 @@ __global__ void __launch_bounds__(128) k_g2p(PartP P, GridP G, MatParams mpar, S
     P.a[PQ0][p] = make_float4(FP[0], FP[1], FP[2], q0.w);
     P.a[PQ1][p] = make_float4(FP[3], FP[4], FP[5], q1.w);
     P.a[PQ2][p] = make_float4(FP[6], FP[7], FP[8], q2.w);
-    keys[p] = (unsigned)((ck * G.ny + cj) * G.nx + ci);
+    keys[p] = sort_key(ci, cj, ck, G.nqx, G.nqy);
     vals[p] = (unsigned)p;
 }
 

@@ -147,7 +147,8 @@ int HybridSolver::advanceFrames(int frames) {
 void HybridSolver::clock(double* dt, double* t, int* frameNo, long long* substeps) const {
     int32_t fr = 0; int64_t ss = 0;
     ck(aep_get_clock(ctx_, dt, t, nullptr, &fr, &ss, nullptr, nullptr), ctx_, "aep_get_clock");
-    if (frameNo) *frameNo = fr; if (substeps) *substeps = ss;
+    if (frameNo) *frameNo = fr;
+    if (substeps) *substeps = ss;
 }
 
 void HybridSolver::fetchPositions() {
