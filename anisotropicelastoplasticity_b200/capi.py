@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaep_b200.so")
+LIB_PATH = os.environ.get("AEP_B200_LIB") or os.path.join(_HERE, "libaep_b200.so")   # override: kernel-variant experiments only
 _LIB = None
 
 NUM_STAGES = 8
@@ -27,7 +27,7 @@ class Config(C.Structure):
                 ("cfl", C.c_double), ("gravity", C.c_double), ("collider_friction", C.c_double), ("snow_hardening", C.c_double),
                 ("sand_h", C.c_double * 4), ("dt_rate_floor", C.c_double), ("frame_dt", C.c_double),
                 ("particle_capacity", C.c_int64), ("slab_axis", C.c_int32), ("slab_lo", C.c_int32), ("slab_hi", C.c_int32),
-                ("sort_every", C.c_int32)]
+                ("sort_every", C.c_int32), ("sort_bricks", C.c_int32), ("_pad1", C.c_int32)]
 
 
 class AepError(RuntimeError):

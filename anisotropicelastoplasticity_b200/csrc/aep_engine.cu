@@ -201,12 +201,12 @@ int do_sort(aep_ctx* c, bool build_keys) {
     const bool slab = c->cfg.slab_axis >= 0;
     int end_bit = c->key_bits;
     if (build_keys && slab) {
-        k_build_keys_slab<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur].a[PX], c->d_keys[0], c->d_vals[0], n, c->G.nqx, c->G.nqy,
+        k_build_keys_slab<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur].a[PX], c->d_keys[0], c->d_vals[0], n, c->G,
                                                               c->cfg.slab_axis, c->cfg.slab_lo, c->cfg.slab_hi, c->key_bits);
         LAUNCH_OK("k_build_keys_slab");
         end_bit = c->key_bits + 1;
     } else if (build_keys) {
-        k_build_keys<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur].a[PX], c->d_keys[0], c->d_vals[0], n, c->G.nqx, c->G.nqy);
+        k_build_keys<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur].a[PX], c->d_keys[0], c->d_vals[0], n, c->G);
         LAUNCH_OK("k_build_keys");
     }
     size_t tmp = c->sort_tmp_bytes;
@@ -325,7 +325,7 @@ int aep_default_config(aep_config* cfg) {
     cfg->cfl = 0.3; cfg->gravity = 9.8; cfg->collider_friction = 0.2; cfg->snow_hardening = 10.0;
     cfg->sand_h[0] = 35.0; cfg->sand_h[1] = 9.0; cfg->sand_h[2] = 0.2; cfg->sand_h[3] = 10.0;
     cfg->dt_rate_floor = 3e2; cfg->frame_dt = 1.0 / 60.0;
-    cfg->particle_capacity = 0; cfg->slab_axis = -1; cfg->slab_lo = 0; cfg->slab_hi = 0; cfg->sort_every = 1;
+    cfg->particle_capacity = 0; cfg->slab_axis = -1; cfg->slab_lo = 0; cfg->slab_hi = 0; cfg->sort_every = 1; cfg->sort_bricks = 0;
     return AEP_OK;
 }
 
@@ -356,7 +356,7 @@ int aep_create(aep_ctx** out, const aep_config* cfg) {
     GridP& G = ctx->G;
     G.nx = cfg->res[0]; G.ny = cfg->res[1]; G.nz = cfg->res[2];
     G.nbx = (G.nx + 7) / 8; G.nby = (G.ny + 7) / 8; G.nbz = (G.nz + 7) / 8;
-    G.nqx = (G.nx + 3) / 4; G.nqy = (G.ny + 3) / 4;
+    G.nqx = (G.nx + 3) / 4; G.nqy = (G.ny + 3) / 4; G.bricks = cfg->sort_bricks ? 1 : 0;
     ctx->nblocks = G.nbx * G.nby * G.nbz;
     ctx->Ng = (size_t)G.nx * G.ny * G.nz;
     for (int a = 0; a < 3; ++a) ctx->h[a] = (cfg->grid_max[a] - cfg->grid_min[a]) / cfg->res[a];      // RegularGrid.cpp:137-139

@@ -45,12 +45,12 @@ __device__ __forceinline__ int cell_axis(int cell, int axis) { return axis == 0 
 
 // keys with particles that left the slab pushed behind every in-slab key
 __global__ void k_build_keys_slab(const float4* __restrict__ X, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals,
-                                  int n, int nqx, int nqy, int axis, int lo, int hi, int key_bits) {
+                                  int n, GridP G, int axis, int lo, int hi, int key_bits) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int c = __float_as_int(X[i].w);
     const int ca = cell_axis(c, axis);
-    const unsigned key = sort_key(cell_i(c), cell_j(c), cell_k(c), nqx, nqy);
+    const unsigned key = sort_key(cell_i(c), cell_j(c), cell_k(c), G);
     keys[i] = (ca < lo || ca >= hi) ? (key | (1u << key_bits)) : key;
     vals[i] = (unsigned)i;
 }

@@ -31,6 +31,7 @@ struct GridP {
     int nx, ny, nz;
     int nbx, nby, nbz;                 // number of 8^3 node blocks per axis
     int nqx, nqy;                      // number of 4^3 cell bricks along x, y (sort order)
+    int bricks;                        // 1: brick-major sort keys, 0: plain cell index
     float hx, hy, hz, ihx, ihy, ihz;
     float mnx, mny, mnz;
     float apic;                        // 3 / hmin^2                       HybridSolver.cpp:175-177
@@ -90,16 +91,17 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // particles at 8 per cell is then a 4x4x2 slab of cells whose stencils share a 7x7x5 node box (245 nodes, 3.9 KB) instead of the
 // 35x4x4 = 560 nodes of 32 cells in a row: the grid gathers of one CTA hit in L1 instead of going to L2.  The scatters only
 // need particles of one cell to be adjacent, which any cell-granular order provides.
-__device__ __forceinline__ unsigned sort_key(int ci, int cj, int ck, int nqx, int nqy) {
-    const unsigned brick = (unsigned)(((ck >> 2) * nqy + (cj >> 2)) * nqx + (ci >> 2));
+__device__ __forceinline__ unsigned sort_key(int ci, int cj, int ck, const GridP& G) {
+    if (!G.bricks) return (unsigned)((ck * G.ny + cj) * G.nx + ci);
+    const unsigned brick = (unsigned)(((ck >> 2) * G.nqy + (cj >> 2)) * G.nqx + (ci >> 2));
     return (brick << 6) | (unsigned)(((ck & 3) << 4) | ((cj & 3) << 2) | (ci & 3));
 }
 __global__ void k_build_keys(const float4* __restrict__ X, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals,
-                             int n, int nqx, int nqy) {
+                             int n, GridP G) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int c = __float_as_int(X[i].w);
-    keys[i] = sort_key(cell_i(c), cell_j(c), cell_k(c), nqx, nqy);
+    keys[i] = sort_key(cell_i(c), cell_j(c), cell_k(c), G);
     vals[i] = (unsigned)i;
 }
 
@@ -266,6 +268,28 @@ __device__ __forceinline__ void flush_row(const GridP& G, float4* __restrict__ d
     }
 }
 
+// Sliding window along x: when the next particle's cell is d = 1..3 cells further along x in the same (j,k) row of cells, only the
+// d nodes that fall out of the 4-node window are reduced to memory and the accumulators shift; x-adjacent cells share 3 of their
+// 4 nodes per row, so a sorted row of C cells costs C+3 reductions per lane instead of 4C.  Returns false when the window cannot
+// slide (the caller then flushes all four nodes).
+__device__ __forceinline__ bool slide_row(const GridP& G, float4* __restrict__ dst, int cur, int next, int j, int k, float4 (&acc)[4], bool mark) {
+    const int d = next - cur;
+    if (d <= 0 || d >= 4 || (next & 1023) - (cur & 1023) != d) return false;
+    const int nj = cell_j(cur) - 1 + j, nk = cell_k(cur) - 1 + k;
+    const bool in_jk = nj >= 0 && nj < G.ny && nk >= 0 && nk < G.nz;
+    float4* row = dst + ((size_t)nk * G.ny + nj) * G.nx;
+    unsigned char* frow = G.flags + ((nk >> 3) * G.nby + (nj >> 3)) * G.nbx;
+    int ni = cell_i(cur) - 1;
+    for (int s = 0; s < d; ++s, ++ni) {
+        if (in_jk && ni >= 0 && ni < G.nx) {
+            atomicAdd(row + ni, acc[0]);
+            if (mark) frow[ni >> 3] = 1;
+        }
+        acc[0] = acc[1]; acc[1] = acc[2]; acc[2] = acc[3]; acc[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return true;
+}
+
 // warp-cooperative v1 mapping (2 nodes per lane), still used by the cloth kernels where runs have length 1
 __device__ __forceinline__ void flush_nodes(const GridP& G, float4* __restrict__ dst, int cell, int oi, int oj, int ok,
                                             const float4& a0, const float4& a1, bool mark) {
@@ -287,9 +311,12 @@ __device__ __forceinline__ float f4c(const float4& v, int i) { return i == 0 ? v
 // ================================================================================================ P2G
 // particleToGrid_ (HybridSolver.cpp:113-231): m_i = sum w m ; p_i = sum w m (v + (3/h^2) B (x_i - x_p)).
 // Per particle the momentum of node offset (i,j,k) is q0 + Qm (i,j,k)^T with Qm = m (3/h^2) B diag(h), q0 = m v - Qm (1+f).
+#ifndef AEP_STAGE_PAD
+#define AEP_STAGE_PAD 1
+#endif
 #define P2G_REC 7
 __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
-    __shared__ float4 stage[8][2][16 * P2G_REC + 1];                         // +1: the two half-warps read different banks in phase B
+    __shared__ float4 stage[8][2][16 * P2G_REC + AEP_STAGE_PAD];                         // +1: the two half-warps read different banks in phase B
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
     if (base >= n) return;                                                   // warp-uniform; no block-level barrier below
@@ -327,8 +354,11 @@ __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
         const float4 r6 = r[6];
         const int c = __float_as_int(r6.w);
         if (c != cur) {
-            flush_row(G, G.mp, cur, j, k, acc, true);
-            acc[0] = zero; acc[1] = zero; acc[2] = zero; acc[3] = zero; cur = c;
+            if (!slide_row(G, G.mp, cur, c, j, k, acc, true)) {
+                flush_row(G, G.mp, cur, j, k, acc, true);
+                acc[0] = zero; acc[1] = zero; acc[2] = zero; acc[3] = zero;
+            }
+            cur = c;
         }
         const float4 nx = r[0], mq = r[3], qa = r[4], qb = r[5];
         const float wy = reinterpret_cast<const float*>(r + 1)[j], wz = reinterpret_cast<const float*>(r + 2)[k];
@@ -437,7 +467,7 @@ __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, cons
 // grad v = sum_i v_i (grad w_i)^T, Fhat = (I + dt grad v) FE, SVD, stress, A = V_p P FE^T.  Phase B (half-warp per particle):
 // f_i -= A grad w_ip.
 __global__ void __launch_bounds__(256, 3) k_forces(PartP P, GridP G, MatParams mpar, const SimClock* __restrict__ clk, int n) {
-    __shared__ float4 stage[8][2][16 * FRC_REC + 1];
+    __shared__ float4 stage[8][2][16 * FRC_REC + AEP_STAGE_PAD];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
     if (base >= n) return;
@@ -480,8 +510,11 @@ __global__ void __launch_bounds__(256, 3) k_forces(PartP P, GridP G, MatParams m
         const float4 r8 = r[8];
         const int c = __float_as_int(r8.w);
         if (c != cur) {
-            flush_row(G, G.f, cur, j, k, acc, false);
-            acc[0] = zero; acc[1] = zero; acc[2] = zero; acc[3] = zero; cur = c;
+            if (!slide_row(G, G.f, cur, c, j, k, acc, false)) {
+                flush_row(G, G.f, cur, j, k, acc, false);
+                acc[0] = zero; acc[1] = zero; acc[2] = zero; acc[3] = zero;
+            }
+            cur = c;
         }
         const float4 nx = r[0], dx = r[1], A0 = r[6], A1 = r[7];
         const float2 yj = reinterpret_cast<const float2*>(r + 2)[j], zk = reinterpret_cast<const float2*>(r + 4)[k];
@@ -642,7 +675,7 @@ __global__ void __launch_bounds__(128, 4) k_g2p(PartP P, GridP G, MatParams mpar
     P.a[PQ0][p] = make_float4(FP[0], FP[1], FP[2], q0.w);
     P.a[PQ1][p] = make_float4(FP[3], FP[4], FP[5], q1.w);
     P.a[PQ2][p] = make_float4(FP[6], FP[7], FP[8], q2.w);
-    keys[p] = sort_key(ci, cj, ck, G.nqx, G.nqy);
+    keys[p] = sort_key(ci, cj, ck, G);
     vals[p] = (unsigned)p;
 }
 

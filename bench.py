@@ -217,7 +217,7 @@ def run_engine(args):
     t_gen = time.perf_counter() - t_gen
     shell = make_shell_scene(res)
     rate_floor = rate_floor_for(res)
-    eng = Engine(shell, device=local, dt_rate_floor=rate_floor, sort_every=args.sort_every)
+    eng = Engine(shell, device=local, dt_rate_floor=rate_floor, sort_every=args.sort_every, sort_bricks=args.sort_bricks)
     eng.upload_packed(n, arrs, sc.SAND_E, sc.SAND_NU, 2.5e-2, 7.5e-3)
     eng.init()
     stream = torch.cuda.ExternalStream(eng.stream, device=local)
@@ -292,6 +292,7 @@ def main():
     ap.add_argument("--ref-res", type=int, default=64, help="grid resolution of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="development: skip the e2e and cpu_baseline legs")
+    ap.add_argument("--sort-bricks", type=int, default=0, help="1: brick-major particle order (aep_config.sort_bricks), 0: cell-index order")
     ap.add_argument("--sort-every", type=int, default=1, help="physical re-sort period in substeps (aep_config.sort_every)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
