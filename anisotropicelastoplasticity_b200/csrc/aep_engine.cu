@@ -72,6 +72,11 @@ struct aep_ctx {
     // staging
     double* d_stage = nullptr; size_t stage_bytes = 0;
 
+    // adaptive re-sort: lagged, non-blocking readback of SimClock::sort_cost
+    static constexpr int RING = 4, LAG = 2;
+    float* h_ring = nullptr; cudaEvent_t ring_ev[RING] = {nullptr, nullptr, nullptr, nullptr};
+    long long step_counter = 0, last_sort_step = -1;
+
     bool profile = false; Timers tm{};
     bool inited = false;
 };
@@ -218,6 +223,8 @@ int do_sort(aep_ctx* c, bool build_keys) {
     LAUNCH_OK("k_reorder");
     c->cur ^= 1;
     if (slab && build_keys && c->pending_leave) { c->n -= c->pending_leave; c->pending_leave = 0; }   // leavers were sorted to the tail
+    cudaMemsetAsync(&c->d_clk->moved_since_sort, 0, 16, c->stream);                                    // moved_since_sort, sort_cost
+    c->steps_since_sort = 0; c->last_sort_step = c->step_counter;
     return AEP_OK;
 }
 
@@ -251,7 +258,7 @@ int do_forces(aep_ctx* c) {
     }
     if (c->n) {
         StageTimer T(c, AEP_STAGE_FORCES);
-        k_forces<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->P[c->cur], c->G, c->mat, c->d_clk, (int)c->n);
+        k_forces<<<cdiv(c->n, FRC_NT), FRC_NT, 0, c->stream>>>(c->P[c->cur], c->G, c->mat, c->d_clk, (int)c->n);
         LAUNCH_OK("k_forces");
     }
     if (c->mesh.nv) {
@@ -273,7 +280,7 @@ int do_grid(aep_ctx* c) {
 }
 
 int do_clock(aep_ctx* c) {
-    k_advance_clock<<<1, 1, 0, c->stream>>>(c->d_clk, c->fixed_dt);
+    k_advance_clock<<<1, 1, 0, c->stream>>>(c->d_clk, c->fixed_dt, (int)c->n);
     LAUNCH_OK("k_advance_clock");
     return AEP_OK;
 }
@@ -281,7 +288,7 @@ int do_clock(aep_ctx* c) {
 int do_g2p(aep_ctx* c) {
     if (c->n) {
         StageTimer T(c, AEP_STAGE_G2P);
-        k_g2p<<<cdiv(c->n, 128), 128, 0, c->stream>>>(c->P[c->cur], c->G, c->mat, c->d_clk, c->d_keys[0], c->d_vals[0], (int)c->n);
+        k_g2p<<<cdiv(c->n, G2P_NT), G2P_NT, 0, c->stream>>>(c->P[c->cur], c->G, c->mat, c->d_clk, c->d_keys[0], c->d_vals[0], (int)c->n);
         LAUNCH_OK("k_g2p");
     }
     if (c->mesh.nv) {
@@ -299,8 +306,24 @@ int do_substep(aep_ctx* c) {
     if ((r = do_g2p(c))) return r;          // HS:903-959
     // HS:963-983: weights at the new positions == re-binning.  Correctness never depends on the order (runs end on a cell
     // change, reductions are atomic); sorting only keeps runs long and gathers local, so it may be done every k-th substep.
-    c->steps_since_sort += 1;
-    if (c->cfg.sort_every <= 1 || c->steps_since_sort >= c->cfg.sort_every) { if ((r = do_sort(c, false))) return r; c->steps_since_sort = 0; }
+    c->steps_since_sort += 1; c->step_counter += 1;
+    bool sort_now;
+    if (c->cfg.sort_every >= 1) sort_now = c->steps_since_sort >= c->cfg.sort_every;
+    else {
+        // adaptive: sort_cost of this substep travels to a pinned ring without blocking; the decision uses the value of LAG substeps
+        // ago (waiting for it keeps the host at most LAG substeps ahead of the device, which never starves the GPU).
+        const int slot = (int)(c->step_counter % aep_ctx::RING);
+        cudaMemcpyAsync(&c->h_ring[slot], &c->d_clk->sort_cost, sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+        cudaEventRecord(c->ring_ev[slot], c->stream);
+        float cost = 0.0f;
+        const long long seen = c->step_counter - aep_ctx::LAG;
+        if (seen > c->last_sort_step && seen > 0) {
+            const int ps = (int)(seen % aep_ctx::RING);
+            cudaEventSynchronize(c->ring_ev[ps]); cost = c->h_ring[ps];
+        }
+        sort_now = cost >= (float)c->cfg.sort_cost_threshold || c->steps_since_sort >= 32;
+    }
+    if (sort_now && (r = do_sort(c, false))) return r;
     if ((r = do_p2g(c, false))) return r;   // HS:987
     return AEP_OK;
 }
@@ -325,7 +348,7 @@ int aep_default_config(aep_config* cfg) {
     cfg->cfl = 0.3; cfg->gravity = 9.8; cfg->collider_friction = 0.2; cfg->snow_hardening = 10.0;
     cfg->sand_h[0] = 35.0; cfg->sand_h[1] = 9.0; cfg->sand_h[2] = 0.2; cfg->sand_h[3] = 10.0;
     cfg->dt_rate_floor = 3e2; cfg->frame_dt = 1.0 / 60.0;
-    cfg->particle_capacity = 0; cfg->slab_axis = -1; cfg->slab_lo = 0; cfg->slab_hi = 0; cfg->sort_every = 1; cfg->sort_bricks = 0;
+    cfg->particle_capacity = 0; cfg->slab_axis = -1; cfg->slab_lo = 0; cfg->slab_hi = 0; cfg->sort_every = 0; cfg->sort_bricks = 0; cfg->sort_cost_threshold = 0.5;
     return AEP_OK;
 }
 
@@ -378,6 +401,8 @@ int aep_create(aep_ctx** out, const aep_config* cfg) {
     SimClock clk{}; clk.frame_dt = cfg->frame_dt; clk.cfl = cfg->cfl; clk.rate_floor = cfg->dt_rate_floor; clk.hmin = ctx->hmin;
     CUC(cudaMemcpyAsync(ctx->d_clk, &clk, sizeof clk, cudaMemcpyHostToDevice, ctx->stream));
     CUC(cudaEventCreate(&ctx->tm.ev[0])); CUC(cudaEventCreate(&ctx->tm.ev[1]));
+    CUC(cudaMallocHost((void**)&ctx->h_ring, aep_ctx::RING * sizeof(float)));
+    for (int i = 0; i < aep_ctx::RING; ++i) { ctx->h_ring[i] = 0.0f; CUC(cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming)); }
     {   // sort keys: (brick << 6) | cell-in-brick, see sort_key()
         const size_t nkeys = (size_t)G.nqx * G.nqy * ((G.nz + 3) / 4) * 64;
         ctx->key_bits = 1; while (((size_t)1 << ctx->key_bits) < nkeys) ctx->key_bits++;
@@ -396,6 +421,8 @@ int aep_destroy(aep_ctx* c) {
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->d_sort_tmp) cudaFree(c->d_sort_tmp);
     mesh_free(c->mesh);
+    if (c->h_ring) cudaFreeHost(c->h_ring);
+    for (int i = 0; i < aep_ctx::RING; ++i) if (c->ring_ev[i]) cudaEventDestroy(c->ring_ev[i]);
     if (c->tm.ev[0]) cudaEventDestroy(c->tm.ev[0]);
     if (c->tm.ev[1]) cudaEventDestroy(c->tm.ev[1]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -581,7 +608,7 @@ int aep_stage_forces(aep_ctx* c, double dt) { int r = require_init(c); if (r) re
 int aep_stage_grid(aep_ctx* c, double dt) {
     int r = require_init(c); if (r) return r; if ((r = aep_set_dt(c, dt))) return r;
     if ((r = do_grid(c))) return r;
-    k_advance_clock<<<1, 1, 0, c->stream>>>(c->d_clk, 2); LAUNCH_OK("k_advance_clock");   // latch vmax, keep dt
+    k_advance_clock<<<1, 1, 0, c->stream>>>(c->d_clk, 2, (int)c->n); LAUNCH_OK("k_advance_clock");   // latch vmax, keep dt
     return AEP_OK;
 }
 int aep_stage_g2p(aep_ctx* c, double dt) { int r = require_init(c); if (r) return r; if ((r = aep_set_dt(c, dt))) return r; return do_g2p(c); }

@@ -55,6 +55,11 @@ struct SimClock {
     unsigned long long escaped;        // particles that tried to leave the grid (clamped), sticky
     float vmax_last;
     int pad;
+    // adaptive re-sort (aep_config.sort_every == 0): particles that changed cell since the last physical sort, and the accumulated
+    // per-substep out-of-order fraction.  Reset together (16 bytes) when the particles are re-sorted.
+    unsigned long long moved_since_sort;
+    float sort_cost;
+    int pad2;
 };
 
 __device__ __forceinline__ int cell_i(int c) { return c & 1023; }
@@ -63,6 +68,7 @@ __device__ __forceinline__ int cell_k(int c) { return (c >> 20) & 1023; }
 __device__ __forceinline__ int cell_pack(int i, int j, int k) { return i | (j << 10) | (k << 20); }
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // per-axis stencil of a thread-owned particle: weights (masked to 0 outside the grid, HybridSolver.cpp:44-46)
 // and clamped node coordinates
@@ -221,10 +227,11 @@ __global__ void __launch_bounds__(256) k_grid_update(GridP G, SimClock* clk) {
 }
 
 // dt rule + frame clipping of HybridSolver.cpp:878-892, one thread, all in double like the reference
-__global__ void k_advance_clock(SimClock* clk, int fixed_dt) {
+__global__ void k_advance_clock(SimClock* clk, int fixed_dt, int n) {
     const float vmax = __uint_as_float(clk->vmax_bits);
     clk->vmax_last = vmax; clk->vmax_bits = 0u;
     if (fixed_dt == 2) return;                                   // stage-level API: only latch max|v|
+    clk->sort_cost += (float)clk->moved_since_sort / (float)max(n, 1);
     if (fixed_dt == 1) {                                         // pinned dt (aep_set_fixed_dt): plain time accumulation
         clk->inner_t += (double)clk->dt; clk->frame_flag = 0;
         if (clk->inner_t >= clk->frame_dt) { clk->inner_t -= clk->frame_dt; clk->t += clk->frame_dt; clk->frame_flag = 1; clk->frame_no += 1; }
@@ -427,31 +434,66 @@ __global__ void __launch_bounds__(256) k_grid_normalise(GridP G) {
     }
 }
 
+// ================================================================================================ shared grid tile for the gathers
+// A warp of 32 cell-sorted particles normally sits in one row of cells (same j,k; 4 cells along x at 8 particles per cell), so the
+// 64-node stencils of its particles live in a (cells+3) x 4 x 4 node box.  The warp stages that box of G.vt in its own slice of
+// shared memory with coalesced loads (all in flight at once) and every lane then gathers with LDS.128 instead of 64 dependent
+// L1/L2 round trips.  Warp-private tiles need no block barrier, so the warps of a CTA drift apart and overlap each other's load
+// and compute phases.  A warp whose particles do not fit the box (row wrap, sparse or unsorted particles, domain faces) takes
+// the global-memory path.
+#ifndef AEP_USE_TILE
+#define AEP_USE_TILE 1
+#endif
+#define TILE_W 12                       // nodes along x held by a warp's tile: up to 9 cells in a row
+#define TILE_SLACK 1                    // nodes left of lane 0's stencil (tolerates slightly out-of-order particles)
+#define TILE_F4 (16 * TILE_W)           // float4 per warp tile (16 (j,k) rows)
+struct TileRef {
+    int ox0, j0, k0;                    // node coordinates of tile[0]
+};
+// warp-uniform: decide whether the tile path applies and, if so, fill the warp's tile.  cell/complete describe the lane's particle.
+__device__ __forceinline__ bool stage_tile(const GridP& G, float4* __restrict__ tile, TileRef& T, int cell, bool complete) {
+    if (!AEP_USE_TILE) return false;
+    const int lane = threadIdx.x & 31;
+    const int cref = __shfl_sync(0xffffffffu, cell, 0);
+    T.ox0 = cell_i(cref) - 1 - TILE_SLACK; T.j0 = cell_j(cref) - 1; T.k0 = cell_k(cref) - 1;
+    const int ci = cell_i(cell);
+    const bool fits = complete && ((cell ^ cref) >> 10) == 0 && (ci - 1) >= T.ox0 && (ci + 2) < T.ox0 + TILE_W;
+    if (!__all_sync(0xffffffffu, fits)) return false;
+    // rows j0..j0+3, k0..k0+3 are inside the grid because every particle of the warp is `complete`; x is clipped to the grid
+#pragma unroll
+    for (int q = 0; q < TILE_F4 / 32; ++q) {
+        const int idx = lane + 32 * q;
+        const int r = idx / TILE_W, x = idx - r * TILE_W, gx = T.ox0 + x;
+        if (gx >= 0 && gx < G.nx) tile[idx] = ldg4(G.vt + ((size_t)(T.k0 + (r >> 2)) * G.ny + (T.j0 + (r & 3))) * G.nx + gx);
+    }
+    __syncwarp();
+    return true;
+}
+
 // ================================================================================================ forces
-// computeGridForces_, particle part (HybridSolver.cpp:252-368).  Phase A (thread per particle): gather
-// grad v = sum_i v_i (grad w_i)^T (x-direction summed first: 6 FMA per node + 9 per row), Fhat = (I + dt grad v) FE, SVD,
-// stress, A = V_p P FE^T.  Phase B (half-warp per particle): f_i -= A grad w_ip.
 #define FRC_REC 9
-// g[3r+c] = sum_i v_i[r] d_c w_i over the 4x4x4 stencil, x summed first.  INTERIOR: every stencil node is inside the grid, so the
-// four nodes of a row are 64 contiguous bytes at a fixed offset from the row pointer (no clamping, immediate-offset loads).
-template <bool INTERIOR>
-__device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, const Axis& ay, const Axis& az, float (&g)[9]) {
+// g[3r+c] = sum_i v_i[r] d_c w_i over the 4x4x4 stencil, x summed first.
+// MODE 0: clamped global loads (stencil cut by a domain face), 1: interior global loads (the four nodes of a row are 64 contiguous
+// bytes at immediate offsets), 2: loads from the CTA's shared tile (xoff = first stencil node relative to the tile).
+template <int MODE>
+__device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, const Axis& ay, const Axis& az, const float4* __restrict__ tile, int xoff,
+                                            float (&g)[9]) {
     int ni[4], nj[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) { ni[o] = INTERIOR ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = INTERIOR ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
-    const float4* base = G.vt + (INTERIOR ? ax.n0 : 0);
+    for (int o = 0; o < 4; ++o) { ni[o] = MODE ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = MODE ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
+    const float4* base = MODE == 2 ? tile + xoff : G.vt + (MODE == 1 ? ax.n0 : 0);
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
-        const int nk = INTERIOR ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
+        const int nk = MODE ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
         const float nzk = sel4(az.N, k), dzk = sel4(az.D, k);
-        const float4* plane = base + (size_t)nk * G.ny * G.nx;
+        const float4* plane = MODE == 2 ? base + k * 4 * TILE_W : base + (size_t)nk * G.ny * G.nx;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float4* row = plane + nj[j] * G.nx;
+            const float4* row = MODE == 2 ? plane + j * TILE_W : plane + nj[j] * G.nx;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float4 v = ldg4(row + ni[i]);
+                const float4 v = MODE == 2 ? row[i] : ldg4(row + ni[i]);
                 a0 = fmaf(v.x, ax.N[i], a0); a1 = fmaf(v.y, ax.N[i], a1); a2 = fmaf(v.z, ax.N[i], a2);
                 b0 = fmaf(v.x, ax.D[i], b0); b1 = fmaf(v.y, ax.D[i], b1); b2 = fmaf(v.z, ax.D[i], b2);
             }
@@ -466,11 +508,14 @@ __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, cons
 // computeGridForces_, particle part (HybridSolver.cpp:252-368).  Phase A (thread per particle): gather
 // grad v = sum_i v_i (grad w_i)^T, Fhat = (I + dt grad v) FE, SVD, stress, A = V_p P FE^T.  Phase B (half-warp per particle):
 // f_i -= A grad w_ip.
-__global__ void __launch_bounds__(256, 3) k_forces(PartP P, GridP G, MatParams mpar, const SimClock* __restrict__ clk, int n) {
-    __shared__ float4 stage[8][2][16 * FRC_REC + AEP_STAGE_PAD];
+#define FRC_NT 128
+__global__ void __launch_bounds__(FRC_NT, 6) k_forces(PartP P, GridP G, MatParams mpar, const SimClock* __restrict__ clk, int n) {
+    __shared__ float4 stage[FRC_NT / 32][2][16 * FRC_REC + AEP_STAGE_PAD];
+    __shared__ float4 tiles[FRC_NT / 32][TILE_F4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
-    if (base >= n) return;
+    float4* tile = tiles[wib];
+    const int base = ((blockIdx.x * FRC_NT + threadIdx.x) >> 5) * 32;
+    if (base >= n) return;                                                       // warp-uniform; no block-level barrier below
     const int cnt = min(32, n - base);
     const float dt = clk->dt;
     {   // ---- phase A
@@ -483,8 +528,10 @@ __global__ void __launch_bounds__(256, 3) k_forces(PartP P, GridP G, MatParams m
         complete &= axis_setup(ay, X.y, cell_j(cell), G.ny, G.ihy);
         complete &= axis_setup(az, X.z, cell_k(cell), G.nz, G.ihz);
         float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (__all_sync(0xffffffffu, complete)) gather_grad<true>(G, ax, ay, az, g);
-        else gather_grad<false>(G, ax, ay, az, g);
+        TileRef T;
+        if (stage_tile(G, tile, T, cell, complete)) gather_grad<2>(G, ax, ay, az, tile, ax.n0 - T.ox0, g);
+        else if (__all_sync(0xffffffffu, complete)) gather_grad<1>(G, ax, ay, az, tile, 0, g);
+        else gather_grad<0>(G, ax, ay, az, tile, 0, g);
         const float FE[9] = { e0.x, e0.y, e0.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z };
         float GF[9], Fh[9], A[9];
         mat_mul(g, FE, GF);
@@ -540,24 +587,25 @@ __global__ void __launch_bounds__(256, 3) k_forces(PartP P, GridP G, MatParams m
 struct G2PSums {
     float va[3], vc[3], B[9], g[9];
 };
-template <bool INTERIOR>
+template <int MODE>
 __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const Axis& ay, const Axis& az, const float (&nrx)[4],
-                                           const float (&rx)[4], const float (&ry)[4], const float (&rz)[4], G2PSums& S) {
+                                           const float (&rx)[4], const float (&ry)[4], const float (&rz)[4], const float4* __restrict__ tile, int xoff,
+                                           G2PSums& S) {
     int ni[4], nj[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) { ni[o] = INTERIOR ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = INTERIOR ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
-    const float4* base = G.vt + (INTERIOR ? ax.n0 : 0);
+    for (int o = 0; o < 4; ++o) { ni[o] = MODE ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = MODE ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
+    const float4* base = MODE == 2 ? tile + xoff : G.vt + (MODE == 1 ? ax.n0 : 0);
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
-        const int nk = INTERIOR ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
+        const int nk = MODE ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
         const float nzk = sel4(az.N, k), dzk = sel4(az.D, k), rzk = sel4(rz, k);
-        const float4* plane = base + (size_t)nk * G.ny * G.nx;
+        const float4* plane = MODE == 2 ? base + k * 4 * TILE_W : base + (size_t)nk * G.ny * G.nx;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float4* row = plane + nj[j] * G.nx;
+            const float4* row = MODE == 2 ? plane + j * TILE_W : plane + nj[j] * G.nx;
             float4 t[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) t[i] = ldg4(row + ni[i]);
+            for (int i = 0; i < 4; ++i) t[i] = MODE == 2 ? row[i] : ldg4(row + ni[i]);
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -593,12 +641,18 @@ __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const
 // advection x = sum w (x_i + dt v~_i) (:942-945), updateDeformationGradient_ (:553-578), updatePlasticity_
 // (:612-681), all in registers, one thread per particle.  The 64-node gather sums along x first (per (j,k) row:
 // a = sum v~ Nx, b = sum v~ Dx, c = sum s v~ Nx, d = sum s v~ Nx rx), then combines rows.  Writes the new sort key.
-__global__ void __launch_bounds__(128, 4) k_g2p(PartP P, GridP G, MatParams mpar, SimClock* __restrict__ clk,
+#define G2P_NT 128
+__global__ void __launch_bounds__(G2P_NT, 4) k_g2p(PartP P, GridP G, MatParams mpar, SimClock* __restrict__ clk,
                                              unsigned int* __restrict__ keys, unsigned int* __restrict__ vals, int n) {
-    const int p_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float4 tiles[G2P_NT / 32][TILE_F4];
+    float4* tile = tiles[threadIdx.x >> 5];
+    const int p_raw = blockIdx.x * G2P_NT + threadIdx.x;
     if ((p_raw & ~31) >= n) return;                                         // whole warp past the end
     const bool live = p_raw < n;                                            // tail lanes recompute the last particle and write nothing:
-    const int p = live ? p_raw : n - 1;                                     // the warp stays converged for the vote below
+    const int p = live ? p_raw : n - 1;                                     // the warp stays converged for the votes below
+    // the deformation gradients are needed only after the gather: pull their lines towards the SM now
+    prefetch_l1(P.a[PE0] + p); prefetch_l1(P.a[PE1] + p); prefetch_l1(P.a[PE2] + p);
+    prefetch_l1(P.a[PQ0] + p); prefetch_l1(P.a[PQ1] + p); prefetch_l1(P.a[PQ2] + p);
     const float dt = clk->dt;
     const float4 X = ldg4(P.a[PX] + p);
     const int cell = __float_as_int(X.w);
@@ -618,8 +672,10 @@ __global__ void __launch_bounds__(128, 4) k_g2p(PartP P, GridP G, MatParams mpar
     for (int i = 0; i < 3; ++i) { S.vc[i] = 0.f; S.va[i] = 0.f; }
 #pragma unroll
     for (int i = 0; i < 9; ++i) { S.B[i] = 0.f; S.g[i] = 0.f; }
-    if (__all_sync(0xffffffffu, complete)) g2p_gather<true>(G, ax, ay, az, nrx, rx, ry, rz, S);
-    else g2p_gather<false>(G, ax, ay, az, nrx, rx, ry, rz, S);
+    TileRef T;
+    if (stage_tile(G, tile, T, cell, complete)) g2p_gather<2>(G, ax, ay, az, nrx, rx, ry, rz, tile, ax.n0 - T.ox0, S);
+    else if (__all_sync(0xffffffffu, complete)) g2p_gather<1>(G, ax, ay, az, nrx, rx, ry, rz, tile, 0, S);
+    else g2p_gather<0>(G, ax, ay, az, nrx, rx, ry, rz, tile, 0, S);
     float (&va)[3] = S.va; float (&B)[9] = S.B; float (&g)[9] = S.g;
     const float vp[3] = { S.va[0] + S.vc[0], S.va[1] + S.vc[1], S.va[2] + S.vc[2] };       // sum w s v~ = sum w v~ - sum_{s=0} w v~
     // ---- advection (HybridSolver.cpp:944): x' = sum w (x_i + dt v~_i) = x + [sum w (x_i - x)] + (sum w - 1) x + dt sum w v~
@@ -662,8 +718,12 @@ __global__ void __launch_bounds__(128, 4) k_g2p(PartP P, GridP G, MatParams mpar
     return_map(mpar, Fh, FE, FP, q);
     const float Jp = mat_det(FP);
     // ---- write back
-    if (!live) return;
     const int ncell = cell_pack(ci, cj, ck);
+    {   // particles that left their cell are out of order until the next physical sort
+        const unsigned mv = __ballot_sync(0xffffffffu, live && ncell != cell);
+        if ((threadIdx.x & 31) == 0 && mv) atomicAdd(&clk->moved_since_sort, (unsigned long long)__popc(mv));
+    }
+    if (!live) return;
     P.a[PX][p] = make_float4(nfx, nfy, nfz, __int_as_float(ncell));
     P.a[PVM][p] = make_float4(vp[0], vp[1], vp[2], q1.w);
     P.a[PC0][p] = make_float4(B[0], B[1], B[2], 0.f);

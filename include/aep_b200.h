@@ -78,10 +78,13 @@ typedef struct aep_config {
     int32_t slab_axis;
     int32_t slab_lo;
     int32_t slab_hi;
-    int32_t sort_every;        /* physical re-sort period in substeps (1 = every substep)                    */
+    int32_t sort_every;        /* physical re-sort of the particle arrays: k >= 1 every k-th substep; 0 (default) adaptive: when the
+                                  accumulated out-of-order fraction (particles that changed cell since the last sort, summed over
+                                  substeps) reaches sort_cost_threshold, or after 32 substeps.  Results never depend on the order. */
     int32_t sort_bricks;       /* 0 (default): order particles by cell index, x fastest; 1: by 4x4x4-cell brick, then cell (better L1 hit rate
                                   of the gathers, but the scatters of one CTA then contend for the same L2 lines: measured slower overall) */
     int32_t _pad1;
+    double sort_cost_threshold; /* 0.5: the extra scatter work of unsorted particles has about paid for one re-sort       */
 } aep_config;
 
 AEP_API int aep_default_config(aep_config* cfg);
