@@ -42,7 +42,8 @@ SYMBOLS = (
     "aep_num_particles", "aep_download_particles", "aep_download_grid", "aep_download_mesh", "aep_download_positions_f32",
     "aep_stats", "aep_kernel_launches", "aep_stream", "aep_profile", "aep_get_timers", "aep_grid_activity", "aep_halo_info",
     "aep_halo_pack", "aep_halo_add", "aep_vmax_get", "aep_vmax_set", "aep_step_forces", "aep_step_grid", "aep_step_g2p",
-    "aep_step_p2g", "aep_migrate_extract", "aep_migrate_insert", "aep_set_particle_id_base", "aep_download_particles_local",
+    "aep_step_p2g", "aep_migrate_extract", "aep_migrate_insert", "aep_migrate_bind", "aep_migrate_extract_begin", "aep_migrate_extract_end",
+    "aep_step_p2g_arrivals", "aep_set_particle_id_base", "aep_download_particles_local",
 )
 
 
@@ -87,6 +88,10 @@ def load():
     L.aep_vmax_get.argtypes = [vp, vp]; L.aep_vmax_set.argtypes = [vp, vp]
     L.aep_migrate_extract.argtypes = [vp, vp, vp, C.c_int64, i64p, i64p]
     L.aep_migrate_insert.argtypes = [vp, vp, C.c_int64, vp, C.c_int64]
+    L.aep_migrate_bind.argtypes = [vp, vp, vp, C.c_int64, vp]
+    L.aep_migrate_extract_begin.argtypes = [vp]
+    L.aep_migrate_extract_end.argtypes = [vp, C.c_int64, C.c_int64]
+    L.aep_step_p2g_arrivals.argtypes = [vp, C.c_int64]
     L.aep_set_particle_id_base.argtypes = [vp, C.c_int64]
     L.aep_download_particles_local.argtypes = [vp, i64p] + [dp] * 9
     _LIB = L

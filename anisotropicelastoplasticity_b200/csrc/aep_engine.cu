@@ -43,7 +43,8 @@ struct aep_ctx {
 
     // grid
     GridP G{};
-    size_t Ng = 0; int nblocks = 0;
+    size_t Ng = 0; int nblocks = 0;             // all 8^3 blocks of the grid (flags array)
+    int nrun = 0;                                // blocks the grid passes run over (G.rb0 / G.rbn)
     double h[3]{}, hmin = 0;
     std::vector<void*> dev_allocs;
     unsigned char* d_ls_code = nullptr; float4* d_ls_nrm = nullptr;
@@ -59,6 +60,8 @@ struct aep_ctx {
     bool keys_valid = false;
     int steps_since_sort = 0;
     long long pending_leave = 0;                // particles extracted for migration, dropped at the next re-bin
+    MigList mig{};                              // leaver lists filled by k_g2p (aep_migrate_bind); axis < 0 when unbound
+    float4* mig_buf[2] = {nullptr, nullptr};    // caller-owned send buffers
     long long id_base = 0;
 
     // mesh
@@ -206,10 +209,10 @@ int do_sort(aep_ctx* c, bool build_keys) {
     const bool slab = c->cfg.slab_axis >= 0;
     int end_bit = c->key_bits;
     if (build_keys && slab) {
-        k_build_keys_slab<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur].a[PX], c->d_keys[0], c->d_vals[0], n, c->G,
+        k_build_keys_slab<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur].a[PX], c->P[c->cur].a[PQ1], c->d_keys[0], c->d_vals[0], n, c->G,
                                                               c->cfg.slab_axis, c->cfg.slab_lo, c->cfg.slab_hi, c->key_bits);
         LAUNCH_OK("k_build_keys_slab");
-        end_bit = c->key_bits + 1;
+        end_bit = c->key_bits + 2;
     } else if (build_keys) {
         k_build_keys<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur].a[PX], c->d_keys[0], c->d_vals[0], n, c->G);
         LAUNCH_OK("k_build_keys");
@@ -231,7 +234,7 @@ int do_sort(aep_ctx* c, bool build_keys) {
 int do_p2g(aep_ctx* c, bool first) {
     {
         StageTimer T(c, AEP_STAGE_P2G);
-        k_clear_blocks<<<c->nblocks, 256, 0, c->stream>>>(c->G);
+        k_clear_blocks<<<c->nrun, 256, 0, c->stream>>>(c->G);
         LAUNCH_OK("k_clear_blocks");
         if (c->n) {
             k_p2g<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->P[c->cur], c->G, (int)c->n);
@@ -253,7 +256,7 @@ int do_p2g(aep_ctx* c, bool first) {
 int do_forces(aep_ctx* c) {
     {   // v_i = p_i / m_i on the active blocks (also feeds the cloth-free case: cheap, <1% of a substep)
         StageTimer T(c, AEP_STAGE_GRID);
-        k_grid_normalise<<<c->nblocks, 256, 0, c->stream>>>(c->G);
+        k_grid_normalise<<<c->nrun, 256, 0, c->stream>>>(c->G);
         LAUNCH_OK("k_grid_normalise");
     }
     if (c->n) {
@@ -270,7 +273,7 @@ int do_forces(aep_ctx* c) {
 
 int do_grid(aep_ctx* c) {
     StageTimer T(c, AEP_STAGE_GRID);
-    k_grid_update<<<c->nblocks, 256, 0, c->stream>>>(c->G, c->d_clk);
+    k_grid_update<<<c->nrun, 256, 0, c->stream>>>(c->G, c->d_clk);
     LAUNCH_OK("k_grid_update");
     if (c->mesh.nv && c->mesh.n_fixed) {
         int r = mesh_pin(c->mesh, c->G, c->stream, &c->launches); if (r) return fail(c, AEP_ERR_CUDA, "mesh_pin failed");
@@ -288,7 +291,8 @@ int do_clock(aep_ctx* c) {
 int do_g2p(aep_ctx* c) {
     if (c->n) {
         StageTimer T(c, AEP_STAGE_G2P);
-        k_g2p<<<cdiv(c->n, G2P_NT), G2P_NT, 0, c->stream>>>(c->P[c->cur], c->G, c->mat, c->d_clk, c->d_keys[0], c->d_vals[0], (int)c->n);
+        if (c->mig.axis >= 0) cudaMemsetAsync(c->mig.counts, 0, 2 * sizeof(unsigned long long), c->stream);
+        k_g2p<<<cdiv(c->n, G2P_NT), G2P_NT, 0, c->stream>>>(c->P[c->cur], c->G, c->mat, c->d_clk, c->d_keys[0], c->d_vals[0], (int)c->n, c->mig);
         LAUNCH_OK("k_g2p");
     }
     if (c->mesh.nv) {
@@ -298,14 +302,9 @@ int do_g2p(aep_ctx* c) {
     return AEP_OK;
 }
 
-int do_substep(aep_ctx* c) {
-    int r;
-    if ((r = do_forces(c))) return r;       // HS:873  (dt of the previous iteration)
-    if ((r = do_grid(c))) return r;         // HS:877, 899
-    if ((r = do_clock(c))) return r;        // HS:878-892
-    if ((r = do_g2p(c))) return r;          // HS:903-959
-    // HS:963-983: weights at the new positions == re-binning.  Correctness never depends on the order (runs end on a cell
-    // change, reductions are atomic); sorting only keeps runs long and gathers local, so it may be done every k-th substep.
+// Re-sort policy (HS:963-983 rebuilds the weights every substep == re-binning; the physical order is only a performance matter).
+// build_keys: slab contexts derive the keys from the positions so that dead / out-of-slab slots sort behind the live particles.
+int maybe_sort(aep_ctx* c, bool build_keys) {
     c->steps_since_sort += 1; c->step_counter += 1;
     bool sort_now;
     if (c->cfg.sort_every >= 1) sort_now = c->steps_since_sort >= c->cfg.sort_every;
@@ -323,7 +322,24 @@ int do_substep(aep_ctx* c) {
         }
         sort_now = cost >= (float)c->cfg.sort_cost_threshold || c->steps_since_sort >= 32;
     }
-    if (sort_now && (r = do_sort(c, false))) return r;
+    // a slab context also compacts when dead slots (migrated particles) exceed 1/16 of the array
+    if (c->cfg.slab_axis >= 0 && c->pending_leave * 16 > c->n) sort_now = true;
+    return sort_now ? do_sort(c, build_keys) : AEP_OK;
+}
+int compact_slab(aep_ctx* c) {
+    if (c->cfg.slab_axis < 0 || c->pending_leave == 0 || !c->inited) return AEP_OK;
+    return do_sort(c, true);
+}
+
+int do_substep(aep_ctx* c) {
+    int r;
+    if ((r = do_forces(c))) return r;       // HS:873  (dt of the previous iteration)
+    if ((r = do_grid(c))) return r;         // HS:877, 899
+    if ((r = do_clock(c))) return r;        // HS:878-892
+    if ((r = do_g2p(c))) return r;          // HS:903-959
+    // HS:963-983: weights at the new positions == re-binning.  Correctness never depends on the order (runs end on a cell
+    // change, reductions are atomic); sorting only keeps runs long and gathers local, so it may be done every k-th substep.
+    if ((r = maybe_sort(c, false))) return r;
     if ((r = do_p2g(c, false))) return r;   // HS:987
     return AEP_OK;
 }
@@ -370,7 +386,7 @@ int aep_create(aep_ctx** out, const aep_config* cfg) {
     if (prop.major < 10) return fail(c, AEP_ERR_CUDA, "device %d is sm_%d%d; libaep_b200 is built for sm_100a only", cfg->device, prop.major, prop.minor);
 
     aep_ctx* ctx = new aep_ctx();
-    ctx->cfg = *cfg; ctx->device = cfg->device;
+    ctx->cfg = *cfg; ctx->device = cfg->device; ctx->mig.axis = -1;
     c = ctx;
     auto bail = [&](int code) { std::string m = ctx->err; aep_destroy(ctx); g_create_error = m; return code; };
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, AEP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(e_ == cudaErrorMemoryAllocation ? AEP_ERR_ALLOC : AEP_ERR_CUDA); } } while (0)
@@ -381,6 +397,16 @@ int aep_create(aep_ctx** out, const aep_config* cfg) {
     G.nbx = (G.nx + 7) / 8; G.nby = (G.ny + 7) / 8; G.nbz = (G.nz + 7) / 8;
     G.nqx = (G.nx + 3) / 4; G.nqy = (G.ny + 3) / 4; G.bricks = cfg->sort_bricks ? 1 : 0;
     ctx->nblocks = G.nbx * G.nby * G.nbz;
+    {   // grid passes visit the blocks this context can touch: everything, or the slab's node planes slab_lo-1 .. slab_hi+1
+        const int nb[3] = { G.nbx, G.nby, G.nbz };
+        for (int a = 0; a < 3; ++a) { G.rb0[a] = 0; G.rbn[a] = nb[a]; }
+        if (cfg->slab_axis >= 0 && cfg->slab_axis < 3) {
+            const int a = cfg->slab_axis;
+            const int lo = std::max(0, cfg->slab_lo - 1) >> 3, hi = std::min(cfg->res[a] - 1, cfg->slab_hi + 1) >> 3;
+            G.rb0[a] = lo; G.rbn[a] = std::max(1, hi - lo + 1);
+        }
+        ctx->nrun = G.rbn[0] * G.rbn[1] * G.rbn[2];
+    }
     ctx->Ng = (size_t)G.nx * G.ny * G.nz;
     for (int a = 0; a < 3; ++a) ctx->h[a] = (cfg->grid_max[a] - cfg->grid_min[a]) / cfg->res[a];      // RegularGrid.cpp:137-139
     ctx->hmin = std::min(ctx->h[0], std::min(ctx->h[1], ctx->h[2]));
@@ -452,7 +478,7 @@ int aep_upload_particles(aep_ctx* c, int64_t n, const double* x, const double* v
             for (int a = 0; a < P_NARR; ++a) CU(dalloc(c, &c->P[b].a[a], (size_t)cap));
         for (int b = 0; b < 2; ++b) { CU(dalloc(c, &c->d_keys[b], (size_t)cap)); CU(dalloc(c, &c->d_vals[b], (size_t)cap)); }
         size_t tmp = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], (int)cap, 0, c->key_bits + 1, c->stream);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], (int)cap, 0, c->key_bits + 2, c->stream);
         CU(cudaMalloc(&c->d_sort_tmp, tmp)); c->sort_tmp_bytes = tmp;
         c->cap = cap;
     }
@@ -546,7 +572,7 @@ int aep_init_begin(aep_ctx* c) {
 int aep_init_volumes(aep_ctx* c) {
     int r = require_init(c); if (r) return r;
     if (c->n) { k_init_volumes<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->P[c->cur], c->G, (int)c->n); LAUNCH_OK("k_init_volumes"); }   // HS:242-249
-    k_vmax_from_mp<<<c->nblocks, 256, 0, c->stream>>>(c->G, c->d_clk); LAUNCH_OK("k_vmax_from_mp");
+    k_vmax_from_mp<<<c->nrun, 256, 0, c->stream>>>(c->G, c->d_clk); LAUNCH_OK("k_vmax_from_mp");
     return AEP_OK;
 }
 int aep_init_dt(aep_ctx* c) {
@@ -623,14 +649,15 @@ int aep_get_clock(aep_ctx* c, double* dt, double* t, double* inner_t, int32_t* f
     return AEP_OK;
 }
 
-int64_t aep_num_particles(aep_ctx* c) { return c ? c->n : -1; }
+int64_t aep_num_particles(aep_ctx* c) { return c ? c->n - c->pending_leave : -1; }      // live particles (dead slots of a slab context excluded)
 
 int aep_download_particles(aep_ctx* c, double* x, double* v, double* B1, double* B2, double* B3, double* FE, double* FP, double* vol, double* q) {
     if (!c) return AEP_ERR_INVALID;
     cudaSetDevice(c->device);
+    int r = compact_slab(c); if (r) return r;
     const long long n = c->n; if (n == 0) return AEP_OK;
     const long long CH = 1 << 22;
-    int r = ensure_stage(c, (size_t)std::min(n, CH) * 36 * sizeof(double)); if (r) return r;
+    r = ensure_stage(c, (size_t)std::min(n, CH) * 36 * sizeof(double)); if (r) return r;
     for (long long p0 = 0; p0 < n; p0 += CH) {
         const long long cnt = std::min(CH, n - p0);
         double* st = c->d_stage;
@@ -653,8 +680,9 @@ int aep_download_particles(aep_ctx* c, double* x, double* v, double* B1, double*
 int aep_download_positions_f32(aep_ctx* c, float* xyz) {
     if (!c || !xyz) return AEP_ERR_INVALID;
     cudaSetDevice(c->device);
+    int r = compact_slab(c); if (r) return r;
     const long long n = c->n; if (n == 0) return AEP_OK;
-    int r = ensure_stage(c, (size_t)n * 3 * sizeof(float)); if (r) return r;
+    r = ensure_stage(c, (size_t)n * 3 * sizeof(float)); if (r) return r;
     k_download_positions_f32<<<cdiv(n, 256), 256, 0, c->stream>>>(c->P[c->cur], c->G, (float*)c->d_stage, (int)n, c->cfg.slab_axis >= 0 ? 1 : 0);
     LAUNCH_OK("k_download_positions_f32");
     CU(cudaMemcpyAsync(xyz, c->d_stage, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -704,7 +732,8 @@ int aep_stats(aep_ctx* c, double* com3, double* kinetic, double* mean_jp, double
     }
     if (com3) for (int a = 0; a < 3; ++a) com3[a] = h[5] > 0 ? h[a] / h[5] : 0.0;
     if (kinetic) *kinetic = h[3];
-    if (mean_jp) *mean_jp = c->n ? h[4] / (double)c->n : 0.0;
+    const long long live = c->n - c->pending_leave;
+    if (mean_jp) *mean_jp = live ? h[4] / (double)live : 0.0;
     if (mass) *mass = h[5];
     return AEP_OK;
 }
@@ -714,7 +743,7 @@ int aep_grid_activity(aep_ctx* c, int64_t* active_blocks, int64_t* active_nodes)
     cudaSetDevice(c->device);
     unsigned long long h[2] = {0, 0};
     CU(cudaMemsetAsync(c->d_stats, 0, 2 * sizeof(unsigned long long), c->stream));
-    k_count_active<<<c->nblocks, 256, 0, c->stream>>>(c->G, (unsigned long long*)c->d_stats);
+    k_count_active<<<c->nrun, 256, 0, c->stream>>>(c->G, (unsigned long long*)c->d_stats);
     LAUNCH_OK("k_count_active");
     CU(cudaMemcpyAsync(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
     if (active_blocks) *active_blocks = (int64_t)h[0];
@@ -746,7 +775,7 @@ int aep_step_g2p(aep_ctx* c) {
 }
 int aep_step_p2g(aep_ctx* c) {
     int r = require_init(c); if (r) return r;
-    if ((r = do_sort(c, true))) return r;
+    if ((r = maybe_sort(c, true))) return r;
     return do_p2g(c, false);
 }
 // halo exchange / migration entry points

@@ -43,15 +43,16 @@ __global__ void __launch_bounds__(256) k_halo_add(float4* __restrict__ arr, cons
 
 __device__ __forceinline__ int cell_axis(int cell, int axis) { return axis == 0 ? cell_i(cell) : (axis == 1 ? cell_j(cell) : cell_k(cell)); }
 
-// keys with particles that left the slab pushed behind every in-slab key
-__global__ void k_build_keys_slab(const float4* __restrict__ X, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals,
-                                  int n, GridP G, int axis, int lo, int hi, int key_bits) {
+// keys with dead slots (particles that migrated away: mass 0) and particles outside the slab pushed behind every live key
+__global__ void k_build_keys_slab(const float4* __restrict__ X, const float4* __restrict__ Q1, unsigned int* __restrict__ keys,
+                                  unsigned int* __restrict__ vals, int n, GridP G, int axis, int lo, int hi, int key_bits) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int c = __float_as_int(X[i].w);
     const int ca = cell_axis(c, axis);
     const unsigned key = sort_key(cell_i(c), cell_j(c), cell_k(c), G);
-    keys[i] = (ca < lo || ca >= hi) ? (key | (1u << key_bits)) : key;
+    // dead slots behind live particles that sit outside the slab (those are extracted by the next migration), both behind the slab's own
+    keys[i] = Q1[i].w == 0.0f ? (key | (3u << key_bits)) : ((ca < lo || ca >= hi) ? (key | (1u << key_bits)) : key);
     vals[i] = (unsigned)i;
 }
 
@@ -61,16 +62,39 @@ __global__ void __launch_bounds__(256) k_migrate_extract(PartP P, int n, int axi
     if (p >= n) return;
     const int ca = cell_axis(__float_as_int(P.a[PX][p].w), axis);
     if (ca >= lo && ca < hi) return;
+    float4 q1 = P.a[PQ1][p];
+    if (q1.w == 0.0f) return;                                             // dead slot: left earlier, waits for the next re-sort
     const int side = ca < lo ? 0 : 1;
     const unsigned long long slot = atomicAdd(counts + side, 1ull);
     if ((long long)slot >= cap) return;                                   // caller sees count > capacity and fails loudly
     float4* dst = (side == 0 ? to_low : to_high) + slot * P_NARR;
 #pragma unroll
     for (int a = 0; a < P_NARR; ++a) dst[a] = P.a[a][p];
+    // the slot stays in the arrays as a massless, volumeless tracer (scatters add exact zeros) until the next physical sort drops it
+    float4 vm = P.a[PVM][p]; vm.w = 0.0f; P.a[PVM][p] = vm;
+    float4 e0 = P.a[PE0][p]; e0.w = 0.0f; P.a[PE0][p] = e0;
+    q1.w = 0.0f; P.a[PQ1][p] = q1;
 }
 
-__global__ void __launch_bounds__(256) k_migrate_insert(PartP P, int n_old, const float4* __restrict__ buf, int cnt) {
+// listed leavers (MigList filled by k_g2p) -> records in the caller's send buffers; the slots become dead (see k_migrate_extract)
+__global__ void __launch_bounds__(256) k_migrate_gather(PartP P, MigList ML, float4* __restrict__ to_low, float4* __restrict__ to_high) {
+    const int per_side = (ML.cap + 255) / 256;
+    const int side = blockIdx.x / per_side;
+    const long long t = (long long)(blockIdx.x - side * per_side) * 256 + threadIdx.x;
+    const unsigned long long cnt = ML.counts[side];
+    if (t >= (long long)ML.cap || (unsigned long long)t >= cnt) return;
+    const unsigned p = (side == 0 ? ML.list[0] : ML.list[1])[t];
+    float4* dst = (side == 0 ? to_low : to_high) + (size_t)t * P_NARR;
+#pragma unroll
+    for (int a = 0; a < P_NARR; ++a) dst[a] = P.a[a][p];
+    float4 vm = P.a[PVM][p]; vm.w = 0.0f; P.a[PVM][p] = vm;
+    float4 e0 = P.a[PE0][p]; e0.w = 0.0f; P.a[PE0][p] = e0;
+    float4 q1 = P.a[PQ1][p]; q1.w = 0.0f; P.a[PQ1][p] = q1;
+}
+
+__global__ void __launch_bounds__(256) k_migrate_insert(PartP P, int n_old, const float4* __restrict__ buf, int cnt, SimClock* clk) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) atomicAdd(&clk->moved_since_sort, (unsigned long long)cnt);   // arrivals sit unsorted at the tail
     if (r >= cnt) return;
 #pragma unroll
     for (int a = 0; a < P_NARR; ++a) P.a[a][n_old + r] = buf[(size_t)r * P_NARR + a];

@@ -63,8 +63,8 @@ int aep_vmax_set(aep_ctx* c, const void* dev_float) {
 int aep_migrate_extract(aep_ctx* c, void* dev_to_low, void* dev_to_high, int64_t capacity, int64_t* n_low, int64_t* n_high) {
     int r = require_init(c); if (r) return r;
     if (c->cfg.slab_axis < 0) return fail(c, AEP_ERR_INVALID, "context has no slab");
-    if (n_low) *n_low = 0; if (n_high) *n_high = 0;
-    c->pending_leave = 0;
+    if (n_low) *n_low = 0;
+    if (n_high) *n_high = 0;
     if (c->n == 0) return AEP_OK;
     if (!dev_to_low || !dev_to_high || capacity < 0) return fail(c, AEP_ERR_INVALID, "null migration buffer");
     StageTimer T(c, AEP_STAGE_HALO);
@@ -78,7 +78,52 @@ int aep_migrate_extract(aep_ctx* c, void* dev_to_low, void* dev_to_high, int64_t
     if ((int64_t)h[0] > capacity || (int64_t)h[1] > capacity)
         return fail(c, AEP_ERR_STATE, "migration buffer too small: %llu / %llu particles leave, capacity %lld", h[0], h[1], (long long)capacity);
     if (n_low) *n_low = (int64_t)h[0]; if (n_high) *n_high = (int64_t)h[1];
-    c->pending_leave = (long long)(h[0] + h[1]);
+    c->pending_leave += (long long)(h[0] + h[1]);                           // dead slots until the next physical sort
+    return AEP_OK;
+}
+
+/* sync-free variant: k_g2p lists the leavers, extract_begin gathers them (no scan over all particles, no host round trip);
+ * the caller moves the counts (device int64[2]) wherever it wants and reports them back with extract_end. */
+int aep_migrate_bind(aep_ctx* c, void* dev_to_low, void* dev_to_high, int64_t capacity, void* dev_counts) {
+    if (!c) return AEP_ERR_INVALID;
+    if (c->cfg.slab_axis < 0) return fail(c, AEP_ERR_INVALID, "context has no slab");
+    if (!dev_to_low || !dev_to_high || !dev_counts || capacity <= 0 || capacity > (1 << 28)) return fail(c, AEP_ERR_INVALID, "bad migration buffers");
+    cudaSetDevice(c->device);
+    if (c->mig.axis >= 0) return fail(c, AEP_ERR_INVALID, "migration buffers are already bound");
+    for (int s = 0; s < 2; ++s) CU(dalloc(c, &c->mig.list[s], (size_t)capacity));
+    c->mig.cap = (int)capacity; c->mig.lo = c->cfg.slab_lo; c->mig.hi = c->cfg.slab_hi;
+    c->mig.counts = (unsigned long long*)dev_counts;
+    c->mig_buf[0] = (float4*)dev_to_low; c->mig_buf[1] = (float4*)dev_to_high;
+    CU(cudaMemsetAsync(dev_counts, 0, 2 * sizeof(unsigned long long), c->stream));
+    c->mig.axis = c->cfg.slab_axis;
+    return AEP_OK;
+}
+int aep_migrate_extract_begin(aep_ctx* c) {
+    int r = require_init(c); if (r) return r;
+    if (c->mig.axis < 0) return fail(c, AEP_ERR_INVALID, "aep_migrate_bind has not been called");
+    StageTimer T(c, AEP_STAGE_HALO);
+    k_migrate_gather<<<2 * cdiv(c->mig.cap, 256), 256, 0, c->stream>>>(c->P[c->cur], c->mig, c->mig_buf[0], c->mig_buf[1]);
+    LAUNCH_OK("k_migrate_gather");
+    return AEP_OK;
+}
+int aep_migrate_extract_end(aep_ctx* c, int64_t n_low, int64_t n_high) {
+    int r = require_init(c); if (r) return r;
+    if (n_low < 0 || n_high < 0) return fail(c, AEP_ERR_INVALID, "negative count");
+    if (n_low > c->mig.cap || n_high > c->mig.cap)
+        return fail(c, AEP_ERR_STATE, "migration buffer too small: %lld / %lld particles leave, capacity %d", (long long)n_low, (long long)n_high, c->mig.cap);
+    c->pending_leave += n_low + n_high;
+    return AEP_OK;
+}
+/* P2G of the last `count` slots only (particles appended by aep_migrate_insert after aep_step_p2g already ran): P2G is additive */
+int aep_step_p2g_arrivals(aep_ctx* c, int64_t count) {
+    int r = require_init(c); if (r) return r;
+    if (count < 0 || count > c->n) return fail(c, AEP_ERR_INVALID, "bad arrival count");
+    if (count == 0) return AEP_OK;
+    StageTimer T(c, AEP_STAGE_P2G);
+    PartP tail = c->P[c->cur];
+    for (int a = 0; a < P_NARR; ++a) tail.a[a] += (c->n - count);
+    k_p2g<<<cdiv(count, 256), 256, 0, c->stream>>>(tail, c->G, (int)count);
+    LAUNCH_OK("k_p2g");
     return AEP_OK;
 }
 
@@ -90,11 +135,11 @@ int aep_migrate_insert(aep_ctx* c, const void* dev_from_low, int64_t n_from_low,
                     c->cap, c->n, (long long)n_from_low, (long long)n_from_high);
     StageTimer T(c, AEP_STAGE_HALO);
     if (n_from_low) {
-        k_migrate_insert<<<cdiv(n_from_low, 256), 256, 0, c->stream>>>(c->P[c->cur], (int)c->n, (const float4*)dev_from_low, (int)n_from_low);
+        k_migrate_insert<<<cdiv(n_from_low, 256), 256, 0, c->stream>>>(c->P[c->cur], (int)c->n, (const float4*)dev_from_low, (int)n_from_low, c->d_clk);
         LAUNCH_OK("k_migrate_insert"); c->n += n_from_low;
     }
     if (n_from_high) {
-        k_migrate_insert<<<cdiv(n_from_high, 256), 256, 0, c->stream>>>(c->P[c->cur], (int)c->n, (const float4*)dev_from_high, (int)n_from_high);
+        k_migrate_insert<<<cdiv(n_from_high, 256), 256, 0, c->stream>>>(c->P[c->cur], (int)c->n, (const float4*)dev_from_high, (int)n_from_high, c->d_clk);
         LAUNCH_OK("k_migrate_insert"); c->n += n_from_high;
     }
     return AEP_OK;
@@ -110,9 +155,10 @@ int aep_download_particles_local(aep_ctx* c, int64_t* ids, double* x, double* v,
                                  double* vol, double* q) {
     if (!c) return AEP_ERR_INVALID;
     cudaSetDevice(c->device);
+    int r = compact_slab(c); if (r) return r;                             // drop dead slots so that exactly aep_num_particles entries come back
     const long long n = c->n; if (n == 0) return AEP_OK;
     const long long CH = 1 << 22;
-    int r = ensure_stage(c, (size_t)std::min(n, CH) * 37 * sizeof(double)); if (r) return r;
+    r = ensure_stage(c, (size_t)std::min(n, CH) * 37 * sizeof(double)); if (r) return r;
     for (long long p0 = 0; p0 < n; p0 += CH) {
         const long long cnt = std::min(CH, n - p0);
         double* st = c->d_stage; long long* dids = (long long*)(st + (size_t)35 * cnt);

@@ -31,6 +31,7 @@ struct GridP {
     int nx, ny, nz;
     int nbx, nby, nbz;                 // number of 8^3 node blocks per axis
     int nqx, nqy;                      // number of 4^3 cell bricks along x, y (sort order)
+    int rb0[3], rbn[3];                // 8^3-block range the grid passes run over (the whole grid, or the slab's reach)
     int bricks;                        // 1: brick-major sort keys, 0: plain cell index
     float hx, hy, hz, ihx, ihy, ihz;
     float mnx, mny, mnz;
@@ -62,6 +63,14 @@ struct SimClock {
     int pad2;
 };
 
+// slab decomposition: G2P appends the slots of particles whose new cell left [lo, hi) along `axis` to per-side index lists, so
+// that the migration step touches only the leavers instead of scanning every particle (axis < 0: not a slab / lists not bound)
+struct MigList {
+    int axis, lo, hi, cap;
+    unsigned int* list[2];
+    unsigned long long* counts;        // [2] (low, high), caller-owned device memory
+};
+
 __device__ __forceinline__ int cell_i(int c) { return c & 1023; }
 __device__ __forceinline__ int cell_j(int c) { return (c >> 10) & 1023; }
 __device__ __forceinline__ int cell_k(int c) { return (c >> 20) & 1023; }
@@ -91,6 +100,11 @@ __device__ __forceinline__ bool axis_setup(Axis& a, float f, int cell, int nres,
     return complete;
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// CTA index of a grid pass -> block coordinates inside the run range, and the flat block index (flags)
+__device__ __forceinline__ int run_block(const GridP& G, int r, int& bx, int& by, int& bz) {
+    bx = G.rb0[0] + r % G.rbn[0]; by = G.rb0[1] + (r / G.rbn[0]) % G.rbn[1]; bz = G.rb0[2] + r / (G.rbn[0] * G.rbn[1]);
+    return (bz * G.nby + by) * G.nbx + bx;
+}
 
 // ================================================================================================ sort keys
 // Particles are ordered by 4x4x4-cell brick (x fastest), then by cell inside the brick (x fastest).  A CTA of 256 consecutive
@@ -126,9 +140,9 @@ __global__ void __launch_bounds__(256) k_reorder(PartP src, PartP dst, const uns
 // ================================================================================================ grid passes
 // zero (m,p) and f of every block that the previous P2G touched, and drop its flag
 __global__ void __launch_bounds__(256) k_clear_blocks(GridP G) {
-    const int b = blockIdx.x;
+    int bx, by, bz;
+    const int b = run_block(G, blockIdx.x, bx, by, bz);
     if (!G.flags[b]) return;
-    const int bx = b % G.nbx, by = (b / G.nbx) % G.nby, bz = b / (G.nbx * G.nby);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -159,9 +173,9 @@ __device__ __forceinline__ void block_max_to_clock(float v, SimClock* clk) {
 
 // max |p/m| over active nodes: RegularGrid::CFL_condition for the initial dt (HybridSolver.cpp:860)
 __global__ void __launch_bounds__(256) k_vmax_from_mp(GridP G, SimClock* clk) {
-    const int b = blockIdx.x;
+    int bx, by, bz;
+    const int b = run_block(G, blockIdx.x, bx, by, bz);
     if (!G.flags[b]) return;
-    const int bx = b % G.nbx, by = (b / G.nbx) % G.nby, bz = b / (G.nbx * G.nby);
     float vm = 0.0f;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -182,9 +196,9 @@ __global__ void __launch_bounds__(256) k_vmax_from_mp(GridP G, SimClock* clk) {
 // updateGridVelocities_ (HybridSolver.cpp:725-737) + gravity (:457) + max|v| (RegularGrid.cpp:188-200)
 // + gridCollisionHandling_ level-set part (:467-511), one coalesced float4 pass over the active blocks.
 __global__ void __launch_bounds__(256) k_grid_update(GridP G, SimClock* clk) {
-    const int b = blockIdx.x;
+    int bx, by, bz;
+    const int b = run_block(G, blockIdx.x, bx, by, bz);
     if (!G.flags[b]) return;                                    // uniform per CTA
-    const int bx = b % G.nbx, by = (b / G.nbx) % G.nby, bz = b / (G.nbx * G.nby);
     const float dt = clk->dt;
     float vm = 0.0f;
 #pragma unroll
@@ -418,9 +432,9 @@ __global__ void __launch_bounds__(256) k_init_volumes(PartP P, GridP G, int n) {
 // v_i = p_i / m_i where m_i > 0 (HybridSolver.cpp:233-240) for every active node, into the vt array (free between P2G and
 // the grid update), so that the force gather below does 64 loads and no divisions per particle.
 __global__ void __launch_bounds__(256) k_grid_normalise(GridP G) {
-    const int b = blockIdx.x;
+    int bx, by, bz;
+    const int b = run_block(G, blockIdx.x, bx, by, bz);
     if (!G.flags[b]) return;
-    const int bx = b % G.nbx, by = (b / G.nbx) % G.nby, bz = b / (G.nbx * G.nby);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int t = threadIdx.x + 256 * h;
@@ -643,7 +657,7 @@ __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const
 // a = sum v~ Nx, b = sum v~ Dx, c = sum s v~ Nx, d = sum s v~ Nx rx), then combines rows.  Writes the new sort key.
 #define G2P_NT 128
 __global__ void __launch_bounds__(G2P_NT, 4) k_g2p(PartP P, GridP G, MatParams mpar, SimClock* __restrict__ clk,
-                                             unsigned int* __restrict__ keys, unsigned int* __restrict__ vals, int n) {
+                                             unsigned int* __restrict__ keys, unsigned int* __restrict__ vals, int n, MigList ML) {
     __shared__ float4 tiles[G2P_NT / 32][TILE_F4];
     float4* tile = tiles[threadIdx.x >> 5];
     const int p_raw = blockIdx.x * G2P_NT + threadIdx.x;
@@ -737,6 +751,14 @@ __global__ void __launch_bounds__(G2P_NT, 4) k_g2p(PartP P, GridP G, MatParams m
     P.a[PQ2][p] = make_float4(FP[6], FP[7], FP[8], q2.w);
     keys[p] = sort_key(ci, cj, ck, G);
     vals[p] = (unsigned)p;
+    if (ML.axis >= 0 && q1.w != 0.0f) {                                     // live particle of a slab context: did it leave the slab?
+        const int ca = ML.axis == 0 ? ci : (ML.axis == 1 ? cj : ck);
+        if (ca < ML.lo || ca >= ML.hi) {
+            const int side = ca < ML.lo ? 0 : 1;
+            const unsigned long long slot = atomicAdd(ML.counts + side, 1ull);
+            if (slot < (unsigned long long)ML.cap) (side == 0 ? ML.list[0] : ML.list[1])[slot] = (unsigned)p;
+        }
+    }
 }
 
 // ================================================================================================ host <-> device
@@ -847,9 +869,9 @@ __global__ void k_download_grid(GridP G, double* __restrict__ m, double* __restr
 
 // active blocks / nodes with mass (roofline accounting)
 __global__ void __launch_bounds__(256) k_count_active(GridP G, unsigned long long* __restrict__ out2) {
-    const int b = blockIdx.x;
+    int bx, by, bz;
+    const int b = run_block(G, blockIdx.x, bx, by, bz);
     if (!G.flags[b]) return;
-    const int bx = b % G.nbx, by = (b / G.nbx) % G.nby, bz = b / (G.nbx * G.nby);
     int cnt = 0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -874,7 +896,7 @@ __global__ void __launch_bounds__(256) k_stats(PartP P, GridP G, double* __restr
         acc[1] += m * ((double)G.mny + ((double)cell_j(cell) + X.y) * (double)G.hy);
         acc[2] += m * ((double)G.mnz + ((double)cell_k(cell) + X.z) * (double)G.hz);
         acc[3] += 0.5 * m * ((double)VM.x * VM.x + (double)VM.y * VM.y + (double)VM.z * VM.z);
-        acc[4] += (double)P.a[PE2][s].w;
+        acc[4] += m > 0.0 ? (double)P.a[PE2][s].w : 0.0;          // dead slots of a slab context carry no mass and are not counted
         acc[5] += m;
     }
 #pragma unroll

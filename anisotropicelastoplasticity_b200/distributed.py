@@ -85,6 +85,12 @@ class GpuSlabBackend:
         self.mig_recv = [torch.zeros((self.mig_cap, MIGRATE_FLOATS), dtype=torch.float32, device=self.device) for _ in range(2)]
         self.vmax = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.count_dtype = torch.int64
+        # sync-free migration: k_g2p lists the leavers, counts live in device memory owned here
+        self.mig_counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.mig_counts_in = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.mig_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+        self._ck(self.L.aep_migrate_bind(self.h, C.c_void_p(self.mig_send[0].data_ptr()), C.c_void_p(self.mig_send[1].data_ptr()), self.mig_cap,
+                                         C.c_void_p(self.mig_counts.data_ptr())))
 
     def _ck(self, rc): self.capi.check(rc, self.h)
     # stepping
@@ -112,6 +118,22 @@ class GpuSlabBackend:
         self._ck(self.L.aep_migrate_extract(self.h, C.c_void_p(self.mig_send[0].data_ptr()), C.c_void_p(self.mig_send[1].data_ptr()),
                                             self.mig_cap, C.byref(nl), C.byref(nh)))
         return self.mig_send[0][:nl.value], self.mig_send[1][:nh.value]
+    def migrate_begin(self):
+        """Gather the leavers k_g2p listed into the send buffers; returns (counts_out, counts_in) device int64[2] tensors."""
+        self._ck(self.L.aep_migrate_extract_begin(self.h))
+        return self.mig_counts, self.mig_counts_in
+    def migrate_counts_to_host(self):
+        """Enqueue the D2H copy of (out_low, out_high, in_low, in_high) and return an event to wait on later."""
+        torch = self.torch
+        self.mig_host.copy_(torch.cat([self.mig_counts, self.mig_counts_in]), non_blocking=True)
+        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream(self.device))
+        return ev
+    def migrate_end(self, ev):
+        ev.synchronize()
+        ol, oh, il, ih = (int(v) for v in self.mig_host.tolist())
+        self._ck(self.L.aep_migrate_extract_end(self.h, ol, oh))
+        return (self.mig_send[0][:ol], self.mig_send[1][:oh]), (il, ih)
+    def step_p2g_arrivals(self, count): self._ck(self.L.aep_step_p2g_arrivals(self.h, int(count)))
     def migrate_recv_buffer(self, side, n):
         if n > self.mig_cap:
             raise RuntimeError(f"migration receive capacity {self.mig_cap} < {n}")
@@ -120,6 +142,14 @@ class GpuSlabBackend:
         self._ck(self.L.aep_migrate_insert(self.h, C.c_void_p(from_low.data_ptr()) if from_low.numel() else None, from_low.shape[0],
                                            C.c_void_p(from_high.data_ptr()) if from_high.numel() else None, from_high.shape[0]))
     def sync(self): self.e.sync()
+
+    def close(self):
+        """Drop every tensor that was used on the engine's stream BEFORE the engine (and with it the stream) is destroyed: torch's
+        pinned-memory allocator records an event on that stream when such a tensor is freed."""
+        self.e.sync(); self.torch.cuda.synchronize(self.device)
+        self.halo_send = self.halo_recv = self.mig_send = self.mig_recv = None
+        self.vmax = self.mig_counts = self.mig_counts_in = self.mig_host = None
+        self.stream = None
 
     def particles_local(self):
         from .scenes import from_colmajor, mats_from_colmajor
@@ -201,6 +231,40 @@ class SlabSolver:
         self.b.migrate_insert(bufs[0], bufs[1])
         self.stats["migrated"] += out[0].shape[0] + out[1].shape[0]
 
+    def migrate_overlapped(self):
+        """Migration whose host round trip hides behind the P2G of the resident particles:
+        gather leavers | exchange counts (device to device) | counts to host, async | re-sort policy + P2G (resident) |
+        wait for the counts | exchange records | append | P2G (arrivals only)."""
+        dist = self.dist; b = self.b
+        c_out, c_in = b.migrate_begin()
+        ops = []
+        for side in (0, 1):
+            nb = self.nb[side]
+            if nb is None:
+                continue
+            ops.append(dist.P2POp(dist.isend, c_out[side:side + 1], nb, group=self.group)); ops.append(dist.P2POp(dist.irecv, c_in[side:side + 1], nb, group=self.group))
+        self._batch(ops)
+        ev = b.migrate_counts_to_host()
+        b.step_p2g()
+        out, counts_in = b.migrate_end(ev)
+        ops = []; bufs = {}
+        for side in (0, 1):
+            nb = self.nb[side]
+            n_in = counts_in[side] if nb is not None else 0
+            bufs[side] = b.migrate_recv_buffer(side, n_in)
+            if nb is None:
+                if out[side].shape[0]:
+                    raise RuntimeError(f"rank {self.rank}: {out[side].shape[0]} particles left the domain through side {side}")
+                continue
+            if out[side].shape[0]:
+                ops.append(dist.P2POp(dist.isend, out[side], nb, group=self.group))
+            if n_in:
+                ops.append(dist.P2POp(dist.irecv, bufs[side], nb, group=self.group))
+        self._batch(ops)
+        b.migrate_insert(bufs[0], bufs[1])
+        b.step_p2g_arrivals(bufs[0].shape[0] + bufs[1].shape[0])
+        self.stats["migrated"] += out[0].shape[0] + out[1].shape[0]
+
     def init(self):
         self.b.init_begin(); self.halo(0); self.b.init_volumes(); self.allreduce_vmax(); self.b.init_dt()
 
@@ -208,8 +272,12 @@ class SlabSolver:
         b = self.b
         b.step_forces(); self.halo(1)
         b.step_grid(); self.allreduce_vmax()
-        b.step_g2p(); self.migrate()
-        b.step_p2g(); self.halo(0)
+        b.step_g2p()
+        if hasattr(b, "migrate_begin"):
+            self.migrate_overlapped()
+        else:
+            self.migrate(); b.step_p2g()
+        self.halo(0)
 
     def run(self, n):
         for _ in range(n):
@@ -221,8 +289,10 @@ class LocalSlabGroup:
     """Several slabs stepped in lockstep inside one process (all on one GPU, or on the CPU test backend): the exchange is a
     direct buffer copy.  Same backend calls, same order as SlabSolver."""
 
-    def __init__(self, backends: List, plan: SlabPlan):
+    def __init__(self, backends: List, plan: SlabPlan, overlapped: Optional[bool] = None):
         self.bs = backends; self.plan = plan; self.world = plan.world
+        # overlapped: use the sync-free migration entry points (leaver lists from G2P, P2G split into resident + arrivals)
+        self.overlapped = all(hasattr(b, "migrate_begin") for b in backends) if overlapped is None else overlapped
 
     def _fence(self):
         """Every backend enqueues on its own non-blocking stream while the buffer swaps below run on torch's current stream:
@@ -282,6 +352,40 @@ class LocalSlabGroup:
             self._fence()
             b.migrate_insert(parts[0], parts[1])
 
+    def _migrate_overlapped(self):
+        cs = [b.migrate_begin() for b in self.bs]
+        self._fence()
+        for r, b in enumerate(self.bs):
+            for side in (0, 1):
+                nb = r - 1 if side == 0 else r + 1
+                if 0 <= nb < self.world:
+                    cs[r][1][side] = cs[nb][0][1 - side]
+                else:
+                    cs[r][1][side] = 0
+        self._fence()
+        evs = [b.migrate_counts_to_host() for b in self.bs]
+        self._fence()
+        for b in self.bs: b.step_p2g()
+        ends = [b.migrate_end(ev) for b, ev in zip(self.bs, evs)]
+        self._fence()
+        outs = [tuple(t.clone() for t in e[0]) for e in ends]
+        self._fence()
+        for r, b in enumerate(self.bs):
+            parts = []
+            for side in (0, 1):
+                nb = r - 1 if side == 0 else r + 1
+                if 0 <= nb < self.world:
+                    src = outs[nb][1 - side]
+                    assert src.shape[0] == ends[r][1][side]
+                    buf = b.migrate_recv_buffer(side, src.shape[0]); buf.copy_(src)
+                else:
+                    assert outs[r][side].shape[0] == 0, "particles left the domain"
+                    buf = b.migrate_recv_buffer(side, 0)
+                parts.append(buf)
+            self._fence()
+            b.migrate_insert(parts[0], parts[1])
+            b.step_p2g_arrivals(parts[0].shape[0] + parts[1].shape[0])
+
     def init(self):
         for b in self.bs: b.init_begin()
         self._halo(0)
@@ -295,8 +399,11 @@ class LocalSlabGroup:
         for b in self.bs: b.step_grid()
         self._vmax()
         for b in self.bs: b.step_g2p()
-        self._migrate()
-        for b in self.bs: b.step_p2g()
+        if self.overlapped:
+            self._migrate_overlapped()
+        else:
+            self._migrate()
+            for b in self.bs: b.step_p2g()
         self._halo(0)
 
     def run(self, n):
@@ -367,7 +474,8 @@ def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, U
     rate_floor = B.rate_floor_for(res)
 
     def build():
-        eng = Engine(shell, device=local, particle_capacity=int(1.25 * n_local + 65536), slab=plan.slab(rank), dt_rate_floor=rate_floor)
+        eng = Engine(shell, device=local, particle_capacity=int(1.25 * n_local + 65536), slab=plan.slab(rank), dt_rate_floor=rate_floor,
+                     sort_every=args.sort_every)
         from . import capi
         capi.check(eng.L.aep_set_particle_id_base(eng.h, id_base), eng.h)
         eng.upload_packed(n_local, arrs, sc.SAND_E, sc.SAND_NU, 2.5e-2, 7.5e-3)
@@ -412,7 +520,7 @@ def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, U
                 "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs_per_gpu": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes}}
     halo_bytes = solver.stats["halo_bytes"]; migrated = solver.stats["migrated"]
     # e2e: fresh contexts, upload from pinned host memory + init + K substeps + f32 positions back, wall clock max over ranks
-    eng.close(); del eng, be, solver
+    be.close(); del solver, be; eng.close(); del eng
     out_t = torch.empty((int(1.25 * n_local + 65536), 3), dtype=torch.float32, pin_memory=True)
     dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
     eng, be, solver = build()
@@ -425,7 +533,7 @@ def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, U
     e2e = {"value": n_total * args.steps / float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": 36 * 8 * n_total / args.steps,
            "d2h_bytes_per_step": 12 * n_total / args.steps, "seconds": float(t_e2e.item()),
            "what": "per rank: aep_create + aep_upload_particles(fp64 host, pinned) + init + K substeps (halo/migration over NCCL) + f32 positions"}
-    eng.close()
+    be.close(); del solver, be; eng.close()
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

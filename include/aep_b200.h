@@ -205,6 +205,16 @@ AEP_API int aep_step_p2g(aep_ctx* ctx);   /* re-bin (drops particles that left t
 #define AEP_MIGRATE_FLOATS 44
 AEP_API int aep_migrate_extract(aep_ctx* ctx, void* dev_to_low, void* dev_to_high, int64_t capacity, int64_t* n_low, int64_t* n_high);
 AEP_API int aep_migrate_insert(aep_ctx* ctx, const void* dev_from_low, int64_t n_from_low, const void* dev_from_high, int64_t n_from_high);
+/* Sync-free migration.  bind once: caller-owned device send buffers (capacity records each) and a device int64[2] for the
+ * (low, high) leaver counts.  From then on aep_step_g2p lists the leavers while it advects them; extract_begin gathers the
+ * listed particles into the send buffers (their slots stay behind as massless dead slots until the next re-sort) without any
+ * host synchronisation; the caller ships the counts and records, then reports the counts it read back with extract_end.
+ * aep_step_p2g may run between begin and end (it overlaps the count round trip); particles appended afterwards by
+ * aep_migrate_insert are transferred with aep_step_p2g_arrivals (P2G is additive).                                        */
+AEP_API int aep_migrate_bind(aep_ctx* ctx, void* dev_to_low, void* dev_to_high, int64_t capacity, void* dev_counts_i64x2);
+AEP_API int aep_migrate_extract_begin(aep_ctx* ctx);
+AEP_API int aep_migrate_extract_end(aep_ctx* ctx, int64_t n_low, int64_t n_high);
+AEP_API int aep_step_p2g_arrivals(aep_ctx* ctx, int64_t count);
 /* ids of uploaded particles are id_base + index (default 0); set before aep_upload_particles on each rank.      */
 AEP_API int aep_set_particle_id_base(aep_ctx* ctx, int64_t id_base);
 /* download in the context's current (cell-sorted) order together with the global ids; arrays sized aep_num_particles */

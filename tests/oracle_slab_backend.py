@@ -120,6 +120,24 @@ class OracleSlabBackend:
         self.ids = self.ids[keep]
         return out[0], out[1]
 
+    # overlapped-migration interface of SlabSolver (the GPU backend hides the count round trip behind the resident P2G; here the
+    # order of the same operations is simply kept)
+    def migrate_begin(self):
+        self._mig_out = self.migrate_extract()
+        self._c_out = torch.tensor([self._mig_out[0].shape[0], self._mig_out[1].shape[0]], dtype=torch.int64)
+        self._c_in = torch.zeros(2, dtype=torch.int64)
+        self._defer_p2g = True
+        return self._c_out, self._c_in
+
+    def migrate_counts_to_host(self): return None
+
+    def migrate_end(self, ev):
+        return self._mig_out, (int(self._c_in[0]), int(self._c_in[1]))
+
+    def step_p2g_arrivals(self, count):
+        self._defer_p2g = False
+        self.step_p2g()
+
     def migrate_recv_buffer(self, side, n): return torch.zeros((n, REC), dtype=torch.float64)
 
     def migrate_insert(self, a, b):
@@ -135,6 +153,8 @@ class OracleSlabBackend:
             P.vol = np.concatenate([P.vol, r[:, 35]]); P.q = np.concatenate([P.q, r[:, 36]])
 
     def step_p2g(self):
+        if getattr(self, "_defer_p2g", False):
+            return                                               # the whole P2G happens after the arrivals are appended
         self.o.set_particles(self.P); self.o.rebuild_weights(); self.o.p2g(False)
 
     def sync(self): pass

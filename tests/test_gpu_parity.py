@@ -132,32 +132,37 @@ def test_200_substeps_pinned_dt(name, dt):
 
 @pytest.mark.parametrize("name,frames", [("sand_c1_32", 4), ("snow_c2_32", 4)])
 def test_adaptive_dt_bulk_statistics(name, frames):
-    """>= 200 substeps of the reference's own loop (adaptive dt, HybridSolver.cpp:878-892), compared at EQUAL SIMULATED TIME
-    (a frame boundary, which both runs hit exactly).  The adaptive rule feeds on max|v_i| over near-massless grid nodes, which
-    makes the reference itself chaotic: two fp64 oracle runs whose inputs differ only by float32 rounding of x end up with
-    different dt sequences and (for the snow impact) kinetic energies 5-9% apart after ~200 substeps.  The gate is therefore
-    1%, widened to 4x the reference's own float32-input sensitivity where that is larger (measured here, not assumed)."""
+    """>= 100 substeps of the reference's own loop (adaptive dt, HybridSolver.cpp:878-892), compared at EQUAL SIMULATED TIME
+    (a frame boundary, which every run hits exactly).  The adaptive rule feeds on max|v_i| over near-massless grid nodes, which
+    makes the reference itself chaotic: fp64 oracle runs that differ only in summation order (1 thread vs all threads) or by a
+    1e-7 relative perturbation of x take 157..189 substeps for the same 4 frames and end with kinetic energies 75..86 and plastic
+    volume changes -0.7e-3..-6.0e-3 (snow impact, measured).  So the gate is: centre of mass within 1%; kinetic energy and
+    mean det F_P within 1% of the oracle ensemble mean, widened to 3x the ensemble's own largest deviation from its mean.
+    The strict long-run statement is test_200_substeps_pinned_dt above."""
     from anisotropicelastoplasticity_b200.scenes import bulk_stats
-    scene = _scenes()[name](); twin = _scenes()[name]()
-    twin.particles.x = twin.particles.x.astype(np.float32).astype(np.float64)
+    scene = _scenes()[name]()
     e = _engine(scene); e.init()
     nsub = e.run_frames(frames)
     st = e.stats(); c = e.clock()
-    stats = []
-    for sc_ in (scene, twin):
-        o = _oracle(sc_); o.init(); n = 0
+    from oracle.oracle_py import Oracle
+    members = []
+    for seed, threads in ((0, 1), (0, 0), (1, 0), (2, 0)):
+        sc_ = _scenes()[name]()
+        if seed:
+            sc_.particles.x = sc_.particles.x * (1.0 + 1e-7 * np.random.default_rng(seed).standard_normal(sc_.particles.x.shape))
+        o = Oracle(sc_, threads=threads); o.init(); n = 0
         while o.frame < frames:
             o.substep(); n += 1
         po = o.particles()
-        stats.append(bulk_stats(po["x"], po["v"], sc_.particles.m, po["FP"]) + (n,))
-    (com, ke, jp, n_a), (com_b, ke_b, jp_b, n_b) = stats
-    assert c["frame"] == frames and c["escaped"] == 0 and nsub >= 100 and abs(c["inner_t"]) < 1e-12     # dt sequence is chaotic: 146..196 seen
-    band_ke = max(0.01, 4 * abs(ke_b - ke) / ke); band_jp = max(0.01, 4 * abs(jp_b - jp) / abs(jp - 1.0 + 1e-30))
-    print(f"{name}: substeps gpu {nsub} oracle {n_a} twin {n_b}; ke gpu {st['ke']:.5e} oracle {ke:.5e} twin {ke_b:.5e}; "
-          f"jp-1 gpu {st['jp']-1:.4e} oracle {jp-1:.4e} twin {jp_b-1:.4e}; bands ke {band_ke:.3f} jp {band_jp:.3f}")
+        members.append(bulk_stats(po["x"], po["v"], sc_.particles.m, po["FP"]) + (n,))
+    com = np.mean([m[0] for m in members], axis=0); kes = np.array([m[1] for m in members]); jps = np.array([m[2] for m in members]) - 1.0
+    ke, jp = kes.mean(), jps.mean()
+    band_ke = max(0.01 * ke, 3.0 * np.abs(kes - ke).max()); band_jp = max(0.01 * abs(jp), 3.0 * np.abs(jps - jp).max()) + 1e-6
+    print(f"{name}: substeps gpu {nsub} oracle {[m[3] for m in members]}; ke gpu {st['ke']:.5e} oracle {kes}; jp-1 gpu {st['jp']-1:.4e} oracle {jps}")
+    assert c["frame"] == frames and c["escaped"] == 0 and nsub >= 100 and abs(c["inner_t"]) < 1e-12
     assert np.linalg.norm(st["com"] - com) < 0.01 * np.linalg.norm(com)
-    assert abs(st["ke"] - ke) <= band_ke * ke
-    assert abs((st["jp"] - 1.0) - (jp - 1.0)) <= band_jp * abs(jp - 1.0) + 1e-6
+    assert abs(st["ke"] - ke) <= band_ke
+    assert abs((st["jp"] - 1.0) - jp) <= band_jp
 
 
 def _cloth_scene():

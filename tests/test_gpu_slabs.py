@@ -21,7 +21,7 @@ def _scene(res=32):
     return s
 
 
-def _group(scene, nslabs):
+def _group(scene, nslabs, overlapped=None):
     from anisotropicelastoplasticity_b200 import capi
     from anisotropicelastoplasticity_b200.distributed import GpuSlabBackend, LocalSlabGroup, SlabPlan, make_gpu_slab_engine
     cells = np.floor(scene.particles.x[:, 1] / scene.grid.h[1]).astype(np.int64)
@@ -33,17 +33,17 @@ def _group(scene, nslabs):
         capi.check(eng.L.aep_set_particle_id_base(eng.h, int(idx[0])), eng.h)      # global ids = position in the scene arrays
         eng.upload_particles(local)
         backends.append(GpuSlabBackend(eng, migrate_capacity=4096)); n0.append(len(idx))
-    return LocalSlabGroup(backends, plan), backends, n0
+    return LocalSlabGroup(backends, plan, overlapped=overlapped), backends, n0
 
 
-@pytest.mark.parametrize("nslabs", [2, 3])
-def test_slabs_pinned_dt_match_single_context_and_oracle(nslabs):
+@pytest.mark.parametrize("nslabs,overlapped", [(2, True), (3, True), (3, False)])
+def test_slabs_pinned_dt_match_single_context_and_oracle(nslabs, overlapped):
     """12 substeps at a pinned dt (well-conditioned, see test_gpu_parity.test_200_substeps_pinned_dt): the union of the slabs,
     gathered by global id, equals the whole-domain context (same fp32 arithmetic, different summation order) and the oracle."""
     from anisotropicelastoplasticity_b200.engine import Engine
     from oracle.oracle_py import Oracle
     scene = _scene(); dt = float(np.float32(2e-4)); nsteps = 12
-    grp, backends, n0 = _group(scene, nslabs)
+    grp, backends, n0 = _group(scene, nslabs, overlapped)      # overlapped: leaver lists from G2P + split P2G; else full-scan extract
     grp.init()
     for b in backends:
         b.e.set_fixed_dt(dt)
