@@ -27,7 +27,7 @@ class Config(C.Structure):
                 ("cfl", C.c_double), ("gravity", C.c_double), ("collider_friction", C.c_double), ("snow_hardening", C.c_double),
                 ("sand_h", C.c_double * 4), ("dt_rate_floor", C.c_double), ("frame_dt", C.c_double),
                 ("particle_capacity", C.c_int64), ("slab_axis", C.c_int32), ("slab_lo", C.c_int32), ("slab_hi", C.c_int32),
-                ("sort_every", C.c_int32), ("sort_bricks", C.c_int32), ("_pad1", C.c_int32), ("sort_cost_threshold", C.c_double)]
+                ("sort_every", C.c_int32), ("sort_bricks", C.c_int32), ("scatter_strips", C.c_int32), ("sort_cost_threshold", C.c_double)]
 
 
 class AepError(RuntimeError):

@@ -237,7 +237,7 @@ int do_p2g(aep_ctx* c, bool first) {
         k_clear_blocks<<<c->nrun, 256, 0, c->stream>>>(c->G);
         LAUNCH_OK("k_clear_blocks");
         if (c->n) {
-            k_p2g<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->P[c->cur], c->G, (int)c->n);
+            k_p2g<<<strided_grid(cdiv(c->n, 256), c->G.strips), 256, 0, c->stream>>>(c->P[c->cur], c->G, (int)c->n);
             LAUNCH_OK("k_p2g");
         }
     }
@@ -364,7 +364,7 @@ int aep_default_config(aep_config* cfg) {
     cfg->cfl = 0.3; cfg->gravity = 9.8; cfg->collider_friction = 0.2; cfg->snow_hardening = 10.0;
     cfg->sand_h[0] = 35.0; cfg->sand_h[1] = 9.0; cfg->sand_h[2] = 0.2; cfg->sand_h[3] = 10.0;
     cfg->dt_rate_floor = 3e2; cfg->frame_dt = 1.0 / 60.0;
-    cfg->particle_capacity = 0; cfg->slab_axis = -1; cfg->slab_lo = 0; cfg->slab_hi = 0; cfg->sort_every = 0; cfg->sort_bricks = 0; cfg->sort_cost_threshold = 0.5;
+    cfg->particle_capacity = 0; cfg->slab_axis = -1; cfg->slab_lo = 0; cfg->slab_hi = 0; cfg->sort_every = 0; cfg->sort_bricks = 0; cfg->sort_cost_threshold = 0.5; cfg->scatter_strips = 64;
     return AEP_OK;
 }
 
@@ -395,7 +395,7 @@ int aep_create(aep_ctx** out, const aep_config* cfg) {
     GridP& G = ctx->G;
     G.nx = cfg->res[0]; G.ny = cfg->res[1]; G.nz = cfg->res[2];
     G.nbx = (G.nx + 7) / 8; G.nby = (G.ny + 7) / 8; G.nbz = (G.nz + 7) / 8;
-    G.nqx = (G.nx + 3) / 4; G.nqy = (G.ny + 3) / 4; G.bricks = cfg->sort_bricks ? 1 : 0;
+    G.nqx = (G.nx + 3) / 4; G.nqy = (G.ny + 3) / 4; G.bricks = cfg->sort_bricks ? 1 : 0; G.strips = std::max(1, cfg->scatter_strips);
     ctx->nblocks = G.nbx * G.nby * G.nbz;
     {   // grid passes visit the blocks this context can touch: everything, or the slab's node planes slab_lo-1 .. slab_hi+1
         const int nb[3] = { G.nbx, G.nby, G.nbz };

@@ -20,7 +20,7 @@ def _p(a):
 
 
 class Engine:
-    def __init__(self, scene: Scene, device: int = 0, particle_capacity: int = 0, slab=None, dt_rate_floor=None, sort_every=None, sort_bricks=None):
+    def __init__(self, scene: Scene, device: int = 0, particle_capacity: int = 0, slab=None, dt_rate_floor=None, sort_every=None, sort_bricks=None, scatter_strips=None):
         self.L = capi.load()
         cfg = capi.Config(); capi.check(self.L.aep_default_config(C.byref(cfg)))
         g = scene.grid
@@ -32,6 +32,8 @@ class Engine:
             cfg.dt_rate_floor = float(dt_rate_floor)
         if sort_every is not None:
             cfg.sort_every = int(sort_every)
+        if scatter_strips is not None:
+            cfg.scatter_strips = int(scatter_strips)
         if sort_bricks is not None:
             cfg.sort_bricks = int(sort_bricks)
         if slab is not None:

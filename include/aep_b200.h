@@ -83,7 +83,8 @@ typedef struct aep_config {
                                   substeps) reaches sort_cost_threshold, or after 32 substeps.  Results never depend on the order. */
     int32_t sort_bricks;       /* 0 (default): order particles by cell index, x fastest; 1: by 4x4x4-cell brick, then cell (better L1 hit rate
                                   of the gathers, but the scatters of one CTA then contend for the same L2 lines: measured slower overall) */
-    int32_t _pad1;
+    int32_t scatter_strips;    /* 64: concurrently running P2G CTAs are spread over this many far-apart parts of the sorted particle
+                                  order so that they do not reduce into the same grid nodes at the same time (L2 atomic contention) */
     double sort_cost_threshold; /* 0.5: the extra scatter work of unsorted particles has about paid for one re-sort       */
 } aep_config;
 
