@@ -36,7 +36,7 @@ struct Timers {
 
 struct aep_ctx {
     aep_config cfg;
-    int device = 0;
+    int device = 0, sm_count = 148;
     cudaStream_t stream = nullptr;
     std::string err;
     long long launches = 0;
@@ -237,7 +237,7 @@ int do_p2g(aep_ctx* c, bool first) {
         k_clear_blocks<<<c->nrun, 256, 0, c->stream>>>(c->G);
         LAUNCH_OK("k_clear_blocks");
         if (c->n) {
-            k_p2g<<<strided_grid(cdiv(c->n, 256), c->G.strips), 256, 0, c->stream>>>(c->P[c->cur], c->G, (int)c->n);
+            p2g_launch(c->stream, c->P[c->cur], c->G, c->n);
             LAUNCH_OK("k_p2g");
         }
     }
@@ -292,7 +292,7 @@ int do_g2p(aep_ctx* c) {
     if (c->n) {
         StageTimer T(c, AEP_STAGE_G2P);
         if (c->mig.axis >= 0) cudaMemsetAsync(c->mig.counts, 0, 2 * sizeof(unsigned long long), c->stream);
-        k_g2p<<<cdiv(c->n, G2P_NT), G2P_NT, 0, c->stream>>>(c->P[c->cur], c->G, c->mat, c->d_clk, c->d_keys[0], c->d_vals[0], (int)c->n, c->mig);
+        g2p_launch(c->stream, c->sm_count, c->P[c->cur], c->G, c->mat, c->d_clk, c->d_keys[0], c->d_vals[0], c->n, c->mig);
         LAUNCH_OK("k_g2p");
     }
     if (c->mesh.nv) {
@@ -386,7 +386,7 @@ int aep_create(aep_ctx** out, const aep_config* cfg) {
     if (prop.major < 10) return fail(c, AEP_ERR_CUDA, "device %d is sm_%d%d; libaep_b200 is built for sm_100a only", cfg->device, prop.major, prop.minor);
 
     aep_ctx* ctx = new aep_ctx();
-    ctx->cfg = *cfg; ctx->device = cfg->device; ctx->mig.axis = -1;
+    ctx->cfg = *cfg; ctx->device = cfg->device; ctx->sm_count = prop.multiProcessorCount; ctx->mig.axis = -1;
     c = ctx;
     auto bail = [&](int code) { std::string m = ctx->err; aep_destroy(ctx); g_create_error = m; return code; };
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, AEP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(e_ == cudaErrorMemoryAllocation ? AEP_ERR_ALLOC : AEP_ERR_CUDA); } } while (0)

@@ -122,7 +122,7 @@ int aep_step_p2g_arrivals(aep_ctx* c, int64_t count) {
     StageTimer T(c, AEP_STAGE_P2G);
     PartP tail = c->P[c->cur];
     for (int a = 0; a < P_NARR; ++a) tail.a[a] += (c->n - count);
-    k_p2g<<<strided_grid(cdiv(count, 256), c->G.strips), 256, 0, c->stream>>>(tail, c->G, (int)count);
+    p2g_launch(c->stream, tail, c->G, count);
     LAUNCH_OK("k_p2g");
     return AEP_OK;
 }

@@ -18,6 +18,7 @@
 #pragma once
 #include <stdint.h>
 #include "aep_math.cuh"
+#include "aep_pack.cuh"
 
 namespace aep {
 
@@ -345,21 +346,98 @@ __device__ __forceinline__ void flush_nodes(const GridP& G, float4* __restrict__
 __device__ __forceinline__ float sel4(const float (&a)[4], int k) { return k == 0 ? a[0] : (k == 1 ? a[1] : (k == 2 ? a[2] : a[3])); }
 __device__ __forceinline__ float f4c(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
+// ---- packed accumulators (aep_pack.cuh): node i of a lane's row is the float4 (lo[i] | hi[i]) = (x, y | z, w)
+struct AccRow {
+    f32x2 lo[4], hi[4];
+};
+__device__ __forceinline__ void acc_zero(AccRow& a) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { a.lo[i] = 0ull; a.hi[i] = 0ull; }
+}
+// same, but pinned behind the reductions that consumed the old values (volatile): see slide_row_pk
+__device__ __forceinline__ void acc_zero_ordered(AccRow& a) {
+    asm volatile("mov.b64 %0, 0;\n\tmov.b64 %1, 0;\n\tmov.b64 %2, 0;\n\tmov.b64 %3, 0;" : "=l"(a.lo[0]), "=l"(a.lo[1]), "=l"(a.lo[2]), "=l"(a.lo[3]));
+    asm volatile("mov.b64 %0, 0;\n\tmov.b64 %1, 0;\n\tmov.b64 %2, 0;\n\tmov.b64 %3, 0;" : "=l"(a.hi[0]), "=l"(a.hi[1]), "=l"(a.hi[2]), "=l"(a.hi[3]));
+}
+// The reduction wants its float4 in an aligned register quad while FFMA2 wants the accumulators in pairs that stay put across
+// the loop; asked for both, ptxas keeps the quads and pays ~20 MOVs per particle on the hot path to shuffle the pairs.  So the
+// (rare) flush bounces the pairs through a lane-private shared-memory slot: STS.64 x2 (pairs only) + LDS.128 into a fresh quad.
+__device__ __forceinline__ float4 requad(float4* slot, f32x2 lo, f32x2 hi) {
+    float4 v;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(slot);
+    asm volatile("st.shared.b64 [%4], %5;\n\tst.shared.b64 [%4+8], %6;\n\tld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "l"(lo), "l"(hi) : "memory");
+    return v;
+}
+__device__ __forceinline__ void flush_row_pk(const GridP& G, float4* __restrict__ dst, float4* slot, int cell, int j, int k, const AccRow& a, bool mark) {
+    const int ni0 = cell_i(cell) - 1, nj = cell_j(cell) - 1 + j, nk = cell_k(cell) - 1 + k;
+    if (nj < 0 || nj >= G.ny || nk < 0 || nk >= G.nz) return;
+    float4* row = dst + ((size_t)nk * G.ny + nj) * G.nx;
+    unsigned char* frow = G.flags + ((nk >> 3) * G.nby + (nj >> 3)) * G.nbx;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ni = ni0 + i;
+        if (ni >= 0 && ni < G.nx) {
+            atomicAdd(row + ni, requad(slot, a.lo[i], a.hi[i]));
+            if (mark && (i == 0 || i == 3 || ni == 0 || ni == G.nx - 1)) frow[ni >> 3] = 1;
+        }
+    }
+}
+// sliding window along x (see slide_row): reduce the d nodes that leave the window, shift the rest
+__device__ __forceinline__ bool slide_row_pk(const GridP& G, float4* __restrict__ dst, float4* slot, int cur, int next, int j, int k, AccRow& a, bool mark) {
+    const int d = next - cur;
+    if (d <= 0 || d >= 4 || (next & 1023) - (cur & 1023) != d) return false;
+    const int nj = cell_j(cur) - 1 + j, nk = cell_k(cur) - 1 + k;
+    const bool in_jk = nj >= 0 && nj < G.ny && nk >= 0 && nk < G.nz;
+    float4* row = dst + ((size_t)nk * G.ny + nj) * G.nx;
+    unsigned char* frow = G.flags + ((nk >> 3) * G.nby + (nj >> 3)) * G.nbx;
+    int ni = cell_i(cur) - 1;
+    for (int s = 0; s < d; ++s, ++ni) {
+        if (in_jk && ni >= 0 && ni < G.nx) {
+            atomicAdd(row + ni, requad(slot, a.lo[0], a.hi[0]));
+            if (mark) frow[ni >> 3] = 1;
+        }
+        // ordered moves (volatile: they stay behind the reduction that consumed node 0), so that the accumulators keep their
+        // registers on the hot path and only this rare path pays for the shift
+        asm volatile("mov.b64 %0, %4;\n\tmov.b64 %1, %5;\n\tmov.b64 %2, %6;\n\tmov.b64 %3, 0;"
+                     : "=l"(a.lo[0]), "=l"(a.lo[1]), "=l"(a.lo[2]), "=l"(a.lo[3]) : "l"(a.lo[1]), "l"(a.lo[2]), "l"(a.lo[3]));
+        asm volatile("mov.b64 %0, %4;\n\tmov.b64 %1, %5;\n\tmov.b64 %2, %6;\n\tmov.b64 %3, 0;"
+                     : "=l"(a.hi[0]), "=l"(a.hi[1]), "=l"(a.hi[2]), "=l"(a.hi[3]) : "l"(a.hi[1]), "l"(a.hi[2]), "l"(a.hi[3]));
+    }
+    return true;
+}
+
 // ================================================================================================ P2G
 // particleToGrid_ (HybridSolver.cpp:113-231): m_i = sum w m ; p_i = sum w m (v + (3/h^2) B (x_i - x_p)).
 // Per particle the momentum of node offset (i,j,k) is q0 + Qm (i,j,k)^T with Qm = m (3/h^2) B diag(h), q0 = m v - Qm (1+f).
-#ifndef AEP_STAGE_PAD
-#define AEP_STAGE_PAD 1
-#endif
-#define P2G_REC 7
+// Phase-A record of one particle: P2G_STRIDE float4, an odd stride so that the 32 STS.128 of phase A are bank-conflict free.
+//   r0 Nx[4]    r1 Ny[4] (read as float [j])    r2 Nz[4] (float [k])
+//   r3 (m, q0x | q0y, q0z)      (mass, momentum) of node offset (0,0,0):  q0 = m v - Qm (1 + f)
+//   r4 r5 r6  (0, Qm[0][c] | Qm[1][c], Qm[2][c]) for c = 0,1,2: what one step along i, j, k adds to (m, p)
+//   r7.x  packed cell index (read on the flush path only)
+// Phase B is bound by shared-memory wavefronts as much as by issue slots (profiles/README.md, v9): every LDS of the two half-warps
+// costs one wavefront per half-warp, so the record holds plain scalars (FFMA2 takes a broadcast .F32 operand) and the end of a
+// run of same-cell particles comes from a ballot of phase A instead of a per-particle load of the cell index.
+#define P2G_STRIDE 9
+#define P2G_HW_PAD 2
+#define P2G_HW_F4 (16 * P2G_STRIDE + P2G_HW_PAD)
+// bit l of the result: the run of same-cell particles ends with the particle of lane l (always at the end of a half-warp)
+__device__ __forceinline__ unsigned run_ends(int cell) {
+    const int lane = threadIdx.x & 31;
+    const int nxt = __shfl_down_sync(0xffffffffu, cell, 1);
+    return __ballot_sync(0xffffffffu, nxt != cell || (lane & 15) == 15);
+}
 __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
-    __shared__ float4 stage[8][2][16 * P2G_REC + AEP_STAGE_PAD];                         // +1: the two half-warps read different banks in phase B
+    __shared__ float4 stage[8][2][P2G_HW_F4];
+    __shared__ float4 bounce[256];                                            // lane-private slots of requad()
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float4* slot = bounce + threadIdx.x;
     const int chunk = strided_chunk(blockIdx.x, (n + 255) / 256, G.strips);
     if (chunk < 0) return;
     const int base = chunk * 256 + wib * 32;
     if (base >= n) return;                                                   // warp-uniform; no block-level barrier below
     const int cnt = min(32, n - base);
+    unsigned ends;
     {   // ---- phase A
         const int p = base + min(lane, cnt - 1);
         const float4 X = ldg4(P.a[PX] + p), VM = ldg4(P.a[PVM] + p);
@@ -374,48 +452,57 @@ __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
         const float q0x = fmaf(m, VM.x, -(Q[0] * gx + Q[1] * gy + Q[2] * gz));
         const float q0y = fmaf(m, VM.y, -(Q[3] * gx + Q[4] * gy + Q[5] * gz));
         const float q0z = fmaf(m, VM.z, -(Q[6] * gx + Q[7] * gy + Q[8] * gz));
-        float4* rec = &stage[wib][lane >> 4][(lane & 15) * P2G_REC];
+        float4* rec = &stage[wib][lane >> 4][(lane & 15) * P2G_STRIDE];
         rec[0] = make_float4(Nx[0], Nx[1], Nx[2], Nx[3]); rec[1] = make_float4(Ny[0], Ny[1], Ny[2], Ny[3]); rec[2] = make_float4(Nz[0], Nz[1], Nz[2], Nz[3]);
         rec[3] = make_float4(m, q0x, q0y, q0z);
-        rec[4] = make_float4(Q[0], Q[1], Q[2], Q[3]); rec[5] = make_float4(Q[4], Q[5], Q[6], Q[7]); rec[6] = make_float4(Q[8], 0.f, 0.f, X.w);
+        rec[4] = make_float4(0.f, Q[0], Q[3], Q[6]); rec[5] = make_float4(0.f, Q[1], Q[4], Q[7]); rec[6] = make_float4(0.f, Q[2], Q[5], Q[8]);
+        rec[7].x = X.w;
+        ends = run_ends(__float_as_int(X.w));
     }
     __syncwarp();
-    // ---- phase B
+    // ---- phase B: half-warp per particle, lane = (j,k) row of the stencil, 4 nodes along x in packed accumulators
     const int hw = lane >> 4, s = lane & 15, j = s & 3, k = s >> 2;
-    const float fj = (float)j, fk = (float)k;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 acc[4] = { zero, zero, zero, zero };
+    float fj = (float)j, fk = (float)k;
+    int yoff = 16 + 4 * j, zoff = 32 + 4 * k;                                 // byte offsets of Ny[j], Nz[k] inside a record
+    // lane constants: ptxas re-derives them from %tid on every trip (8 instructions) unless they come out of something it cannot
+    // rematerialise -- an identity shuffle
+    fj = __shfl_sync(0xffffffffu, fj, lane); fk = __shfl_sync(0xffffffffu, fk, lane);
+    yoff = __shfl_sync(0xffffffffu, yoff, lane); zoff = __shfl_sync(0xffffffffu, zoff, lane);
+    const f32x2 J = pk1(fj), K = pk1(fk);
+    ends >>= hw * 16;
+    AccRow acc; acc_zero(acc);
     const float4* recs = &stage[wib][hw][0];
-    int cur = __float_as_int(recs[6].w);
-#pragma unroll 2
+#pragma unroll 1
     for (int it = 0; it < 16; ++it) {
-        const float4* r = recs + it * P2G_REC;
-        const float4 r6 = r[6];
-        const int c = __float_as_int(r6.w);
-        if (c != cur) {
-            if (!slide_row(G, G.mp, cur, c, j, k, acc, true)) {
-                flush_row(G, G.mp, cur, j, k, acc, true);
-                acc[0] = zero; acc[1] = zero; acc[2] = zero; acc[3] = zero;
+        const float4* r = recs + it * P2G_STRIDE;
+        const float4 nx = r[0];
+        const float wyz = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(r) + yoff) * *reinterpret_cast<const float*>(reinterpret_cast<const char*>(r) + zoff);
+        const ulonglong2 b0 = ld_pairs(r + 3), si = ld_pairs(r + 4), sj = ld_pairs(r + 5), sk = ld_pairs(r + 6);
+        f32x2 Tlo = fma2(sj.x, J, fma2(sk.x, K, b0.x));                        // (m, px) of node (0, j, k)
+        f32x2 Thi = fma2(sj.y, J, fma2(sk.y, K, b0.y));                        // (py, pz)
+        f32x2 W = pk1(nx.x * wyz);
+        acc.lo[0] = fma2(W, Tlo, acc.lo[0]); acc.hi[0] = fma2(W, Thi, acc.hi[0]);
+        Tlo = add2(Tlo, si.x); Thi = add2(Thi, si.y); W = pk1(nx.y * wyz);
+        acc.lo[1] = fma2(W, Tlo, acc.lo[1]); acc.hi[1] = fma2(W, Thi, acc.hi[1]);
+        Tlo = add2(Tlo, si.x); Thi = add2(Thi, si.y); W = pk1(nx.z * wyz);
+        acc.lo[2] = fma2(W, Tlo, acc.lo[2]); acc.hi[2] = fma2(W, Thi, acc.hi[2]);
+        Tlo = add2(Tlo, si.x); Thi = add2(Thi, si.y); W = pk1(nx.w * wyz);
+        acc.lo[3] = fma2(W, Tlo, acc.lo[3]); acc.hi[3] = fma2(W, Thi, acc.hi[3]);
+        if ((ends >> it) & 1u) {                                              // the run of particles sharing this cell ends here
+            const int cur = __float_as_int(r[7].x);
+            const int nxt = (it == 15) ? -1 : __float_as_int(r[P2G_STRIDE + 7].x);
+            if (!slide_row_pk(G, G.mp, slot, cur, nxt, j, k, acc, true)) {
+                flush_row_pk(G, G.mp, slot, cur, j, k, acc, true);
+                acc_zero_ordered(acc);
             }
-            cur = c;
-        }
-        const float4 nx = r[0], mq = r[3], qa = r[4], qb = r[5];
-        const float wy = reinterpret_cast<const float*>(r + 1)[j], wz = reinterpret_cast<const float*>(r + 2)[k];
-        const float wyz = wy * wz;
-        const float bx = fmaf(qa.y, fj, fmaf(qa.z, fk, mq.y));              // q0 + Q[:,1] j + Q[:,2] k
-        const float by = fmaf(qb.x, fj, fmaf(qb.y, fk, mq.z));
-        const float bz = fmaf(qb.w, fj, fmaf(r6.x, fk, mq.w));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float w = f4c(nx, i) * wyz;
-            const float fi = (float)i;
-            acc[i].x = fmaf(w, mq.x, acc[i].x);
-            acc[i].y = fmaf(w, fmaf(qa.x, fi, bx), acc[i].y);
-            acc[i].z = fmaf(w, fmaf(qa.w, fi, by), acc[i].z);
-            acc[i].w = fmaf(w, fmaf(qb.z, fi, bz), acc[i].w);
         }
     }
-    flush_row(G, G.mp, cur, j, k, acc, true);
+}
+
+// launch helper shared by the engine, the slab arrivals and the mesh transfers
+inline void p2g_launch(cudaStream_t st, const PartP& P, const GridP& G, long long n) {
+    const int chunks = (int)((n + 255) / 256);
+    k_p2g<<<strided_grid(chunks, G.strips), 256, 0, st>>>(P, G, (int)n);
 }
 
 // first P2G only: rho_p = sum_i w m_i / (hx hy hz), V_p = m_p / rho_p           HybridSolver.cpp:242-249
@@ -503,7 +590,6 @@ __device__ __forceinline__ bool stage_tile(const GridP& G, float4* __restrict__ 
 }
 
 // ================================================================================================ forces
-#define FRC_REC 9
 // g[3r+c] = sum_i v_i[r] d_c w_i over the 4x4x4 stencil, x summed first.
 // MODE 0: clamped global loads (stencil cut by a domain face), 1: interior global loads (the four nodes of a row are 64 contiguous
 // bytes at immediate offsets), 2: loads from the CTA's shared tile (xoff = first stencil node relative to the tile).
@@ -540,16 +626,27 @@ __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, cons
 // computeGridForces_, particle part (HybridSolver.cpp:252-368).  Phase A (thread per particle): gather
 // grad v = sum_i v_i (grad w_i)^T, Fhat = (I + dt grad v) FE, SVD, stress, A = V_p P FE^T.  Phase B (half-warp per particle):
 // f_i -= A grad w_ip.
+// Phase-A record of one particle for the force scatter (FRC_STRIDE float4, odd stride: conflict-free STS.128), plain scalars like P2G's:
+//   r0 Nx[4]   r1 Dx[4]   r2 r3 (Ny_j, Dy_j) pairs, read as float2 [j]   r4 r5 (Nz_k, Dz_k), float2 [k]
+//   r6 r7 r8  columns of A = -V_p P FE^T:  (A[0][c], A[1][c] | A[2][c], 0)
+//   r9.x  packed cell index (flush path only)
+// The warp's grid tile of phase A lives in the same shared memory: it is dead once the gather is done.
 #define FRC_NT 128
+#define FRC_STRIDE 11
+#define FRC_HW_PAD 2
+#define FRC_WARP_F4 (2 * (16 * FRC_STRIDE + FRC_HW_PAD))
+static_assert(FRC_WARP_F4 >= TILE_F4, "the gather tile is aliased onto the warp's record area");
 __global__ void __launch_bounds__(FRC_NT, 6) k_forces(PartP P, GridP G, MatParams mpar, const SimClock* __restrict__ clk, int n) {
-    __shared__ float4 stage[FRC_NT / 32][2][16 * FRC_REC + AEP_STAGE_PAD];
-    __shared__ float4 tiles[FRC_NT / 32][TILE_F4];
+    __shared__ float4 stage[FRC_NT / 32][FRC_WARP_F4];
+    __shared__ float4 bounce[FRC_NT];                                          // lane-private slots of requad()
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    float4* tile = tiles[wib];
+    float4* slot = bounce + threadIdx.x;
+    float4* tile = stage[wib];
     const int base = blockIdx.x * FRC_NT + wib * 32;        // consecutive chunks: the gather of phase A lives on L1/L2 locality (strided: 2% slower)
     if (base >= n) return;                                                       // warp-uniform; no block-level barrier below
     const int cnt = min(32, n - base);
     const float dt = clk->dt;
+    unsigned ends;
     {   // ---- phase A
         const int p = base + min(lane, cnt - 1);
         const float4 X = ldg4(P.a[PX] + p);
@@ -570,43 +667,46 @@ __global__ void __launch_bounds__(FRC_NT, 6) k_forces(PartP P, GridP G, MatParam
 #pragma unroll
         for (int i = 0; i < 9; ++i) Fh[i] = fmaf(dt, GF[i], FE[i]);              // HybridSolver.cpp:306
         stress_times_FEt(mpar, Fh, FE, (lane < cnt) ? -e0.w : 0.0f, e2.w, A);    // A := -V_p P FE^T (sign of :356-366 folded in); padding lanes: zero volume
-        float4* rec = &stage[wib][lane >> 4][(lane & 15) * FRC_REC];
+        __syncwarp();                                                            // every lane is done with the tile: reuse it for the records
+        float4* rec = stage[wib] + (lane >> 4) * (16 * FRC_STRIDE + FRC_HW_PAD) + (lane & 15) * FRC_STRIDE;
         rec[0] = make_float4(ax.N[0], ax.N[1], ax.N[2], ax.N[3]); rec[1] = make_float4(ax.D[0], ax.D[1], ax.D[2], ax.D[3]);
         rec[2] = make_float4(ay.N[0], ay.D[0], ay.N[1], ay.D[1]); rec[3] = make_float4(ay.N[2], ay.D[2], ay.N[3], ay.D[3]);
         rec[4] = make_float4(az.N[0], az.D[0], az.N[1], az.D[1]); rec[5] = make_float4(az.N[2], az.D[2], az.N[3], az.D[3]);
-        rec[6] = make_float4(A[0], A[1], A[2], A[3]); rec[7] = make_float4(A[4], A[5], A[6], A[7]); rec[8] = make_float4(A[8], 0.f, 0.f, X.w);
+        rec[6] = make_float4(A[0], A[3], A[6], 0.f); rec[7] = make_float4(A[1], A[4], A[7], 0.f); rec[8] = make_float4(A[2], A[5], A[8], 0.f);
+        rec[9].x = X.w;
+        ends = run_ends(cell);
     }
     __syncwarp();
-    // ---- phase B: f_i[r] += sum_c A(r,c) d_c w   with d_x w = Dx Ny Nz, d_y w = Nx Dy Nz, d_z w = Nx Ny Dz   (HybridSolver.cpp:356-366)
+    // ---- phase B: f_i += A grad w_i  with  grad w_i = (Dx_i Ny Nz, Nx_i Dy Nz, Nx_i Ny Dz)   (HybridSolver.cpp:356-366)
+    //      = Dx_i U + Nx_i V,  U = A[:,0] Ny Nz,  V = A[:,1] Dy Nz + A[:,2] Ny Dz  per (j,k) row
     const int hw = lane >> 4, s = lane & 15, j = s & 3, k = s >> 2;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 acc[4] = { zero, zero, zero, zero };
-    const float4* recs = &stage[wib][hw][0];
-    int cur = __float_as_int(recs[8].w);
-#pragma unroll 2
+    int yoff = 32 + 8 * j, zoff = 64 + 8 * k;                                 // byte offsets of (Ny,Dy)[j], (Nz,Dz)[k] inside a record
+    asm volatile("" : "+r"(yoff), "+r"(zoff));                                // lane constants: keep them in registers
+    ends >>= hw * 16;
+    AccRow acc; acc_zero(acc);
+    const float4* recs = stage[wib] + hw * (16 * FRC_STRIDE + FRC_HW_PAD);
+#pragma unroll 1
     for (int it = 0; it < 16; ++it) {
-        const float4* r = recs + it * FRC_REC;
-        const float4 r8 = r[8];
-        const int c = __float_as_int(r8.w);
-        if (c != cur) {
-            if (!slide_row(G, G.f, cur, c, j, k, acc, false)) {
-                flush_row(G, G.f, cur, j, k, acc, false);
-                acc[0] = zero; acc[1] = zero; acc[2] = zero; acc[3] = zero;
+        const float4* r = recs + it * FRC_STRIDE;
+        const float4 nx = r[0], dx = r[1];
+        const float2 yj = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(r) + yoff), zk = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(r) + zoff);
+        const ulonglong2 a0 = ld_pairs(r + 6), a1 = ld_pairs(r + 7), a2 = ld_pairs(r + 8);
+        const f32x2 AA = pk1(yj.x * zk.x), BB = pk1(yj.y * zk.x), CC = pk1(yj.x * zk.y);          // Ny Nz, Dy Nz, Ny Dz
+        const f32x2 Ulo = mul2(a0.x, AA), Uhi = mul2(a0.y, AA);
+        const f32x2 Vlo = fma2(a1.x, BB, mul2(a2.x, CC)), Vhi = fma2(a1.y, BB, mul2(a2.y, CC));
+        acc.lo[0] = fma2(Ulo, pk1(dx.x), fma2(Vlo, pk1(nx.x), acc.lo[0])); acc.hi[0] = fma2(Uhi, pk1(dx.x), fma2(Vhi, pk1(nx.x), acc.hi[0]));
+        acc.lo[1] = fma2(Ulo, pk1(dx.y), fma2(Vlo, pk1(nx.y), acc.lo[1])); acc.hi[1] = fma2(Uhi, pk1(dx.y), fma2(Vhi, pk1(nx.y), acc.hi[1]));
+        acc.lo[2] = fma2(Ulo, pk1(dx.z), fma2(Vlo, pk1(nx.z), acc.lo[2])); acc.hi[2] = fma2(Uhi, pk1(dx.z), fma2(Vhi, pk1(nx.z), acc.hi[2]));
+        acc.lo[3] = fma2(Ulo, pk1(dx.w), fma2(Vlo, pk1(nx.w), acc.lo[3])); acc.hi[3] = fma2(Uhi, pk1(dx.w), fma2(Vhi, pk1(nx.w), acc.hi[3]));
+        if ((ends >> it) & 1u) {                                              // the run of particles sharing this cell ends here
+            const int cur = __float_as_int(r[9].x);
+            const int nxt = (it == 15) ? -1 : __float_as_int(r[FRC_STRIDE + 9].x);
+            if (!slide_row_pk(G, G.f, slot, cur, nxt, j, k, acc, false)) {
+                flush_row_pk(G, G.f, slot, cur, j, k, acc, false);
+                acc_zero_ordered(acc);
             }
-            cur = c;
-        }
-        const float4 nx = r[0], dx = r[1], A0 = r[6], A1 = r[7];
-        const float2 yj = reinterpret_cast<const float2*>(r + 2)[j], zk = reinterpret_cast<const float2*>(r + 4)[k];
-        const float a = yj.x * zk.x, b = yj.y * zk.x, cc = yj.x * zk.y;          // Ny Nz, Dy Nz, Ny Dz
-        const float ux = A0.x * a, uy = A0.w * a, uz = A1.z * a;                 // A[:,0] Ny Nz         (times Dx_i)
-        const float vx = fmaf(A0.y, b, A0.z * cc), vy = fmaf(A1.x, b, A1.y * cc), vz = fmaf(A1.w, b, r8.x * cc);   // (times Nx_i)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float d = f4c(dx, i), w = f4c(nx, i);
-            acc[i].x = fmaf(ux, d, fmaf(vx, w, acc[i].x)); acc[i].y = fmaf(uy, d, fmaf(vy, w, acc[i].y)); acc[i].z = fmaf(uz, d, fmaf(vz, w, acc[i].z));
         }
     }
-    flush_row(G, G.f, cur, j, k, acc, false);
 }
 
 // ================================================================================================ G2P
@@ -777,6 +877,12 @@ __global__ void __launch_bounds__(G2P_NT, 4) k_g2p(PartP P, GridP G, MatParams m
             if (slot < (unsigned long long)ML.cap) (side == 0 ? ML.list[0] : ML.list[1])[slot] = (unsigned)p;
         }
     }
+}
+
+inline void g2p_launch(cudaStream_t st, int sm_count, const PartP& P, const GridP& G, const MatParams& mat, SimClock* clk, unsigned int* keys,
+                       unsigned int* vals, long long n, const MigList& ML) {
+    (void)sm_count;
+    k_g2p<<<(unsigned)((n + G2P_NT - 1) / G2P_NT), G2P_NT, 0, st>>>(P, G, mat, clk, keys, vals, (int)n, ML);
 }
 
 // ================================================================================================ host <-> device

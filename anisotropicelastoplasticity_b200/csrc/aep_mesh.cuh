@@ -417,8 +417,8 @@ inline int mesh_p2g(MeshState& m, const GridP& G, cudaStream_t s, long long* lau
     PartP pv{}, pe{};
     pv.a[PX] = m.d.VX; pv.a[PVM] = m.d.VVM; pv.a[PC0] = m.d.VC0; pv.a[PC1] = m.d.VC1; pv.a[PC2] = m.d.VC2;
     pe.a[PX] = m.d.EX; pe.a[PVM] = m.d.EVM; pe.a[PC0] = m.d.EC0; pe.a[PC1] = m.d.EC1; pe.a[PC2] = m.d.EC2;
-    k_p2g<<<strided_grid((int)((m.nv + 255) / 256), G.strips), 256, 0, s>>>(pv, G, (int)m.nv);
-    k_p2g<<<strided_grid((int)((m.nf + 255) / 256), G.strips), 256, 0, s>>>(pe, G, (int)m.nf);
+    p2g_launch(s, pv, G, m.nv);
+    p2g_launch(s, pe, G, m.nf);
     *launches += 2;
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
