@@ -45,6 +45,8 @@ struct aep_ctx {
     GridP G{};
     size_t Ng = 0; int nblocks = 0;             // all 8^3 blocks of the grid (flags array)
     int nrun = 0;                                // blocks the grid passes run over (G.rb0 / G.rbn)
+    unsigned int *d_blist = nullptr, *d_bcount = nullptr;   // compact list of the flagged blocks among them (k_list_blocks)
+    int pass_ctas = 1;                           // persistent grid of the grid passes
     double h[3]{}, hmin = 0;
     std::vector<void*> dev_allocs;
     unsigned char* d_ls_code = nullptr; float4* d_ls_nrm = nullptr;
@@ -231,10 +233,19 @@ int do_sort(aep_ctx* c, bool build_keys) {
     return AEP_OK;
 }
 
+// the flagged blocks of the run range as a compact list (flags change with every P2G and every halo add: rebuilt per pass, ~5 us)
+int list_blocks(aep_ctx* c) {
+    cudaMemsetAsync(c->d_bcount, 0, sizeof(unsigned int), c->stream);
+    k_list_blocks<<<cdiv(c->nrun, 256), 256, 0, c->stream>>>(c->G, c->nrun, c->d_blist, c->d_bcount);
+    LAUNCH_OK("k_list_blocks");
+    return AEP_OK;
+}
+
 int do_p2g(aep_ctx* c, bool first) {
     {
         StageTimer T(c, AEP_STAGE_P2G);
-        k_clear_blocks<<<c->nrun, 256, 0, c->stream>>>(c->G);
+        if (int r = list_blocks(c)) return r;
+        k_clear_blocks<<<c->pass_ctas, 256, 0, c->stream>>>(c->G, c->d_blist, c->d_bcount);
         LAUNCH_OK("k_clear_blocks");
         if (c->n) {
             p2g_launch(c->stream, c->P[c->cur], c->G, c->n);
@@ -256,7 +267,8 @@ int do_p2g(aep_ctx* c, bool first) {
 int do_forces(aep_ctx* c) {
     {   // v_i = p_i / m_i on the active blocks (also feeds the cloth-free case: cheap, <1% of a substep)
         StageTimer T(c, AEP_STAGE_GRID);
-        k_grid_normalise<<<c->nrun, 256, 0, c->stream>>>(c->G);
+        if (int r = list_blocks(c)) return r;
+        k_grid_normalise<<<c->pass_ctas, 256, 0, c->stream>>>(c->G, c->d_blist, c->d_bcount);
         LAUNCH_OK("k_grid_normalise");
     }
     if (c->n) {
@@ -273,7 +285,8 @@ int do_forces(aep_ctx* c) {
 
 int do_grid(aep_ctx* c) {
     StageTimer T(c, AEP_STAGE_GRID);
-    k_grid_update<<<c->nrun, 256, 0, c->stream>>>(c->G, c->d_clk);
+    if (int r = list_blocks(c)) return r;
+    k_grid_update<<<c->pass_ctas, 256, 0, c->stream>>>(c->G, c->d_clk, c->d_blist, c->d_bcount);
     LAUNCH_OK("k_grid_update");
     if (c->mesh.nv && c->mesh.n_fixed) {
         int r = mesh_pin(c->mesh, c->G, c->stream, &c->launches); if (r) return fail(c, AEP_ERR_CUDA, "mesh_pin failed");
@@ -418,6 +431,8 @@ int aep_create(aep_ctx** out, const aep_config* cfg) {
     G.gravity = (float)cfg->gravity; G.friction = (float)cfg->collider_friction;
     CUC(dalloc(ctx, &G.mp, ctx->Ng)); CUC(dalloc(ctx, &G.f, ctx->Ng)); CUC(dalloc(ctx, &G.vt, ctx->Ng));
     CUC(dalloc(ctx, &G.flags, (size_t)ctx->nblocks));
+    CUC(dalloc(ctx, &ctx->d_blist, (size_t)ctx->nrun)); CUC(dalloc(ctx, &ctx->d_bcount, 1));
+    ctx->pass_ctas = std::max(1, std::min(ctx->nrun, ctx->sm_count * 8));
     CUC(cudaMemsetAsync(G.mp, 0, ctx->Ng * sizeof(float4), ctx->stream));
     CUC(cudaMemsetAsync(G.f, 0, ctx->Ng * sizeof(float4), ctx->stream));
     CUC(cudaMemsetAsync(G.vt, 0, ctx->Ng * sizeof(float4), ctx->stream));

@@ -140,23 +140,40 @@ __global__ void __launch_bounds__(256) k_reorder(PartP src, PartP dst, const uns
 }
 
 // ================================================================================================ grid passes
+// Compact list of the flagged 8^3 blocks (run indices, see run_block).  The dam break occupies 7 % of the 512^3 grid: launching
+// one CTA per block of the whole grid cost each pass ~0.2 ms of CTAs that only read a zero flag (0.77 ms of a 16.4 ms substep for
+// the three passes); with the list a pass is a persistent grid over the occupied blocks and runs at memory speed.
+__global__ void __launch_bounds__(256) k_list_blocks(GridP G, int nrun, unsigned int* __restrict__ list, unsigned int* __restrict__ count) {
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    bool on = false;
+    if (r < nrun) { int bx, by, bz; on = G.flags[run_block(G, r, bx, by, bz)] != 0; }
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (on) list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)r;
+}
+
 // zero (m,p) and f of every block that the previous P2G touched, and drop its flag
-__global__ void __launch_bounds__(256) k_clear_blocks(GridP G) {
-    int bx, by, bz;
-    const int b = run_block(G, blockIdx.x, bx, by, bz);
-    if (!G.flags[b]) return;
+__global__ void __launch_bounds__(256) k_clear_blocks(GridP G, const unsigned int* __restrict__ list, const unsigned int* __restrict__ count) {
+    const unsigned nb = *count;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (unsigned q = blockIdx.x; q < nb; q += gridDim.x) {
+        int bx, by, bz;
+        const int b = run_block(G, (int)list[q], bx, by, bz);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int t = threadIdx.x + 256 * h;
-        const int i = bx * 8 + (t & 7), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t >> 6);
-        if (i < G.nx && j < G.ny && k < G.nz) {
-            const size_t n = ((size_t)k * G.ny + j) * G.nx + i;
-            G.mp[n] = z; G.f[n] = z;
+        for (int h = 0; h < 2; ++h) {
+            const int t = threadIdx.x + 256 * h;
+            const int i = bx * 8 + (t & 7), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t >> 6);
+            if (i < G.nx && j < G.ny && k < G.nz) {
+                const size_t n = ((size_t)k * G.ny + j) * G.nx + i;
+                G.mp[n] = z; G.f[n] = z;
+            }
         }
+        if (threadIdx.x == 0) G.flags[b] = 0;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) G.flags[b] = 0;
 }
 
 __device__ __forceinline__ void block_max_to_clock(float v, SimClock* clk) {
@@ -197,12 +214,13 @@ __global__ void __launch_bounds__(256) k_vmax_from_mp(GridP G, SimClock* clk) {
 
 // updateGridVelocities_ (HybridSolver.cpp:725-737) + gravity (:457) + max|v| (RegularGrid.cpp:188-200)
 // + gridCollisionHandling_ level-set part (:467-511), one coalesced float4 pass over the active blocks.
-__global__ void __launch_bounds__(256) k_grid_update(GridP G, SimClock* clk) {
-    int bx, by, bz;
-    const int b = run_block(G, blockIdx.x, bx, by, bz);
-    if (!G.flags[b]) return;                                    // uniform per CTA
+__global__ void __launch_bounds__(256) k_grid_update(GridP G, SimClock* clk, const unsigned int* __restrict__ list, const unsigned int* __restrict__ count) {
+    const unsigned nb = *count;
     const float dt = clk->dt;
     float vm = 0.0f;
+    for (unsigned q = blockIdx.x; q < nb; q += gridDim.x) {
+    int bx, by, bz;
+    run_block(G, (int)list[q], bx, by, bz);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int t = threadIdx.x + 256 * h;
@@ -238,6 +256,7 @@ __global__ void __launch_bounds__(256) k_grid_update(GridP G, SimClock* clk) {
             }
             G.vt[n] = make_float4(vx, vy, vz, s);
         }
+    }
     }
     block_max_to_clock(vm, clk);
 }
@@ -379,7 +398,8 @@ __device__ __forceinline__ void flush_row_pk(const GridP& G, float4* __restrict_
         const int ni = ni0 + i;
         if (ni >= 0 && ni < G.nx) {
             atomicAdd(row + ni, requad(slot, a.lo[i], a.hi[i]));
-            if (mark && (i == 0 || i == 3 || ni == 0 || ni == G.nx - 1)) frow[ni >> 3] = 1;
+            // block flags: the first node of the window in the grid, and the last one when it sits in another 8-block
+            if (mark && (i == 0 || ni == 0 || ((i == 3 || ni == G.nx - 1) && (ni >> 3) != (max(ni0, 0) >> 3)))) frow[ni >> 3] = 1;
         }
     }
 }
@@ -395,7 +415,9 @@ __device__ __forceinline__ bool slide_row_pk(const GridP& G, float4* __restrict_
     for (int s = 0; s < d; ++s, ++ni) {
         if (in_jk && ni >= 0 && ni < G.nx) {
             atomicAdd(row + ni, requad(slot, a.lo[0], a.hi[0]));
-            if (mark) frow[ni >> 3] = 1;
+            // a node that slides out marks its block only when it is the block's last one: a block the window has left behind saw
+            // its last node slide out, and the blocks under the window are marked by the flush that ends the run
+            if (mark && (ni & 7) == 7) frow[ni >> 3] = 1;
         }
         // ordered moves (volatile: they stay behind the reduction that consumed node 0), so that the accumulators keep their
         // registers on the hot path and only this rare path pays for the shift
@@ -421,47 +443,32 @@ __device__ __forceinline__ bool slide_row_pk(const GridP& G, float4* __restrict_
 #define P2G_STRIDE 9
 #define P2G_HW_PAD 2
 #define P2G_HW_F4 (16 * P2G_STRIDE + P2G_HW_PAD)
-// bit l of the result: the run of same-cell particles ends with the particle of lane l (always at the end of a half-warp)
+// bit l of the result: the run of same-cell particles ends with the particle of lane l
 __device__ __forceinline__ unsigned run_ends(int cell) {
     const int lane = threadIdx.x & 31;
     const int nxt = __shfl_down_sync(0xffffffffu, cell, 1);
     return __ballot_sync(0xffffffffu, nxt != cell || (lane & 15) == 15);
 }
+// Every flush costs one LSU wavefront per lane and node (the 16 rows of a half-warp lie in 16 different cache lines), and P2G is
+// bound by exactly those wavefronts plus the shared-memory reads (l1tex data-pipe 97 % busy, profiles/r1_v9c).  A half-warp
+// therefore keeps its window open over P2G_ROUNDS x 16 consecutive particles instead of 16: with 8 particles per cell the
+// reductions per lane drop from 5 per 16 particles to 19 per 128 (measured: 3.77 ms at 1 round, 3.05 at 4, 2.95 at 8, 2.91 at 16).  Round r of a warp loads, per half-warp h, the particles
+// base + h*16*ROUNDS + r*16 + (lane & 15), so each half-warp walks one contiguous piece of the sorted order.
+#ifndef P2G_ROUNDS
+#define P2G_ROUNDS 8
+#endif
+#define P2G_CTA_PARTICLES (256 * P2G_ROUNDS)
 __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
     __shared__ float4 stage[8][2][P2G_HW_F4];
     __shared__ float4 bounce[256];                                            // lane-private slots of requad()
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float4* slot = bounce + threadIdx.x;
-    const int chunk = strided_chunk(blockIdx.x, (n + 255) / 256, G.strips);
+    const int chunk = strided_chunk(blockIdx.x, (n + P2G_CTA_PARTICLES - 1) / P2G_CTA_PARTICLES, G.strips);
     if (chunk < 0) return;
-    const int base = chunk * 256 + wib * 32;
-    if (base >= n) return;                                                   // warp-uniform; no block-level barrier below
-    const int cnt = min(32, n - base);
-    unsigned ends;
-    {   // ---- phase A
-        const int p = base + min(lane, cnt - 1);
-        const float4 X = ldg4(P.a[PX] + p), VM = ldg4(P.a[PVM] + p);
-        const float4 c0 = ldg4(P.a[PC0] + p), c1 = ldg4(P.a[PC1] + p), c2 = ldg4(P.a[PC2] + p);
-        float Nx[4], Ny[4], Nz[4], D[4];
-        bspline4(X.x, Nx, D); bspline4(X.y, Ny, D); bspline4(X.z, Nz, D);
-        const float m = (lane < cnt) ? VM.w : 0.0f;                          // padding lanes repeat the last particle with zero mass
-        const float k = m * G.apic;
-        float Q[9] = { k * c0.x * G.hx, k * c0.y * G.hy, k * c0.z * G.hz, k * c1.x * G.hx, k * c1.y * G.hy, k * c1.z * G.hz,
-                       k * c2.x * G.hx, k * c2.y * G.hy, k * c2.z * G.hz };
-        const float gx = 1.0f + X.x, gy = 1.0f + X.y, gz = 1.0f + X.z;       // x_i - x_p = h (o - (1 + f))
-        const float q0x = fmaf(m, VM.x, -(Q[0] * gx + Q[1] * gy + Q[2] * gz));
-        const float q0y = fmaf(m, VM.y, -(Q[3] * gx + Q[4] * gy + Q[5] * gz));
-        const float q0z = fmaf(m, VM.z, -(Q[6] * gx + Q[7] * gy + Q[8] * gz));
-        float4* rec = &stage[wib][lane >> 4][(lane & 15) * P2G_STRIDE];
-        rec[0] = make_float4(Nx[0], Nx[1], Nx[2], Nx[3]); rec[1] = make_float4(Ny[0], Ny[1], Ny[2], Ny[3]); rec[2] = make_float4(Nz[0], Nz[1], Nz[2], Nz[3]);
-        rec[3] = make_float4(m, q0x, q0y, q0z);
-        rec[4] = make_float4(0.f, Q[0], Q[3], Q[6]); rec[5] = make_float4(0.f, Q[1], Q[4], Q[7]); rec[6] = make_float4(0.f, Q[2], Q[5], Q[8]);
-        rec[7].x = X.w;
-        ends = run_ends(__float_as_int(X.w));
-    }
-    __syncwarp();
-    // ---- phase B: half-warp per particle, lane = (j,k) row of the stencil, 4 nodes along x in packed accumulators
     const int hw = lane >> 4, s = lane & 15, j = s & 3, k = s >> 2;
+    const int hbase = chunk * P2G_CTA_PARTICLES + wib * (32 * P2G_ROUNDS) + hw * (16 * P2G_ROUNDS);      // first particle of this half-warp
+    if (chunk * P2G_CTA_PARTICLES + wib * (32 * P2G_ROUNDS) >= n) return;    // warp-uniform; no block-level barrier below
+    const int hend = hbase + 16 * P2G_ROUNDS;                                // one past its last particle (may exceed n)
     float fj = (float)j, fk = (float)k;
     int yoff = 16 + 4 * j, zoff = 32 + 4 * k;                                 // byte offsets of Ny[j], Nz[k] inside a record
     // lane constants: ptxas re-derives them from %tid on every trip (8 instructions) unless they come out of something it cannot
@@ -469,31 +476,62 @@ __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
     fj = __shfl_sync(0xffffffffu, fj, lane); fk = __shfl_sync(0xffffffffu, fk, lane);
     yoff = __shfl_sync(0xffffffffu, yoff, lane); zoff = __shfl_sync(0xffffffffu, zoff, lane);
     const f32x2 J = pk1(fj), K = pk1(fk);
-    ends >>= hw * 16;
     AccRow acc; acc_zero(acc);
     const float4* recs = &stage[wib][hw][0];
 #pragma unroll 1
-    for (int it = 0; it < 16; ++it) {
-        const float4* r = recs + it * P2G_STRIDE;
-        const float4 nx = r[0];
-        const float wyz = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(r) + yoff) * *reinterpret_cast<const float*>(reinterpret_cast<const char*>(r) + zoff);
-        const ulonglong2 b0 = ld_pairs(r + 3), si = ld_pairs(r + 4), sj = ld_pairs(r + 5), sk = ld_pairs(r + 6);
-        f32x2 Tlo = fma2(sj.x, J, fma2(sk.x, K, b0.x));                        // (m, px) of node (0, j, k)
-        f32x2 Thi = fma2(sj.y, J, fma2(sk.y, K, b0.y));                        // (py, pz)
-        f32x2 W = pk1(nx.x * wyz);
-        acc.lo[0] = fma2(W, Tlo, acc.lo[0]); acc.hi[0] = fma2(W, Thi, acc.hi[0]);
-        Tlo = add2(Tlo, si.x); Thi = add2(Thi, si.y); W = pk1(nx.y * wyz);
-        acc.lo[1] = fma2(W, Tlo, acc.lo[1]); acc.hi[1] = fma2(W, Thi, acc.hi[1]);
-        Tlo = add2(Tlo, si.x); Thi = add2(Thi, si.y); W = pk1(nx.z * wyz);
-        acc.lo[2] = fma2(W, Tlo, acc.lo[2]); acc.hi[2] = fma2(W, Thi, acc.hi[2]);
-        Tlo = add2(Tlo, si.x); Thi = add2(Thi, si.y); W = pk1(nx.w * wyz);
-        acc.lo[3] = fma2(W, Tlo, acc.lo[3]); acc.hi[3] = fma2(W, Thi, acc.hi[3]);
-        if ((ends >> it) & 1u) {                                              // the run of particles sharing this cell ends here
-            const int cur = __float_as_int(r[7].x);
-            const int nxt = (it == 15) ? -1 : __float_as_int(r[P2G_STRIDE + 7].x);
-            if (!slide_row_pk(G, G.mp, slot, cur, nxt, j, k, acc, true)) {
-                flush_row_pk(G, G.mp, slot, cur, j, k, acc, true);
-                acc_zero_ordered(acc);
+    for (int round = 0; round < P2G_ROUNDS; ++round) {
+        unsigned ends;
+        {   // ---- phase A: thread per particle
+            const int q = hbase + round * 16 + s;                            // may lie past the end: such lanes repeat the last particle with zero mass
+            const int p = min(q, n - 1);
+            const float4 X = ldg4(P.a[PX] + p), VM = ldg4(P.a[PVM] + p);
+            const float4 c0 = ldg4(P.a[PC0] + p), c1 = ldg4(P.a[PC1] + p), c2 = ldg4(P.a[PC2] + p);
+            // cell of the half-warp's next particle (-1 behind its last one): the lines are the ones the neighbouring lanes load
+            const int ncell = (q + 1 < hend) ? __float_as_int(__ldg(&P.a[PX][min(q + 1, n - 1)].w)) : -1;
+            float Nx[4], Ny[4], Nz[4], D[4];
+            bspline4(X.x, Nx, D); bspline4(X.y, Ny, D); bspline4(X.z, Nz, D);
+            const float m = (q < n) ? VM.w : 0.0f;
+            const float km = m * G.apic;
+            float Q[9] = { km * c0.x * G.hx, km * c0.y * G.hy, km * c0.z * G.hz, km * c1.x * G.hx, km * c1.y * G.hy, km * c1.z * G.hz,
+                           km * c2.x * G.hx, km * c2.y * G.hy, km * c2.z * G.hz };
+            const float gx = 1.0f + X.x, gy = 1.0f + X.y, gz = 1.0f + X.z;   // x_i - x_p = h (o - (1 + f))
+            const float q0x = fmaf(m, VM.x, -(Q[0] * gx + Q[1] * gy + Q[2] * gz));
+            const float q0y = fmaf(m, VM.y, -(Q[3] * gx + Q[4] * gy + Q[5] * gz));
+            const float q0z = fmaf(m, VM.z, -(Q[6] * gx + Q[7] * gy + Q[8] * gz));
+            __syncwarp();                                                    // phase B of the round before is done with the records
+            float4* rec = &stage[wib][hw][s * P2G_STRIDE];
+            rec[0] = make_float4(Nx[0], Nx[1], Nx[2], Nx[3]); rec[1] = make_float4(Ny[0], Ny[1], Ny[2], Ny[3]); rec[2] = make_float4(Nz[0], Nz[1], Nz[2], Nz[3]);
+            rec[3] = make_float4(m, q0x, q0y, q0z);
+            rec[4] = make_float4(0.f, Q[0], Q[3], Q[6]); rec[5] = make_float4(0.f, Q[1], Q[4], Q[7]); rec[6] = make_float4(0.f, Q[2], Q[5], Q[8]);
+            rec[7] = make_float4(X.w, __int_as_float(ncell), 0.f, 0.f);
+            ends = __ballot_sync(0xffffffffu, ncell != __float_as_int(X.w));
+        }
+        __syncwarp();
+        // ---- phase B: half-warp per particle, lane = (j,k) row of the stencil, 4 nodes along x in packed accumulators
+        ends >>= hw * 16;
+#pragma unroll 1
+        for (int it = 0; it < 16; ++it) {
+            const float4* r = recs + it * P2G_STRIDE;
+            const float4 nx = r[0];
+            const float wyz = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(r) + yoff) * *reinterpret_cast<const float*>(reinterpret_cast<const char*>(r) + zoff);
+            const ulonglong2 b0 = ld_pairs(r + 3), si = ld_pairs(r + 4), sj = ld_pairs(r + 5), sk = ld_pairs(r + 6);
+            f32x2 Tlo = fma2(sj.x, J, fma2(sk.x, K, b0.x));                    // (m, px) of node (0, j, k)
+            f32x2 Thi = fma2(sj.y, J, fma2(sk.y, K, b0.y));                    // (py, pz)
+            f32x2 W = pk1(nx.x * wyz);
+            acc.lo[0] = fma2(W, Tlo, acc.lo[0]); acc.hi[0] = fma2(W, Thi, acc.hi[0]);
+            Tlo = add2(Tlo, si.x); Thi = add2(Thi, si.y); W = pk1(nx.y * wyz);
+            acc.lo[1] = fma2(W, Tlo, acc.lo[1]); acc.hi[1] = fma2(W, Thi, acc.hi[1]);
+            Tlo = add2(Tlo, si.x); Thi = add2(Thi, si.y); W = pk1(nx.z * wyz);
+            acc.lo[2] = fma2(W, Tlo, acc.lo[2]); acc.hi[2] = fma2(W, Thi, acc.hi[2]);
+            Tlo = add2(Tlo, si.x); Thi = add2(Thi, si.y); W = pk1(nx.w * wyz);
+            acc.lo[3] = fma2(W, Tlo, acc.lo[3]); acc.hi[3] = fma2(W, Thi, acc.hi[3]);
+            if ((ends >> it) & 1u) {                                          // the run of particles sharing this cell ends here
+                const float2 cn = *reinterpret_cast<const float2*>(r + 7);
+                const int cur = __float_as_int(cn.x), nxt = __float_as_int(cn.y);
+                if (!slide_row_pk(G, G.mp, slot, cur, nxt, j, k, acc, true)) {
+                    flush_row_pk(G, G.mp, slot, cur, j, k, acc, true);
+                    acc_zero_ordered(acc);
+                }
             }
         }
     }
@@ -501,7 +539,7 @@ __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
 
 // launch helper shared by the engine, the slab arrivals and the mesh transfers
 inline void p2g_launch(cudaStream_t st, const PartP& P, const GridP& G, long long n) {
-    const int chunks = (int)((n + 255) / 256);
+    const int chunks = (int)((n + P2G_CTA_PARTICLES - 1) / P2G_CTA_PARTICLES);
     k_p2g<<<strided_grid(chunks, G.strips), 256, 0, st>>>(P, G, (int)n);
 }
 
@@ -536,10 +574,11 @@ __global__ void __launch_bounds__(256) k_init_volumes(PartP P, GridP G, int n) {
 
 // v_i = p_i / m_i where m_i > 0 (HybridSolver.cpp:233-240) for every active node, into the vt array (free between P2G and
 // the grid update), so that the force gather below does 64 loads and no divisions per particle.
-__global__ void __launch_bounds__(256) k_grid_normalise(GridP G) {
+__global__ void __launch_bounds__(256) k_grid_normalise(GridP G, const unsigned int* __restrict__ list, const unsigned int* __restrict__ count) {
+    const unsigned nb = *count;
+    for (unsigned q = blockIdx.x; q < nb; q += gridDim.x) {
     int bx, by, bz;
-    const int b = run_block(G, blockIdx.x, bx, by, bz);
-    if (!G.flags[b]) return;
+    run_block(G, (int)list[q], bx, by, bz);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int t = threadIdx.x + 256 * h;
@@ -550,6 +589,7 @@ __global__ void __launch_bounds__(256) k_grid_normalise(GridP G) {
             const float im = mp.x > 0.0f ? 1.0f / mp.x : 0.0f;
             G.vt[n] = make_float4(mp.y * im, mp.z * im, mp.w * im, 1.0f);
         }
+    }
     }
 }
 
@@ -636,7 +676,10 @@ __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, cons
 #define FRC_HW_PAD 2
 #define FRC_WARP_F4 (2 * (16 * FRC_STRIDE + FRC_HW_PAD))
 static_assert(FRC_WARP_F4 >= TILE_F4, "the gather tile is aliased onto the warp's record area");
-__global__ void __launch_bounds__(FRC_NT, 6) k_forces(PartP P, GridP G, MatParams mpar, const SimClock* __restrict__ clk, int n) {
+#ifndef FRC_MIN_CTAS
+#define FRC_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP G, MatParams mpar, const SimClock* __restrict__ clk, int n) {
     __shared__ float4 stage[FRC_NT / 32][FRC_WARP_F4];
     __shared__ float4 bounce[FRC_NT];                                          // lane-private slots of requad()
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -769,6 +812,209 @@ __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const
     }
 }
 
+// Two builds of the G2P kernel: the default (one CTA per 128 particles, register-staged tile) and -DAEP_G2P_PIPE=1, a
+// persistent-warp variant that software-pipelines every memory round trip of a chunk behind the arithmetic of the chunk before.
+// The pipelined variant removes the long-scoreboard stalls it was written for but executes 6 % more instructions and misses
+// the instruction cache more often, and loses by 5-8 % on B200 (profiles/README.md, v9b / v9d), so it is not the default.
+#ifndef AEP_G2P_PIPE
+#define AEP_G2P_PIPE 0
+#endif
+#if AEP_G2P_PIPE
+// asynchronous version of stage_tile: the warp's grid tile is fetched with cp.async (no registers, no wait) for a chunk whose X
+// records are already in registers, so that the copy flies behind the arithmetic of the chunk before.  Warp-uniform result.
+__device__ __forceinline__ void cp_async16(float4* smem_dst, const float4* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_stream(float4* smem_dst, const float4* gsrc) {      // L2 only: streaming particle data stays out of L1
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }   // all but the N most recent groups
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ bool tile_issue(const GridP& G, float4* __restrict__ tile, TileRef& T, int cell) {
+    if (!AEP_USE_TILE) return false;
+    const int lane = threadIdx.x & 31;
+    const int ci = cell_i(cell), cj = cell_j(cell), ck = cell_k(cell);
+    const bool complete = ci >= 1 && ci + 2 < G.nx && cj >= 1 && cj + 2 < G.ny && ck >= 1 && ck + 2 < G.nz;     // == axis_setup's
+    const int cref = __shfl_sync(0xffffffffu, cell, 0);
+    T.ox0 = cell_i(cref) - 1 - TILE_SLACK; T.j0 = cell_j(cref) - 1; T.k0 = cell_k(cref) - 1;
+    const bool fits = complete && ((cell ^ cref) >> 10) == 0 && (ci - 1) >= T.ox0 && (ci + 2) < T.ox0 + TILE_W;
+    if (!__all_sync(0xffffffffu, fits)) return false;
+#pragma unroll
+    for (int q = 0; q < TILE_F4 / 32; ++q) {
+        const int idx = lane + 32 * q;
+        const int r = idx / TILE_W, x = idx - r * TILE_W, gx = T.ox0 + x;
+        if (gx >= 0 && gx < G.nx) cp_async16(tile + idx, G.vt + ((size_t)(T.k0 + (r >> 2)) * G.ny + (T.j0 + (r & 3))) * G.nx + gx);
+    }
+    return true;
+}
+
+// updateParticleVelocities_ (HybridSolver.cpp:739-745), updateAffineMomenta_ with damp 0 (:760-825, :908-917),
+// advection x = sum w (x_i + dt v~_i) (:942-945), updateDeformationGradient_ (:553-578), updatePlasticity_
+// (:612-681), all in registers, one thread per particle.  Writes the new sort key.
+//
+// Persistent warps: G2P_CTAS_PER_SM CTAs per SM, every warp walks chunks of 32 cell-sorted particles with a grid stride.  A chunk
+// used to open with two dependent memory round trips (X from DRAM, then the grid tile whose position X decides) and to wait
+// again for F_E / F_P after the gather: 20 % of the kernel's stall samples at 4 warps per scheduler
+// (profiles/r1_v8_k_g2p_sass_summary.txt).  Everything a chunk needs now arrives by cp.async while the chunk before it computes --
+// X two chunks ahead, F_E / F_P one chunk ahead, the grid tile as soon as the gather of the current chunk is done with the
+// buffer -- into the warp's own shared memory, so no prefetched value ever occupies a register (a register-staged variant
+// spilled the prefetched X at once and stalled on the spill store: profiles/README.md, v9b).
+#define G2P_NT 128
+#define G2P_CTAS_PER_SM 4
+struct G2PWarpSmem {
+    float4 tile[TILE_F4];
+    float4 x[2][32];
+    float4 eq[6][32];
+};
+__global__ void __launch_bounds__(G2P_NT, G2P_CTAS_PER_SM) k_g2p(PartP P, GridP G, MatParams mpar, SimClock* __restrict__ clk,
+                                             unsigned int* __restrict__ keys, unsigned int* __restrict__ vals, int n, MigList ML) {
+    __shared__ G2PWarpSmem wsm[G2P_NT / 32];
+    const int lane = threadIdx.x & 31;
+    G2PWarpSmem& W = wsm[threadIdx.x >> 5];
+    float4* tile = W.tile;
+    const int nchunks = (n + 31) >> 5, wstride = gridDim.x * (G2P_NT / 32);
+    int chunk = blockIdx.x * (G2P_NT / 32) + (threadIdx.x >> 5);            // the warps of a CTA take neighbouring chunks (shared L1 lines)
+    if (chunk >= nchunks) return;
+    const float dt = clk->dt;
+    TileRef T;
+    bool use_tile;
+    int buf = 0;
+    {   // prologue: X of the first chunk (waited for), then its tile, its F_E / F_P and the X of the second chunk in flight
+        const int p = min(chunk * 32 + lane, n - 1);
+        cp_async16_stream(&W.x[0][lane], P.a[PX] + p);
+        cp_async_wait_all();
+        use_tile = tile_issue(G, tile, T, __float_as_int(W.x[0][lane].w));
+        cp_async_commit();                                                  // group "tile"
+#pragma unroll
+        for (int a = 0; a < 6; ++a) cp_async16_stream(&W.eq[a][lane], P.a[PE0 + a] + p);
+        if (chunk + wstride < nchunks) cp_async16_stream(&W.x[1][lane], P.a[PX] + min((chunk + wstride) * 32 + lane, n - 1));
+        cp_async_commit();                                                  // group "particle data"
+    }
+    for (;;) {
+        const int p_raw = chunk * 32 + lane;
+        const bool live = p_raw < n;                                        // tail lanes recompute the last particle and write nothing:
+        const int p = live ? p_raw : n - 1;                                 // the warp stays converged for the votes below
+        const int next = chunk + wstride;
+        const bool more = next < nchunks;                                   // warp-uniform
+        cp_async_wait_group<1>();                                           // the tile has landed; this chunk's F_E / F_P and the next X may still fly
+        __syncwarp();
+        const float4 X = W.x[buf][lane];
+        const int cell = __float_as_int(X.w);
+        int ci = cell_i(cell), cj = cell_j(cell), ck = cell_k(cell);
+        Axis ax, ay, az;
+        bool complete = axis_setup(ax, X.x, ci, G.nx, G.ihx);
+        complete &= axis_setup(ay, X.y, cj, G.ny, G.ihy);
+        complete &= axis_setup(az, X.z, ck, G.nz, G.ihz);
+        float rx[4], ry[4], rz[4];                                              // x_i - x_p per axis: h (o - 1 - f)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) { rx[o] = G.hx * ((float)(o - 1) - X.x); ry[o] = G.hy * ((float)(o - 1) - X.y); rz[o] = G.hz * ((float)(o - 1) - X.z); }
+        float nrx[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) nrx[o] = ax.N[o] * rx[o];
+        G2PSums S;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { S.vc[i] = 0.f; S.va[i] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { S.B[i] = 0.f; S.g[i] = 0.f; }
+        if (use_tile) g2p_gather<2>(G, ax, ay, az, nrx, rx, ry, rz, tile, ax.n0 - T.ox0, S);
+        else g2p_gather<0>(G, ax, ay, az, nrx, rx, ry, rz, tile, 0, S);      // rare (row ends, freshly moved particles, domain faces): clamped global loads
+        cp_async_wait_group<0>();                                           // F_E / F_P of this chunk, X of the next
+        __syncwarp();                                                       // every lane is done with the tile
+        if (more) use_tile = tile_issue(G, tile, T, __float_as_int(W.x[buf ^ 1][lane].w));
+        cp_async_commit();                                                  // group "tile" of the next chunk
+        float (&va)[3] = S.va; float (&B)[9] = S.B; float (&g)[9] = S.g;
+        const float vp[3] = { S.va[0] + S.vc[0], S.va[1] + S.vc[1], S.va[2] + S.vc[2] };       // sum w s v~ = sum w v~ - sum_{s=0} w v~
+        // ---- advection (HybridSolver.cpp:944): x' = sum w (x_i + dt v~_i) = x + [sum w (x_i - x)] + (sum w - 1) x + dt sum w v~
+        // the bracket and (sum w - 1) vanish unless the stencil is truncated by the domain boundary (:44-46); both are separable.
+        float dxp = dt * va[0], dyp = dt * va[1], dzp = dt * va[2];
+        if (!complete) {
+            const float sx = ax.N[0] + ax.N[1] + ax.N[2] + ax.N[3], sy = ay.N[0] + ay.N[1] + ay.N[2] + ay.N[3], sz = az.N[0] + az.N[1] + az.N[2] + az.N[3];
+            const float mx = nrx[0] + nrx[1] + nrx[2] + nrx[3];
+            const float my = ay.N[0] * ry[0] + ay.N[1] * ry[1] + ay.N[2] * ry[2] + ay.N[3] * ry[3];
+            const float mz = az.N[0] * rz[0] + az.N[1] * rz[1] + az.N[2] * rz[2] + az.N[3] * rz[3];
+            const float s0 = sx * sy * sz;
+            const float xw = fmaf((float)ci + X.x, G.hx, G.mnx), yw = fmaf((float)cj + X.y, G.hy, G.mny), zw = fmaf((float)ck + X.z, G.hz, G.mnz);
+            dxp += mx * sy * sz + (s0 - 1.0f) * xw; dyp += sx * my * sz + (s0 - 1.0f) * yw; dzp += sx * sy * mz + (s0 - 1.0f) * zw;
+        }
+        float nfx = fmaf(dxp, G.ihx, X.x), nfy = fmaf(dyp, G.ihy, X.y), nfz = fmaf(dzp, G.ihz, X.z);
+        {
+            const float flx = floorf(nfx), fly = floorf(nfy), flz = floorf(nfz);
+            nfx -= flx; nfy -= fly; nfz -= flz; ci += (int)flx; cj += (int)fly; ck += (int)flz;
+            nfx = fminf(nfx, 0.99999994f); nfy = fminf(nfy, 0.99999994f); nfz = fminf(nfz, 0.99999994f);
+            const int cci = clampi(ci, 0, G.nx - 1), ccj = clampi(cj, 0, G.ny - 1), cck = clampi(ck, 0, G.nz - 1);
+            const bool nan = !(nfx == nfx) || !(nfy == nfy) || !(nfz == nfz);
+            if (cci != ci || ccj != cj || cck != ck || nan) {
+                if (live) atomicAdd(&clk->escaped, 1ull);
+                if (!(nfx == nfx)) nfx = 0.5f;
+                if (!(nfy == nfy)) nfy = 0.5f;
+                if (!(nfz == nfz)) nfz = 0.5f;
+            }
+            ci = cci; cj = ccj; ck = cck;
+        }
+        // ---- deformation gradient + plasticity
+        const float4 e0 = W.eq[0][lane], e1 = W.eq[1][lane], e2 = W.eq[2][lane];
+        const float4 q0 = W.eq[3][lane], q1 = W.eq[4][lane], q2 = W.eq[5][lane];
+        float FE[9] = { e0.x, e0.y, e0.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z };
+        float FP[9] = { q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z };
+        float GF[9], Fh[9];
+        mat_mul(g, FE, GF);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Fh[i] = fmaf(dt, GF[i], FE[i]);                  // HybridSolver.cpp:575
+        float q = e1.w;
+        return_map(mpar, Fh, FE, FP, q);
+        const float Jp = mat_det(FP);
+        // ---- write back
+        const int ncell = cell_pack(ci, cj, ck);
+        {   // particles that left their cell are out of order until the next physical sort
+            const unsigned mv = __ballot_sync(0xffffffffu, live && ncell != cell);
+            if ((threadIdx.x & 31) == 0 && mv) atomicAdd(&clk->moved_since_sort, (unsigned long long)__popc(mv));
+        }
+        if (live) {
+            P.a[PX][p] = make_float4(nfx, nfy, nfz, __int_as_float(ncell));
+            P.a[PVM][p] = make_float4(vp[0], vp[1], vp[2], q1.w);
+            P.a[PC0][p] = make_float4(B[0], B[1], B[2], 0.f);
+            P.a[PC1][p] = make_float4(B[3], B[4], B[5], 0.f);
+            P.a[PC2][p] = make_float4(B[6], B[7], B[8], 0.f);
+            P.a[PE0][p] = make_float4(FE[0], FE[1], FE[2], e0.w);
+            P.a[PE1][p] = make_float4(FE[3], FE[4], FE[5], q);
+            P.a[PE2][p] = make_float4(FE[6], FE[7], FE[8], Jp);
+            P.a[PQ0][p] = make_float4(FP[0], FP[1], FP[2], q0.w);
+            P.a[PQ1][p] = make_float4(FP[3], FP[4], FP[5], q1.w);
+            P.a[PQ2][p] = make_float4(FP[6], FP[7], FP[8], q2.w);
+            keys[p] = sort_key(ci, cj, ck, G);
+            vals[p] = (unsigned)p;
+            if (ML.axis >= 0 && q1.w != 0.0f) {                                     // live particle of a slab context: did it leave the slab?
+                const int ca = ML.axis == 0 ? ci : (ML.axis == 1 ? cj : ck);
+                if (ca < ML.lo || ca >= ML.hi) {
+                    const int side = ca < ML.lo ? 0 : 1;
+                    const unsigned long long slot = atomicAdd(ML.counts + side, 1ull);
+                    if (slot < (unsigned long long)ML.cap) (side == 0 ? ML.list[0] : ML.list[1])[slot] = (unsigned)p;
+                }
+            }
+        }
+        if (!more) break;
+        // F_E / F_P of the next chunk and X of the one after it: this lane's slots were consumed above
+        {
+            const int pn = min(next * 32 + lane, n - 1);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) cp_async16_stream(&W.eq[a][lane], P.a[PE0 + a] + pn);
+            if (next + wstride < nchunks) cp_async16_stream(&W.x[buf][lane], P.a[PX] + min((next + wstride) * 32 + lane, n - 1));
+            cp_async_commit();                                              // group "particle data" of the next chunk
+        }
+        chunk = next; buf ^= 1;
+    }
+}
+
+inline void g2p_launch(cudaStream_t st, int sm_count, const PartP& P, const GridP& G, const MatParams& mat, SimClock* clk, unsigned int* keys,
+                       unsigned int* vals, long long n, const MigList& ML) {
+    const long long chunks = (n + 31) / 32, per_cta = G2P_NT / 32;
+    const int grid = (int)std::min<long long>((chunks + per_cta - 1) / per_cta, (long long)sm_count * G2P_CTAS_PER_SM);
+    k_g2p<<<grid, G2P_NT, 0, st>>>(P, G, mat, clk, keys, vals, (int)n, ML);
+}
+
+#else
 // updateParticleVelocities_ (HybridSolver.cpp:739-745), updateAffineMomenta_ with damp 0 (:760-825, :908-917),
 // advection x = sum w (x_i + dt v~_i) (:942-945), updateDeformationGradient_ (:553-578), updatePlasticity_
 // (:612-681), all in registers, one thread per particle.  The 64-node gather sums along x first (per (j,k) row:
@@ -885,6 +1131,7 @@ inline void g2p_launch(cudaStream_t st, int sm_count, const PartP& P, const Grid
     k_g2p<<<(unsigned)((n + G2P_NT - 1) / G2P_NT), G2P_NT, 0, st>>>(P, G, mat, clk, keys, vals, (int)n, ML);
 }
 
+#endif  // AEP_G2P_PIPE
 // ================================================================================================ host <-> device
 // fp64 reference layouts -> packed fp32 records.  `st` is a staged chunk: columns of length cnt, in the order
 // x(3) v(3) B1(3) B2(3) B3(3) m vol q, then FE (cnt x 9, column-major per particle), FP likewise.

@@ -516,7 +516,7 @@ def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, U
     sub_gbs = sub_bytes / (ms * 1e-3 / args.steps) / 1e9 / world
     roofline = {"bound": "hbm", "kernel": {"forces": "k_forces", "g2p": "k_g2p", "p2g": "k_p2g", "grid": "k_grid_update", "sort": "cub radix sort + k_reorder"}[dom],
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth, MEASURED_PEAKS.json", "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom], "stage_ms": stage_ms, "rank": 0,
+                "traffic": B.ncu_traffic({"forces": "k_forces", "g2p": "k_g2p", "p2g": "k_p2g"}.get(dom, ""), eng.n_particles), "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom], "stage_ms": stage_ms, "rank": 0,
                 "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs_per_gpu": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes}}
     halo_bytes = solver.stats["halo_bytes"]; migrated = solver.stats["migrated"]
     # e2e: fresh contexts, upload from pinned host memory + init + K substeps + f32 positions back, wall clock max over ranks

@@ -40,6 +40,19 @@ BYTES_NODE = 172.0
 STAGE_BYTES = {"forces": (52.0, 24.0), "g2p": (224.0, 24.0), "p2g": (64.0, 44.0), "grid": (0.0, 52.0), "sort": (0.0, 0.0)}
 
 
+def ncu_traffic(kernel, particles):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed `ncu --set full` capture of this
+    build (profiles/ncu_traffic.json, written from the capture by tools/ncu_traffic.py).  The capture is of the bench workload at
+    512^3; other sizes get it scaled per particle.  None when the file does not cover the kernel."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        k = t["kernels"][kernel]
+        return (k["dram_bytes_read"] + k["dram_bytes_write"]) * particles / t["particles"]
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -248,7 +261,7 @@ def run_engine(args):
     sub_gbs = sub_bytes / (ms * 1e-3 / args.steps) / 1e9
     roofline = {"bound": "hbm", "kernel": {"forces": "k_forces", "g2p": "k_g2p", "p2g": "k_p2g", "grid": "k_grid_update", "sort": "cub radix sort + k_reorder"}[dom],
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth, MEASURED_PEAKS.json", "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": ncu_traffic({"forces": "k_forces", "g2p": "k_g2p", "p2g": "k_p2g"}.get(dom, ""), n),
                 "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom],
                 "stage_ms": stage_ms,
                 "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes, "active_blocks": blocks}}
