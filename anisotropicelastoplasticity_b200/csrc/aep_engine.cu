@@ -367,6 +367,21 @@ int require_init(aep_ctx* c) {
 }  // namespace
 
 // ======================================================================================================== C ABI
+// particle arrays (two copies: the re-sort ping-pongs), sort keys and cub's scratch.  Done by aep_create when the configuration names
+// a capacity, so that a solver that is created once and fed many scenes / frames pays for the 23 GB of cudaMalloc once.
+static int ensure_particle_capacity(aep_ctx* c, long long cap) {
+    if (cap <= c->cap) return AEP_OK;
+    if (c->cap) return fail(c, AEP_ERR_INVALID, "particle capacity can only be set once per context");
+    for (int b = 0; b < 2; ++b)
+        for (int a = 0; a < P_NARR; ++a) CU(dalloc(c, &c->P[b].a[a], (size_t)cap));
+    for (int b = 0; b < 2; ++b) { CU(dalloc(c, &c->d_keys[b], (size_t)cap)); CU(dalloc(c, &c->d_vals[b], (size_t)cap)); }
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], (int)cap, 0, c->key_bits + 2, c->stream);
+    CU(cudaMalloc(&c->d_sort_tmp, tmp)); c->sort_tmp_bytes = tmp;
+    c->cap = cap;
+    return AEP_OK;
+}
+
 extern "C" {
 
 int aep_default_config(aep_config* cfg) {
@@ -448,6 +463,7 @@ int aep_create(aep_ctx** out, const aep_config* cfg) {
         const size_t nkeys = (size_t)G.nqx * G.nqy * ((G.nz + 3) / 4) * 64;
         ctx->key_bits = 1; while (((size_t)1 << ctx->key_bits) < nkeys) ctx->key_bits++;
     }
+    if (cfg->particle_capacity > 0 && ensure_particle_capacity(ctx, cfg->particle_capacity)) return bail(AEP_ERR_ALLOC);
     CUC(cudaStreamSynchronize(ctx->stream));
 #undef CUC
     *out = ctx;
@@ -486,17 +502,7 @@ int aep_upload_particles(aep_ctx* c, int64_t n, const double* x, const double* v
     if (!c || n < 0 || (n > 0 && (!x || !v || !B1 || !B2 || !B3 || !FE || !FP || !m || !vol || !q))) return fail(c, AEP_ERR_INVALID, "null particle array");
     if (n >= (1ll << 31) - 64) return fail(c, AEP_ERR_INVALID, "too many particles for one context");
     cudaSetDevice(c->device);
-    const long long cap = std::max<long long>(n, c->cfg.particle_capacity);
-    if (cap > c->cap) {
-        if (c->cap) return fail(c, AEP_ERR_INVALID, "particle capacity can only be set once per context");
-        for (int b = 0; b < 2; ++b)
-            for (int a = 0; a < P_NARR; ++a) CU(dalloc(c, &c->P[b].a[a], (size_t)cap));
-        for (int b = 0; b < 2; ++b) { CU(dalloc(c, &c->d_keys[b], (size_t)cap)); CU(dalloc(c, &c->d_vals[b], (size_t)cap)); }
-        size_t tmp = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], (int)cap, 0, c->key_bits + 2, c->stream);
-        CU(cudaMalloc(&c->d_sort_tmp, tmp)); c->sort_tmp_bytes = tmp;
-        c->cap = cap;
-    }
+    if (int r = ensure_particle_capacity(c, std::max<long long>(n, c->cfg.particle_capacity))) return r;
     c->n = n; c->cur = 0;
     // material constants (HS:261-265, 634-638)
     const double lambda = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu), mu = E / 2.0 / (1.0 + nu);
@@ -522,9 +528,9 @@ int aep_upload_particles(aep_ctx* c, int64_t n, const double* x, const double* v
         CU(cudaMemcpyAsync(st + (size_t)27 * cnt, FP + (size_t)9 * p0, 9 * cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         k_upload_convert<<<cdiv(cnt, 256), 256, 0, c->stream>>>(c->P[0], c->G, st, (int)cnt, (int)p0, c->id_base + p0, c->cfg.grid_min[0], c->cfg.grid_min[1],
                                                                c->cfg.grid_min[2], c->h[0], c->h[1], c->h[2], c->d_clk);
-        LAUNCH_OK("k_upload_convert");
-        CU(cudaStreamSynchronize(c->stream));
+        LAUNCH_OK("k_upload_convert");                                        // the staging buffer is reused in stream order
     }
+    CU(cudaStreamSynchronize(c->stream));                                    // the caller's arrays are free again
     c->inited = false;
     return AEP_OK;
 }

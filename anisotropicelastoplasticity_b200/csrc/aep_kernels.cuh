@@ -603,6 +603,10 @@ __global__ void __launch_bounds__(256) k_grid_normalise(GridP G, const unsigned 
 #ifndef AEP_USE_TILE
 #define AEP_USE_TILE 1
 #endif
+// Warps that cannot use the tile gather straight from global memory with clamped indices (MODE 0).  A second fallback with
+// unclamped "interior" addressing (MODE 1) was 5 % faster on the ~1 % of warps that take it but made both gather kernels 17 %
+// larger; the instruction cache matters more (no_instruction stalls, profiles/README.md v10).
+#define AEP_FALLBACK_MODE 0
 #define TILE_W 12                       // nodes along x held by a warp's tile: up to 9 cells in a row
 #define TILE_SLACK 1                    // nodes left of lane 0's stencil (tolerates slightly out-of-order particles)
 #define TILE_F4 (16 * TILE_W)           // float4 per warp tile (16 (j,k) rows)
@@ -702,8 +706,7 @@ __global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP 
         float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         TileRef T;
         if (stage_tile(G, tile, T, cell, complete)) gather_grad<2>(G, ax, ay, az, tile, ax.n0 - T.ox0, g);
-        else if (__all_sync(0xffffffffu, complete)) gather_grad<1>(G, ax, ay, az, tile, 0, g);
-        else gather_grad<0>(G, ax, ay, az, tile, 0, g);
+        else gather_grad<AEP_FALLBACK_MODE>(G, ax, ay, az, tile, 0, g);           // rare: row ends, freshly moved particles, domain faces
         const float FE[9] = { e0.x, e0.y, e0.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z };
         float GF[9], Fh[9], A[9];
         mat_mul(g, FE, GF);
@@ -761,6 +764,7 @@ __global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP 
 // the correction branch runs only for rows that contain a sticking node.
 struct G2PSums {
     float va[3], vc[3], B[9], g[9];
+    float smin;                          // min of the s flags seen: 0 iff the stencil holds a sticking node
 };
 template <int MODE>
 __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const Axis& ay, const Axis& az, const float (&nrx)[4],
@@ -797,18 +801,29 @@ __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const
             S.B[0] = fmaf(d0, nn, S.B[0]); S.B[1] = fmaf(u0, ry[j], S.B[1]); S.B[2] = fmaf(u0, rzk, S.B[2]);
             S.B[3] = fmaf(d1, nn, S.B[3]); S.B[4] = fmaf(u1, ry[j], S.B[4]); S.B[5] = fmaf(u1, rzk, S.B[5]);
             S.B[6] = fmaf(d2, nn, S.B[6]); S.B[7] = fmaf(u2, ry[j], S.B[7]); S.B[8] = fmaf(u2, rzk, S.B[8]);
-            if (t[0].w * t[1].w * t[2].w * t[3].w == 0.0f) {                 // a sticking node in this row (rare)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float w = (t[i].w == 0.0f) ? -ax.N[i] * nn : 0.0f;
-                    const float cx = w * t[i].x, cy = w * t[i].y, cz = w * t[i].z;
-                    S.vc[0] += cx; S.vc[1] += cy; S.vc[2] += cz;
-                    S.B[0] = fmaf(cx, rx[i], S.B[0]); S.B[1] = fmaf(cx, ry[j], S.B[1]); S.B[2] = fmaf(cx, rzk, S.B[2]);
-                    S.B[3] = fmaf(cy, rx[i], S.B[3]); S.B[4] = fmaf(cy, ry[j], S.B[4]); S.B[5] = fmaf(cy, rzk, S.B[5]);
-                    S.B[6] = fmaf(cz, rx[i], S.B[6]); S.B[7] = fmaf(cz, ry[j], S.B[7]); S.B[8] = fmaf(cz, rzk, S.B[8]);
-                }
-            }
+            S.smin = fminf(fminf(S.smin, fminf(t[0].w, t[1].w)), fminf(t[2].w, t[3].w));   // 0 iff a sticking node was seen (FMNMX: ALU pipe)
         }
+    }
+}
+// second pass, taken only by particles whose stencil holds a sticking node (next to the collider): subtract w v~ of those nodes
+// from v_p and B.  Kept out of the gather loop and rolled up: the hot loop stays branch-free and half as long.
+template <int MODE>
+__device__ __forceinline__ void g2p_stick_correction(const GridP& G, const Axis& ax, const Axis& ay, const Axis& az, const float (&rx)[4],
+                                                  const float (&ry)[4], const float (&rz)[4], const float4* __restrict__ tile, int xoff, G2PSums& S) {
+#pragma unroll 1
+    for (int n = 0; n < 64; ++n) {
+        const int i = n & 3, j = (n >> 2) & 3, k = n >> 4;
+        float4 t;
+        if (MODE == 2) t = tile[xoff + (k * 4 + j) * TILE_W + i];
+        else t = ldg4(G.vt + ((size_t)clampi(az.n0 + k, 0, G.nz - 1) * G.ny + clampi(ay.n0 + j, 0, G.ny - 1)) * G.nx + clampi(ax.n0 + i, 0, G.nx - 1));
+        if (t.w != 0.0f) continue;
+        const float w = -sel4(ax.N, i) * sel4(ay.N, j) * sel4(az.N, k);
+        const float cx = w * t.x, cy = w * t.y, cz = w * t.z;
+        const float rxi = sel4(rx, i), ryj = sel4(ry, j), rzk = sel4(rz, k);
+        S.vc[0] += cx; S.vc[1] += cy; S.vc[2] += cz;
+        S.B[0] = fmaf(cx, rxi, S.B[0]); S.B[1] = fmaf(cx, ryj, S.B[1]); S.B[2] = fmaf(cx, rzk, S.B[2]);
+        S.B[3] = fmaf(cy, rxi, S.B[3]); S.B[4] = fmaf(cy, ryj, S.B[4]); S.B[5] = fmaf(cy, rzk, S.B[5]);
+        S.B[6] = fmaf(cz, rxi, S.B[6]); S.B[7] = fmaf(cz, ryj, S.B[7]); S.B[8] = fmaf(cz, rzk, S.B[8]);
     }
 }
 
@@ -918,8 +933,9 @@ __global__ void __launch_bounds__(G2P_NT, G2P_CTAS_PER_SM) k_g2p(PartP P, GridP 
         for (int i = 0; i < 3; ++i) { S.vc[i] = 0.f; S.va[i] = 0.f; }
 #pragma unroll
         for (int i = 0; i < 9; ++i) { S.B[i] = 0.f; S.g[i] = 0.f; }
-        if (use_tile) g2p_gather<2>(G, ax, ay, az, nrx, rx, ry, rz, tile, ax.n0 - T.ox0, S);
-        else g2p_gather<0>(G, ax, ay, az, nrx, rx, ry, rz, tile, 0, S);      // rare (row ends, freshly moved particles, domain faces): clamped global loads
+        S.smin = 1.0f;
+        if (use_tile) { g2p_gather<2>(G, ax, ay, az, nrx, rx, ry, rz, tile, ax.n0 - T.ox0, S); if (S.smin == 0.0f) g2p_stick_correction<2>(G, ax, ay, az, rx, ry, rz, tile, ax.n0 - T.ox0, S); }
+        else { g2p_gather<0>(G, ax, ay, az, nrx, rx, ry, rz, tile, 0, S); if (S.smin == 0.0f) g2p_stick_correction<0>(G, ax, ay, az, rx, ry, rz, tile, 0, S); }
         cp_async_wait_group<0>();                                           // F_E / F_P of this chunk, X of the next
         __syncwarp();                                                       // every lane is done with the tile
         if (more) use_tile = tile_issue(G, tile, T, __float_as_int(W.x[buf ^ 1][lane].w));
@@ -1050,10 +1066,15 @@ __global__ void __launch_bounds__(G2P_NT, 4) k_g2p(PartP P, GridP G, MatParams m
     for (int i = 0; i < 3; ++i) { S.vc[i] = 0.f; S.va[i] = 0.f; }
 #pragma unroll
     for (int i = 0; i < 9; ++i) { S.B[i] = 0.f; S.g[i] = 0.f; }
+    S.smin = 1.0f;
     TileRef T;
-    if (stage_tile(G, tile, T, cell, complete)) g2p_gather<2>(G, ax, ay, az, nrx, rx, ry, rz, tile, ax.n0 - T.ox0, S);
-    else if (__all_sync(0xffffffffu, complete)) g2p_gather<1>(G, ax, ay, az, nrx, rx, ry, rz, tile, 0, S);
-    else g2p_gather<0>(G, ax, ay, az, nrx, rx, ry, rz, tile, 0, S);
+    if (stage_tile(G, tile, T, cell, complete)) {
+        g2p_gather<2>(G, ax, ay, az, nrx, rx, ry, rz, tile, ax.n0 - T.ox0, S);
+        if (S.smin == 0.0f) g2p_stick_correction<2>(G, ax, ay, az, rx, ry, rz, tile, ax.n0 - T.ox0, S);
+    } else {                                                                 // rare: row ends, freshly moved particles, domain faces
+        g2p_gather<AEP_FALLBACK_MODE>(G, ax, ay, az, nrx, rx, ry, rz, tile, 0, S);
+        if (S.smin == 0.0f) g2p_stick_correction<0>(G, ax, ay, az, rx, ry, rz, tile, 0, S);
+    }
     float (&va)[3] = S.va; float (&B)[9] = S.B; float (&g)[9] = S.g;
     const float vp[3] = { S.va[0] + S.vc[0], S.va[1] + S.vc[1], S.va[2] + S.vc[2] };       // sum w s v~ = sum w v~ - sum_{s=0} w v~
     // ---- advection (HybridSolver.cpp:944): x' = sum w (x_i + dt v~_i) = x + [sum w (x_i - x)] + (sum w - 1) x + dt sum w v~

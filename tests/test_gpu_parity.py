@@ -75,6 +75,46 @@ def test_stagewise_parity(name):
     assert e.clock()["escaped"] == 0
 
 
+def _sticking_scene(material):
+    """A block that overlaps the ground plane and moves into it almost vertically: |v_t| < 0.2 |v_n| on the collider nodes."""
+    from anisotropicelastoplasticity_b200 import scenes as sc
+    scene = sc.small_block(material=material, res=16, cells=3, seed=11, perturb=False)
+    rng = np.random.default_rng(12)
+    sc.perturb_state(scene.particles, rng, strain=1e-2, vel=0.0, affine=0.02)       # small B: the node velocities follow v
+    scene.particles.v = np.array([0.05, 0.02, -1.0]) + 0.02 * rng.standard_normal(scene.particles.v.shape)
+    return scene
+
+
+@pytest.mark.parametrize("material", ["sand", "snow"])
+def test_sticking_collider_nodes(material):
+    """Nodes that stick to the collider (HS:494-502: v = 0 while the pre-friction copy keeps v~) take the second pass of k_g2p
+    (g2p_stick_correction).  The scene must contain such nodes, and the particles whose stencil touches one must match the oracle
+    in v and B (they use the post-friction field) as well as in x and F (pre-friction field)."""
+    from anisotropicelastoplasticity_b200 import scenes as sc
+    scene = _sticking_scene(sc.SAND if material == "sand" else sc.SNOW)
+    e = _engine(scene); o = _oracle(scene)
+    e.init(); o.init()
+    dt0 = o.dt
+    e.stage_forces(dt0); o.stage_forces(dt0); e.stage_grid(dt0); o.stage_grid_update(dt0)
+    vmax_o = o.cfl_condition() * scene.grid.h.min(); o.stage_collide()
+    go = o.grid()
+    stick = (np.abs(go["vt"]).sum(axis=1) > 0) & (np.abs(go["v"]).sum(axis=1) == 0)
+    assert stick.sum() >= 5, "scene no longer exercises the sticking branch"
+    res = scene.grid.res; h = scene.grid.h
+    ijk = np.stack(np.unravel_index(np.nonzero(stick)[0], (res[2], res[1], res[0])), axis=1)[:, ::-1]      # node index = (k*ny + j)*nx + i
+    xs = np.asarray(scene.grid.mn, float) + ijk * h
+    px = o.particles()["x"]
+    near = np.zeros(len(px), bool)
+    for xn in xs:
+        near |= (np.abs(px - xn) < 2 * h).all(axis=1)                       # node inside the particle's cubic support
+    assert near.sum() >= 8
+    dt1 = 0.3 / max(300.0, vmax_o / h.min())
+    e.stage_g2p(dt1); o.stage_g2p(dt1)
+    pe, po = e.particles(), o.particles()
+    for k, tol in (("x", TOL), ("v", TOL), ("FE", TOL), ("B", 1e-4)):
+        assert relerr(pe[k][near], po[k][near]) < tol, k
+
+
 @pytest.mark.parametrize("name", ["sand_block", "snow_block", "sand_corner"])
 def test_golden_substeps(name):
     """Committed golden vectors (numpy/scipy literal transcription): 3 full substeps with the on-device dt rule."""
