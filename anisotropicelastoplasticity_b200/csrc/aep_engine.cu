@@ -273,7 +273,7 @@ int do_forces(aep_ctx* c) {
     }
     if (c->n) {
         StageTimer T(c, AEP_STAGE_FORCES);
-        k_forces<<<cdiv(c->n, FRC_NT), FRC_NT, 0, c->stream>>>(c->P[c->cur], c->G, c->mat, c->d_clk, (int)c->n);
+        forces_launch(c->stream, c->sm_count, c->P[c->cur], c->G, c->mat, c->d_clk, c->n);
         LAUNCH_OK("k_forces");
     }
     if (c->mesh.nv) {

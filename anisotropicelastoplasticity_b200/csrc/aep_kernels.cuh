@@ -633,6 +633,36 @@ __device__ __forceinline__ bool stage_tile(const GridP& G, float4* __restrict__ 
     return true;
 }
 
+// asynchronous version of stage_tile: the warp's grid tile is fetched with cp.async (no registers, no wait) for a chunk whose X
+// records are already in registers, so that the copy flies behind the arithmetic of the chunk before.  Warp-uniform result.
+__device__ __forceinline__ void cp_async16(float4* smem_dst, const float4* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_stream(float4* smem_dst, const float4* gsrc) {      // L2 only: streaming particle data stays out of L1
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }   // all but the N most recent groups
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ bool tile_issue(const GridP& G, float4* __restrict__ tile, TileRef& T, int cell) {
+    if (!AEP_USE_TILE) return false;
+    const int lane = threadIdx.x & 31;
+    const int ci = cell_i(cell), cj = cell_j(cell), ck = cell_k(cell);
+    const bool complete = ci >= 1 && ci + 2 < G.nx && cj >= 1 && cj + 2 < G.ny && ck >= 1 && ck + 2 < G.nz;     // == axis_setup's
+    const int cref = __shfl_sync(0xffffffffu, cell, 0);
+    T.ox0 = cell_i(cref) - 1 - TILE_SLACK; T.j0 = cell_j(cref) - 1; T.k0 = cell_k(cref) - 1;
+    const bool fits = complete && ((cell ^ cref) >> 10) == 0 && (ci - 1) >= T.ox0 && (ci + 2) < T.ox0 + TILE_W;
+    if (!__all_sync(0xffffffffu, fits)) return false;
+#pragma unroll
+    for (int q = 0; q < TILE_F4 / 32; ++q) {
+        const int idx = lane + 32 * q;
+        const int r = idx / TILE_W, x = idx - r * TILE_W, gx = T.ox0 + x;
+        if (gx >= 0 && gx < G.nx) cp_async16(tile + idx, G.vt + ((size_t)(T.k0 + (r >> 2)) * G.ny + (T.j0 + (r & 3))) * G.nx + gx);
+    }
+    return true;
+}
+
 // ================================================================================================ forces
 // g[3r+c] = sum_i v_i[r] d_c w_i over the 4x4x4 stencil, x summed first.
 // MODE 0: clamped global loads (stencil cut by a domain face), 1: interior global loads (the four nodes of a row are 64 contiguous
@@ -683,6 +713,9 @@ static_assert(FRC_WARP_F4 >= TILE_F4, "the gather tile is aliased onto the warp'
 #ifndef FRC_MIN_CTAS
 #define FRC_MIN_CTAS 6
 #endif
+// One CTA per 128 particles.  A persistent-warp build with cp.async prefetch of X / F_E and an early tile request (the recipe that
+// gained 7 % in k_g2p) was measured at 7.73 ms against 6.53 ms here: the tile shares its memory with the records of phase B, so
+// it cannot be fetched ahead, and the loop costs more than the two remaining waits (profiles/README.md, v10d).
 __global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP G, MatParams mpar, const SimClock* __restrict__ clk, int n) {
     __shared__ float4 stage[FRC_NT / 32][FRC_WARP_F4];
     __shared__ float4 bounce[FRC_NT];                                          // lane-private slots of requad()
@@ -753,6 +786,11 @@ __global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP 
             }
         }
     }
+}
+
+inline void forces_launch(cudaStream_t st, int sm_count, const PartP& P, const GridP& G, const MatParams& mat, const SimClock* clk, long long n) {
+    (void)sm_count;
+    k_forces<<<(unsigned)((n + FRC_NT - 1) / FRC_NT), FRC_NT, 0, st>>>(P, G, mat, clk, (int)n);
 }
 
 // ================================================================================================ G2P
@@ -827,44 +865,14 @@ __device__ __forceinline__ void g2p_stick_correction(const GridP& G, const Axis&
     }
 }
 
-// Two builds of the G2P kernel: the default (one CTA per 128 particles, register-staged tile) and -DAEP_G2P_PIPE=1, a
-// persistent-warp variant that software-pipelines every memory round trip of a chunk behind the arithmetic of the chunk before.
-// The pipelined variant removes the long-scoreboard stalls it was written for but executes 6 % more instructions and misses
-// the instruction cache more often, and loses by 5-8 % on B200 (profiles/README.md, v9b / v9d), so it is not the default.
+// Two builds of the G2P kernel: the default, persistent warps that software-pipeline every memory round trip of a chunk behind the
+// arithmetic of the chunk before, and -DAEP_G2P_PIPE=0, one CTA per 128 particles with a register-staged tile.  While the
+// kernel was 3800-4200 SASS instructions the pipelined form lost 5-8 % to instruction-cache misses and loop overhead
+// (profiles/README.md, v9b / v9d); on the slimmed kernel (2700-3000 instructions) it wins 7 % (6.20 -> 5.76 ms, v10c).
 #ifndef AEP_G2P_PIPE
-#define AEP_G2P_PIPE 0
+#define AEP_G2P_PIPE 1
 #endif
 #if AEP_G2P_PIPE
-// asynchronous version of stage_tile: the warp's grid tile is fetched with cp.async (no registers, no wait) for a chunk whose X
-// records are already in registers, so that the copy flies behind the arithmetic of the chunk before.  Warp-uniform result.
-__device__ __forceinline__ void cp_async16(float4* smem_dst, const float4* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async16_stream(float4* smem_dst, const float4* gsrc) {      // L2 only: streaming particle data stays out of L1
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }   // all but the N most recent groups
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ bool tile_issue(const GridP& G, float4* __restrict__ tile, TileRef& T, int cell) {
-    if (!AEP_USE_TILE) return false;
-    const int lane = threadIdx.x & 31;
-    const int ci = cell_i(cell), cj = cell_j(cell), ck = cell_k(cell);
-    const bool complete = ci >= 1 && ci + 2 < G.nx && cj >= 1 && cj + 2 < G.ny && ck >= 1 && ck + 2 < G.nz;     // == axis_setup's
-    const int cref = __shfl_sync(0xffffffffu, cell, 0);
-    T.ox0 = cell_i(cref) - 1 - TILE_SLACK; T.j0 = cell_j(cref) - 1; T.k0 = cell_k(cref) - 1;
-    const bool fits = complete && ((cell ^ cref) >> 10) == 0 && (ci - 1) >= T.ox0 && (ci + 2) < T.ox0 + TILE_W;
-    if (!__all_sync(0xffffffffu, fits)) return false;
-#pragma unroll
-    for (int q = 0; q < TILE_F4 / 32; ++q) {
-        const int idx = lane + 32 * q;
-        const int r = idx / TILE_W, x = idx - r * TILE_W, gx = T.ox0 + x;
-        if (gx >= 0 && gx < G.nx) cp_async16(tile + idx, G.vt + ((size_t)(T.k0 + (r >> 2)) * G.ny + (T.j0 + (r & 3))) * G.nx + gx);
-    }
-    return true;
-}
-
 // updateParticleVelocities_ (HybridSolver.cpp:739-745), updateAffineMomenta_ with damp 0 (:760-825, :908-917),
 // advection x = sum w (x_i + dt v~_i) (:942-945), updateDeformationGradient_ (:553-578), updatePlasticity_
 // (:612-681), all in registers, one thread per particle.  Writes the new sort key.
