@@ -71,8 +71,9 @@ typedef struct aep_config {
     double sand_h[4];          /* 35, 9, 0.2, 10, HS:641-644                                                 */
     double dt_rate_floor;      /* 300, HS:860,878   dt = cfl / max(rate_floor, vmax/hmin)                    */
     double frame_dt;           /* 1/60, HS:880-884                                                           */
-    int64_t particle_capacity; /* 0 = exactly what aep_upload_particles is given; >0 reserves room for
-                                  particles migrating in from neighbouring ranks                             */
+    int64_t particle_capacity; /* 0 = exactly what aep_upload_particles is given, allocated by the first upload; >0: the
+                                  particle arrays are allocated by aep_create for this many particles (room for particles
+                                  migrating in from neighbouring ranks; keeps cudaMalloc out of the upload)  */
     /* spatial slab owned by this context (multi-GPU).  Cells [slab_lo, slab_hi) along slab_axis.
      * slab_axis < 0: the context owns the whole grid.                                                        */
     int32_t slab_axis;
