@@ -9,12 +9,14 @@
 //     Q0 = (FP row 0, id)   Q1 = (FP row 1, m)  Q2 = (FP row 2, -)
 //   grid arrays, node index = (k*ny + j)*nx + i  (RegularGrid.cpp:164-168)
 //     mp = (m, px, py, pz)   f = (fx, fy, fz, -)   vt = (v~x, v~y, v~z, s)  with v = s * v~  (s in {0,1})
-//   block flags: one byte per 8x8x8 node block, set by P2G; grid passes skip unflagged blocks.
+//   block flags: one byte per 8x8x8 node block, set by P2G; grid passes run over the compact list of flagged blocks.
 //
-// Scatter strategy: shared-memory float atomics are CAS loops on sm_100 (ATOMS.CAST.SPIN) while global memory
-// has native vector reductions (REDG.E.ADD.F32x4).  So a warp walks its 32 cell-sorted particles one at a time,
-// the 32 lanes own the 64 stencil nodes (2 each) and accumulate in registers over the run of particles that share
-// a cell; one REDG.F32x4 per node per run goes to L2.  No atomics in the inner loop, no shared memory.
+// Scatter strategy: shared-memory float atomics are CAS loops on sm_100 (ATOMS.CAST.SPIN) while global memory has native vector
+// reductions (REDG.E.ADD.F32x4).  So nothing is accumulated in shared memory: a half-warp walks a run of cell-sorted particles,
+// its 16 lanes own the 16 (j,k) rows of the 4x4x4 stencil and keep the 4 nodes of their row in registers while the particles
+// stay in one cell (and slide the 4-node window when the next cell is an x-neighbour); a node goes to L2 with one REDG.F32x4 when
+// it leaves the window.  Gather strategy: the (cells+3) x 4 x 4 node box of a warp's 32 particles is staged once in the warp's
+// own shared memory and every lane reads its 64 nodes from there.
 #pragma once
 #include <stdint.h>
 #include "aep_math.cuh"
@@ -293,44 +295,12 @@ __global__ void k_initial_dt(SimClock* clk) {                      // HybridSolv
 //   phase A  thread-per-particle: everything that depends on the particle only (1-D weights, affine / stress matrices)
 //            goes to a per-warp shared-memory record;
 //   phase B  one HALF-WARP per particle, 16 lanes = the 16 (j,k) rows of the 4x4x4 stencil, each lane owns the 4 nodes
-//            along x of its row and accumulates in registers over the run of particles that share a cell; a run ends with
-//            4 REDG.E.ADD.F32x4 per lane (64 B contiguous per row).  No atomics and no shuffles in the inner loop.
-__device__ __forceinline__ void flush_row(const GridP& G, float4* __restrict__ dst, int cell, int j, int k, const float4 (&acc)[4], bool mark) {
-    const int ni0 = cell_i(cell) - 1, nj = cell_j(cell) - 1 + j, nk = cell_k(cell) - 1 + k;
-    if (nj < 0 || nj >= G.ny || nk < 0 || nk >= G.nz) return;
-    float4* row = dst + ((size_t)nk * G.ny + nj) * G.nx;
-    unsigned char* frow = G.flags + ((nk >> 3) * G.nby + (nj >> 3)) * G.nbx;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int ni = ni0 + i;
-        if (ni >= 0 && ni < G.nx) {
-            atomicAdd(row + ni, acc[i]);
-            if (mark && (i == 0 || i == 3 || ni == 0 || ni == G.nx - 1)) frow[ni >> 3] = 1;
-        }
-    }
-}
-
+//            along x of its row and accumulates in registers (packed fp32x2, aep_pack.cuh) over the run of particles that share
+//            a cell.  No atomics and no shuffles in the inner loop.
 // Sliding window along x: when the next particle's cell is d = 1..3 cells further along x in the same (j,k) row of cells, only the
 // d nodes that fall out of the 4-node window are reduced to memory and the accumulators shift; x-adjacent cells share 3 of their
-// 4 nodes per row, so a sorted row of C cells costs C+3 reductions per lane instead of 4C.  Returns false when the window cannot
-// slide (the caller then flushes all four nodes).
-__device__ __forceinline__ bool slide_row(const GridP& G, float4* __restrict__ dst, int cur, int next, int j, int k, float4 (&acc)[4], bool mark) {
-    const int d = next - cur;
-    if (d <= 0 || d >= 4 || (next & 1023) - (cur & 1023) != d) return false;
-    const int nj = cell_j(cur) - 1 + j, nk = cell_k(cur) - 1 + k;
-    const bool in_jk = nj >= 0 && nj < G.ny && nk >= 0 && nk < G.nz;
-    float4* row = dst + ((size_t)nk * G.ny + nj) * G.nx;
-    unsigned char* frow = G.flags + ((nk >> 3) * G.nby + (nj >> 3)) * G.nbx;
-    int ni = cell_i(cur) - 1;
-    for (int s = 0; s < d; ++s, ++ni) {
-        if (in_jk && ni >= 0 && ni < G.nx) {
-            atomicAdd(row + ni, acc[0]);
-            if (mark) frow[ni >> 3] = 1;
-        }
-        acc[0] = acc[1]; acc[1] = acc[2]; acc[2] = acc[3]; acc[3] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    return true;
-}
+// 4 nodes per row, so a sorted row of C cells costs C+3 reductions per lane instead of 4C.  slide_row_pk returns false when the window
+// cannot slide (the caller then flushes all four nodes with flush_row_pk).
 
 // CTA -> chunk of the sorted particle order for the scatter kernels.  Consecutive CTAs run concurrently; if they also worked on
 // consecutive chunks, neighbouring rows and planes of cells would reduce into the same grid nodes at the same time and the L2
@@ -363,7 +333,6 @@ __device__ __forceinline__ void flush_nodes(const GridP& G, float4* __restrict__
 }
 
 __device__ __forceinline__ float sel4(const float (&a)[4], int k) { return k == 0 ? a[0] : (k == 1 ? a[1] : (k == 2 ? a[2] : a[3])); }
-__device__ __forceinline__ float f4c(const float4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
 // ---- packed accumulators (aep_pack.cuh): node i of a lane's row is the float4 (lo[i] | hi[i]) = (x, y | z, w)
 struct AccRow {
@@ -665,18 +634,18 @@ __device__ __forceinline__ bool tile_issue(const GridP& G, float4* __restrict__ 
 
 // ================================================================================================ forces
 // g[3r+c] = sum_i v_i[r] d_c w_i over the 4x4x4 stencil, x summed first.
-// MODE 0: clamped global loads (stencil cut by a domain face), 1: interior global loads (the four nodes of a row are 64 contiguous
-// bytes at immediate offsets), 2: loads from the CTA's shared tile (xoff = first stencil node relative to the tile).
+// MODE 0: clamped global loads (fallback: stencil cut by a domain face, warp not in one row of cells), MODE 2: loads from the warp's
+// shared tile (xoff = first stencil node relative to the tile).
 template <int MODE>
 __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, const Axis& ay, const Axis& az, const float4* __restrict__ tile, int xoff,
                                             float (&g)[9]) {
     int ni[4], nj[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) { ni[o] = MODE ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = MODE ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
-    const float4* base = MODE == 2 ? tile + xoff : G.vt + (MODE == 1 ? ax.n0 : 0);
+    for (int o = 0; o < 4; ++o) { ni[o] = MODE == 2 ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = MODE == 2 ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
+    const float4* base = MODE == 2 ? tile + xoff : G.vt;
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
-        const int nk = MODE ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
+        const int nk = MODE == 2 ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
         const float nzk = sel4(az.N, k), dzk = sel4(az.D, k);
         const float4* plane = MODE == 2 ? base + k * 4 * TILE_W : base + (size_t)nk * G.ny * G.nx;
 #pragma unroll
@@ -810,11 +779,11 @@ __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const
                                            G2PSums& S) {
     int ni[4], nj[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) { ni[o] = MODE ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = MODE ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
-    const float4* base = MODE == 2 ? tile + xoff : G.vt + (MODE == 1 ? ax.n0 : 0);
+    for (int o = 0; o < 4; ++o) { ni[o] = MODE == 2 ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = MODE == 2 ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
+    const float4* base = MODE == 2 ? tile + xoff : G.vt;
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
-        const int nk = MODE ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
+        const int nk = MODE == 2 ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
         const float nzk = sel4(az.N, k), dzk = sel4(az.D, k), rzk = sel4(rz, k);
         const float4* plane = MODE == 2 ? base + k * 4 * TILE_W : base + (size_t)nk * G.ny * G.nx;
 #pragma unroll
