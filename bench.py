@@ -136,6 +136,19 @@ def packed_rest_state(x, mass, pinned=False):
     return [xs, v, b1, b2, b3, fe, fp, m, vol, q], keep
 
 
+def perturb_packed(arrs, strain, seed=17, chunk=1 << 22):
+    """Development option (--perturb): a state in which every branch of the substep works -- random elastic strains of scale
+    `strain` (the SVDs need 2-3 sweeps, sand yields), velocities of scale 30*strain m/s (particles change cells, the re-sort
+    policy fires).  The headline line is measured on the rest state the workload names; this shows what a flowing state costs."""
+    rng = np.random.default_rng(seed)
+    xs, v, b1, b2, b3, fe, fp, m, vol, q = arrs
+    n = fe.shape[0]
+    for p0 in range(0, n, chunk):
+        p1 = min(n, p0 + chunk)
+        fe[p0:p1] += strain * rng.standard_normal((p1 - p0, 9))
+        v[:, p0:p1] += 30.0 * strain * rng.standard_normal((3, p1 - p0))
+
+
 def rate_floor_for(res):
     """dt = cfl / max(rate_floor, vmax/h) (HybridSolver.cpp:860,878).  The reference's literal 300 (dt <= 1e-3 s) is tuned to its
     own coarse grid (h = 0.044, main.cpp:53-69): with sand's p-wave speed ~19 m/s it gives c dt / h = 0.43 there, but 9.8 on a
@@ -227,6 +240,8 @@ def run_engine(args):
     mass = sc.SAND_RHO * (1.0 / res) ** 3 / 8.0
     arrs, keep = packed_rest_state(x, mass, pinned=True)
     del x
+    if args.perturb > 0.0:
+        perturb_packed(arrs, args.perturb)
     t_gen = time.perf_counter() - t_gen
     shell = make_shell_scene(res)
     rate_floor = rate_floor_for(res)
@@ -267,7 +282,7 @@ def run_engine(args):
                 "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes, "active_blocks": blocks}}
     if args.quick:
         print(json.dumps({"metric": METRIC, "value": value, "ms_per_step": ms / args.steps, "sort_every": args.sort_every, "stage_ms": stage_ms,
-                          "gpu_launches": int(launches), "sim": clk, "active_nodes": nodes, "particles": n}))
+                          "gpu_launches": int(launches), "sim": clk, "active_nodes": nodes, "particles": n, "perturb": args.perturb}))
         return
     # ---- e2e: host fp64 state -> device, K substeps, f32 positions back (HybridSolver::solve's host-visible traffic)
     eng.close(); del eng
@@ -305,6 +320,7 @@ def main():
     ap.add_argument("--ref-res", type=int, default=64, help="grid resolution of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="development: skip the e2e and cpu_baseline legs")
+    ap.add_argument("--perturb", type=float, default=0.0, help="development: random strain scale added to the rest state (0 = the named workload)")
     ap.add_argument("--sort-bricks", type=int, default=0, help="1: brick-major particle order (aep_config.sort_bricks), 0: cell-index order")
     ap.add_argument("--sort-every", type=int, default=0, help="physical re-sort period in substeps (aep_config.sort_every); 0 = adaptive (default)")
     args = ap.parse_args()
