@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include "aep_math.cuh"
 #include "aep_pack.cuh"
+#include "aep_scatter.cuh"
 
 namespace aep {
 
@@ -334,14 +335,7 @@ __device__ __forceinline__ void flush_nodes(const GridP& G, float4* __restrict__
 
 __device__ __forceinline__ float sel4(const float (&a)[4], int k) { return k == 0 ? a[0] : (k == 1 ? a[1] : (k == 2 ? a[2] : a[3])); }
 
-// ---- packed accumulators (aep_pack.cuh): node i of a lane's row is the float4 (lo[i] | hi[i]) = (x, y | z, w)
-struct AccRow {
-    f32x2 lo[4], hi[4];
-};
-__device__ __forceinline__ void acc_zero(AccRow& a) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { a.lo[i] = 0ull; a.hi[i] = 0ull; }
-}
+// ---- packed accumulators: AccRow (aep_scatter.cuh)
 // same, but pinned behind the reductions that consumed the old values (volatile): see slide_row_pk
 __device__ __forceinline__ void acc_zero_ordered(AccRow& a) {
     asm volatile("mov.b64 %0, 0;\n\tmov.b64 %1, 0;\n\tmov.b64 %2, 0;\n\tmov.b64 %3, 0;" : "=l"(a.lo[0]), "=l"(a.lo[1]), "=l"(a.lo[2]), "=l"(a.lo[3]));
@@ -401,15 +395,10 @@ __device__ __forceinline__ bool slide_row_pk(const GridP& G, float4* __restrict_
 // ================================================================================================ P2G
 // particleToGrid_ (HybridSolver.cpp:113-231): m_i = sum w m ; p_i = sum w m (v + (3/h^2) B (x_i - x_p)).
 // Per particle the momentum of node offset (i,j,k) is q0 + Qm (i,j,k)^T with Qm = m (3/h^2) B diag(h), q0 = m v - Qm (1+f).
-// Phase-A record of one particle: P2G_STRIDE float4, an odd stride so that the 32 STS.128 of phase A are bank-conflict free.
-//   r0 Nx[4]    r1 Ny[4] (read as float [j])    r2 Nz[4] (float [k])
-//   r3 (m, q0x | q0y, q0z)      (mass, momentum) of node offset (0,0,0):  q0 = m v - Qm (1 + f)
-//   r4 r5 r6  (0, Qm[0][c] | Qm[1][c], Qm[2][c]) for c = 0,1,2: what one step along i, j, k adds to (m, p)
-//   r7.x  packed cell index (read on the flush path only)
+// Phase-A record of one particle: see p2g_make_record (aep_scatter.cuh).
 // Phase B is bound by shared-memory wavefronts as much as by issue slots (profiles/README.md, v9): every LDS of the two half-warps
 // costs one wavefront per half-warp, so the record holds plain scalars (FFMA2 takes a broadcast .F32 operand) and the end of a
 // run of same-cell particles comes from a ballot of phase A instead of a per-particle load of the cell index.
-#define P2G_STRIDE 9
 #define P2G_HW_PAD 2
 #define P2G_HW_F4 (16 * P2G_STRIDE + P2G_HW_PAD)
 // bit l of the result: the run of same-cell particles ends with the particle of lane l
@@ -457,22 +446,9 @@ __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
             const float4 c0 = ldg4(P.a[PC0] + p), c1 = ldg4(P.a[PC1] + p), c2 = ldg4(P.a[PC2] + p);
             // cell of the half-warp's next particle (-1 behind its last one): the lines are the ones the neighbouring lanes load
             const int ncell = (q + 1 < hend) ? __float_as_int(__ldg(&P.a[PX][min(q + 1, n - 1)].w)) : -1;
-            float Nx[4], Ny[4], Nz[4], D[4];
-            bspline4(X.x, Nx, D); bspline4(X.y, Ny, D); bspline4(X.z, Nz, D);
             const float m = (q < n) ? VM.w : 0.0f;
-            const float km = m * G.apic;
-            float Q[9] = { km * c0.x * G.hx, km * c0.y * G.hy, km * c0.z * G.hz, km * c1.x * G.hx, km * c1.y * G.hy, km * c1.z * G.hz,
-                           km * c2.x * G.hx, km * c2.y * G.hy, km * c2.z * G.hz };
-            const float gx = 1.0f + X.x, gy = 1.0f + X.y, gz = 1.0f + X.z;   // x_i - x_p = h (o - (1 + f))
-            const float q0x = fmaf(m, VM.x, -(Q[0] * gx + Q[1] * gy + Q[2] * gz));
-            const float q0y = fmaf(m, VM.y, -(Q[3] * gx + Q[4] * gy + Q[5] * gz));
-            const float q0z = fmaf(m, VM.z, -(Q[6] * gx + Q[7] * gy + Q[8] * gz));
             __syncwarp();                                                    // phase B of the round before is done with the records
-            float4* rec = &stage[wib][hw][s * P2G_STRIDE];
-            rec[0] = make_float4(Nx[0], Nx[1], Nx[2], Nx[3]); rec[1] = make_float4(Ny[0], Ny[1], Ny[2], Ny[3]); rec[2] = make_float4(Nz[0], Nz[1], Nz[2], Nz[3]);
-            rec[3] = make_float4(m, q0x, q0y, q0z);
-            rec[4] = make_float4(0.f, Q[0], Q[3], Q[6]); rec[5] = make_float4(0.f, Q[1], Q[4], Q[7]); rec[6] = make_float4(0.f, Q[2], Q[5], Q[8]);
-            rec[7] = make_float4(X.w, __int_as_float(ncell), 0.f, 0.f);
+            p2g_make_record(&stage[wib][hw][s * P2G_STRIDE], X, VM, c0, c1, c2, m, G.apic, G.hx, G.hy, G.hz, __int_as_float(ncell));
             ends = __ballot_sync(0xffffffffu, ncell != __float_as_int(X.w));
         }
         __syncwarp();
@@ -481,19 +457,7 @@ __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
 #pragma unroll 1
         for (int it = 0; it < 16; ++it) {
             const float4* r = recs + it * P2G_STRIDE;
-            const float4 nx = r[0];
-            const float wyz = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(r) + yoff) * *reinterpret_cast<const float*>(reinterpret_cast<const char*>(r) + zoff);
-            const ulonglong2 b0 = ld_pairs(r + 3), si = ld_pairs(r + 4), sj = ld_pairs(r + 5), sk = ld_pairs(r + 6);
-            f32x2 Tlo = fma2(sj.x, J, fma2(sk.x, K, b0.x));                    // (m, px) of node (0, j, k)
-            f32x2 Thi = fma2(sj.y, J, fma2(sk.y, K, b0.y));                    // (py, pz)
-            f32x2 W = pk1(nx.x * wyz);
-            acc.lo[0] = fma2(W, Tlo, acc.lo[0]); acc.hi[0] = fma2(W, Thi, acc.hi[0]);
-            Tlo = add2(Tlo, si.x); Thi = add2(Thi, si.y); W = pk1(nx.y * wyz);
-            acc.lo[1] = fma2(W, Tlo, acc.lo[1]); acc.hi[1] = fma2(W, Thi, acc.hi[1]);
-            Tlo = add2(Tlo, si.x); Thi = add2(Thi, si.y); W = pk1(nx.z * wyz);
-            acc.lo[2] = fma2(W, Tlo, acc.lo[2]); acc.hi[2] = fma2(W, Thi, acc.hi[2]);
-            Tlo = add2(Tlo, si.x); Thi = add2(Thi, si.y); W = pk1(nx.w * wyz);
-            acc.lo[3] = fma2(W, Tlo, acc.lo[3]); acc.hi[3] = fma2(W, Thi, acc.hi[3]);
+            p2g_row_accumulate(r, yoff, zoff, J, K, acc);
             if ((ends >> it) & 1u) {                                          // the run of particles sharing this cell ends here
                 const float2 cn = *reinterpret_cast<const float2*>(r + 7);
                 const int cur = __float_as_int(cn.x), nxt = __float_as_int(cn.y);
@@ -669,13 +633,9 @@ __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, cons
 // computeGridForces_, particle part (HybridSolver.cpp:252-368).  Phase A (thread per particle): gather
 // grad v = sum_i v_i (grad w_i)^T, Fhat = (I + dt grad v) FE, SVD, stress, A = V_p P FE^T.  Phase B (half-warp per particle):
 // f_i -= A grad w_ip.
-// Phase-A record of one particle for the force scatter (FRC_STRIDE float4, odd stride: conflict-free STS.128), plain scalars like P2G's:
-//   r0 Nx[4]   r1 Dx[4]   r2 r3 (Ny_j, Dy_j) pairs, read as float2 [j]   r4 r5 (Nz_k, Dz_k), float2 [k]
-//   r6 r7 r8  columns of A = -V_p P FE^T:  (A[0][c], A[1][c] | A[2][c], 0)
-//   r9.x  packed cell index (flush path only)
+// Phase-A record of one particle for the force scatter: see frc_make_record (aep_scatter.cuh).
 // The warp's grid tile of phase A lives in the same shared memory: it is dead once the gather is done.
 #define FRC_NT 128
-#define FRC_STRIDE 11
 #define FRC_HW_PAD 2
 #define FRC_WARP_F4 (2 * (16 * FRC_STRIDE + FRC_HW_PAD))
 static_assert(FRC_WARP_F4 >= TILE_F4, "the gather tile is aliased onto the warp's record area");
@@ -717,11 +677,7 @@ __global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP 
         stress_times_FEt(mpar, Fh, FE, (lane < cnt) ? -e0.w : 0.0f, e2.w, A);    // A := -V_p P FE^T (sign of :356-366 folded in); padding lanes: zero volume
         __syncwarp();                                                            // every lane is done with the tile: reuse it for the records
         float4* rec = stage[wib] + (lane >> 4) * (16 * FRC_STRIDE + FRC_HW_PAD) + (lane & 15) * FRC_STRIDE;
-        rec[0] = make_float4(ax.N[0], ax.N[1], ax.N[2], ax.N[3]); rec[1] = make_float4(ax.D[0], ax.D[1], ax.D[2], ax.D[3]);
-        rec[2] = make_float4(ay.N[0], ay.D[0], ay.N[1], ay.D[1]); rec[3] = make_float4(ay.N[2], ay.D[2], ay.N[3], ay.D[3]);
-        rec[4] = make_float4(az.N[0], az.D[0], az.N[1], az.D[1]); rec[5] = make_float4(az.N[2], az.D[2], az.N[3], az.D[3]);
-        rec[6] = make_float4(A[0], A[3], A[6], 0.f); rec[7] = make_float4(A[1], A[4], A[7], 0.f); rec[8] = make_float4(A[2], A[5], A[8], 0.f);
-        rec[9].x = X.w;
+        frc_make_record(rec, ax.N, ax.D, ay.N, ay.D, az.N, az.D, A, X.w);
         ends = run_ends(cell);
     }
     __syncwarp();
@@ -736,16 +692,7 @@ __global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP 
 #pragma unroll 1
     for (int it = 0; it < 16; ++it) {
         const float4* r = recs + it * FRC_STRIDE;
-        const float4 nx = r[0], dx = r[1];
-        const float2 yj = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(r) + yoff), zk = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(r) + zoff);
-        const ulonglong2 a0 = ld_pairs(r + 6), a1 = ld_pairs(r + 7), a2 = ld_pairs(r + 8);
-        const f32x2 AA = pk1(yj.x * zk.x), BB = pk1(yj.y * zk.x), CC = pk1(yj.x * zk.y);          // Ny Nz, Dy Nz, Ny Dz
-        const f32x2 Ulo = mul2(a0.x, AA), Uhi = mul2(a0.y, AA);
-        const f32x2 Vlo = fma2(a1.x, BB, mul2(a2.x, CC)), Vhi = fma2(a1.y, BB, mul2(a2.y, CC));
-        acc.lo[0] = fma2(Ulo, pk1(dx.x), fma2(Vlo, pk1(nx.x), acc.lo[0])); acc.hi[0] = fma2(Uhi, pk1(dx.x), fma2(Vhi, pk1(nx.x), acc.hi[0]));
-        acc.lo[1] = fma2(Ulo, pk1(dx.y), fma2(Vlo, pk1(nx.y), acc.lo[1])); acc.hi[1] = fma2(Uhi, pk1(dx.y), fma2(Vhi, pk1(nx.y), acc.hi[1]));
-        acc.lo[2] = fma2(Ulo, pk1(dx.z), fma2(Vlo, pk1(nx.z), acc.lo[2])); acc.hi[2] = fma2(Uhi, pk1(dx.z), fma2(Vhi, pk1(nx.z), acc.hi[2]));
-        acc.lo[3] = fma2(Ulo, pk1(dx.w), fma2(Vlo, pk1(nx.w), acc.lo[3])); acc.hi[3] = fma2(Uhi, pk1(dx.w), fma2(Vhi, pk1(nx.w), acc.hi[3]));
+        frc_row_accumulate(r, yoff, zoff, acc);
         if ((ends >> it) & 1u) {                                              // the run of particles sharing this cell ends here
             const int cur = __float_as_int(r[9].x);
             const int nxt = (it == 15) ? -1 : __float_as_int(r[FRC_STRIDE + 9].x);

@@ -9,7 +9,15 @@
 #define __forceinline__ inline
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 static inline float __fdividef(float a, float b) { return a / b; }
+// the few CUDA vector types the scatter header uses
+#define __restrict__
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) ulonglong2 { unsigned long long x, y; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+using std::fmaf;
 #include "../anisotropicelastoplasticity_b200/csrc/aep_math.cuh"
+#include "../anisotropicelastoplasticity_b200/csrc/aep_scatter.cuh"
 
 using namespace aep;
 extern "C" {
@@ -40,5 +48,33 @@ long h_svd_sweeps() { return g_svd_sweeps; }
 void h_gram_schmidt(const float* d1, const float* d2, const float* d3, float* Q, float* R) {
     float a[3], b[3], c[3], q[9], r[9]; std::memcpy(a, d1, 12); std::memcpy(b, d2, 12); std::memcpy(c, d3, 12);
     gram_schmidt(a, b, c, q, r); std::memcpy(Q, q, 36); std::memcpy(R, r, 36);
+}
+// ---- the two scatters, exactly as the kernels run them: phase A record, then the 16 (j,k) lanes of phase B
+// out[((k*4 + j)*4 + i)*4 + c] = contribution of the particle to node offset (i,j,k), c = (m, px, py, pz) resp. (fx, fy, fz, -)
+void h_p2g_scatter(const float* f, const float* v, const float* B, float m, const float* h, float* out) {
+    const float hmin = std::fmin(h[0], std::fmin(h[1], h[2]));
+    const float apic = 3.0f / hmin / hmin;                                   // HybridSolver.cpp:175-177
+    float4 rec[P2G_STRIDE];
+    p2g_make_record(rec, make_float4(f[0], f[1], f[2], 0.f), make_float4(v[0], v[1], v[2], m), make_float4(B[0], B[1], B[2], 0.f),
+                    make_float4(B[3], B[4], B[5], 0.f), make_float4(B[6], B[7], B[8], 0.f), m, apic, h[0], h[1], h[2], 0.f);
+    for (int k = 0; k < 4; ++k)
+        for (int j = 0; j < 4; ++j) {
+            AccRow acc; acc_zero(acc);
+            p2g_row_accumulate(rec, 16 + 4 * j, 32 + 4 * k, pk1((float)j), pk1((float)k), acc);
+            for (int i = 0; i < 4; ++i) { const float4 q = quad(acc.lo[i], acc.hi[i]); std::memcpy(out + ((k * 4 + j) * 4 + i) * 4, &q, 16); }
+        }
+}
+void h_frc_scatter(const float* f, const float* A, const float* h, float* out) {
+    float N[3][4], D[3][4];
+    for (int a = 0; a < 3; ++a) { bspline4(f[a], N[a], D[a]); for (int o = 0; o < 4; ++o) D[a][o] *= 1.0f / h[a]; }    // axis_setup scales D by 1/h
+    float a9[9]; std::memcpy(a9, A, 36);
+    float4 rec[FRC_STRIDE];
+    frc_make_record(rec, N[0], D[0], N[1], D[1], N[2], D[2], a9, 0.f);
+    for (int k = 0; k < 4; ++k)
+        for (int j = 0; j < 4; ++j) {
+            AccRow acc; acc_zero(acc);
+            frc_row_accumulate(rec, 32 + 8 * j, 64 + 8 * k, acc);
+            for (int i = 0; i < 4; ++i) { const float4 q = quad(acc.lo[i], acc.hi[i]); std::memcpy(out + ((k * 4 + j) * 4 + i) * 4, &q, 16); }
+        }
 }
 }

@@ -89,3 +89,64 @@ def test_stress_and_return_map_vs_oracle(H, mat, E, nu):
             assert np.abs(FPo.reshape(3, 3) - FP9.reshape(3, 3).T).max() < 3e-6
             assert abs(q.value - q64.value) < 3e-6
         assert worst / amax < 3e-7 / strain + 1e-6, (strain, worst / amax)
+
+
+def _weights64(f):
+    """cubic B-spline values of the 4 stencil nodes of a particle at cell fraction f, fp64, straight from interpolation.cpp:9-16
+    via the oracle: node o sits at signed distance u = f + 1 - o (in cells)."""
+    return np.array([op.cubic_bspline(f + 1 - o) for o in range(4)])
+
+
+def _dweights64(f, h):
+    """d w / d x_p per axis = N'(u) / h (HybridSolver.cpp:48-57, interpolation.cpp:18-33)"""
+    return np.array([op.dcubic_bspline(f + 1 - o) for o in range(4)]) / h
+
+
+def test_p2g_scatter_rows_match_reference_formula(H):
+    """The packed phase-B code of k_p2g (aep_scatter.cuh: record + 16 row accumulations, run here on the host) against
+    HybridSolver.cpp:113-231 written out directly: m_i += w m, p_i += w m (v + (3/h_min^2) B (x_i - x_p))."""
+    H.h_p2g_scatter.argtypes = [fp, fp, fp, C.c_float, fp, fp]
+    rng = np.random.default_rng(5)
+    for trial in range(200):
+        f = f32(rng.random(3) * 0.999); v = f32(rng.standard_normal(3)); B = f32(0.1 * rng.standard_normal((3, 3)))
+        h = f32(np.array([1 / 64, 1 / 48, 1 / 80]) if trial % 2 else np.full(3, 1 / 128)); m = np.float32(abs(rng.standard_normal()) + 0.1)
+        out = np.zeros(64 * 4, np.float32)
+        H.h_p2g_scatter(P(f), P(v), P(B.ravel()), C.c_float(m), P(h), P(out))
+        out = out.reshape(4, 4, 4, 4)                                       # [k][j][i][c]
+        f64 = f.astype(np.float64); h64 = h.astype(np.float64); B64 = B.astype(np.float64); v64 = v.astype(np.float64); m64 = float(m)
+        W = [_weights64(f64[a]) for a in range(3)]
+        apic = 3.0 / h64.min() ** 2
+        ref = np.zeros((4, 4, 4, 4))
+        for k in range(4):
+            for j in range(4):
+                for i in range(4):
+                    w = W[0][i] * W[1][j] * W[2][k]
+                    r = h64 * (np.array([i, j, k]) - 1.0 - f64)             # x_i - x_p
+                    ref[k, j, i, 0] = w * m64
+                    ref[k, j, i, 1:] = w * m64 * (v64 + apic * (B64 @ r))
+        assert np.abs(out[..., 0] - ref[..., 0]).max() < 2e-6 * np.abs(ref[..., 0]).max()
+        assert np.abs(out[..., 1:] - ref[..., 1:]).max() < 3e-6 * np.abs(ref[..., 1:]).max()
+        assert abs(out[..., 0].sum() - m64) < 2e-6 * m64                    # partition of unity through the packed path
+
+
+def test_force_scatter_rows_match_reference_formula(H):
+    """The packed phase-B code of k_forces against HybridSolver.cpp:356-366: f_i += A grad w_i."""
+    H.h_frc_scatter.argtypes = [fp, fp, fp, fp]
+    rng = np.random.default_rng(6)
+    for trial in range(200):
+        f = f32(rng.random(3) * 0.999); A = f32(rng.standard_normal((3, 3)))
+        h = f32(np.array([1 / 64, 1 / 48, 1 / 80]) if trial % 2 else np.full(3, 1 / 128))
+        out = np.zeros(64 * 4, np.float32)
+        H.h_frc_scatter(P(f), P(A.ravel()), P(h), P(out))
+        out = out.reshape(4, 4, 4, 4)
+        f64 = f.astype(np.float64); h64 = h.astype(np.float64); A64 = A.astype(np.float64)
+        N = [_weights64(f64[a]) for a in range(3)]; Dn = [_dweights64(f64[a], h64[a]) for a in range(3)]
+        ref = np.zeros((4, 4, 4, 3))
+        for k in range(4):
+            for j in range(4):
+                for i in range(4):
+                    g = np.array([Dn[0][i] * N[1][j] * N[2][k], N[0][i] * Dn[1][j] * N[2][k], N[0][i] * N[1][j] * Dn[2][k]])
+                    ref[k, j, i] = A64 @ g
+        assert np.abs(out[..., :3] - ref).max() < 3e-6 * np.abs(ref).max()
+        assert np.abs(out[..., 3]).max() == 0.0                             # the fourth lane of the force record stays zero
+        assert np.abs(out[..., :3].sum(axis=(0, 1, 2))).max() < 2e-5 * np.abs(ref).max()   # sum_i grad w_i = 0: no net force from one particle
