@@ -22,6 +22,7 @@
 #include "aep_math.cuh"
 #include "aep_pack.cuh"
 #include "aep_scatter.cuh"
+#include "aep_gather.cuh"
 
 namespace aep {
 
@@ -29,26 +30,6 @@ enum { PX = 0, PVM, PC0, PC1, PC2, PE0, PE1, PE2, PQ0, PQ1, PQ2, P_NARR };
 
 struct PartP {
     float4* a[P_NARR];
-};
-
-struct GridP {
-    int nx, ny, nz;
-    int nbx, nby, nbz;                 // number of 8^3 node blocks per axis
-    int nqx, nqy;                      // number of 4^3 cell bricks along x, y (sort order)
-    int rb0[3], rbn[3];                // 8^3-block range the grid passes run over (the whole grid, or the slab's reach)
-    int bricks;                        // 1: brick-major sort keys, 0: plain cell index
-    int strips;                        // scatter kernels: CTAs that run concurrently work on `strips` far-apart parts of the sorted order
-    float hx, hy, hz, ihx, ihy, ihz;
-    float mnx, mny, mnz;
-    float apic;                        // 3 / hmin^2                       HybridSolver.cpp:175-177
-    float inv_cell_vol;                // 1 / (hx hy hz)                   HybridSolver.cpp:246
-    float gravity, friction;
-    float4* mp;
-    float4* f;
-    float4* vt;
-    unsigned char* flags;
-    const unsigned char* ls_code;      // 0 outside, 1..6 axis normals (+x -x +y -y +z -z), 7 general (ls_nrm)
-    const float4* ls_nrm;
 };
 
 // simulation clock + reductions, lives in device memory so that n substeps need no host round trip
@@ -81,30 +62,8 @@ __device__ __forceinline__ int cell_j(int c) { return (c >> 10) & 1023; }
 __device__ __forceinline__ int cell_k(int c) { return (c >> 20) & 1023; }
 __device__ __forceinline__ int cell_pack(int i, int j, int k) { return i | (j << 10) | (k << 20); }
 
-__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// per-axis stencil of a thread-owned particle: weights (masked to 0 outside the grid, HybridSolver.cpp:44-46)
-// and clamped node coordinates
-struct Axis {
-    float N[4], D[4];
-    int n0;            // first node (cell - 1), may be -1
-};
-__device__ __forceinline__ bool axis_setup(Axis& a, float f, int cell, int nres, float ih) {
-    bspline4(f, a.N, a.D);
-    a.n0 = cell - 1;
-    bool complete = true;
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-        const int n = a.n0 + o;
-        const bool in = (n >= 0) && (n < nres);
-        complete &= in;
-        a.N[o] = in ? a.N[o] : 0.0f;
-        a.D[o] = in ? a.D[o] * ih : 0.0f;
-    }
-    return complete;
-}
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 // CTA index of a grid pass -> block coordinates inside the run range, and the flat block index (flags)
 __device__ __forceinline__ int run_block(const GridP& G, int r, int& bx, int& by, int& bz) {
     bx = G.rb0[0] + r % G.rbn[0]; by = G.rb0[1] + (r / G.rbn[0]) % G.rbn[1]; bz = G.rb0[2] + r / (G.rbn[0] * G.rbn[1]);
@@ -333,7 +292,6 @@ __device__ __forceinline__ void flush_nodes(const GridP& G, float4* __restrict__
     }
 }
 
-__device__ __forceinline__ float sel4(const float (&a)[4], int k) { return k == 0 ? a[0] : (k == 1 ? a[1] : (k == 2 ? a[2] : a[3])); }
 
 // ---- packed accumulators: AccRow (aep_scatter.cuh)
 // same, but pinned behind the reductions that consumed the old values (volatile): see slide_row_pk
@@ -536,13 +494,6 @@ __global__ void __launch_bounds__(256) k_grid_normalise(GridP G, const unsigned 
 #ifndef AEP_USE_TILE
 #define AEP_USE_TILE 1
 #endif
-// Warps that cannot use the tile gather straight from global memory with clamped indices (MODE 0).  A second fallback with
-// unclamped "interior" addressing (MODE 1) was 5 % faster on the ~1 % of warps that take it but made both gather kernels 17 %
-// larger; the instruction cache matters more (no_instruction stalls, profiles/README.md v10).
-#define AEP_FALLBACK_MODE 0
-#define TILE_W 12                       // nodes along x held by a warp's tile: up to 9 cells in a row
-#define TILE_SLACK 1                    // nodes left of lane 0's stencil (tolerates slightly out-of-order particles)
-#define TILE_F4 (16 * TILE_W)           // float4 per warp tile (16 (j,k) rows)
 struct TileRef {
     int ox0, j0, k0;                    // node coordinates of tile[0]
 };
@@ -597,39 +548,6 @@ __device__ __forceinline__ bool tile_issue(const GridP& G, float4* __restrict__ 
 }
 
 // ================================================================================================ forces
-// g[3r+c] = sum_i v_i[r] d_c w_i over the 4x4x4 stencil, x summed first.
-// MODE 0: clamped global loads (fallback: stencil cut by a domain face, warp not in one row of cells), MODE 2: loads from the warp's
-// shared tile (xoff = first stencil node relative to the tile).
-template <int MODE>
-__device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, const Axis& ay, const Axis& az, const float4* __restrict__ tile, int xoff,
-                                            float (&g)[9]) {
-    int ni[4], nj[4];
-#pragma unroll
-    for (int o = 0; o < 4; ++o) { ni[o] = MODE == 2 ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = MODE == 2 ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
-    const float4* base = MODE == 2 ? tile + xoff : G.vt;
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-        const int nk = MODE == 2 ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
-        const float nzk = sel4(az.N, k), dzk = sel4(az.D, k);
-        const float4* plane = MODE == 2 ? base + k * 4 * TILE_W : base + (size_t)nk * G.ny * G.nx;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4* row = MODE == 2 ? plane + j * TILE_W : plane + nj[j] * G.nx;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 v = MODE == 2 ? row[i] : ldg4(row + ni[i]);
-                a0 = fmaf(v.x, ax.N[i], a0); a1 = fmaf(v.y, ax.N[i], a1); a2 = fmaf(v.z, ax.N[i], a2);
-                b0 = fmaf(v.x, ax.D[i], b0); b1 = fmaf(v.y, ax.D[i], b1); b2 = fmaf(v.z, ax.D[i], b2);
-            }
-            const float nn = ay.N[j] * nzk, dn = ay.D[j] * nzk, nd = ay.N[j] * dzk;
-            g[0] = fmaf(b0, nn, g[0]); g[1] = fmaf(a0, dn, g[1]); g[2] = fmaf(a0, nd, g[2]);
-            g[3] = fmaf(b1, nn, g[3]); g[4] = fmaf(a1, dn, g[4]); g[5] = fmaf(a1, nd, g[5]);
-            g[6] = fmaf(b2, nn, g[6]); g[7] = fmaf(a2, dn, g[7]); g[8] = fmaf(a2, nd, g[8]);
-        }
-    }
-}
-
 // computeGridForces_, particle part (HybridSolver.cpp:252-368).  Phase A (thread per particle): gather
 // grad v = sum_i v_i (grad w_i)^T, Fhat = (I + dt grad v) FE, SVD, stress, A = V_p P FE^T.  Phase B (half-warp per particle):
 // f_i -= A grad w_ip.
@@ -710,77 +628,6 @@ inline void forces_launch(cudaStream_t st, int sm_count, const PartP& P, const G
 }
 
 // ================================================================================================ G2P
-// The 64-node gather of G2P.  Per (j,k) row the x direction is summed first over v~ only:
-//   a = sum v~ Nx, b = sum v~ Dx, d = sum v~ Nx rx           (9 FMA per node)
-// then the rows are combined into  va = sum w v~,  g = sum v~ (grad w)^T,  B~ = sum w v~ (x_i - x_p)^T.
-// The post-friction velocity is v = s v~ with s in {0,1} and s = 0 only on sticking collider nodes (k_grid_update), so
-//   v_p = va - sum_{s=0} w v~   and   B = B~ - sum_{s=0} w v~ (x_i - x_p)^T;
-// the correction branch runs only for rows that contain a sticking node.
-struct G2PSums {
-    float va[3], vc[3], B[9], g[9];
-    float smin;                          // min of the s flags seen: 0 iff the stencil holds a sticking node
-};
-template <int MODE>
-__device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const Axis& ay, const Axis& az, const float (&nrx)[4],
-                                           const float (&rx)[4], const float (&ry)[4], const float (&rz)[4], const float4* __restrict__ tile, int xoff,
-                                           G2PSums& S) {
-    int ni[4], nj[4];
-#pragma unroll
-    for (int o = 0; o < 4; ++o) { ni[o] = MODE == 2 ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = MODE == 2 ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
-    const float4* base = MODE == 2 ? tile + xoff : G.vt;
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-        const int nk = MODE == 2 ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
-        const float nzk = sel4(az.N, k), dzk = sel4(az.D, k), rzk = sel4(rz, k);
-        const float4* plane = MODE == 2 ? base + k * 4 * TILE_W : base + (size_t)nk * G.ny * G.nx;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4* row = MODE == 2 ? plane + j * TILE_W : plane + nj[j] * G.nx;
-            float4 t[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) t[i] = MODE == 2 ? row[i] : ldg4(row + ni[i]);
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                a0 = fmaf(t[i].x, ax.N[i], a0); a1 = fmaf(t[i].y, ax.N[i], a1); a2 = fmaf(t[i].z, ax.N[i], a2);
-                b0 = fmaf(t[i].x, ax.D[i], b0); b1 = fmaf(t[i].y, ax.D[i], b1); b2 = fmaf(t[i].z, ax.D[i], b2);
-                d0 = fmaf(t[i].x, nrx[i], d0); d1 = fmaf(t[i].y, nrx[i], d1); d2 = fmaf(t[i].z, nrx[i], d2);
-            }
-            const float nn = ay.N[j] * nzk, dn = ay.D[j] * nzk, nd = ay.N[j] * dzk;
-            const float u0 = a0 * nn, u1 = a1 * nn, u2 = a2 * nn;            // sum_i w v~_i over the row
-            S.va[0] += u0; S.va[1] += u1; S.va[2] += u2;
-            S.g[0] = fmaf(b0, nn, S.g[0]); S.g[1] = fmaf(a0, dn, S.g[1]); S.g[2] = fmaf(a0, nd, S.g[2]);
-            S.g[3] = fmaf(b1, nn, S.g[3]); S.g[4] = fmaf(a1, dn, S.g[4]); S.g[5] = fmaf(a1, nd, S.g[5]);
-            S.g[6] = fmaf(b2, nn, S.g[6]); S.g[7] = fmaf(a2, dn, S.g[7]); S.g[8] = fmaf(a2, nd, S.g[8]);
-            S.B[0] = fmaf(d0, nn, S.B[0]); S.B[1] = fmaf(u0, ry[j], S.B[1]); S.B[2] = fmaf(u0, rzk, S.B[2]);
-            S.B[3] = fmaf(d1, nn, S.B[3]); S.B[4] = fmaf(u1, ry[j], S.B[4]); S.B[5] = fmaf(u1, rzk, S.B[5]);
-            S.B[6] = fmaf(d2, nn, S.B[6]); S.B[7] = fmaf(u2, ry[j], S.B[7]); S.B[8] = fmaf(u2, rzk, S.B[8]);
-            S.smin = fminf(fminf(S.smin, fminf(t[0].w, t[1].w)), fminf(t[2].w, t[3].w));   // 0 iff a sticking node was seen (FMNMX: ALU pipe)
-        }
-    }
-}
-// second pass, taken only by particles whose stencil holds a sticking node (next to the collider): subtract w v~ of those nodes
-// from v_p and B.  Kept out of the gather loop and rolled up: the hot loop stays branch-free and half as long.
-template <int MODE>
-__device__ __forceinline__ void g2p_stick_correction(const GridP& G, const Axis& ax, const Axis& ay, const Axis& az, const float (&rx)[4],
-                                                  const float (&ry)[4], const float (&rz)[4], const float4* __restrict__ tile, int xoff, G2PSums& S) {
-#pragma unroll 1
-    for (int n = 0; n < 64; ++n) {
-        const int i = n & 3, j = (n >> 2) & 3, k = n >> 4;
-        float4 t;
-        if (MODE == 2) t = tile[xoff + (k * 4 + j) * TILE_W + i];
-        else t = ldg4(G.vt + ((size_t)clampi(az.n0 + k, 0, G.nz - 1) * G.ny + clampi(ay.n0 + j, 0, G.ny - 1)) * G.nx + clampi(ax.n0 + i, 0, G.nx - 1));
-        if (t.w != 0.0f) continue;
-        const float w = -sel4(ax.N, i) * sel4(ay.N, j) * sel4(az.N, k);
-        const float cx = w * t.x, cy = w * t.y, cz = w * t.z;
-        const float rxi = sel4(rx, i), ryj = sel4(ry, j), rzk = sel4(rz, k);
-        S.vc[0] += cx; S.vc[1] += cy; S.vc[2] += cz;
-        S.B[0] = fmaf(cx, rxi, S.B[0]); S.B[1] = fmaf(cx, ryj, S.B[1]); S.B[2] = fmaf(cx, rzk, S.B[2]);
-        S.B[3] = fmaf(cy, rxi, S.B[3]); S.B[4] = fmaf(cy, ryj, S.B[4]); S.B[5] = fmaf(cy, rzk, S.B[5]);
-        S.B[6] = fmaf(cz, rxi, S.B[6]); S.B[7] = fmaf(cz, ryj, S.B[7]); S.B[8] = fmaf(cz, rzk, S.B[8]);
-    }
-}
-
 // Two builds of the G2P kernel: the default, persistent warps that software-pipeline every memory round trip of a chunk behind the
 // arithmetic of the chunk before, and -DAEP_G2P_PIPE=0, one CTA per 128 particles with a register-staged tile.  While the
 // kernel was 3800-4200 SASS instructions the pipelined form lost 5-8 % to instruction-cache misses and loop overhead

@@ -18,6 +18,8 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 r;
 using std::fmaf;
 #include "../anisotropicelastoplasticity_b200/csrc/aep_math.cuh"
 #include "../anisotropicelastoplasticity_b200/csrc/aep_scatter.cuh"
+#include "../anisotropicelastoplasticity_b200/csrc/aep_gather.cuh"
+#include <vector>
 
 using namespace aep;
 extern "C" {
@@ -76,5 +78,56 @@ void h_frc_scatter(const float* f, const float* A, const float* h, float* out) {
             frc_row_accumulate(rec, 32 + 8 * j, 64 + 8 * k, acc);
             for (int i = 0; i < 4; ++i) { const float4 q = quad(acc.lo[i], acc.hi[i]); std::memcpy(out + ((k * 4 + j) * 4 + i) * 4, &q, 16); }
         }
+}
+// ---- the two gathers, exactly as the kernels run them.  vt: nx*ny*nz nodes x (v~x, v~y, v~z, s), node index (k*ny + j)*nx + i.
+// use_tile = 1: the nodes are first staged like stage_tile / tile_issue do (the particle must have a complete stencil), MODE 2;
+// use_tile = 0: clamped loads from the grid, MODE 0 (stencils cut by a domain face).
+static GridP small_grid(int nx, int ny, int nz, const float* vt, const float* h) {
+    GridP G{}; G.nx = nx; G.ny = ny; G.nz = nz; G.hx = h[0]; G.hy = h[1]; G.hz = h[2];
+    G.ihx = 1.0f / h[0]; G.ihy = 1.0f / h[1]; G.ihz = 1.0f / h[2];
+    G.vt = reinterpret_cast<float4*>(const_cast<float*>(vt));
+    return G;
+}
+static int fill_tile(const GridP& G, const int* cell, std::vector<float4>& tile) {      // returns xoff of the particle's first node
+    const int ox0 = cell[0] - 1 - TILE_SLACK, j0 = cell[1] - 1, k0 = cell[2] - 1;
+    tile.assign(TILE_F4, make_float4(1e30f, 1e30f, 1e30f, 1.0f));                       // poison: entries outside the box must not be read
+    for (int idx = 0; idx < TILE_F4; ++idx) {
+        const int r = idx / TILE_W, x = idx - r * TILE_W, gx = ox0 + x;
+        if (gx >= 0 && gx < G.nx) tile[idx] = G.vt[((size_t)(k0 + (r >> 2)) * G.ny + (j0 + (r & 3))) * G.nx + gx];
+    }
+    return (cell[0] - 1) - ox0;
+}
+void h_gather_grad(int nx, int ny, int nz, const float* vt, const int* cell, const float* f, const float* h, int use_tile, float* g9) {
+    const GridP G = small_grid(nx, ny, nz, vt, h);
+    Axis ax, ay, az;
+    axis_setup(ax, f[0], cell[0], nx, G.ihx); axis_setup(ay, f[1], cell[1], ny, G.ihy); axis_setup(az, f[2], cell[2], nz, G.ihz);
+    float g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<float4> tile;
+    if (use_tile) { const int xoff = fill_tile(G, cell, tile); gather_grad<2>(G, ax, ay, az, tile.data(), xoff, g); }
+    else gather_grad<0>(G, ax, ay, az, nullptr, 0, g);
+    std::memcpy(g9, g, 36);
+}
+void h_g2p_gather(int nx, int ny, int nz, const float* vt, const int* cell, const float* f, const float* h, int use_tile,
+                  float* va, float* vc, float* B, float* g, float* smin) {
+    const GridP G = small_grid(nx, ny, nz, vt, h);
+    Axis ax, ay, az;
+    axis_setup(ax, f[0], cell[0], nx, G.ihx); axis_setup(ay, f[1], cell[1], ny, G.ihy); axis_setup(az, f[2], cell[2], nz, G.ihz);
+    float rx[4], ry[4], rz[4], nrx[4];                                                  // as in k_g2p: x_i - x_p per axis
+    for (int o = 0; o < 4; ++o) { rx[o] = G.hx * ((float)(o - 1) - f[0]); ry[o] = G.hy * ((float)(o - 1) - f[1]); rz[o] = G.hz * ((float)(o - 1) - f[2]); }
+    for (int o = 0; o < 4; ++o) nrx[o] = ax.N[o] * rx[o];
+    G2PSums S;
+    for (int i = 0; i < 3; ++i) { S.vc[i] = 0.f; S.va[i] = 0.f; }
+    for (int i = 0; i < 9; ++i) { S.B[i] = 0.f; S.g[i] = 0.f; }
+    S.smin = 1.0f;
+    std::vector<float4> tile;
+    if (use_tile) {
+        const int xoff = fill_tile(G, cell, tile);
+        g2p_gather<2>(G, ax, ay, az, nrx, rx, ry, rz, tile.data(), xoff, S);
+        if (S.smin == 0.0f) g2p_stick_correction<2>(G, ax, ay, az, rx, ry, rz, tile.data(), xoff, S);
+    } else {
+        g2p_gather<0>(G, ax, ay, az, nrx, rx, ry, rz, nullptr, 0, S);
+        if (S.smin == 0.0f) g2p_stick_correction<0>(G, ax, ay, az, rx, ry, rz, nullptr, 0, S);
+    }
+    std::memcpy(va, S.va, 12); std::memcpy(vc, S.vc, 12); std::memcpy(B, S.B, 36); std::memcpy(g, S.g, 36); *smin = S.smin;
 }
 }

@@ -150,3 +150,65 @@ def test_force_scatter_rows_match_reference_formula(H):
         assert np.abs(out[..., :3] - ref).max() < 3e-6 * np.abs(ref).max()
         assert np.abs(out[..., 3]).max() == 0.0                             # the fourth lane of the force record stays zero
         assert np.abs(out[..., :3].sum(axis=(0, 1, 2))).max() < 2e-5 * np.abs(ref).max()   # sum_i grad w_i = 0: no net force from one particle
+
+
+ip = C.POINTER(C.c_int)
+
+
+def _gather_reference(vt, res, cell, f64, h64):
+    """HybridSolver.cpp:269-301 / 739-825 written out: sums over the in-grid nodes of the 4x4x4 stencil (truncated, not renormalised,
+    at the domain faces, HS:44-46).  Returns va = sum w v~, vp = sum w s v~, g = sum v~ (grad w)^T, B = sum w s v~ (x_i - x_p)^T."""
+    nx, ny, nz = res
+    N = [_weights64(f64[a]) for a in range(3)]; Dn = [_dweights64(f64[a], h64[a]) for a in range(3)]
+    va = np.zeros(3); vp = np.zeros(3); g = np.zeros((3, 3)); B = np.zeros((3, 3)); any_stick = False
+    for k in range(4):
+        for j in range(4):
+            for i in range(4):
+                n = (cell[0] - 1 + i, cell[1] - 1 + j, cell[2] - 1 + k)
+                if not (0 <= n[0] < nx and 0 <= n[1] < ny and 0 <= n[2] < nz):
+                    continue
+                t = vt[(n[2] * ny + n[1]) * nx + n[0]].astype(np.float64)
+                w = N[0][i] * N[1][j] * N[2][k]
+                gw = np.array([Dn[0][i] * N[1][j] * N[2][k], N[0][i] * Dn[1][j] * N[2][k], N[0][i] * N[1][j] * Dn[2][k]])
+                r = h64 * (np.array([i, j, k]) - 1.0 - f64)
+                va += w * t[:3]; g += np.outer(t[:3], gw)
+                vp += w * t[3] * t[:3]; B += w * t[3] * np.outer(t[:3], r)
+                any_stick |= t[3] == 0.0
+    return va, vp, g, B, any_stick
+
+
+@pytest.mark.parametrize("use_tile", [1, 0])
+def test_gathers_match_reference_formulas(H, use_tile):
+    """gather_grad (k_forces) and g2p_gather + g2p_stick_correction (k_g2p) from aep_gather.cuh, run on the host: tile path on
+    interior cells, clamped grid path on cells whose stencil is cut by a domain face; a fifth of the nodes stick (s = 0)."""
+    H.h_gather_grad.argtypes = [C.c_int, C.c_int, C.c_int, fp, ip, fp, fp, C.c_int, fp]
+    H.h_g2p_gather.argtypes = [C.c_int, C.c_int, C.c_int, fp, ip, fp, fp, C.c_int, fp, fp, fp, fp, fp]
+    rng = np.random.default_rng(8 + use_tile)
+    res = (9, 7, 8)
+    for trial in range(150):
+        vt = f32(rng.standard_normal((res[0] * res[1] * res[2], 4)))
+        stick_here = trial % 3 != 0
+        vt[:, 3] = (rng.random(len(vt)) > 0.2).astype(np.float32) if stick_here else 1.0
+        if use_tile:
+            cell = np.array([rng.integers(1, res[a] - 2) for a in range(3)], np.int32)          # complete stencil
+        else:
+            cell = np.array([rng.choice([0, res[a] - 1, res[a] - 2, rng.integers(0, res[a])]) for a in range(3)], np.int32)
+        f = f32(rng.random(3) * 0.999); h = f32([1 / 64, 1 / 48, 1 / 80])
+        f64 = f.astype(np.float64); h64 = h.astype(np.float64)
+        va_r, vp_r, g_r, B_r, any_stick = _gather_reference(vt, res, cell, f64, h64)
+        g9 = np.zeros(9, np.float32)
+        H.h_gather_grad(res[0], res[1], res[2], P(vt.ravel()), cell.ctypes.data_as(ip), P(f), P(h), use_tile, P(g9))
+        gscale = np.abs(g_r).max()
+        assert np.abs(g9.reshape(3, 3) - g_r).max() < 3e-6 * gscale
+        va = np.zeros(3, np.float32); vc = np.zeros(3, np.float32); B = np.zeros(9, np.float32); g = np.zeros(9, np.float32); smin = C.c_float(-1)
+        H.h_g2p_gather(res[0], res[1], res[2], P(vt.ravel()), cell.ctypes.data_as(ip), P(f), P(h), use_tile, P(va), P(vc), P(B), P(g), C.byref(smin))
+        assert np.abs(g.reshape(3, 3) - g_r).max() < 3e-6 * gscale
+        assert np.abs(va - va_r).max() < 3e-6 * max(1.0, np.abs(va_r).max())
+        assert np.abs((va.astype(np.float64) + vc) - vp_r).max() < 3e-6 * max(1.0, np.abs(va_r).max())          # v_p = sum w s v~
+        assert np.abs(B.reshape(3, 3) - B_r).max() < 3e-6 * max(np.abs(B_r).max(), h64.max())
+        # the flag that triggers the correction pass: 0 iff an in-stencil node sticks (clamped duplicates of a face node may add
+        # a spurious 0 with zero weight, which only costs the second pass)
+        if any_stick:
+            assert smin.value == 0.0
+        elif use_tile:
+            assert smin.value == 1.0
