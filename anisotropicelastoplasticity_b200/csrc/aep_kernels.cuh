@@ -648,7 +648,9 @@ inline void forces_launch(cudaStream_t st, int sm_count, const PartP& P, const G
 // buffer -- into the warp's own shared memory, so no prefetched value ever occupies a register (a register-staged variant
 // spilled the prefetched X at once and stalled on the spill store: profiles/README.md, v9b).
 #define G2P_NT 128
+#ifndef G2P_CTAS_PER_SM
 #define G2P_CTAS_PER_SM 4
+#endif
 struct G2PWarpSmem {
     float4 tile[TILE_F4];
     float4 x[2][32];
