@@ -49,8 +49,10 @@ def _p(a):
 class Oracle:
     """One simulation on the CPU oracle; method names mirror the C ABI of the engine (include/aep_b200.h)."""
 
+    _load = staticmethod(lambda: lib())        # oracle/ref_py.py swaps in the reference's own code behind the same entry points
+
     def __init__(self, scene: Scene, threads: int = 1, rate_floor: float = 3e2):
-        L = lib(); self.L = L
+        L = self._load(); self.L = L
         g = scene.grid
         mn = np.asarray(g.mn, np.float64); mx = np.asarray(g.mx, np.float64); res = np.asarray(g.res, np.int32)
         self.h = C.c_void_p(L.orc_create(_p(mn), _p(mx), res.ctypes.data_as(C.POINTER(C.c_int))))
@@ -79,9 +81,12 @@ class Oracle:
                            faces.ctypes.data_as(C.POINTER(C.c_int)), _p(colmajor(m.ev)), _p(np.ascontiguousarray(m.em)),
                            _p(np.ascontiguousarray(m.evol)), _p(eB), _p(ed), _p(eD), _p(fixed),
                            C.c_double(m.mu), C.c_double(m.lam), C.c_double(m.shear), C.c_double(m.stiff), C.c_double(m.fric))
+        self._set_levelset(scene)
+
+    def _set_levelset(self, scene):
         if scene.levelset.kind != 0:
             par = np.ascontiguousarray(scene.levelset.params, np.float64)
-            L.orc_set_levelset(self.h, C.c_int(scene.levelset.kind), _p(par))
+            self.L.orc_set_levelset(self.h, C.c_int(scene.levelset.kind), _p(par))
 
     def __del__(self):
         try:
