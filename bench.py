@@ -2,8 +2,8 @@
 """bench.py -- particle-substeps/s of the full MPM substep (HybridSolver.cpp:867-1032) on N B200s.
 
   python bench.py --gpus N --steps K --warmup W            # this engine (libaep_b200.so through the C ABI)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port; the reference
-                                                           # itself cannot be built here: Eigen/libigl/GLFW absent)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path: its own sources compiled against a
+                                                           # MiniEigen stand-in (oracle/_ref), else the oracle port
 
 Workload (config.workload): BASELINE.json configs[4], the synthetic 64M-particle sand dam break on a 512^3 grid --
 the configuration the headline target is quoted on; it fits one B200 (~33 GB), so it is also the N=1 workload and
@@ -165,36 +165,60 @@ def make_shell_scene(res):
     return sc.Scene("C5_dam_break", g, sc.SAND, None, None, ls)
 
 
+REF_NOTE = ("the reference's own unmodified sources (HybridSolver.cpp etc.) compiled against the MiniEigen stand-in "
+            "(oracle/_ref/libaep_ref.so; this image has no Eigen), serial like the reference")
+
+
+def _timed_substeps(sim, seconds_budget, max_steps, warmup):
+    for _ in range(warmup):
+        sim.substep()
+    n = 0; t0 = time.perf_counter()
+    while True:
+        sim.substep(); n += 1
+        el = time.perf_counter() - t0
+        if el > seconds_budget or n >= max_steps:
+            return n, el
+
+
 def cpu_baseline(threads, seconds_budget=20.0, res=64):
-    """The oracle (CPU restatement of the reference's path) on a bounded sample of the same workload: the C5 dam break at
-    res^3 (same particles per cell, same material, same collider), 2 warm-up + timed substeps."""
+    """The reference's CPU path on a bounded sample of the same workload: the C5 dam break at res^3 (same particles per
+    cell, same material, same collider).  kind "reference" = the reference's own code (oracle/_ref, built in the dev container
+    from /root/reference and shipped as a .so); the oracle port's figure on the same sample rides along under "port" (it is
+    ~7x faster than the reference because it never builds the sparse weight matrices).  Falls back to the port alone only
+    if the reference library is missing."""
+    from oracle import ref_py
     from oracle.oracle_py import Oracle
     scene = sc.c5_dam_break(res=res)
     o = Oracle(scene, threads=threads, rate_floor=rate_floor_for(res)); o.init()
     used = o.L.orc_get_threads(o.h)
-    for _ in range(2):
-        o.substep()
-    n = 0; t0 = time.perf_counter()
-    while True:
-        o.substep(); n += 1
-        el = time.perf_counter() - t0
-        if el > seconds_budget or n >= 200:
-            break
-    return {"value": scene.particles.n * n / el, "unit": UNIT, "cores": int(used), "kind": "port",
+    have_ref = ref_py.available()
+    n, el = _timed_substeps(o, seconds_budget / 2 if have_ref else seconds_budget, 200, 2)
+    port = {"value": scene.particles.n * n / el, "unit": UNIT, "cores": int(used), "kind": "port",
             "sample": f"C5 dam break at {res}^3 grid, {scene.particles.n} particles, {n} substeps in {el:.1f} s (fp64 oracle, oracle/mpm_oracle.cpp)"}
+    if not have_ref:
+        return port
+    r = ref_py.Reference(scene, rate_floor=rate_floor_for(res)); r.init()
+    n, el = _timed_substeps(r, seconds_budget, 50, 1)
+    return {"value": scene.particles.n * n / el, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"C5 dam break at {res}^3 grid, {scene.particles.n} particles, {n} substeps in {el:.1f} s; {REF_NOTE}", "port": port}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path on the host cores.  The reference cannot be
-    compiled here (needs Eigen + libigl + GLFW + GLEW), so this times the oracle port with all host threads."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores -- its own code (oracle/_ref) when
+    that library is present, else the oracle port with all host threads.  The reference is serial, so one core is
+    all the host threads it can use."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import ref_py
     from oracle.oracle_py import Oracle
     res = args.ref_res
     scene = sc.c5_dam_break(res=res)
-    o = Oracle(scene, threads=0, rate_floor=rate_floor_for(res)); o.init()
-    used = o.L.orc_get_threads(o.h)
+    if ref_py.available():
+        o = ref_py.Reference(scene, rate_floor=rate_floor_for(res)); kind = "reference"; used = 1; what = REF_NOTE
+    else:
+        o = Oracle(scene, threads=0, rate_floor=rate_floor_for(res)); kind = "port"; used = o.L.orc_get_threads(o.h); what = "fp64 oracle port, all host threads"
+    o.init()
     for _ in range(args.warmup):
         o.substep()
     t0 = time.perf_counter()
@@ -205,8 +229,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, res_override=res, note="bounded sample of the workload: same scene at a smaller grid"),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": int(used), "kind": "port",
-                             "sample": f"C5 dam break at {res}^3 grid, {scene.particles.n} particles, {args.steps} substeps"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": int(used), "kind": kind,
+                             "sample": f"C5 dam break at {res}^3 grid, {scene.particles.n} particles, {args.steps} substeps; {what}"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 

@@ -1,9 +1,9 @@
-"""Diagnostic (not a test): the engine against the reference-generated fixtures tests/golden/ref_*.npz with the reference's
+"""Diagnostic (not a test; lives under tests/ because it loads the oracle / the fixtures, which only test code may): the engine against the reference-generated fixtures tests/golden/ref_*.npz with the reference's
 time steps replayed; prints the error table tests/test_reference_pin.py's GPU tolerances were chosen from.  Never asserts.
-Usage on the GPU box: python tools/gpu_refpin_report.py > gpurun_out/refpin.txt"""
+Usage on the GPU box: python tests/diag/gpu_refpin_report.py > gpurun_out/refpin.txt"""
 import os, sys, time, traceback
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import load_golden, relerr
 from anisotropicelastoplasticity_b200.engine import Engine
 

@@ -1,8 +1,8 @@
-"""Diagnostic (not a test): per-stage engine-vs-oracle error table on several scenes; never asserts.
-Usage on the GPU box: python tools/gpu_report.py > gpurun_out/report.txt"""
+"""Diagnostic (not a test; lives under tests/ because it loads the oracle / the fixtures, which only test code may): per-stage engine-vs-oracle error table on several scenes; never asserts.
+Usage on the GPU box: python tests/diag/gpu_report.py > gpurun_out/report.txt"""
 import os, sys, time, traceback
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 from anisotropicelastoplasticity_b200 import scenes as sc
 from anisotropicelastoplasticity_b200.engine import Engine
 from oracle.oracle_py import Oracle

@@ -3,6 +3,7 @@
 //   host_driver run <scene.bin> <out.bin> <mode> <n> [outdir]
 //        mode = substeps : begin(CFL); advance(n); finish()         (parity against the oracle is done by the Python test)
 //        mode = solve    : solve(CFL, maxt = n/60 - 1/120, alpha)   -> n frames, particle_N.obj / mesh_N.obj in outdir
+//   host_driver objmesh <in.obj> <out.bin> density thickness E nu shear stiff angle_deg    (loader parity vs the reference's)
 // Scene file = what tests/test_host_cpp.py writes: [int32 count] then per array: char name[32], int32 dtype (0 f64, 1 i32),
 // int64 length, raw data.
 #include <cmath>
@@ -194,9 +195,27 @@ static int run(int argc, char** argv) {
     return 0;
 }
 
+// host_driver objmesh <in.obj> <out.bin> density thickness E nu shear stiff angle_deg : what LagrangianMesh::ObjMesh derives
+static int objmesh(char** argv) {
+    LagrangianMesh M = LagrangianMesh::ObjMesh(argv[2], std::atof(argv[4]), std::atof(argv[5]), std::atof(argv[6]), std::atof(argv[7]),
+                                               std::atof(argv[8]), std::atof(argv[9]), std::atof(argv[10]));
+    Writer w(argv[3]);
+    std::vector<double> F((size_t)M.faces.size()); for (std::ptrdiff_t i = 0; i < M.faces.size(); ++i) F[(size_t)i] = M.faces.data()[i];
+    const double c[3] = {M.mu, M.lambda, M.frictionCoeff};
+    w.put("vx", M.vertexPositions.data(), M.vertexPositions.size()); w.put("faces", F.data(), (int64_t)F.size());
+    w.put("vm", M.vertexMasses.data(), M.vertexMasses.size()); w.put("vvol", M.vertexVolumes.data(), M.vertexVolumes.size());
+    w.put("em", M.elementMasses.data(), M.elementMasses.size()); w.put("evol", M.elementVolumes.data(), M.elementVolumes.size());
+    w.put("D1", M.elementRestDirections_1().data(), M.elementRestDirections_1().size());
+    w.put("D2", M.elementRestDirections_2().data(), M.elementRestDirections_2().size());
+    w.put("D3", M.elementRestDirections_3().data(), M.elementRestDirections_3().size());
+    w.put("ex", M.elementPositions.data(), M.elementPositions.size()); w.put("consts", c, 3);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     try {
         if (argc >= 3 && std::string(argv[1]) == "unit") return unit(argv[2]);
+        if (argc >= 11 && std::string(argv[1]) == "objmesh") return objmesh(argv);
         if (argc >= 6 && std::string(argv[1]) == "run") return run(argc, argv);
         std::fprintf(stderr, "usage: host_driver unit <tmpdir> | run <scene.bin> <out.bin> substeps|solve <n> [outdir]\n");
         return 2;

@@ -308,3 +308,43 @@ def test_engine_reproduces_reference_solve_frame():
     assert (ejp - 1.0) == pytest.approx(jp - 1.0, rel=0.01, abs=1e-6)
     assert np.allclose(d["obj_xyz"], p["x"], rtol=1e-4)                                # the frame file the reference wrote
     e.close()
+
+
+# ------------------------------------------------------------------------------------------------ host C++ layer vs the reference
+@live
+def test_host_objmesh_loader_matches_reference(tmp_path):
+    """LagrangianMesh::ObjMesh of libaep_host.so against the reference's loader (LagrangianMesh.cpp:197-352) on the same OBJ
+    file (comments, vn/vt lines, positions parsed as float like the reference does): vertex/element masses and volumes, rest
+    directions, centroids, Lame constants and tan(friction angle).  Pure host code: no GPU involved."""
+    import subprocess
+    from test_host_cpp import DRIVER, _build, read_blob
+    _build()
+    rng = np.random.default_rng(5); n = 6
+    gx, gy = np.meshgrid(np.linspace(0.1, 0.9, n), np.linspace(0.2, 0.7, n), indexing="ij")
+    V = np.stack([gx.ravel(), gy.ravel(), 0.6 + 0.02 * rng.standard_normal(n * n)], axis=1)
+    F = []
+    for i in range(n - 1):
+        for j in range(n - 1):
+            a = i * n + j; F += [(a, a + n, a + n + 1), (a, a + n + 1, a + 1)]
+    obj = tmp_path / "cloth.obj"
+    with open(obj, "w") as f:
+        f.write("# cloth\no sheet\n")
+        for v in V:
+            f.write(f"v {v[0]:.7f} {v[1]:.7f} {v[2]:.7f}\n")
+        f.write("vt 0.5 0.5\nvn 0 0 1\n")
+        for t in F:
+            f.write(f"f {t[0] + 1} {t[1] + 1} {t[2] + 1}\n")
+    par = (2e3, 0.04, 200.0, 0.3, 12.0, 4e4, 25.0)                         # main.cpp:77-78 with shear and friction switched on
+    ref = ref_py.obj_mesh(str(obj), *par)
+    out = tmp_path / "mesh.bin"
+    subprocess.check_call([DRIVER, "objmesh", str(obj), str(out)] + [repr(float(p)) for p in par])
+    got = read_blob(str(out)); nv, nf = n * n, len(F)
+    cm = lambda a, k: a.reshape(3, k).T
+    assert np.array_equal(cm(got["faces"], nf).astype(int), ref["faces"]) and np.array_equal(ref["faces"], np.array(F))
+    assert np.array_equal(cm(got["vx"], nv), ref["vx"])                     # both parse through float
+    for k in ("vm", "vvol", "em", "evol"):
+        assert relerr(got[k], ref[k]) < 1e-14, k
+    for a, k in enumerate(("D1", "D2", "D3")):
+        assert relerr(cm(got[k], nf), ref["eD"][a]) < 1e-14, k
+    assert np.allclose(got["consts"], [ref["mu"], ref["lam"], ref["fric"]], rtol=1e-15)
+    assert ref["fric"] == pytest.approx(np.tan(np.deg2rad(25.0)), rel=1e-15)   # LagrangianMesh.cpp:351
