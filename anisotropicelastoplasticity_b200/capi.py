@@ -43,7 +43,7 @@ SYMBOLS = (
     "aep_stats", "aep_kernel_launches", "aep_stream", "aep_profile", "aep_get_timers", "aep_grid_activity", "aep_halo_info",
     "aep_halo_pack", "aep_halo_add", "aep_vmax_get", "aep_vmax_set", "aep_step_forces", "aep_step_grid", "aep_step_g2p",
     "aep_step_p2g", "aep_migrate_extract", "aep_migrate_insert", "aep_migrate_bind", "aep_migrate_extract_begin", "aep_migrate_extract_end",
-    "aep_step_p2g_arrivals", "aep_set_particle_id_base", "aep_download_particles_local",
+    "aep_step_p2g_arrivals", "aep_set_particle_id_base", "aep_download_particles_local", "aep_resume", "aep_set_clock",
 )
 
 
@@ -74,6 +74,8 @@ def load():
     for name in ("aep_stage_forces", "aep_stage_grid", "aep_stage_g2p", "aep_set_dt", "aep_set_fixed_dt"):
         getattr(L, name).argtypes = [vp, C.c_double]
     L.aep_get_clock.argtypes = [vp, dp, dp, dp, C.POINTER(C.c_int32), i64p, dp, i64p]
+    L.aep_resume.argtypes = [vp]
+    L.aep_set_clock.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int64]
     L.aep_download_particles.argtypes = [vp] + [dp] * 9
     L.aep_download_grid.argtypes = [vp] + [dp] * 4
     L.aep_download_mesh.argtypes = [vp] + [dp] * 7

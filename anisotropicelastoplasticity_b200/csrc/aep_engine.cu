@@ -651,6 +651,19 @@ int aep_set_fixed_dt(aep_ctx* c, double dt) {
     c->fixed_dt = 0;
     return AEP_OK;
 }
+// restart: a saved state is uploaded like a fresh one, then only binned and transferred to the grid -- the particle
+// volumes are part of the state (HS:242-249 runs once, on the very first P2G) and the clock is put back by aep_set_clock
+int aep_resume(aep_ctx* c) { return aep_init_begin(c); }
+int aep_set_clock(aep_ctx* c, double dt, double t, double inner_t, int32_t frame_no, int64_t substeps) {
+    if (!c) return AEP_ERR_INVALID;
+    if (!(dt > 0.0) || !(t >= 0.0) || !(inner_t >= 0.0) || frame_no < 0 || substeps < 0) return fail(c, AEP_ERR_INVALID, "aep_set_clock: dt must be > 0, times and counters >= 0");
+    cudaSetDevice(c->device);
+    SimClock clk;
+    CU(cudaMemcpyAsync(&clk, c->d_clk, sizeof clk, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
+    clk.dt = (float)dt; clk.t = t; clk.inner_t = inner_t; clk.frame_no = frame_no; clk.frame_flag = 0; clk.substeps = substeps;
+    CU(cudaMemcpyAsync(c->d_clk, &clk, sizeof clk, cudaMemcpyHostToDevice, c->stream)); CU(cudaStreamSynchronize(c->stream));
+    return AEP_OK;
+}
 int aep_stage_forces(aep_ctx* c, double dt) { int r = require_init(c); if (r) return r; if ((r = aep_set_dt(c, dt))) return r; return do_forces(c); }
 int aep_stage_grid(aep_ctx* c, double dt) {
     int r = require_init(c); if (r) return r; if ((r = aep_set_dt(c, dt))) return r;

@@ -122,7 +122,7 @@ void HybridSolver::uploadAll_() {
     }
 }
 
-void HybridSolver::begin(double CFL) {
+void HybridSolver::createContext_(double CFL) {
     if (!rg_) throw std::invalid_argument("HybridSolver: setRegularGrid first");
     if (!ps_ && !mesh_) throw std::invalid_argument("HybridSolver: nothing to simulate (no ParticleSystem, no LagrangianMesh)");
     if (ctx_) { aep_destroy(ctx_); ctx_ = nullptr; }
@@ -131,6 +131,9 @@ void HybridSolver::begin(double CFL) {
     for (int a = 0; a < 3; ++a) { cfg_.grid_min[a] = rg_->minBound()[a]; cfg_.grid_max[a] = rg_->maxBound()[a]; cfg_.res[a] = rg_->resolution()[a]; }
     ck(aep_create(&ctx_, &cfg_), nullptr, "aep_create");
     uploadAll_();
+}
+void HybridSolver::begin(double CFL) {
+    createContext_(CFL);
     ck(aep_init(ctx_), ctx_, "aep_init");
     substeps_ = 0;
 }
@@ -157,32 +160,140 @@ void HybridSolver::fetchPositions() {
     if (mesh_) ck(aep_download_mesh(ctx_, mesh_->vertexPositions.data(), nullptr, nullptr, mesh_->elementPositions.data(), nullptr, nullptr, nullptr), ctx_, "aep_download_mesh");
 }
 
+void HybridSolver::downloadAll_() {
+    std::lock_guard<std::mutex> lk(mtx_);
+    if (ps_) {
+        ParticleSystem& p = *ps_;
+        std::vector<double> FE(9 * p.elasticDeformationGradients.size()), FP(FE.size());
+        ck(aep_download_particles(ctx_, p.positions.data(), p.velocities.data(), p.affineMomenta_1.data(), p.affineMomenta_2.data(),
+                                  p.affineMomenta_3.data(), FE.data(), FP.data(), p.volumes.data(), p.plasticAmount.data()), ctx_, "aep_download_particles");
+        unflat9(FE, p.elasticDeformationGradients); unflat9(FP, p.plasticDeformationGradients);
+        for (std::ptrdiff_t i = 0; i < p.masses.size(); ++i) p.densities[i] = p.volumes[i] > 0 ? p.masses[i] / p.volumes[i] : 0.0;   // HybridSolver.cpp:246-248
+    }
+    if (mesh_) {
+        LagrangianMesh& m = *mesh_;
+        const size_t nv = (size_t)m.vertexPositions.rows(), nf = (size_t)m.faces.rows();
+        std::vector<double> vB(9 * nv), eB(9 * nf), ed(9 * nf);
+        ck(aep_download_mesh(ctx_, m.vertexPositions.data(), m.vertexVelocities.data(), vB.data(), m.elementPositions.data(),
+                             m.elementVelocities.data(), eB.data(), ed.data()), ctx_, "aep_download_mesh");
+        unstack3(vB, m.vertexAffineMomenta_1, m.vertexAffineMomenta_2, m.vertexAffineMomenta_3);
+        unstack3(eB, m.elementAffineMomenta_1, m.elementAffineMomenta_2, m.elementAffineMomenta_3);
+        unstack3(ed, m.elementDirections_1, m.elementDirections_2, m.elementDirections_3);
+    }
+    rg_->allocateHostMirrors();
+    ck(aep_download_grid(ctx_, rg_->masses.data(), rg_->velocities.data(), rg_->forces.data(), nullptr), ctx_, "aep_download_grid");
+}
+
 void HybridSolver::finish() {
     if (!ctx_) return;
-    {
-        std::lock_guard<std::mutex> lk(mtx_);
-        if (ps_) {
-            ParticleSystem& p = *ps_;
-            std::vector<double> FE(9 * p.elasticDeformationGradients.size()), FP(FE.size());
-            ck(aep_download_particles(ctx_, p.positions.data(), p.velocities.data(), p.affineMomenta_1.data(), p.affineMomenta_2.data(),
-                                      p.affineMomenta_3.data(), FE.data(), FP.data(), p.volumes.data(), p.plasticAmount.data()), ctx_, "aep_download_particles");
-            unflat9(FE, p.elasticDeformationGradients); unflat9(FP, p.plasticDeformationGradients);
-            for (std::ptrdiff_t i = 0; i < p.masses.size(); ++i) p.densities[i] = p.volumes[i] > 0 ? p.masses[i] / p.volumes[i] : 0.0;   // HybridSolver.cpp:246-248
-        }
-        if (mesh_) {
-            LagrangianMesh& m = *mesh_;
-            const size_t nv = (size_t)m.vertexPositions.rows(), nf = (size_t)m.faces.rows();
-            std::vector<double> vB(9 * nv), eB(9 * nf), ed(9 * nf);
-            ck(aep_download_mesh(ctx_, m.vertexPositions.data(), m.vertexVelocities.data(), vB.data(), m.elementPositions.data(),
-                                 m.elementVelocities.data(), eB.data(), ed.data()), ctx_, "aep_download_mesh");
-            unstack3(vB, m.vertexAffineMomenta_1, m.vertexAffineMomenta_2, m.vertexAffineMomenta_3);
-            unstack3(eB, m.elementAffineMomenta_1, m.elementAffineMomenta_2, m.elementAffineMomenta_3);
-            unstack3(ed, m.elementDirections_1, m.elementDirections_2, m.elementDirections_3);
-        }
-        rg_->allocateHostMirrors();
-        ck(aep_download_grid(ctx_, rg_->masses.data(), rg_->velocities.data(), rg_->forces.data(), nullptr), ctx_, "aep_download_grid");
-    }
+    downloadAll_();
     aep_destroy(ctx_); ctx_ = nullptr;
+}
+
+// ---- checkpoint / restart ------------------------------------------------------------------------------------------------
+namespace {
+struct BlobWriter {
+    FILE* f; int32_t cnt = 0;
+    explicit BlobWriter(const std::string& p) : f(std::fopen(p.c_str(), "wb")) {
+        if (!f) throw std::runtime_error("cannot write " + p);
+        std::fwrite(&cnt, 4, 1, f);
+    }
+    void put(const char* name, const double* p, int64_t len) {
+        char nm[32] = {0}; std::strncpy(nm, name, 31); const int32_t dt = 0;
+        std::fwrite(nm, 32, 1, f); std::fwrite(&dt, 4, 1, f); std::fwrite(&len, 8, 1, f); if (len) std::fwrite(p, 8, (size_t)len, f); ++cnt;
+    }
+    void put9(const char* name, const std::vector<Matrix3d>& M) { const std::vector<double> v = flat9(M); put(name, v.data(), (int64_t)v.size()); }
+    ~BlobWriter() { std::fseek(f, 0, SEEK_SET); std::fwrite(&cnt, 4, 1, f); std::fclose(f); }
+};
+// reads array `name` of exactly `len` doubles into dst
+struct BlobReader {
+    std::vector<std::pair<std::string, std::vector<double>>> a;
+    explicit BlobReader(const std::string& p) {
+        FILE* f = std::fopen(p.c_str(), "rb");
+        if (!f) throw std::runtime_error("cannot open checkpoint " + p);
+        int32_t cnt = 0; bool ok = std::fread(&cnt, 4, 1, f) == 1 && cnt >= 0 && cnt < 4096;
+        for (int i = 0; ok && i < cnt; ++i) {
+            char nm[33] = {0}; int32_t dt = 0; int64_t len = 0;
+            ok = std::fread(nm, 32, 1, f) == 1 && std::fread(&dt, 4, 1, f) == 1 && std::fread(&len, 8, 1, f) == 1 && dt == 0 && len >= 0;
+            if (!ok) break;
+            std::vector<double> v((size_t)len);
+            ok = len == 0 || std::fread(v.data(), 8, (size_t)len, f) == (size_t)len;
+            a.emplace_back(nm, std::move(v));
+        }
+        std::fclose(f);
+        if (!ok) throw std::runtime_error("malformed checkpoint " + p);
+    }
+    const std::vector<double>& get(const char* name, size_t len) const {
+        for (const auto& e : a) if (e.first == name) {
+            if (e.second.size() != len) throw std::runtime_error(std::string("checkpoint array ") + name + " has " + std::to_string(e.second.size()) + " values, the bound container needs " + std::to_string(len));
+            return e.second;
+        }
+        throw std::runtime_error(std::string("checkpoint has no array ") + name);
+    }
+    void into(const char* name, double* dst, size_t len) const { const std::vector<double>& v = get(name, len); if (len) std::memcpy(dst, v.data(), len * 8); }
+};
+}  // namespace
+
+void HybridSolver::writeStateFile(const std::string& path, const ParticleSystem* ps, const LagrangianMesh* mesh, const double clock5[5]) {
+    BlobWriter w(path);
+    const double version = 1.0;
+    w.put("aep_checkpoint", &version, 1); w.put("clock", clock5, 5);                      // dt, t, inner_t, frame_no, substeps
+    if (ps) {
+        w.put("p_x", ps->positions.data(), ps->positions.size()); w.put("p_v", ps->velocities.data(), ps->velocities.size());
+        w.put("p_B1", ps->affineMomenta_1.data(), ps->affineMomenta_1.size()); w.put("p_B2", ps->affineMomenta_2.data(), ps->affineMomenta_2.size());
+        w.put("p_B3", ps->affineMomenta_3.data(), ps->affineMomenta_3.size());
+        w.put9("p_FE", ps->elasticDeformationGradients); w.put9("p_FP", ps->plasticDeformationGradients);
+        w.put("p_m", ps->masses.data(), ps->masses.size()); w.put("p_vol", ps->volumes.data(), ps->volumes.size());
+        w.put("p_q", ps->plasticAmount.data(), ps->plasticAmount.size());
+    }
+    if (mesh) {
+        const LagrangianMesh& m = *mesh;
+        w.put("m_vx", m.vertexPositions.data(), m.vertexPositions.size()); w.put("m_vv", m.vertexVelocities.data(), m.vertexVelocities.size());
+        w.put("m_ex", m.elementPositions.data(), m.elementPositions.size()); w.put("m_ev", m.elementVelocities.data(), m.elementVelocities.size());
+        const std::vector<double> vB = stack3(m.vertexAffineMomenta_1, m.vertexAffineMomenta_2, m.vertexAffineMomenta_3);
+        const std::vector<double> eB = stack3(m.elementAffineMomenta_1, m.elementAffineMomenta_2, m.elementAffineMomenta_3);
+        const std::vector<double> ed = stack3(m.elementDirections_1, m.elementDirections_2, m.elementDirections_3);
+        w.put("m_vB", vB.data(), (int64_t)vB.size()); w.put("m_eB", eB.data(), (int64_t)eB.size()); w.put("m_ed", ed.data(), (int64_t)ed.size());
+    }
+}
+
+void HybridSolver::readStateFile(const std::string& path, ParticleSystem* ps, LagrangianMesh* mesh, double clock5[5]) {
+    const BlobReader r(path);
+    if (r.get("aep_checkpoint", 1)[0] != 1.0) throw std::runtime_error("unsupported checkpoint version in " + path);
+    r.into("clock", clock5, 5);
+    if (ps) {
+        ParticleSystem& p = *ps; const size_t n = (size_t)p.masses.size();
+        r.into("p_x", p.positions.data(), 3 * n); r.into("p_v", p.velocities.data(), 3 * n);
+        r.into("p_B1", p.affineMomenta_1.data(), 3 * n); r.into("p_B2", p.affineMomenta_2.data(), 3 * n); r.into("p_B3", p.affineMomenta_3.data(), 3 * n);
+        unflat9(r.get("p_FE", 9 * n), p.elasticDeformationGradients); unflat9(r.get("p_FP", 9 * n), p.plasticDeformationGradients);
+        r.into("p_m", p.masses.data(), n); r.into("p_vol", p.volumes.data(), n); r.into("p_q", p.plasticAmount.data(), n);
+    }
+    if (mesh) {
+        LagrangianMesh& m = *mesh; const size_t nv = (size_t)m.vertexPositions.rows(), nf = (size_t)m.faces.rows();
+        r.into("m_vx", m.vertexPositions.data(), 3 * nv); r.into("m_vv", m.vertexVelocities.data(), 3 * nv);
+        r.into("m_ex", m.elementPositions.data(), 3 * nf); r.into("m_ev", m.elementVelocities.data(), 3 * nf);
+        unstack3(r.get("m_vB", 9 * nv), m.vertexAffineMomenta_1, m.vertexAffineMomenta_2, m.vertexAffineMomenta_3);
+        unstack3(r.get("m_eB", 9 * nf), m.elementAffineMomenta_1, m.elementAffineMomenta_2, m.elementAffineMomenta_3);
+        unstack3(r.get("m_ed", 9 * nf), m.elementDirections_1, m.elementDirections_2, m.elementDirections_3);
+    }
+}
+
+void HybridSolver::saveCheckpoint(const std::string& path) {
+    if (!ctx_) throw std::logic_error("HybridSolver::saveCheckpoint outside begin()/finish()");
+    downloadAll_();
+    double c[5]; int32_t fr = 0; int64_t ss = 0;
+    ck(aep_get_clock(ctx_, &c[0], &c[1], &c[2], &fr, &ss, nullptr, nullptr), ctx_, "aep_get_clock");
+    c[3] = fr; c[4] = (double)ss;
+    writeStateFile(path, ps_, mesh_, c);
+}
+
+void HybridSolver::resume(const std::string& path, double CFL) {
+    double c[5];
+    readStateFile(path, ps_, mesh_, c);                          // throws before any GPU work if the file does not fit the containers
+    createContext_(CFL);
+    ck(aep_resume(ctx_), ctx_, "aep_resume");
+    ck(aep_set_clock(ctx_, c[0], c[1], c[2], (int32_t)c[3], (int64_t)c[4]), ctx_, "aep_set_clock");
+    substeps_ = (long long)c[4];
 }
 
 void HybridSolver::writeFrame_(int frameNo) {                                   // HybridSolver.cpp:991-1030: "v x y z" lines, faces 1-based

@@ -112,6 +112,35 @@ class Engine:
     def set_dt(self, dt): capi.check(self.L.aep_set_dt(self.h, float(dt)), self.h)
     def set_fixed_dt(self, dt): capi.check(self.L.aep_set_fixed_dt(self.h, float(dt)), self.h)
 
+    # ------------------------------------------------------------------ checkpoint / restart
+    def checkpoint(self):
+        """Everything needed to continue this run elsewhere: particle and mesh state in the reference's layouts + the clock."""
+        c = self.clock()
+        out = dict(clock=np.array([c["dt"], c["t"], c["inner_t"], c["frame"], c["substeps"]], np.float64))
+        if self.n_particles:
+            out.update({"p_" + k: v for k, v in self.particles().items()})
+        if self.nv:
+            out.update({"m_" + k: v for k, v in self.mesh().items()})
+        return out
+
+    @classmethod
+    def resume(cls, scene: Scene, ckpt, **kw):
+        """A new context that continues from `ckpt` (Engine.checkpoint(), or np.load of its np.savez).  `scene` supplies what a
+        checkpoint does not carry: grid, material constants, masses, mesh topology and rest state, collider."""
+        import copy
+        s = copy.deepcopy(scene)
+        if s.particles is not None:
+            p = s.particles
+            p.x, p.v, p.B, p.FE, p.FP, p.vol, p.q = (np.array(ckpt["p_" + k]) for k in ("x", "v", "B", "FE", "FP", "vol", "q"))
+        if s.mesh is not None:
+            m = s.mesh
+            m.vx, m.vv, m.vB, m.ev, m.eB, m.ed = (np.array(ckpt["m_" + k]) for k in ("vx", "vv", "vB", "ev", "eB", "ed"))
+        e = cls(s, **kw)
+        capi.check(e.L.aep_resume(e.h), e.h)
+        dt, t, inner_t, frame, substeps = (float(v) for v in np.asarray(ckpt["clock"]))
+        capi.check(e.L.aep_set_clock(e.h, dt, t, inner_t, int(frame), int(substeps)), e.h)
+        return e
+
     def clock(self):
         dt = C.c_double(); t = C.c_double(); it = C.c_double(); fr = C.c_int32(); ss = C.c_int64(); vm = C.c_double(); esc = C.c_int64()
         capi.check(self.L.aep_get_clock(self.h, C.byref(dt), C.byref(t), C.byref(it), C.byref(fr), C.byref(ss), C.byref(vm), C.byref(esc)), self.h)

@@ -9,7 +9,8 @@
  *
  * Extensions (no reference counterpart, all optional): setMaterialType (the reference hard-codes SAND at
  * HybridSolver.cpp:873,955,959), setAnalyticLevelSet (device-side primitives instead of sampling a std::function),
- * setOutputDirectory / setWriteFrames, config(), begin / advance / finish for callers that want to drive substeps.
+ * setOutputDirectory / setWriteFrames, config(), begin / advance / finish for callers that want to drive substeps,
+ * saveCheckpoint / resume.
  */
 #ifndef AEP_HOST_HYBRIDSOLVER_H
 #define AEP_HOST_HYBRIDSOLVER_H
@@ -48,6 +49,8 @@ private:
     long long substeps_ = 0;
 
     void uploadAll_();
+    void downloadAll_();
+    void createContext_(double CFL);
     void writeFrame_(int frameNo);
 public:
     std::mutex mtx_;
@@ -79,5 +82,13 @@ public:
     void finish();                                   /* all state -> containers (incl. grid mirrors), destroy the context */
     void clock(double* dt, double* t, int* frameNo, long long* substeps) const;
     aep_ctx* context() { return ctx_; }
+    /* checkpoint / restart (the reference has none).  saveCheckpoint: between begin() and finish(), brings the
+     * full state into the containers and writes it with the clock.  resume: instead of begin() -- fills the bound containers
+     * (same particle / vertex / face counts as when saved) from the file, uploads them and continues with the saved clock.
+     * File = int32 count, then per array: char name[32], int32 dtype (0 f64), int64 length, raw data.                      */
+    void saveCheckpoint(const std::string& path);
+    void resume(const std::string& path, double CFL);
+    static void writeStateFile(const std::string& path, const ParticleSystem* ps, const LagrangianMesh* mesh, const double clock5[5]);
+    static void readStateFile(const std::string& path, ParticleSystem* ps, LagrangianMesh* mesh, double clock5[5]);
 };
 #endif

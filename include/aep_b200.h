@@ -146,6 +146,14 @@ AEP_API int aep_set_fixed_dt(aep_ctx* ctx, double dt);
 AEP_API int aep_get_clock(aep_ctx* ctx, double* dt, double* t, double* inner_t, int32_t* frame_no,
                           int64_t* substeps, double* vmax, int64_t* escaped);
 
+/* ---- restart (the reference has none) ---------------------------------------------------
+ * A checkpoint is what the downloads below return plus aep_get_clock's dt, t, inner_t, frame_no, substeps.  To continue
+ * from one: aep_create, upload the saved state (vol = the saved volumes), the collider, then aep_resume INSTEAD of
+ * aep_init (bins the particles and runs the mass/momentum P2G of HS:987; does not recompute volumes, HS:242-249, nor
+ * the initial dt, HS:860) and aep_set_clock.  The next aep_substep is then the one the saved run would have done.      */
+AEP_API int aep_resume(aep_ctx* ctx);
+AEP_API int aep_set_clock(aep_ctx* ctx, double dt, double t, double inner_t, int32_t frame_no, int64_t substeps);
+
 /* ---- state download (original particle order, reference layouts; any pointer may be NULL) --------------- */
 AEP_API int64_t aep_num_particles(aep_ctx* ctx);
 AEP_API int aep_download_particles(aep_ctx* ctx, double* x, double* v, double* B1, double* B2, double* B3,

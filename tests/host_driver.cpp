@@ -3,6 +3,7 @@
 //   host_driver run <scene.bin> <out.bin> <mode> <n> [outdir]
 //        mode = substeps : begin(CFL); advance(n); finish()         (parity against the oracle is done by the Python test)
 //        mode = solve    : solve(CFL, maxt = n/60 - 1/120, alpha)   -> n frames, particle_N.obj / mesh_N.obj in outdir
+//        mode = ckpt_save / ckpt_resume : n substeps + saveCheckpoint(<outdir>/state.ckpt) + n substeps / resume(...) + n substeps
 //   host_driver objmesh <in.obj> <out.bin> density thickness E nu shear stiff angle_deg    (loader parity vs the reference's)
 // Scene file = what tests/test_host_cpp.py writes: [int32 count] then per array: char name[32], int32 dtype (0 f64, 1 i32),
 // int64 length, raw data.
@@ -122,6 +123,33 @@ static int unit(const std::string& tmp) {
     REQUIRE(!sheet.vertexIsFixed(0)); sheet.bindConstraints(&fixed); REQUIRE(sheet.vertexIsFixed(0) && sheet.vertexIsFixed(4) && !sheet.vertexIsFixed(1));
     VectorXd wrong(3); threw = false; try { sheet.bindConstraints(&wrong); } catch (const std::invalid_argument&) { threw = true; } REQUIRE(threw);
     threw = false; try { LagrangianMesh::ObjMesh(tmp + "/missing.obj", 1, 1, 1, 0.3, 0, 0, 0); } catch (const std::runtime_error&) { threw = true; } REQUIRE(threw);
+    // ---- checkpoint file round trip (host only): containers + clock -> file -> scrambled containers -> identical again
+    {
+        ParticleSystem a = ParticleSystem::SandBlock(Vector3d(0.3, 0.3, 0.15), Vector3d(0.6, 0.6, 0.65), 0.08, 300, 7);
+        for (int p = 0; p < 300; ++p) { a.affineMomenta_2(p, 1) = 0.25 * p; a.elasticDeformationGradients[p](0, 2) = 1e-3 * p; a.plasticAmount[p] = 0.01 * p; a.volumes[p] = 1e-6 * (p + 1); }
+        LagrangianMesh sa = LagrangianMesh::SquareSheet(4, Vector3d(0.1, 0.2, 0.7), 0.6, 2e3, 0.04, 200, 0.3, 0.0, 4e4, 30.0);
+        sa.elementDirections_3(5, 1) = 0.125; sa.vertexAffineMomenta_3(2, 0) = -2.0; sa.vertexVelocities(7, 2) = -0.5;
+        const double clk[5] = {2.5e-4, 3.0 / 60.0, 0.004, 3.0, 123.0};
+        const std::string ck = tmp + "/state.ckpt";
+        HybridSolver::writeStateFile(ck, &a, &sa, clk);
+        ParticleSystem b = ParticleSystem::SandBlock(Vector3d(0.3, 0.3, 0.15), Vector3d(0.6, 0.6, 0.65), 0.08, 300, 99);   // other seed: different state
+        LagrangianMesh sb3 = LagrangianMesh::SquareSheet(4, Vector3d(0.0, 0.0, 0.5), 0.6, 2e3, 0.04, 200, 0.3, 0.0, 4e4, 30.0);
+        double got[5] = {0, 0, 0, 0, 0};
+        HybridSolver::readStateFile(ck, &b, &sb3, got);
+        for (int i = 0; i < 5; ++i) REQUIRE(got[i] == clk[i]);
+        for (int p = 0; p < 300; ++p) {
+            for (int c = 0; c < 3; ++c) REQUIRE(b.positions(p, c) == a.positions(p, c) && b.affineMomenta_2(p, c) == a.affineMomenta_2(p, c));
+            REQUIRE(b.elasticDeformationGradients[p](0, 2) == a.elasticDeformationGradients[p](0, 2) && b.plasticAmount[p] == a.plasticAmount[p] && b.volumes[p] == a.volumes[p]);
+        }
+        REQUIRE(sb3.elementDirections_3(5, 1) == 0.125 && sb3.vertexAffineMomenta_3(2, 0) == -2.0 && sb3.vertexVelocities(7, 2) == -0.5);
+        REQUIRE(sb3.vertexPositions(3, 0) == sa.vertexPositions(3, 0) && sb3.elementPositions(1, 2) == sa.elementPositions(1, 2));
+        ParticleSystem small = ParticleSystem::SandBall(Vector3d(0, 0, 0), 0.2, 10, 1);
+        threw = false; try { HybridSolver::readStateFile(ck, &small, nullptr, got); } catch (const std::runtime_error&) { threw = true; } REQUIRE(threw);   // wrong particle count
+        threw = false; try { HybridSolver::readStateFile(tmp + "/nope.ckpt", &b, nullptr, got); } catch (const std::runtime_error&) { threw = true; } REQUIRE(threw);
+        { std::ofstream bad(tmp + "/bad.ckpt", std::ios::binary); bad << "not a checkpoint"; }
+        threw = false; try { HybridSolver::readStateFile(tmp + "/bad.ckpt", &b, nullptr, got); } catch (const std::runtime_error&) { threw = true; } REQUIRE(threw);
+        HybridSolver idle; threw = false; try { idle.saveCheckpoint(ck); } catch (const std::logic_error&) { threw = true; } REQUIRE(threw);              // no running context
+    }
     // ---- HybridSolver argument checks that need no GPU
     HybridSolver hs; threw = false; try { hs.begin(0.3); } catch (const std::invalid_argument&) { threw = true; } REQUIRE(threw);
     std::printf("host unit OK\n");
@@ -169,7 +197,15 @@ static int run(int argc, char** argv) {
     if (sc.size() > 4 && sc[4] > 0) solver.config().dt_rate_floor = sc[4];
     solver.setOutputDirectory(outdir); solver.setVerbose(false);
     double info[4] = {0, 0, 0, 0};
-    if (mode == "substeps") {
+    if (mode == "ckpt_save" || mode == "ckpt_resume") {
+        // ckpt_save: n substeps, checkpoint to <outdir>/state.ckpt, n more.  ckpt_resume: resume from that file, n substeps.
+        solver.setWriteFrames(false);
+        if (mode == "ckpt_save") { solver.begin(sc[1]); if (b.d.count("fixed_dt")) aep_set_fixed_dt(solver.context(), b.d.at("fixed_dt")[0]); solver.advance(n); solver.saveCheckpoint(outdir + "/state.ckpt"); }
+        else { solver.resume(outdir + "/state.ckpt", sc[1]); if (b.d.count("fixed_dt")) aep_set_fixed_dt(solver.context(), b.d.at("fixed_dt")[0]); }
+        solver.advance(n);
+        int fr; long long ss; solver.clock(&info[0], &info[1], &fr, &ss); info[2] = fr; info[3] = (double)ss;
+        solver.finish();
+    } else if (mode == "substeps") {
         solver.setWriteFrames(false);
         solver.begin(sc[1]); solver.advance(n);
         int fr; long long ss; solver.clock(&info[0], &info[1], &fr, &ss); info[2] = fr; info[3] = (double)ss;

@@ -67,12 +67,13 @@ def scene_blob(scene, ls_mode=0, rate_floor=0.0):
     return a
 
 
-def run_driver(tmp_path, scene, mode, n, ls_mode=0, tag="a"):
+def run_driver(tmp_path, scene, mode, n, ls_mode=0, tag="a", outdir=None, extra=None):
     from anisotropicelastoplasticity_b200.scenes import from_colmajor, mats_from_colmajor
     if not os.path.exists(DRIVER):
         _build()
-    sin = str(tmp_path / f"scene_{tag}.bin"); sout = str(tmp_path / f"out_{tag}.bin"); outdir = str(tmp_path / f"frames_{tag}")
-    write_blob(sin, scene_blob(scene, ls_mode))
+    sin = str(tmp_path / f"scene_{tag}.bin"); sout = str(tmp_path / f"out_{tag}.bin"); outdir = outdir or str(tmp_path / f"frames_{tag}")
+    blob = scene_blob(scene, ls_mode); blob.update(extra or {})
+    write_blob(sin, blob)
     r = subprocess.run([DRIVER, "run", sin, sout, mode, str(n), outdir], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     o = read_blob(sout)
