@@ -7,11 +7,13 @@
 // reference legs may load this library.  The shipped engine (libaep_b200.so)
 // never links, loads or calls anything in oracle/.
 //
-// PARITY UNPINNED BY THE REFERENCE: the reference ships no tests / golden vectors
-// and cannot be compiled here (needs Eigen 3, libigl<=1.x, GLFW, GLEW; none are
-// installed, no network).  This restatement is pinned instead against an
-// independent numpy/scipy transcription of the reference's sparse-matrix
-// algebra (oracle/literal_numpy.py -> tests/golden/*.npz) and analytic KATs.
+// PINNED TO THE REFERENCE'S OWN CODE: the reference's unmodified sources are compiled where they lie under
+// /root/reference against a from-scratch Eigen/igl stand-in (oracle/ref_shim, oracle/ref_driver.cpp ->
+// oracle/_ref/libaep_ref.so; the image has no Eigen, libigl, GLFW or GLEW, and the reference ships no tests or
+// golden vectors of its own).  tests/test_reference_pin.py holds this restatement to that library -- live where it
+// is built, and everywhere through the fixtures it wrote (tests/golden/ref_*.npz, oracle/make_ref_golden.py) -- at
+// fp64 rounding, including one whole frame run by HybridSolver::solve itself.  A second, independent pin is the
+// numpy/scipy transcription of the reference's sparse-matrix algebra (oracle/literal_numpy.py -> tests/golden/*.npz).
 //
 // Every function cites the reference file:line it restates.  "HS" = HybridSolver.cpp,
 // "LM" = LagrangianMesh.cpp, "RG" = RegularGrid.cpp, "IP" = interpolation.cpp,

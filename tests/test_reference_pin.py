@@ -348,3 +348,29 @@ def test_host_objmesh_loader_matches_reference(tmp_path):
         assert relerr(cm(got[k], nf), ref["eD"][a]) < 1e-14, k
     assert np.allclose(got["consts"], [ref["mu"], ref["lam"], ref["fric"]], rtol=1e-15)
     assert ref["fric"] == pytest.approx(np.tan(np.deg2rad(25.0)), rel=1e-15)   # LagrangianMesh.cpp:351
+
+
+@live
+def test_pinned_vertex_block_wraps_at_domain_face_like_the_reference():
+    """Quirk (HS:513-550): around every stencil node of a pinned cloth vertex the reference zeroes a 3x3x3 node block, checking
+    only the FLAT index (HS:538-539), so at a domain face i = -1 / i = nx wrap into the neighbouring grid row.  A sheet whose
+    pinned corner sits one cell from the x = 0 face, with every node moving: the zeroed node set must be the reference's."""
+    from anisotropicelastoplasticity_b200 import scenes as sc
+    from oracle.ref_py import Reference
+    n = 5; res = 12; h = 1.0 / res
+    mesh = sc.make_cloth(n, n, (1.2 * h, 3.3 * h, 6.4 * h), (0.9 * h, 0, 0), (0, 0.9 * h, 0), fixed_ids=(0,))
+    mesh.vv[:] = (0.3, -0.2, 0.5)
+    g = sc.GridSpec(np.zeros(3), np.ones(3), np.array([res] * 3))
+    scene = sc.Scene("pin_at_face", g, sc.SAND, None, mesh, sc.LevelSetSpec())
+    o = Oracle(scene); r = Reference(scene); o.init(); r.init()
+    ng = g.n_nodes; rng = np.random.default_rng(3)
+    m_all = np.full(ng, 0.5); v_all = 1.0 + rng.random((ng, 3))                     # every node of the grid carries mass and moves
+    for s in (o, r):
+        s.set_grid(m=m_all, v=v_all); s.stage_collide()
+    go, gr = o.grid(), r.grid()
+    zo = np.abs(go["v"]).sum(axis=1) == 0; zr = np.abs(gr["v"]).sum(axis=1) == 0
+    assert zr.sum() > 27 and np.array_equal(zo, zr)
+    assert np.array_equal(np.abs(go["vt"]).sum(axis=1) == 0, np.abs(gr["vt"]).sum(axis=1) == 0)     # the pre-friction copy too (HS:542)
+    i = np.nonzero(zr)[0] % res
+    assert (i == 0).any() and (i == res - 1).any(), "the block did not wrap: move the pinned vertex closer to the face"   # i = -1 landed in the previous row
+    assert np.array_equal(go["v"], gr["v"]) and np.array_equal(go["vt"], gr["vt"])
