@@ -374,3 +374,46 @@ def test_pinned_vertex_block_wraps_at_domain_face_like_the_reference():
     i = np.nonzero(zr)[0] % res
     assert (i == 0).any() and (i == res - 1).any(), "the block did not wrap: move the pinned vertex closer to the face"   # i = -1 landed in the previous row
     assert np.array_equal(go["v"], gr["v"]) and np.array_equal(go["vt"], gr["vt"])
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs[0], exact size
+def _c1_exact():
+    """BASELINE.json configs[0]: the sand-block drop, 104 361 particles on a 64^3 grid -- "runnable on the reference CPU path",
+    so it is run there.  The state is strained and moving so that the SVDs, the Drucker-Prager projection and the APIC terms all work."""
+    from anisotropicelastoplasticity_b200 import scenes as sc
+    s = sc.c1_sand_block(res=64)
+    sc.perturb_state(s.particles, np.random.default_rng(3), strain=1e-2, vel=0.3, affine=1.0)
+    return s
+
+
+def _reference_run(scene, nsteps):
+    """dt0, dts and final state of the reference's own code; same keys as the fixtures."""
+    from oracle.make_ref_golden import run_reference
+    return run_reference(scene, nsteps)
+
+
+@live
+def test_c1_exact_oracle_vs_reference():
+    scene = _c1_exact(); d = _reference_run(scene, 2)
+    o = Oracle(scene, threads=0); o.init()
+    assert o.dt == pytest.approx(float(d["dt0"]), rel=1e-12) and relerr(o.particles()["vol"], d["vol_init"]) < 1e-13
+    replay(o, scene, d["dt0"], d["dts"], rule_rel=1e-6)
+    compare_states(o, scene, d)
+
+
+@live
+@pytest.mark.gpu
+def test_c1_exact_engine_vs_reference():
+    """The engine against the reference's own code, run live on the box's host (oracle/_ref travels with the repo), on
+    configs[0] at its full size: two passes of the loop body with the reference's time steps replayed."""
+    from anisotropicelastoplasticity_b200.engine import Engine
+    scene = _c1_exact(); d = _reference_run(scene, 2)
+    e = Engine(scene); e.init()
+    assert e.dt == pytest.approx(float(d["dt0"]), rel=2e-6) and relerr(e.particles()["vol"], d["vol_init"]) < 1e-5
+    engine_replay(e, d)
+    p = e.particles(); g = e.grid()
+    assert relerr(g["m"], d["o_gm"]) < 1e-5 and relerr(mom(g["m"], g["v"]), mom(d["o_gm"], d["o_gv"])) < 2e-5
+    for k, tol in (("x", 1e-5), ("v", 2e-5), ("FE", 1e-5), ("FP", 1e-5), ("B", 1e-4)):
+        assert relerr(p[k], d["o_" + k]) < tol, k
+    assert np.abs(p["q"] - d["o_q"]).max() < 5e-5 and e.clock()["escaped"] == 0
+    e.close()
