@@ -602,26 +602,37 @@ public:
     const std::vector<int>& rowidx() const { return rowidx_; }
     const std::vector<T>& values() const { return val_; }
 
-    // compressed column storage, rows ascending inside a column, duplicates summed
+    // compressed column storage, rows ascending inside a column, duplicates summed.  Two counting passes (O(nnz), like Eigen's
+    // own two-transpose scheme); columns are only sorted / merged when some entries did not arrive in strictly ascending row order.
     template <class It> void setFromTriplets(It b, It e) {
         std::vector<int> cnt(cols_ + 1, 0);
         for (It it = b; it != e; ++it) { assert(it->row() >= 0 && it->row() < rows_ && it->col() >= 0 && it->col() < cols_); ++cnt[it->col() + 1]; }
         for (int c = 0; c < cols_; ++c) cnt[c + 1] += cnt[c];
-        std::vector<int> ri(cnt[cols_]); std::vector<T> va(cnt[cols_]);
+        rowidx_.assign(cnt[cols_], 0); val_.assign(cnt[cols_], T(0));
         std::vector<int> fill(cnt.begin(), cnt.end() - 1);
-        for (It it = b; it != e; ++it) { int k = fill[it->col()]++; ri[k] = it->row(); va[k] = it->value(); }
-        colptr_.assign(cols_ + 1, 0); rowidx_.clear(); val_.clear(); rowidx_.reserve(ri.size()); val_.reserve(va.size());
+        bool ordered = true;
+        for (It it = b; it != e; ++it) {
+            const int c = it->col(), k = fill[c]++;
+            rowidx_[k] = it->row(); val_[k] = it->value();
+            if (k > cnt[c] && rowidx_[k - 1] >= rowidx_[k]) ordered = false;
+        }
+        colptr_ = cnt;
+        if (ordered) return;
+        std::vector<int> ri; std::vector<T> va; ri.reserve(rowidx_.size()); va.reserve(val_.size());
         std::vector<std::pair<int, T>> tmp;
         for (int c = 0; c < cols_; ++c) {
             tmp.clear();
-            for (int k = cnt[c]; k < cnt[c + 1]; ++k) tmp.push_back(std::make_pair(ri[k], va[k]));
+            for (int k = cnt[c]; k < cnt[c + 1]; ++k) tmp.push_back(std::make_pair(rowidx_[k], val_[k]));
             std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<int, T>& x, const std::pair<int, T>& y) { return x.first < y.first; });
+            const int start = static_cast<int>(ri.size());
             for (size_t k = 0; k < tmp.size(); ++k) {
-                if (!rowidx_.empty() && static_cast<int>(rowidx_.size()) > colptr_[c] && rowidx_.back() == tmp[k].first) val_.back() += tmp[k].second;
-                else { rowidx_.push_back(tmp[k].first); val_.push_back(tmp[k].second); }
+                if (static_cast<int>(ri.size()) > start && ri.back() == tmp[k].first) va.back() += tmp[k].second;
+                else { ri.push_back(tmp[k].first); va.push_back(tmp[k].second); }
             }
-            colptr_[c + 1] = static_cast<int>(rowidx_.size());
+            colptr_[c] = start;
         }
+        colptr_[cols_] = static_cast<int>(ri.size());
+        rowidx_.swap(ri); val_.swap(va);
     }
     T coeff(int r, int c) const {
         for (int k = colptr_[c]; k < colptr_[c + 1]; ++k) if (rowidx_[k] == r) return val_[k];
