@@ -3,6 +3,15 @@
 // reference (HybridSolver.cpp:269-301, 739-825).  MODE 2 reads a warp's shared-memory tile, MODE 0 the grid itself.
 #pragma once
 #include "aep_math.cuh"
+#include "aep_pack.cuh"
+
+// -DAEP_GATHER_PK=1 (development, not the default build): the inner loops of both gathers in packed fp32x2 form.  The float4 of
+// a node arrives from LDS.128 / LDG.128 as two aligned register pairs (x,y) and (z,s), so a_xy += (x,y) * N and a_zs += (z,s) * N
+// are two FFMA2 instead of three FFMA (the s lane rides along unused).  Every lane performs exactly the scalar sequence of
+// fmaf's, so the results are bit-identical to the default form (tests/test_device_math_host.py checks that on the host).
+#ifndef AEP_GATHER_PK
+#define AEP_GATHER_PK 0
+#endif
 
 namespace aep {
 
@@ -31,6 +40,14 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return *p; }
 #else
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 #endif
+// a node's float4 as the two register pairs (x,y), (z,w)
+template <int MODE> __device__ __forceinline__ ulonglong2 node_pairs(const float4* p) {
+#ifdef AEP_HOST_MATH_TEST
+    return ld_pairs(p);
+#else
+    return MODE == 2 ? ld_pairs(p) : __ldg(reinterpret_cast<const ulonglong2*>(p));
+#endif
+}
 // per-axis stencil of a thread-owned particle: weights (masked to 0 outside the grid, HybridSolver.cpp:44-46)
 // and clamped node coordinates
 struct Axis {
@@ -71,6 +88,9 @@ __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, cons
 #pragma unroll
     for (int o = 0; o < 4; ++o) { ni[o] = MODE == 2 ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = MODE == 2 ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
     const float4* base = MODE == 2 ? tile + xoff : G.vt;
+#if AEP_GATHER_PK
+    f32x2 g03 = pk(g[0], g[3]), g14 = pk(g[1], g[4]), g25 = pk(g[2], g[5]);     // rows 0 and 1 of grad v as pairs over the row index
+#endif
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
         const int nk = MODE == 2 ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
@@ -79,6 +99,20 @@ __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, cons
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float4* row = MODE == 2 ? plane + j * TILE_W : plane + nj[j] * G.nx;
+#if AEP_GATHER_PK
+            const float nn = ay.N[j] * nzk, dn = ay.D[j] * nzk, nd = ay.N[j] * dzk;
+            f32x2 axy = 0ull, azs = 0ull, bxy = 0ull, bzs = 0ull;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const ulonglong2 q = node_pairs<MODE>(MODE == 2 ? row + i : row + ni[i]);
+                const f32x2 nw = pk1(ax.N[i]), dw = pk1(ax.D[i]);
+                axy = fma2(q.x, nw, axy); azs = fma2(q.y, nw, azs);
+                bxy = fma2(q.x, dw, bxy); bzs = fma2(q.y, dw, bzs);
+            }
+            g03 = fma2(bxy, pk1(nn), g03); g14 = fma2(axy, pk1(dn), g14); g25 = fma2(axy, pk1(nd), g25);
+            const float a2 = lo_of(azs), b2 = lo_of(bzs);
+            g[6] = fmaf(b2, nn, g[6]); g[7] = fmaf(a2, dn, g[7]); g[8] = fmaf(a2, nd, g[8]);
+#else
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -90,8 +124,12 @@ __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, cons
             g[0] = fmaf(b0, nn, g[0]); g[1] = fmaf(a0, dn, g[1]); g[2] = fmaf(a0, nd, g[2]);
             g[3] = fmaf(b1, nn, g[3]); g[4] = fmaf(a1, dn, g[4]); g[5] = fmaf(a1, nd, g[5]);
             g[6] = fmaf(b2, nn, g[6]); g[7] = fmaf(a2, dn, g[7]); g[8] = fmaf(a2, nd, g[8]);
+#endif
         }
     }
+#if AEP_GATHER_PK
+    upk(g03, g[0], g[3]); upk(g14, g[1], g[4]); upk(g25, g[2], g[5]);
+#endif
 }
 
 // The 64-node gather of G2P.  Per (j,k) row the x direction is summed first over v~ only:
@@ -112,6 +150,11 @@ __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const
 #pragma unroll
     for (int o = 0; o < 4; ++o) { ni[o] = MODE == 2 ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = MODE == 2 ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
     const float4* base = MODE == 2 ? tile + xoff : G.vt;
+#if AEP_GATHER_PK
+    f32x2 va01 = pk(S.va[0], S.va[1]);
+    f32x2 g03 = pk(S.g[0], S.g[3]), g14 = pk(S.g[1], S.g[4]), g25 = pk(S.g[2], S.g[5]);
+    f32x2 B03 = pk(S.B[0], S.B[3]), B14 = pk(S.B[1], S.B[4]), B25 = pk(S.B[2], S.B[5]);
+#endif
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
         const int nk = MODE == 2 ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
@@ -120,6 +163,29 @@ __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float4* row = MODE == 2 ? plane + j * TILE_W : plane + nj[j] * G.nx;
+#if AEP_GATHER_PK
+            const float nn = ay.N[j] * nzk, dn = ay.D[j] * nzk, nd = ay.N[j] * dzk;
+            ulonglong2 q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = node_pairs<MODE>(MODE == 2 ? row + i : row + ni[i]);
+            f32x2 axy = 0ull, azs = 0ull, bxy = 0ull, bzs = 0ull, dxy = 0ull, dzs = 0ull;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const f32x2 nw = pk1(ax.N[i]), dw = pk1(ax.D[i]), rw = pk1(nrx[i]);
+                axy = fma2(q[i].x, nw, axy); azs = fma2(q[i].y, nw, azs);
+                bxy = fma2(q[i].x, dw, bxy); bzs = fma2(q[i].y, dw, bzs);
+                dxy = fma2(q[i].x, rw, dxy); dzs = fma2(q[i].y, rw, dzs);
+            }
+            const f32x2 nn2 = pk1(nn);
+            const f32x2 u01 = mul2(axy, nn2);                                   // sum_i w v~_i over the row, components x and y
+            const float a2 = lo_of(azs), b2 = lo_of(bzs), d2 = lo_of(dzs), u2 = a2 * nn;
+            va01 = add2(va01, u01); S.va[2] += u2;
+            g03 = fma2(bxy, nn2, g03); g14 = fma2(axy, pk1(dn), g14); g25 = fma2(axy, pk1(nd), g25);
+            S.g[6] = fmaf(b2, nn, S.g[6]); S.g[7] = fmaf(a2, dn, S.g[7]); S.g[8] = fmaf(a2, nd, S.g[8]);
+            B03 = fma2(dxy, nn2, B03); B14 = fma2(u01, pk1(ry[j]), B14); B25 = fma2(u01, pk1(rzk), B25);
+            S.B[6] = fmaf(d2, nn, S.B[6]); S.B[7] = fmaf(u2, ry[j], S.B[7]); S.B[8] = fmaf(u2, rzk, S.B[8]);
+            S.smin = fminf(fminf(S.smin, fminf(hi_of(q[0].y), hi_of(q[1].y))), fminf(hi_of(q[2].y), hi_of(q[3].y)));
+#else
             float4 t[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) t[i] = MODE == 2 ? row[i] : ldg4(row + ni[i]);
@@ -140,8 +206,14 @@ __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const
             S.B[3] = fmaf(d1, nn, S.B[3]); S.B[4] = fmaf(u1, ry[j], S.B[4]); S.B[5] = fmaf(u1, rzk, S.B[5]);
             S.B[6] = fmaf(d2, nn, S.B[6]); S.B[7] = fmaf(u2, ry[j], S.B[7]); S.B[8] = fmaf(u2, rzk, S.B[8]);
             S.smin = fminf(fminf(S.smin, fminf(t[0].w, t[1].w)), fminf(t[2].w, t[3].w));   // 0 iff a sticking node was seen (FMNMX: ALU pipe)
+#endif
         }
     }
+#if AEP_GATHER_PK
+    upk(va01, S.va[0], S.va[1]);
+    upk(g03, S.g[0], S.g[3]); upk(g14, S.g[1], S.g[4]); upk(g25, S.g[2], S.g[5]);
+    upk(B03, S.B[0], S.B[3]); upk(B14, S.B[1], S.B[4]); upk(B25, S.B[2], S.B[5]);
+#endif
 }
 // second pass, taken only by particles whose stencil holds a sticking node (next to the collider): subtract w v~ of those nodes
 // from v_p and B.  Kept out of the gather loop and rolled up: the hot loop stays branch-free and half as long.

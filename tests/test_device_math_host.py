@@ -212,3 +212,32 @@ def test_gathers_match_reference_formulas(H, use_tile):
             assert smin.value == 0.0
         elif use_tile:
             assert smin.value == 1.0
+
+
+def test_packed_gather_variant_is_bit_identical(H, tmp_path):
+    """-DAEP_GATHER_PK=1 (opt-in build of k_forces / k_g2p: inner gather loops as packed fp32x2 FFMA2 on the (x,y), (z,s) register
+    pairs of each node) performs, lane by lane, exactly the scalar sequence of fmaf's: its results must equal the default form
+    BIT FOR BIT, on the tile path and on the clamped path, with and without sticking nodes."""
+    so = str(tmp_path / "libmath_host_pk.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DAEP_GATHER_PK=1", "-o", so, os.path.join(HERE, "cpu_math_harness.cpp")])
+    K = C.CDLL(so)
+    for h in (H, K):
+        h.h_gather_grad.argtypes = [C.c_int, C.c_int, C.c_int, fp, ip, fp, fp, C.c_int, fp]
+        h.h_g2p_gather.argtypes = [C.c_int, C.c_int, C.c_int, fp, ip, fp, fp, C.c_int, fp, fp, fp, fp, fp]
+    rng = np.random.default_rng(21); res = (9, 7, 8)
+    for trial in range(200):
+        use_tile = trial % 2
+        vt = f32(rng.standard_normal((res[0] * res[1] * res[2], 4)))
+        vt[:, 3] = (rng.random(len(vt)) > 0.2).astype(np.float32) if trial % 3 else 1.0
+        cell = (np.array([rng.integers(1, res[a] - 2) for a in range(3)], np.int32) if use_tile else
+                np.array([rng.choice([0, res[a] - 1, res[a] - 2, rng.integers(0, res[a])]) for a in range(3)], np.int32))
+        f = f32(rng.random(3) * 0.999); hh = f32([1 / 64, 1 / 48, 1 / 80])
+        out = []
+        for h in (H, K):
+            g9 = np.zeros(9, np.float32); h.h_gather_grad(res[0], res[1], res[2], P(vt.ravel()), cell.ctypes.data_as(ip), P(f), P(hh), use_tile, P(g9))
+            va = np.zeros(3, np.float32); vc = np.zeros(3, np.float32); B = np.zeros(9, np.float32); g = np.zeros(9, np.float32); smin = C.c_float(-1)
+            h.h_g2p_gather(res[0], res[1], res[2], P(vt.ravel()), cell.ctypes.data_as(ip), P(f), P(hh), use_tile, P(va), P(vc), P(B), P(g), C.byref(smin))
+            out.append((g9, va, vc, B, g, np.float32(smin.value)))
+        for a, b in zip(*out):
+            assert np.array_equal(np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32))
