@@ -75,6 +75,9 @@ class Reference(Oracle):
 
     def __init__(self, scene: Scene, rate_floor: float = 3e2):
         super().__init__(scene, threads=1, rate_floor=rate_floor)
+        err = self.L.ref_last_error(self.h)
+        if err:                                                  # e.g. a parameter the reference hard-codes was asked to differ
+            raise RuntimeError(err.decode())
 
     def _set_levelset(self, scene):
         ls = scene.levelset
