@@ -53,6 +53,13 @@ struct Vec3 {
 template <typename T> inline Vec3<T> operator*(T s, const Vec3<T>& a) { return a * s; }
 using Vector3d = Vec3<double>;
 using Vector3i = Vec3<int>;
+struct Vector4f {                                           /* viewer.core.background_color in main.cpp:97 */
+    float v[4];
+    Vector4f() : v{0.f, 0.f, 0.f, 0.f} {}
+    Vector4f(float a, float b, float c, float d) : v{a, b, c, d} {}
+    float& operator[](int i) { return v[i]; }
+    const float& operator[](int i) const { return v[i]; }
+};
 
 struct VectorXd {
     std::vector<double> s;

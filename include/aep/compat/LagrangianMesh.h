@@ -1,0 +1,3 @@
+/* LagrangianMesh.h -- same file name as the reference's header (AnisotropicElastoplasticity/LagrangianMesh.h): put include/aep/compat on the include
+ * path in place of the reference's source directory and `#include "LagrangianMesh.h"` resolves to the B200 host class. */
+#include "../LagrangianMesh.h"

@@ -1,0 +1,3 @@
+/* LevelSet.h -- same file name as the reference's header (AnisotropicElastoplasticity/LevelSet.h): put include/aep/compat on the include
+ * path in place of the reference's source directory and `#include "LevelSet.h"` resolves to the B200 host class. */
+#include "../LevelSet.h"

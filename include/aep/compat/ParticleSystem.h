@@ -1,0 +1,3 @@
+/* ParticleSystem.h -- same file name as the reference's header (AnisotropicElastoplasticity/ParticleSystem.h): put include/aep/compat on the include
+ * path in place of the reference's source directory and `#include "ParticleSystem.h"` resolves to the B200 host class. */
+#include "../ParticleSystem.h"
