@@ -81,7 +81,7 @@ def test_reference_main_fails_loudly_without_gpu(tmp_path):
 @pytest.mark.gpu
 def test_reference_main_runs_on_the_engine(tmp_path):
     nv, nf = write_square_obj(str(tmp_path / "square_hr2x06.obj"))
-    r = subprocess.run([_exe()], cwd=str(tmp_path), capture_output=True, text=True, timeout=300, env=dict(os.environ, AEP_HEADLESS_SECONDS="4"))
+    r = subprocess.run([_exe()], cwd=str(tmp_path), capture_output=True, text=True, timeout=300, env=dict(os.environ, AEP_HEADLESS_SECONDS="10"))
     assert r.returncode == 0, r.stderr[-2000:]
     assert "headless viewer" in r.stderr
     frames = sorted(os.listdir(tmp_path / "mesh"), key=lambda s: int(s.split("_")[1].split(".")[0]))
