@@ -77,6 +77,49 @@ def test_reference_main_fails_loudly_without_gpu(tmp_path):
     assert not os.path.exists(tmp_path / "mesh" / "mesh_0.obj")
 
 
+def oracle_first_frame(obj_path):
+    """main.cpp's scene (grid main.cpp:53-69, mesh parameters :77-78, pins :71-75, ground :88-89) on the CPU oracle: vertex positions
+    when the first 1/60 s frame completes.  From rest the dt rule sits on its 1e-3 ceiling, so this frame is not chaotic."""
+    import math
+    from anisotropicelastoplasticity_b200 import scenes as sc
+    from oracle.oracle_py import Oracle
+    V, F = [], []
+    for ln in open(obj_path):
+        if ln.startswith("v "):
+            V.append([float(np.float32(t)) for t in ln.split()[1:4]])          # the loader parses positions as float (LagrangianMesh.cpp:217,229)
+        elif ln.startswith("f "):
+            F.append([int(t) - 1 for t in ln.split()[1:4]])
+    V = np.array(V); F = np.array(F, np.int32)
+    gl = 1.0 / (math.sqrt(565) - 1); mn = np.array([-2.5, -1.25, -1.67]); mx = np.array([1.25, 1.25, 1.67])
+    res = np.array([int((mx[a] - mn[a]) / gl + 0.5) for a in range(3)])
+    mesh = sc.make_cloth(2, 2, (0, 0, 0), (1, 0, 0), (0, 1, 0))                 # only for the material rules; geometry replaced below
+    v1, v2, v3 = V[F[:, 0]], V[F[:, 1]], V[F[:, 2]]
+    la, lb, lc = (np.linalg.norm(a, axis=1) for a in (v2 - v1, v3 - v2, v1 - v3)); sp = 0.5 * (la + lb + lc)
+    evol = 0.25 * np.sqrt(np.maximum(sp * (sp - la) * (sp - lb) * (sp - lc), 0.0)) * 0.04      # LagrangianMesh.cpp:311-315
+    vvol = np.zeros(len(V))
+    for c in range(3):
+        np.add.at(vvol, F[:, c], evol)
+    nrm = np.cross(v2 - v1, v3 - v1); nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    eD = np.stack([v2 - v1, v3 - v1, nrm]); nv, nf = len(V), len(F)
+    fixed = np.zeros(nv); fixed[:2] = 1.0
+    m = sc.Mesh(vx=V, vv=np.zeros((nv, 3)), vm=2e3 * vvol, vvol=vvol, vB=np.zeros((nv, 3, 3)), faces=F, ev=np.zeros((nf, 3)), em=2e3 * evol, evol=evol,
+                eB=np.zeros((nf, 3, 3)), ed=eD.copy(), eD=eD, fixed=fixed, mu=mesh.mu, lam=mesh.lam, shear=0.0, stiff=4e4, fric=0.0)
+    scene = sc.Scene("main_cpp", sc.GridSpec(mn, mx, res), sc.SAND, None, m, sc.LevelSetSpec(sc.LS_GROUND, np.array([-1.4, 0, 0, 0, 0, 0, 0, 0.0])))
+    o = Oracle(scene, threads=0); o.init()
+    while o.frame < 1:
+        o.substep()
+    return o.mesh()["vx"]
+
+
+def test_oracle_first_frame_of_main_scene(tmp_path):
+    """CPU: the expectation the GPU test below holds main.cpp's run to."""
+    nv, nf = write_square_obj(str(tmp_path / "square_hr2x06.obj"))
+    x = oracle_first_frame(str(tmp_path / "square_hr2x06.obj"))
+    assert x.shape == (565, 3) and np.isfinite(x).all()
+    assert x[48:, 2].mean() == pytest.approx(-0.5 * 9.8 / 3600.0, rel=0.05)             # free fall for 1/60 s, minus what the pins hold back
+    assert np.abs(x[:2, 2]).max() < 1e-12                                               # pinned
+
+
 @have
 @pytest.mark.gpu
 def test_reference_main_runs_on_the_engine(tmp_path):
@@ -90,6 +133,7 @@ def test_reference_main_runs_on_the_engine(tmp_path):
     v0, f0 = read_obj(str(tmp_path / "mesh" / frames[0])); v1, f1 = read_obj(str(tmp_path / "mesh" / later))
     assert v0.shape == (nv, 3) and f0 == nf and v1.shape == (nv, 3) and f1 == nf
     assert np.isfinite(v0).all() and np.isfinite(v1).all()
+    assert np.abs(v0 - oracle_first_frame(str(tmp_path / "square_hr2x06.obj"))).max() < 1e-4      # frame 0 is the oracle's frame 0 (OBJ text: 6 digits)
     free = np.arange(nv) >= 48                                            # rows away from the two pinned vertices
     assert v1[free, 2].mean() < v0[free, 2].mean() < 0.0                  # the sheet falls (gravity is -z, HS:457), frame after frame
     assert np.abs(v1[:2] - np.array([[-0.5, -0.5, 0.0], [-0.5 + 1.0 / 23, -0.5, 0.0]])).max() < 0.02      # pinned vertices stay (main.cpp:71-75, HS:513-550)
