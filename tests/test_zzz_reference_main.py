@@ -77,12 +77,12 @@ def test_reference_main_fails_loudly_without_gpu(tmp_path):
     assert not os.path.exists(tmp_path / "mesh" / "mesh_0.obj")
 
 
-def oracle_first_frame(obj_path):
-    """main.cpp's scene (grid main.cpp:53-69, mesh parameters :77-78, pins :71-75, ground :88-89) on the CPU oracle: vertex positions
-    when the first 1/60 s frame completes.  From rest the dt rule sits on its 1e-3 ceiling, so this frame is not chaotic."""
+def main_scene(obj_path):
+    """main.cpp's scene (grid main.cpp:53-69, mesh parameters :77-78, pins :71-75, ground :88-89).  The oracle's positions when
+    the first 1/60 s frame completes are the expectation below: from rest the dt rule sits on its 1e-3 ceiling, so this frame
+    is not chaotic."""
     import math
     from anisotropicelastoplasticity_b200 import scenes as sc
-    from oracle.oracle_py import Oracle
     V, F = [], []
     for ln in open(obj_path):
         if ln.startswith("v "):
@@ -104,8 +104,12 @@ def oracle_first_frame(obj_path):
     fixed = np.zeros(nv); fixed[:2] = 1.0
     m = sc.Mesh(vx=V, vv=np.zeros((nv, 3)), vm=2e3 * vvol, vvol=vvol, vB=np.zeros((nv, 3, 3)), faces=F, ev=np.zeros((nf, 3)), em=2e3 * evol, evol=evol,
                 eB=np.zeros((nf, 3, 3)), ed=eD.copy(), eD=eD, fixed=fixed, mu=mesh.mu, lam=mesh.lam, shear=0.0, stiff=4e4, fric=0.0)
-    scene = sc.Scene("main_cpp", sc.GridSpec(mn, mx, res), sc.SAND, None, m, sc.LevelSetSpec(sc.LS_GROUND, np.array([-1.4, 0, 0, 0, 0, 0, 0, 0.0])))
-    o = Oracle(scene, threads=0); o.init()
+    return sc.Scene("main_cpp", sc.GridSpec(mn, mx, res), sc.SAND, None, m, sc.LevelSetSpec(sc.LS_GROUND, np.array([-1.4, 0, 0, 0, 0, 0, 0, 0.0])))
+
+
+def oracle_first_frame(obj_path):
+    from oracle.oracle_py import Oracle
+    o = Oracle(main_scene(obj_path), threads=0); o.init()
     while o.frame < 1:
         o.substep()
     return o.mesh()["vx"]
@@ -118,6 +122,21 @@ def test_oracle_first_frame_of_main_scene(tmp_path):
     assert x.shape == (565, 3) and np.isfinite(x).all()
     assert x[48:, 2].mean() == pytest.approx(-0.5 * 9.8 / 3600.0, rel=0.05)             # free fall for 1/60 s, minus what the pins hold back
     assert np.abs(x[:2, 2]).max() < 1e-12                                               # pinned
+
+
+def test_reference_solve_on_main_scene_matches_oracle(tmp_path):
+    """CPU, live: HybridSolver::solve ITSELF (the reference's code, oracle/_ref) on main.cpp's scene for one frame, mesh_0.obj
+    included, against the oracle."""
+    from oracle import ref_py
+    if not ref_py.available():
+        pytest.skip("oracle/_ref/libaep_ref.so not built and /root/reference absent")
+    write_square_obj(str(tmp_path / "square_hr2x06.obj"))
+    scene = main_scene(str(tmp_path / "square_hr2x06.obj"))
+    r = ref_py.Reference(scene); r.solve(0.0, str(tmp_path))
+    x = oracle_first_frame(str(tmp_path / "square_hr2x06.obj"))
+    assert np.abs(r.mesh()["vx"] - x).max() < 1e-10
+    v, nf = read_obj(str(tmp_path / "mesh" / "mesh_0.obj"))
+    assert nf == scene.mesh.nf and np.allclose(v, x, rtol=2e-5, atol=1e-9) and not os.path.exists(tmp_path / "mesh" / "mesh_1.obj")
 
 
 @have
