@@ -460,3 +460,18 @@ def test_degenerate_deformation_gradients_match_reference(material):
     keep = np.ones(p.n, bool); keep[3] = False
     assert relerr(pr["FE"][keep], po["FE"][keep]) < 1e-9 and relerr(pr["FP"][keep], po["FP"][keep]) < 1e-9
     assert np.isfinite(pr["FE"]).all() and np.isfinite(po["FE"]).all()
+
+
+@live
+def test_reference_solve_frame_numbering(tmp_path):
+    """`while (t <= maxt)` with t += 1/60 per finished frame (HS:867,883): maxt = 1.5/60 writes particle_0.obj and particle_1.obj and
+    stops -- the convention HybridSolver::solve of libaep_host.so reproduces (tests/test_host_cpp.py, maxt = n/60 - 1/120 -> n frames)."""
+    from anisotropicelastoplasticity_b200 import scenes as sc
+    from oracle.ref_py import Reference
+    scene = sc.small_block(material=sc.SAND, res=12, cells=2, seed=61, lo=(0.34, 0.34, 0.34))
+    r = Reference(scene); r.solve(1.5 / 60.0, str(tmp_path))
+    assert sorted(os.listdir(tmp_path / "particle")) == ["particle_0.obj", "particle_1.obj"]
+    assert os.listdir(tmp_path / "mesh") == []                                    # the directory is made (HS:858), no mesh bound
+    lines = open(tmp_path / "particle" / "particle_1.obj").read().splitlines()
+    assert len(lines) == scene.particles.n and all(ln.startswith("v ") and len(ln.split()) == 4 for ln in lines)
+    assert np.allclose(np.array([[float(t) for t in ln.split()[1:]] for ln in lines]), r.particles()["x"], rtol=2e-5)
