@@ -184,3 +184,22 @@ def test_hybrid_solver_solve_writes_reference_frames(tmp_path):
     # two runs of 2 frames agree to ~1e-3 in x, not bitwise.  Exact agreement is asserted by the substep tests above.
     e = Engine(scene); e.init(); e.run_frames(2); pe = e.particles()
     assert relerr(got["x"], pe["x"]) < 2e-2 and e.clock()["frame"] == 2
+
+
+def test_host_library_builds_and_passes_with_an_eigen_api(tmp_path):
+    """include/aep/EigenShim.h steps aside when <Eigen/Core> exists, so that a maintainer's containers hold real Eigen matrices.
+    This image has no Eigen; the closest thing is the independent implementation of the Eigen API that the reference itself is
+    compiled against for the oracle pin (oracle/ref_shim -- test infrastructure, only used here as a compile target).  The host
+    sources and the host unit checks must build and pass against it unchanged (-DAEP_USE_REAL_EIGEN)."""
+    shim = os.path.join(ROOT, "oracle", "ref_shim"); host = os.path.join(PKG, "csrc", "host")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    flags = ["-O1", "-std=c++17", "-fPIC", "-w", "-DAEP_USE_REAL_EIGEN", "-I" + shim]
+    so = str(tmp_path / "libaep_host.so")
+    _build()
+    subprocess.check_call([cxx] + flags + ["-shared", "-o", so, os.path.join(host, "containers.cpp"), os.path.join(host, "HybridSolver.cpp"),
+                                           "-L" + PKG, "-laep_b200", "-Wl,-rpath," + PKG])
+    exe = str(tmp_path / "host_driver")
+    subprocess.check_call([cxx] + flags + ["-o", exe, os.path.join(ROOT, "tests", "host_driver.cpp"), "-L" + str(tmp_path), "-laep_host", "-L" + PKG, "-laep_b200",
+                                           "-Wl,-rpath," + str(tmp_path), "-Wl,-rpath," + PKG])
+    r = subprocess.run([exe, "unit", str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "host unit OK" in r.stdout, r.stderr
