@@ -15,13 +15,17 @@ from conftest import ROOT
 EXE = os.path.join(ROOT, "tests", "_bin", "ref_main")
 REF_MAIN = "/root/reference/AnisotropicElastoplasticity/main.cpp"
 have = pytest.mark.skipif(not (os.path.exists(EXE) or os.path.exists(REF_MAIN)), reason="tests/_bin/ref_main not built and /root/reference absent")
+# the two bindings of INTEGRATION.md: A = main.cpp against the host classes of libaep_host.so (include/aep/compat);
+# B = main.cpp + the reference's own container classes + integration/HybridSolver_b200.cpp in place of HybridSolver.cpp
+BINDINGS = pytest.mark.parametrize("binding", ["A_host_classes", "B_reference_classes_patched_solve"])
 
 
-def _exe():
+def _exe(binding="A_host_classes"):
     import __graft_entry__ as g
     g.build_host()
-    assert os.path.exists(EXE)
-    return EXE
+    exe = EXE if binding.startswith("A") else EXE + "_patched"
+    assert os.path.exists(exe)
+    return exe
 
 
 def write_square_obj(path, n=24, drop=11, side=1.0, z=0.0):
@@ -66,13 +70,28 @@ def test_reference_main_builds_against_host_library():
 
 
 @have
-def test_reference_main_fails_loudly_without_gpu(tmp_path):
+def test_reference_classes_build_with_the_patched_solve():
+    """Binding B: everything is the reference's except HybridSolver.cpp; the loop's stage methods are gone from the binary, the
+    containers are the reference's own (defined inside it), and the only library it needs is the C ABI."""
+    exe = _exe("B")
+    syms = subprocess.run(["nm", "-C", exe], capture_output=True, text=True).stdout
+    for gone in ("evaluateInterpolationWeights_", "particleToGrid_", "computeGridForces_", "updatePlasticity_"):
+        assert gone not in syms, gone
+    for mine in (" T HybridSolver::solve(", " T LagrangianMesh::ObjMesh(", " T ParticleSystem::SandCylinder(", " T RegularGrid::RegularGrid("):
+        assert mine in syms, mine
+    needed = subprocess.run(["readelf", "-d", exe], capture_output=True, text=True).stdout
+    assert "libaep_b200.so" in needed and "libaep_host.so" not in needed
+
+
+@have
+@BINDINGS
+def test_reference_main_fails_loudly_without_gpu(tmp_path, binding):
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     nv, nf = write_square_obj(str(tmp_path / "square_hr2x06.obj"))
     assert nv == 565
-    r = subprocess.run([_exe()], cwd=str(tmp_path), capture_output=True, text=True, timeout=120, env=dict(os.environ, AEP_HEADLESS_SECONDS="3"))
+    r = subprocess.run([_exe(binding)], cwd=str(tmp_path), capture_output=True, text=True, timeout=120, env=dict(os.environ, AEP_HEADLESS_SECONDS="3"))
     assert r.returncode != 0 and "no CPU fallback" in r.stderr          # the solve thread dies on aep_create: nothing is simulated on the CPU
     assert not os.path.exists(tmp_path / "mesh" / "mesh_0.obj")
 
@@ -141,9 +160,10 @@ def test_reference_solve_on_main_scene_matches_oracle(tmp_path):
 
 @have
 @pytest.mark.gpu
-def test_reference_main_runs_on_the_engine(tmp_path):
+@BINDINGS
+def test_reference_main_runs_on_the_engine(tmp_path, binding):
     nv, nf = write_square_obj(str(tmp_path / "square_hr2x06.obj"))
-    r = subprocess.run([_exe()], cwd=str(tmp_path), capture_output=True, text=True, timeout=300, env=dict(os.environ, AEP_HEADLESS_SECONDS="10"))
+    r = subprocess.run([_exe(binding)], cwd=str(tmp_path), capture_output=True, text=True, timeout=300, env=dict(os.environ, AEP_HEADLESS_SECONDS="10"))
     assert r.returncode == 0, r.stderr[-2000:]
     assert "headless viewer" in r.stderr
     frames = sorted(os.listdir(tmp_path / "mesh"), key=lambda s: int(s.split("_")[1].split(".")[0]))
