@@ -336,6 +336,37 @@ def run_engine(args):
     print(json.dumps(line))
 
 
+def run_engine_config(args):
+    """--config C1..C4 (development; the contract line is the default C5 run): one of BASELINE.json's other configurations through the
+    same engine, state resident in HBM, K substeps timed with CUDA events on the engine's stream.  The unit count of a cloth scene is
+    Np + Nv + Nf (vertices and element centroids are transferred like particles, HS:838-849)."""
+    import torch
+    from anisotropicelastoplasticity_b200.engine import Engine
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU path")
+    local = int(os.environ.get("LOCAL_RANK", "0")); torch.cuda.set_device(local)
+    t_gen = time.perf_counter(); scene = sc.CONFIGS[args.config](); t_gen = time.perf_counter() - t_gen
+    units = (scene.particles.n if scene.particles is not None else 0) + (scene.mesh.nv + scene.mesh.nf if scene.mesh is not None else 0)
+    res = int(max(scene.grid.res))
+    eng = Engine(scene, device=local, dt_rate_floor=rate_floor_for(res), sort_every=args.sort_every); eng.init()
+    stream = torch.cuda.ExternalStream(eng.stream, device=local)
+    eng.run(args.warmup); eng.sync()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    launches0 = eng.kernel_launches
+    torch.cuda.synchronize(); ev0.record(stream); eng.run(args.steps); ev1.record(stream); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1); launches = eng.kernel_launches - launches0
+    eng.profile(True); eng.run(max(3, min(args.steps, 10))); eng.sync(); tm = eng.timers(); eng.profile(False)
+    blocks, nodes = eng.grid_activity(); clk = eng.clock()
+    print(json.dumps({"metric": METRIC, "value": units * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": ms / args.steps, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"BASELINE {args.config}: {scene.name}", "grid": [int(r) for r in scene.grid.res], "units": units,
+                                 "particles": scene.particles.n if scene.particles is not None else 0,
+                                 "mesh": [scene.mesh.nv, scene.mesh.nf] if scene.mesh is not None else None, "rate_floor": rate_floor_for(res)},
+                      "stage_ms": {k: (v[0] / v[1] if v[1] else 0.0) for k, v in tm.items()}, "gpu_launches": int(launches), "active_nodes": nodes,
+                      "sim": {"dt": clk["dt"], "t": clk["t"] + clk["inner_t"], "escaped": clk["escaped"]}, "setup_s": {"generate": t_gen}}))
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,6 +377,7 @@ def main():
     ap.add_argument("--ref-res", type=int, default=64, help="grid resolution of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="development: skip the e2e and cpu_baseline legs")
+    ap.add_argument("--config", default="C5", choices=["C1", "C2", "C3", "C4", "C5"], help="development: another BASELINE configuration (1 GPU, short JSON); C5 = the contract workload")
     ap.add_argument("--perturb", type=float, default=0.0, help="development: random strain scale added to the rest state (0 = the named workload)")
     ap.add_argument("--sort-bricks", type=int, default=0, help="1: brick-major particle order (aep_config.sort_bricks), 0: cell-index order")
     ap.add_argument("--sort-every", type=int, default=0, help="physical re-sort period in substeps (aep_config.sort_every); 0 = adaptive (default)")
@@ -353,6 +385,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "C5":
+        run_engine_config(args)
     else:
         run_engine(args)
 
