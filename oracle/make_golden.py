@@ -1,8 +1,8 @@
 """Generate tests/golden/*.npz from the numpy/scipy literal transcription (oracle/literal_numpy.py).
 
 Run:  python -m oracle.make_golden      (from the repo root; a few seconds)
-The reference itself cannot be built here (Eigen/libigl/GLFW absent), so these vectors come from the independent
-sparse-matrix transcription of its algebra; tests pin the C++ oracle (and through it the CUDA engine) to them.
+These vectors come from the independent sparse-matrix transcription of the reference's algebra -- the SECOND pin of the C++
+oracle; the first is the reference's own code (oracle/_ref, oracle/make_ref_golden.py -> tests/golden/ref_*.npz).
 Each file holds the full initial state and the state after `nsteps` iterations of the HybridSolver.cpp:867-1032 loop.
 """
 from __future__ import annotations
