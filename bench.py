@@ -247,6 +247,15 @@ def workload_config(args, res_override=None, note=None, n_particles=None):
     return cfg
 
 
+def transfers_roofline(stage_ms, n, nodes, peak):
+    """The two transfers BASELINE.json's north star singles out ("P2G+G2P at 50% or more of the HBM roofline per GPU"): their
+    algorithmic bytes (SURVEY.md 8d split) over the sum of their stage times."""
+    ms = stage_ms.get("p2g", 0.0) + stage_ms.get("g2p", 0.0)
+    b = sum(STAGE_BYTES[k][0] * n + STAGE_BYTES[k][1] * nodes for k in ("p2g", "g2p"))
+    gbs = b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    return {"algorithmic_bytes": b, "ms": ms, "achieved_gbs": gbs, "frac": gbs / peak if peak else None}
+
+
 def run_engine(args):
     import torch
     from anisotropicelastoplasticity_b200.engine import Engine
@@ -305,7 +314,8 @@ def run_engine(args):
                 "frac": achieved / peak, "traffic": ncu_traffic({"forces": "k_forces", "g2p": "k_g2p", "p2g": "k_p2g"}.get(dom, ""), n),
                 "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom],
                 "stage_ms": stage_ms,
-                "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes, "active_blocks": blocks}}
+                "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes, "active_blocks": blocks},
+                "p2g_g2p": transfers_roofline(stage_ms, n, nodes, peak)}
     if args.quick:
         print(json.dumps({"metric": METRIC, "value": value, "ms_per_step": ms / args.steps, "sort_every": args.sort_every, "stage_ms": stage_ms,
                           "gpu_launches": int(launches), "sim": clk, "active_nodes": nodes, "particles": n, "perturb": args.perturb}))
