@@ -180,6 +180,14 @@ def _timed_substeps(sim, seconds_budget, max_steps, warmup):
             return n, el
 
 
+def _stage_share(sim):
+    """Where the CPU run spends its time, by stage of the loop body (weights = evaluateInterpolationWeights_, HS:18-97: the
+    reference's own triplet loops and the four setFromTriplets; forces HS:252-458; grid HS:725-737,460-551; g2p HS:739-825,940-951,
+    553-723; p2g HS:113-250)."""
+    t = sim.timers(); tot = sum(t.values()) or 1.0
+    return {k: round(float(v) / tot, 3) for k, v in t.items()}
+
+
 def cpu_baseline(threads, seconds_budget=20.0, res=64):
     """The reference's CPU path on a bounded sample of the same workload: the C5 dam break at res^3 (same particles per
     cell, same material, same collider).  kind "reference" = the reference's own code (oracle/_ref, built in the dev container
@@ -200,7 +208,8 @@ def cpu_baseline(threads, seconds_budget=20.0, res=64):
     r = ref_py.Reference(scene, rate_floor=rate_floor_for(res)); r.init()
     n, el = _timed_substeps(r, seconds_budget, 50, 1)
     return {"value": scene.particles.n * n / el, "unit": UNIT, "cores": 1, "kind": "reference",
-            "sample": f"C5 dam break at {res}^3 grid, {scene.particles.n} particles, {n} substeps in {el:.1f} s; {REF_NOTE}", "port": port}
+            "sample": f"C5 dam break at {res}^3 grid, {scene.particles.n} particles, {n} substeps in {el:.1f} s; {REF_NOTE}",
+            "stage_share": _stage_share(r), "port": port}
 
 
 def run_reference(args):
@@ -230,7 +239,8 @@ def run_reference(args):
             "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, res_override=res, note="bounded sample of the workload: same scene at a smaller grid"),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": int(used), "kind": kind,
-                             "sample": f"C5 dam break at {res}^3 grid, {scene.particles.n} particles, {args.steps} substeps; {what}"},
+                             "sample": f"C5 dam break at {res}^3 grid, {scene.particles.n} particles, {args.steps} substeps; {what}",
+                             "stage_share": _stage_share(o)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
