@@ -458,41 +458,27 @@ def test_reference_solve_frame_numbering(tmp_path):
     assert np.allclose(np.array([[float(t) for t in ln.split()[1:]] for ln in lines]), r.particles()["x"], rtol=2e-5)
 
 
+def _replay_pair(o, r, nsteps=2):
+    """nsteps of the reference free-running, the oracle replaying its time steps (forces / grid update with the lagged one)."""
+    dts = [r.substep() for _ in range(nsteps)]
+    dt_lag = float(o.dt)
+    for dt in dts:
+        o.stage_forces(dt_lag); o.stage_grid_update(dt_lag); o.stage_collide(); o.stage_g2p(float(dt)); o.rebuild_weights(); o.p2g(False); dt_lag = float(dt)
+
+
 @live
 def test_random_scenes_oracle_vs_reference():
-    """40 seeded random scenes (anisotropic grids, 30-150 scattered particles anywhere at least 2 cells inside the domain -- also
-    isolated ones with mostly massless stencils --, random F_E / F_P / B / v / q, both materials, ground or wall-corner collider cutting
-    through the cloud): init + 2 substeps, time steps replayed.  A sweep for disagreements in corners no hand-made scene visits."""
-    from anisotropicelastoplasticity_b200 import scenes as sc
+    """40 seeded random particle scenes (tests/random_scenes.py): init + 2 substeps, time steps replayed.  A sweep for disagreements
+    in corners no hand-made scene visits."""
     from oracle.ref_py import Reference
+    from random_scenes import random_particle_scene
     worst = 0.0
     for seed in range(40):
-        rng = np.random.default_rng(1000 + seed)
-        res = rng.integers(8, 15, size=3); mn = rng.uniform(-1.0, 0.5, size=3); mx = mn + rng.uniform(0.8, 1.6, size=3)
-        g = sc.GridSpec(mn, mx, res); h = g.h
-        n = int(rng.integers(30, 150))
-        centre = mn + (2.5 + rng.random(3) * (res - 5)) * h
-        x = np.clip(centre + rng.standard_normal((n, 3)) * h * rng.uniform(0.3, 2.0), mn + 2.01 * h, mx - 2.01 * h)
-        material = sc.SAND if seed % 2 else sc.SNOW
-        E, nu = (sc.SAND_E, sc.SAND_NU) if material == sc.SAND else (sc.SNOW_E, sc.SNOW_NU)
-        F = np.eye(3) + 0.05 * rng.standard_normal((n, 3, 3)); FP = np.eye(3) + 0.03 * rng.standard_normal((n, 3, 3))
-        ps = sc.Particles(x=x, v=rng.standard_normal((n, 3)), B=0.5 * rng.standard_normal((n, 3, 3)), FE=F, FP=FP, m=rng.uniform(0.5, 2.0, n) * 1e-3,
-                          vol=np.ones(n), q=rng.uniform(0.0, 0.5, n), E=E, nu=nu)
-        if seed % 3 == 0:
-            ls = sc.LevelSetSpec(sc.LS_GROUND, np.array([centre[2] - 0.3 * h[2], 0, 0, 0, 0, 0, 0, 0.0]))
-        elif seed % 3 == 1:
-            ls = sc.LevelSetSpec(sc.LS_WALL2GROUND, np.array([centre[0] + 0.4 * h[0], centre[1] + 1.3 * h[1], centre[2] - 1.1 * h[2], 0, 0, 0, 0, 0.0]))
-        else:
-            ls = sc.LevelSetSpec()
-        scene = sc.Scene(f"random_{seed}", g, material, ps, None, ls)
+        scene = random_particle_scene(seed)
         o = Oracle(scene); r = Reference(scene); o.init(); r.init()
         assert o.dt == pytest.approx(r.dt, rel=1e-9), seed
         assert relerr(o.particles()["vol"], r.particles()["vol"]) < 1e-12, seed
-        dts = [r.substep() for _ in range(2)]
-        # replay on the oracle (forces / grid update with the lagged step)
-        dt_lag = float(o.dt)
-        for dt in dts:
-            o.stage_forces(dt_lag); o.stage_grid_update(dt_lag); o.stage_collide(); o.stage_g2p(float(dt)); o.rebuild_weights(); o.p2g(False); dt_lag = float(dt)
+        _replay_pair(o, r)
         po, pr = o.particles(), r.particles(); go, gr = o.grid(), r.grid()
         errs = [relerr(po[k], pr[k]) for k in ("x", "v", "B", "FE", "FP")] + [relerr(go["m"], gr["m"]), relerr(mom(go["m"], go["v"]), mom(gr["m"], gr["v"])), relerr(go["f"], gr["f"])]
         errs.append(float(np.abs(po["q"] - pr["q"]).max()))
@@ -503,46 +489,18 @@ def test_random_scenes_oracle_vs_reference():
 
 @live
 def test_random_cloth_scenes_oracle_vs_reference():
-    """24 seeded random cloth scenes: a sheet in a random orientation (rotated rest frame), stretched / sheared / crumpled vertex
-    positions, normal directors d3 both longer and shorter than 1 (both branches of HS:414 and HS:699-716), random shear stiffness and
-    friction angle (0 included: the cone collapses), random pinned vertices, with and without sand above it, ground collider through
-    the sheet.  init + 2 substeps with the reference's time steps replayed."""
-    from anisotropicelastoplasticity_b200 import scenes as sc
+    """24 seeded random cloth scenes (tests/random_scenes.py), with and without sand: init + 2 substeps, time steps replayed."""
     from oracle.ref_py import Reference
+    from random_scenes import random_cloth_scene
     worst = 0.0
     for seed in range(24):
-        rng = np.random.default_rng(2000 + seed)
-        res = rng.integers(10, 15, size=3); g = sc.GridSpec(np.zeros(3), np.ones(3) * rng.uniform(0.9, 1.3), res); h = g.h
-        n = int(rng.integers(4, 8)); edge = float(h.min()) * rng.uniform(0.7, 1.2)
-        Q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
-        du, dv = Q[:, 0] * edge, Q[:, 1] * edge
-        centre = g.mx * 0.5
-        origin = centre - 0.5 * (n - 1) * (du + dv)
-        shear = float(rng.choice([0.0, 20.0, 200.0])); ang = float(rng.choice([0.0, 10.0, 40.0]))
-        fixed = tuple(int(v) for v in rng.choice(n * n, size=int(rng.integers(0, 3)), replace=False))
-        mesh = sc.make_cloth(n, n, origin, du, dv, shear=shear, friction_angle_deg=ang, stiff=float(rng.choice([4e4, 1e3])), fixed_ids=fixed)
-        mesh.vx = mesh.vx + 0.08 * edge * rng.standard_normal(mesh.vx.shape)                       # stretched / crumpled
-        mesh.vx = np.clip(mesh.vx, 2.01 * h, g.mx - 2.01 * h)
-        mesh.vv = 0.5 * rng.standard_normal(mesh.vv.shape); mesh.ev = 0.5 * rng.standard_normal(mesh.ev.shape)
-        mesh.vB = 0.3 * rng.standard_normal(mesh.vB.shape); mesh.eB = 0.3 * rng.standard_normal(mesh.eB.shape)
-        mesh.ed[0] = mesh.vx[mesh.faces[:, 1]] - mesh.vx[mesh.faces[:, 0]]; mesh.ed[1] = mesh.vx[mesh.faces[:, 2]] - mesh.vx[mesh.faces[:, 0]]
-        mesh.ed[2] = mesh.ed[2] * rng.uniform(0.8, 1.2, size=(mesh.nf, 1)) + 0.1 * rng.standard_normal((mesh.nf, 3))
-        ps = None
-        if seed % 2:
-            m = int(rng.integers(20, 80)); x = np.clip(centre + np.array([0, 0, 1.5 * h[2]]) + rng.standard_normal((m, 3)) * h, 2.01 * h, g.mx - 2.01 * h)
-            ps = sc.Particles(x=x, v=rng.standard_normal((m, 3)), B=0.3 * rng.standard_normal((m, 3, 3)), FE=np.eye(3) + 0.03 * rng.standard_normal((m, 3, 3)),
-                              FP=np.tile(np.eye(3), (m, 1, 1)), m=np.full(m, 2e-3), vol=np.ones(m), q=np.zeros(m), E=sc.SAND_E, nu=sc.SAND_NU)
-        ls = sc.LevelSetSpec(sc.LS_GROUND, np.array([centre[2] - 0.2 * h[2], 0, 0, 0, 0, 0, 0, 0.0])) if seed % 3 else sc.LevelSetSpec()
-        scene = sc.Scene(f"random_cloth_{seed}", g, sc.SAND, ps, mesh, ls)
+        scene = random_cloth_scene(seed)
         o = Oracle(scene); r = Reference(scene); o.init(); r.init()
         assert o.dt == pytest.approx(r.dt, rel=1e-9), seed
-        dts = [r.substep() for _ in range(2)]
-        dt_lag = float(o.dt)
-        for dt in dts:
-            o.stage_forces(dt_lag); o.stage_grid_update(dt_lag); o.stage_collide(); o.stage_g2p(float(dt)); o.rebuild_weights(); o.p2g(False); dt_lag = float(dt)
+        _replay_pair(o, r)
         mo, mr = o.mesh(), r.mesh(); go, gr = o.grid(), r.grid()
         errs = [relerr(mo[k], mr[k]) for k in ("vx", "vv", "vB", "ex", "ev", "eB", "ed")] + [relerr(go["m"], gr["m"]), relerr(mom(go["m"], go["v"]), mom(gr["m"], gr["v"])), relerr(go["f"], gr["f"])]
-        if ps is not None:
+        if scene.particles is not None:
             po, pr = o.particles(), r.particles()
             errs += [relerr(po[k], pr[k]) for k in ("x", "v", "FE", "FP")]
         assert max(errs) < 1e-9, (seed, errs)

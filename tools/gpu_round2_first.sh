@@ -10,6 +10,7 @@ mkdir -p gpurun_out
 PKG=$PWD/anisotropicelastoplasticity_b200
 timeout 1200 python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider > gpurun_out/pytest_${TAG}.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_${TAG}.txt
 timeout 120 python tests/diag/gpu_refpin_report.py > gpurun_out/refpin_${TAG}.txt 2>&1
+timeout 300 python tests/diag/gpu_random_report.py > gpurun_out/random_${TAG}.txt 2>&1; tail -n 1 gpurun_out/random_${TAG}.txt | cut -c1-900
 if [ -f $PKG/libaep_b200_gpk.so ]; then
   AEP_B200_LIB=$PKG/libaep_b200_gpk.so timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_reference_pin.py -m gpu -q --no-header -rf -p no:cacheprovider > gpurun_out/pytest_${TAG}_gpk.txt 2>&1; echo "pytest gpk rc=$?" >> gpurun_out/pytest_${TAG}_gpk.txt
   tools/gpu_ab2.sh ${TAG} default gpk
