@@ -6,7 +6,8 @@ import os, sys, traceback
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import relerr
-from random_scenes import random_cloth_scene, random_particle_scene
+from random_scenes import degenerate_scene, random_cloth_scene, random_particle_scene
+from anisotropicelastoplasticity_b200 import scenes as sc
 from anisotropicelastoplasticity_b200.engine import Engine
 from oracle.ref_py import Reference
 
@@ -18,7 +19,8 @@ def note(tag, out):
     for k, v in out.items():
         if v > worst.get(k, (0.0, ""))[0]: worst[k] = (v, tag)
 
-for kind, gen, count in (("particles", random_particle_scene, 40), ("cloth", random_cloth_scene, 24)):
+for kind, gen, count in (("particles", random_particle_scene, 40), ("cloth", random_cloth_scene, 24),
+                         ("degenerate", lambda i: degenerate_scene(sc.SAND if i else sc.SNOW)[0], 2)):
     for seed in range(count):
         try:
             scene = gen(seed)

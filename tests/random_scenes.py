@@ -54,3 +54,19 @@ def random_cloth_scene(seed):
                           FP=np.tile(np.eye(3), (m, 1, 1)), m=np.full(m, 2e-3), vol=np.ones(m), q=np.zeros(m), E=sc.SAND_E, nu=sc.SAND_NU)
     ls = sc.LevelSetSpec(sc.LS_GROUND, np.array([centre[2] - 0.2 * h[2], 0, 0, 0, 0, 0, 0, 0.0])) if seed % 3 else sc.LevelSetSpec()
     return sc.Scene(f"random_cloth_{seed}", g, sc.SAND, ps, mesh, ls)
+
+
+def degenerate_scene(material):
+    """Particles whose F_E is special: identity, two equal singular values, a pure rotation, a reflection (det < 0), strong compression,
+    strong anisotropy, nearly singular, uniform dilation; particles exactly on a grid node, on a cell face and on a cell edge."""
+    scene = sc.small_block(material=material, res=14, cells=3, seed=55, lo=(0.36, 0.36, 0.3))
+    p = scene.particles; rng = np.random.default_rng(56); h = 1.0 / 14
+    Q, _ = np.linalg.qr(rng.standard_normal((3, 3))); Q2, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    special = [np.eye(3), Q @ np.diag([1.05, 1.05, 0.9]) @ Q2.T, Q, Q @ np.diag([1.0, 1.0, -1.0]) @ Q.T, 0.6 * np.eye(3) + 0.01 * rng.standard_normal((3, 3)),
+               Q @ np.diag([1.6, 1.0, 0.7]) @ Q2.T, Q @ np.diag([1.0, 0.9, 1e-3]) @ Q2.T, np.diag([1.02, 1.02, 1.02])]
+    for k, F in enumerate(special):
+        p.FE[k] = F
+    p.x[10] = np.array([6, 6, 6]) * h                      # exactly on a node
+    p.x[11] = np.array([6.0, 6.37, 5.81]) * h              # on a cell face
+    p.x[12] = np.array([6.5, 7.0, 6.0]) * h                # on a cell edge
+    return scene, len(special)

@@ -412,16 +412,9 @@ def test_degenerate_deformation_gradients_match_reference(material):
     a grid node and on a cell face exercise the `N > 0` filter of HS:60 and the truncation of HS:34-36."""
     from anisotropicelastoplasticity_b200 import scenes as sc
     from oracle.ref_py import Reference
-    scene = sc.small_block(material=sc.SAND if material == "sand" else sc.SNOW, res=14, cells=3, seed=55, lo=(0.36, 0.36, 0.3))
-    p = scene.particles; rng = np.random.default_rng(56); h = 1.0 / 14
-    Q, _ = np.linalg.qr(rng.standard_normal((3, 3))); Q2, _ = np.linalg.qr(rng.standard_normal((3, 3)))
-    special = [np.eye(3), Q @ np.diag([1.05, 1.05, 0.9]) @ Q2.T, Q, Q @ np.diag([1.0, 1.0, -1.0]) @ Q.T, 0.6 * np.eye(3) + 0.01 * rng.standard_normal((3, 3)),
-               Q @ np.diag([1.6, 1.0, 0.7]) @ Q2.T, Q @ np.diag([1.0, 0.9, 1e-3]) @ Q2.T, np.diag([1.02, 1.02, 1.02])]
-    for k, F in enumerate(special):
-        p.FE[k] = F
-    p.x[10] = np.array([6, 6, 6]) * h                      # exactly on a node
-    p.x[11] = np.array([6.0, 6.37, 5.81]) * h              # on a cell face
-    p.x[12] = np.array([6.5, 7.0, 6.0]) * h                # on a cell edge
+    from random_scenes import degenerate_scene
+    scene, n_special = degenerate_scene(sc.SAND if material == "sand" else sc.SNOW)
+    p = scene.particles
     o = Oracle(scene); r = Reference(scene); o.init(); r.init()
     assert relerr(r.grid()["m"], o.grid()["m"]) < 1e-13 and relerr(r.particles()["vol"], o.particles()["vol"]) < 1e-13
     dt = 2e-4
@@ -431,7 +424,6 @@ def test_degenerate_deformation_gradients_match_reference(material):
     for s in (o, r):
         s.stage_grid_update(dt); s.stage_collide(); s.stage_g2p(dt)
     po, pr = o.particles(), r.particles()
-    n = len(special)
     for k in ("x", "v", "B", "q"):
         assert relerr(pr[k], po[k]) < 1e-10, k
     # F_E F_P (the total deformation) is what the SVD's freedom cannot touch; F_E and F_P individually agree too unless the
