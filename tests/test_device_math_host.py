@@ -241,3 +241,35 @@ def test_packed_gather_variant_is_bit_identical(H, tmp_path):
             out.append((g9, va, vc, B, g, np.float32(smin.value)))
         for a, b in zip(*out):
             assert np.array_equal(np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32))
+
+
+@pytest.mark.parametrize("mat,E,nu", [(1, 3.537e5, 0.3), (0, 1.4e5, 0.2)])
+def test_degenerate_deformation_gradients_device_math(H, mat, E, nu):
+    """The fp32 SVD / stress / return mapping of aep_math.cuh on the matrices where an SVD is not unique or ill-conditioned: identity,
+    two equal singular values, pure rotation, reflection (det < 0), strong compression, strong anisotropy, a singular value of 1e-3,
+    uniform dilation -- against the fp64 oracle (itself held to the reference's code on the same cases, tests/test_reference_pin.py).
+    Stress: 3e-5 relative plus the noise floor of a 1e-6 strain (a rotation has zero stress; what fp32 returns is rounding of ln 1)."""
+    L = op.lib()
+    L.orc_particle_stress.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, dp, dp, dp, C.c_double, dp]
+    L.orc_particle_return_map.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp, dp, dp]
+    cm = lambda M: np.ascontiguousarray(M.T).ravel()
+    rng = np.random.default_rng(56)
+    Q, _ = np.linalg.qr(rng.standard_normal((3, 3))); Q2, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    special = [np.eye(3), Q @ np.diag([1.05, 1.05, 0.9]) @ Q2.T, Q, Q @ np.diag([1.0, 1.0, -1.0]) @ Q.T, 0.6 * np.eye(3) + 0.01 * rng.standard_normal((3, 3)),
+               Q @ np.diag([1.6, 1.0, 0.7]) @ Q2.T, Q @ np.diag([1.0, 0.9, 1e-3]) @ Q2.T, np.diag([1.02, 1.02, 1.02])]
+    vol = 1e-6; mu = E / 2.0 / (1.0 + nu)
+    for F in special:
+        Fh = f32(F); FE = Fh.copy(); FPm = f32(np.eye(3))
+        A = np.zeros(9, np.float32); H.h_stress(mat, E, nu, P(Fh.ravel()), P(FE.ravel()), C.c_float(vol), C.c_float(1.0), P(A))
+        A64 = np.zeros(9)
+        L.orc_particle_stress(mat, E, nu, 10.0, D(cm(Fh.astype(np.float64))), D(cm(FE.astype(np.float64))), D(cm(FPm.astype(np.float64))), vol, D(A64))
+        A64 = A64.reshape(3, 3).T
+        assert np.isfinite(A).all() and np.abs(A.reshape(3, 3) - A64).max() < 3e-5 * np.abs(A64).max() + 2e-6 * vol * mu
+        FEo = np.zeros(9, np.float32); FPo = FPm.copy().ravel(); q = C.c_float(0.1)
+        H.h_return_map(mat, E, nu, 2.5e-2, 7.5e-3, P(Fh.ravel()), P(FEo), P(FPo), C.byref(q))
+        FE9 = np.zeros(9); FP9 = cm(FPm.astype(np.float64)).copy(); q64 = C.c_double(0.1)
+        L.orc_particle_return_map(mat, E, nu, 2.5e-2, 7.5e-3, D(cm(Fh.astype(np.float64))), D(FE9), D(FP9), C.byref(q64))
+        tot32 = FEo.reshape(3, 3).astype(np.float64) @ FPo.reshape(3, 3); tot64 = FE9.reshape(3, 3).T @ FP9.reshape(3, 3).T
+        assert np.isfinite(FEo).all() and np.isfinite(FPo).all()
+        assert np.abs(tot32 - tot64).max() < 1e-6 and abs(q.value - q64.value) < 1e-6            # F_E F_P is what the SVD's freedom cannot touch
+        assert np.abs(FEo.reshape(3, 3) - FE9.reshape(3, 3).T).max() < 1e-6 and np.abs(FPo.reshape(3, 3) - FP9.reshape(3, 3).T).max() < 1e-6
