@@ -150,7 +150,9 @@ AEP_API int aep_get_clock(aep_ctx* ctx, double* dt, double* t, double* inner_t, 
  * A checkpoint is what the downloads below return plus aep_get_clock's dt, t, inner_t, frame_no, substeps.  To continue
  * from one: aep_create, upload the saved state (vol = the saved volumes), the collider, then aep_resume INSTEAD of
  * aep_init (bins the particles and runs the mass/momentum P2G of HS:987; does not recompute volumes, HS:242-249, nor
- * the initial dt, HS:860) and aep_set_clock.  The next aep_substep is then the one the saved run would have done.      */
+ * the initial dt, HS:860) and aep_set_clock.  The next aep_substep is then the one the saved run would have done.
+ * aep_set_fixed_dt is not part of the clock: re-apply it if the saved run used it.  Tested for whole-grid contexts; a slab
+ * decomposition is restarted by re-partitioning the saved global state (distributed.py), not rank by rank.               */
 AEP_API int aep_resume(aep_ctx* ctx);
 AEP_API int aep_set_clock(aep_ctx* ctx, double dt, double t, double inner_t, int32_t frame_no, int64_t substeps);
 
