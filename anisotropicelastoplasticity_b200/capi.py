@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("AEP_B200_LIB") or os.path.join(_HERE, "libaep_b200.so
 _LIB = None
 
 NUM_STAGES = 8
-STAGES = ("sort", "p2g", "forces", "grid", "g2p", "mesh", "halo", "_")
+STAGES = ("sort", "p2g", "forces", "grid", "g2p", "mesh", "halo", "g2p2g")
 MIGRATE_FLOATS = 44
 
 dp = C.POINTER(C.c_double)
@@ -27,7 +27,8 @@ class Config(C.Structure):
                 ("cfl", C.c_double), ("gravity", C.c_double), ("collider_friction", C.c_double), ("snow_hardening", C.c_double),
                 ("sand_h", C.c_double * 4), ("dt_rate_floor", C.c_double), ("frame_dt", C.c_double),
                 ("particle_capacity", C.c_int64), ("slab_axis", C.c_int32), ("slab_lo", C.c_int32), ("slab_hi", C.c_int32),
-                ("sort_every", C.c_int32), ("sort_bricks", C.c_int32), ("scatter_strips", C.c_int32), ("sort_cost_threshold", C.c_double)]
+                ("sort_every", C.c_int32), ("sort_bricks", C.c_int32), ("scatter_strips", C.c_int32), ("sort_cost_threshold", C.c_double),
+                ("vmax_min_mass_fraction", C.c_double), ("coulomb_friction", C.c_int32), ("use_graph", C.c_int32)]
 
 
 class AepError(RuntimeError):
@@ -44,7 +45,10 @@ SYMBOLS = (
     "aep_halo_pack", "aep_halo_add", "aep_vmax_get", "aep_vmax_set", "aep_step_forces", "aep_step_grid", "aep_step_g2p",
     "aep_step_p2g", "aep_migrate_extract", "aep_migrate_insert", "aep_migrate_bind", "aep_migrate_extract_begin", "aep_migrate_extract_end",
     "aep_step_p2g_arrivals", "aep_set_particle_id_base", "aep_download_particles_local", "aep_resume", "aep_set_clock",
+    "aep_set_escaped", "aep_set_collider_motion", "aep_init_dt_async", "aep_frame_positions_begin", "aep_frame_positions_wait", "aep_get_counters",
+    "aep_comm_export", "aep_comm_connect", "aep_comm_connect_local", "aep_group_init", "aep_group_run",
 )
+COMM_BLOB_BYTES = 256
 
 
 def load():
@@ -66,7 +70,7 @@ def load():
     L.aep_upload_mesh.argtypes = [vp, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, C.POINTER(C.c_int32), dp, dp, dp, dp, dp, dp, dp] + [C.c_double] * 5
     L.aep_set_levelset_analytic.argtypes = [vp, C.c_int, dp]
     L.aep_set_levelset_samples.argtypes = [vp, C.POINTER(C.c_uint8), dp]
-    for name in ("aep_destroy", "aep_sync", "aep_init", "aep_init_begin", "aep_init_volumes", "aep_init_dt", "aep_init_begin", "aep_init_volumes", "aep_init_dt", "aep_substep", "aep_step_forces", "aep_step_grid", "aep_step_g2p", "aep_step_p2g"):
+    for name in ("aep_destroy", "aep_sync", "aep_init", "aep_init_begin", "aep_init_volumes", "aep_init_dt", "aep_init_dt_async", "aep_substep", "aep_step_forces", "aep_step_grid", "aep_step_g2p", "aep_step_p2g", "aep_frame_positions_wait"):
         getattr(L, name).argtypes = [vp]
     L.aep_run.argtypes = [vp, C.c_int]
     L.aep_run_frames.argtypes = [vp, C.c_int, C.c_int, i64p]
@@ -96,6 +100,15 @@ def load():
     L.aep_step_p2g_arrivals.argtypes = [vp, C.c_int64]
     L.aep_set_particle_id_base.argtypes = [vp, C.c_int64]
     L.aep_download_particles_local.argtypes = [vp, i64p] + [dp] * 9
+    L.aep_set_escaped.argtypes = [vp, C.c_int64]
+    L.aep_set_collider_motion.argtypes = [vp, dp]
+    L.aep_frame_positions_begin.argtypes = [vp, C.POINTER(C.c_float)]
+    L.aep_get_counters.argtypes = [vp, i64p, i64p, i64p, i64p]
+    L.aep_comm_export.argtypes = [vp, vp, C.c_int64]
+    L.aep_comm_connect.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.aep_comm_connect_local.argtypes = [C.POINTER(vp), C.c_int, C.c_int64]
+    L.aep_group_init.argtypes = [C.POINTER(vp), C.c_int]
+    L.aep_group_run.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
     _LIB = L
     return L
 

@@ -27,6 +27,13 @@ struct GridP {
     float apic;                        // 3 / hmin^2                       HybridSolver.cpp:175-177
     float inv_cell_vol;                // 1 / (hx hy hz)                   HybridSolver.cpp:246
     float gravity, friction;
+    long long sy, sz;                  // element strides of the node index along y and z (x is contiguous): node = k*sz + j*sy + i.
+                                       // Whole-grid contexts: sy = nx, sz = nx*ny (RegularGrid.cpp:164-168).  A slab context allocates only
+                                       // its own node planes and makes the slab axis the slowest one; the array pointers are then biased
+                                       // so that global (i,j,k) still index them.
+    int a0[3], a1[3];                  // node range [a0, a1) per axis that this context's grid arrays hold (the whole grid, or the slab's reach)
+    int v0[3], v1[3];                  // node range whose sums are complete after the halo exchange: the grid passes compute only there (a slab
+                                       // also holds one scratch plane per side that only catches the scatter of particles about to migrate)
     float4* mp;
     float4* f;
     float4* vt;
@@ -34,6 +41,8 @@ struct GridP {
     const unsigned char* ls_code;      // 0 outside, 1..6 axis normals (+x -x +y -y +z -z), 7 general (ls_nrm)
     const float4* ls_nrm;
 };
+
+__host__ __device__ __forceinline__ size_t nidx(const GridP& G, int i, int j, int k) { return (size_t)((long long)k * G.sz + (long long)j * G.sy + i); }
 
 #ifdef AEP_HOST_MATH_TEST
 __device__ __forceinline__ float4 ldg4(const float4* p) { return *p; }
@@ -75,9 +84,9 @@ __device__ __forceinline__ float sel4(const float (&a)[4], int k) { return k == 
 // unclamped "interior" addressing (MODE 1) was 5 % faster on the ~1 % of warps that take it but made both gather kernels 17 %
 // larger; the instruction cache matters more (no_instruction stalls, profiles/README.md v10).
 #define AEP_FALLBACK_MODE 0
-#define TILE_W 12                       // nodes along x held by a warp's tile: up to 9 cells in a row
+#define TILE_W 8                        // nodes along x held by a half-warp's tile: 16 cell-sorted particles span up to 5 cells in a row
 #define TILE_SLACK 1                    // nodes left of lane 0's stencil (tolerates slightly out-of-order particles)
-#define TILE_F4 (16 * TILE_W)           // float4 per warp tile (16 (j,k) rows)
+#define TILE_F4 (16 * TILE_W)           // float4 per half-warp tile (16 (j,k) rows): 2 KB
 // g[3r+c] = sum_i v_i[r] d_c w_i over the 4x4x4 stencil, x summed first.
 // MODE 0: clamped global loads (fallback: stencil cut by a domain face, warp not in one row of cells), MODE 2: loads from the warp's
 // shared tile (xoff = first stencil node relative to the tile).
@@ -95,10 +104,10 @@ __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, cons
     for (int k = 0; k < 4; ++k) {
         const int nk = MODE == 2 ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
         const float nzk = sel4(az.N, k), dzk = sel4(az.D, k);
-        const float4* plane = MODE == 2 ? base + k * 4 * TILE_W : base + (size_t)nk * G.ny * G.nx;
+        const float4* plane = MODE == 2 ? base + k * 4 * TILE_W : base + (size_t)((long long)nk * G.sz);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float4* row = MODE == 2 ? plane + j * TILE_W : plane + nj[j] * G.nx;
+            const float4* row = MODE == 2 ? plane + j * TILE_W : plane + (size_t)((long long)nj[j] * G.sy);
 #if AEP_GATHER_PK
             const float nn = ay.N[j] * nzk, dn = ay.D[j] * nzk, nd = ay.N[j] * dzk;
             f32x2 axy = 0ull, azs = 0ull, bxy = 0ull, bzs = 0ull;
@@ -140,7 +149,7 @@ __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, cons
 // the correction branch runs only for rows that contain a sticking node.
 struct G2PSums {
     float va[3], vc[3], B[9], g[9];
-    float smin;                          // min of the s flags seen: 0 iff the stencil holds a sticking node
+    float smin;                          // min of the s factors seen: < 1 iff the stencil holds a node slowed by friction (0: sticking)
 };
 template <int MODE>
 __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const Axis& ay, const Axis& az, const float (&nrx)[4],
@@ -159,10 +168,10 @@ __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const
     for (int k = 0; k < 4; ++k) {
         const int nk = MODE == 2 ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
         const float nzk = sel4(az.N, k), dzk = sel4(az.D, k), rzk = sel4(rz, k);
-        const float4* plane = MODE == 2 ? base + k * 4 * TILE_W : base + (size_t)nk * G.ny * G.nx;
+        const float4* plane = MODE == 2 ? base + k * 4 * TILE_W : base + (size_t)((long long)nk * G.sz);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float4* row = MODE == 2 ? plane + j * TILE_W : plane + nj[j] * G.nx;
+            const float4* row = MODE == 2 ? plane + j * TILE_W : plane + (size_t)((long long)nj[j] * G.sy);
 #if AEP_GATHER_PK
             const float nn = ay.N[j] * nzk, dn = ay.D[j] * nzk, nd = ay.N[j] * dzk;
             ulonglong2 q[4];
@@ -225,9 +234,10 @@ __device__ __forceinline__ void g2p_stick_correction(const GridP& G, const Axis&
         const int i = n & 3, j = (n >> 2) & 3, k = n >> 4;
         float4 t;
         if (MODE == 2) t = tile[xoff + (k * 4 + j) * TILE_W + i];
-        else t = ldg4(G.vt + ((size_t)clampi(az.n0 + k, 0, G.nz - 1) * G.ny + clampi(ay.n0 + j, 0, G.ny - 1)) * G.nx + clampi(ax.n0 + i, 0, G.nx - 1));
-        if (t.w != 0.0f) continue;
-        const float w = -sel4(ax.N, i) * sel4(ay.N, j) * sel4(az.N, k);
+        else t = ldg4(G.vt + nidx(G, clampi(ax.n0 + i, 0, G.nx - 1), clampi(ay.n0 + j, 0, G.ny - 1), clampi(az.n0 + k, 0, G.nz - 1)));
+        if (t.w == 1.0f) continue;
+        // v = s v~: s = 0 on sticking nodes (the reference, HS:494-502); 0 < s < 1 only with the opt-in Coulomb friction
+        const float w = (t.w - 1.0f) * sel4(ax.N, i) * sel4(ay.N, j) * sel4(az.N, k);
         const float cx = w * t.x, cy = w * t.y, cz = w * t.z;
         const float rxi = sel4(rx, i), ryj = sel4(ry, j), rzk = sel4(rz, k);
         S.vc[0] += cx; S.vc[1] += cy; S.vc[2] += cz;

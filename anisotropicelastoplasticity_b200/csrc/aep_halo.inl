@@ -1,4 +1,5 @@
-// aep_halo.inl -- C ABI of the slab decomposition (included inside extern "C" of aep_engine.cu).
+// aep_halo.inl -- C ABI of the caller-driven slab exchange (included inside extern "C" of aep_engine.cu): the caller owns the
+// communication buffers and moves the bytes.  The peer-memory exchange that runs inside aep_substep is in aep_comm.inl.
 static int slab_check(aep_ctx* c, int side, bool* has) {
     if (!c) return AEP_ERR_INVALID;
     if (c->cfg.slab_axis < 0 || c->cfg.slab_axis > 2) return fail(c, AEP_ERR_INVALID, "context has no slab (cfg.slab_axis < 0)");
@@ -9,7 +10,7 @@ static int slab_check(aep_ctx* c, int side, bool* has) {
     return AEP_OK;
 }
 static PlaneMap plane_map(aep_ctx* c, int side) {
-    PlaneMap M; M.axis = c->cfg.slab_axis; M.nplanes = 3;
+    PlaneMap M; M.axis = c->cfg.slab_axis; M.nplanes = 3;                 // un-fused path: P2G runs after the migration, 3 shared planes
     M.plane0 = (side == 0 ? c->cfg.slab_lo : c->cfg.slab_hi) - 1;
     if (M.axis == 0) { M.nu = c->G.ny; M.nv = c->G.nz; } else if (M.axis == 1) { M.nu = c->G.nx; M.nv = c->G.nz; } else { M.nu = c->G.nx; M.nv = c->G.ny; }
     return M;
@@ -90,6 +91,7 @@ int aep_migrate_bind(aep_ctx* c, void* dev_to_low, void* dev_to_high, int64_t ca
     if (!dev_to_low || !dev_to_high || !dev_counts || capacity <= 0 || capacity > (1 << 28)) return fail(c, AEP_ERR_INVALID, "bad migration buffers");
     cudaSetDevice(c->device);
     if (c->mig.axis >= 0) return fail(c, AEP_ERR_INVALID, "migration buffers are already bound");
+    if (c->comm.exported) return fail(c, AEP_ERR_INVALID, "this context uses the peer-memory exchange (aep_comm_export)");
     for (int s = 0; s < 2; ++s) CU(dalloc(c, &c->mig.list[s], (size_t)capacity));
     c->mig.cap = (int)capacity; c->mig.lo = c->cfg.slab_lo; c->mig.hi = c->cfg.slab_hi;
     c->mig.counts = (unsigned long long*)dev_counts;
@@ -147,6 +149,7 @@ int aep_migrate_insert(aep_ctx* c, const void* dev_from_low, int64_t n_from_low,
 
 int aep_set_particle_id_base(aep_ctx* c, int64_t id_base) {
     if (!c || id_base < 0) return AEP_ERR_INVALID;
+    if (id_base >= (1ll << 31)) return fail(c, AEP_ERR_INVALID, "particle ids are 32-bit on the device: id_base must stay below 2^31");
     c->id_base = id_base;
     return AEP_OK;
 }
@@ -162,7 +165,7 @@ int aep_download_particles_local(aep_ctx* c, int64_t* ids, double* x, double* v,
     for (long long p0 = 0; p0 < n; p0 += CH) {
         const long long cnt = std::min(CH, n - p0);
         double* st = c->d_stage; long long* dids = (long long*)(st + (size_t)35 * cnt);
-        k_download_local<<<cdiv(cnt, 256), 256, 0, c->stream>>>(c->P[c->cur], c->G, st, dids, (int)p0, (int)cnt, c->cfg.grid_min[0], c->cfg.grid_min[1],
+        k_download_local<<<cdiv(cnt, 256), 256, 0, c->stream>>>(c->P[c->cur], st, dids, (int)p0, (int)cnt, c->cfg.grid_min[0], c->cfg.grid_min[1],
                                                                c->cfg.grid_min[2], c->h[0], c->h[1], c->h[2]);
         LAUNCH_OK("k_download_local");
         double* mats[5] = { x, v, B1, B2, B3 };

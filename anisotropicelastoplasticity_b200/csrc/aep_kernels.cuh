@@ -1,22 +1,25 @@
-// aep_kernels.cuh -- sm_100a kernels of the MPM substep (particles: sand / snow).
+// aep_kernels.cuh -- sm_100a kernels of the MPM substep: data layout, clock, grid passes, scatter machinery, stand-alone P2G,
+// host <-> device conversion.  The two big particle kernels (forces, fused G2P + P2G) live in aep_particle.cuh.
 //
 // Device data layout (all fp32, 16-byte records so every particle access is one LDG/STG.128):
 //   particle arrays (struct of float4 arrays, index = slot in cell-sorted order)
 //     X  = (fx, fy, fz, cell)     fractional position inside the cell, packed cell (i | j<<10 | k<<20)
-//     VM = (vx, vy, vz, m)
-//     C0..C2 = rows of the APIC matrix B                                   (.w unused)
-//     E0 = (FE row 0, vol)  E1 = (FE row 1, q)  E2 = (FE row 2, det F_P)
-//     Q0 = (FP row 0, id)   Q1 = (FP row 1, m)  Q2 = (FP row 2, -)
-//   grid arrays, node index = (k*ny + j)*nx + i  (RegularGrid.cpp:164-168)
-//     mp = (m, px, py, pz)   f = (fx, fy, fz, -)   vt = (v~x, v~y, v~z, s)  with v = s * v~  (s in {0,1})
-//   block flags: one byte per 8x8x8 node block, set by P2G; grid passes run over the compact list of flagged blocks.
+//     V  = (vx, vy, vz, B00)      velocity and the 9 entries of the APIC matrix B (row-major) in 12 floats:
+//     C0 = (B01, B02, B10, B11)   written by G2P, read by P2G only -- in the fused substep they never leave the SM between the two
+//     C1 = (B12, B20, B21, B22)
+//     E0 = (FE row 0, vol)  E1 = (FE row 1, q)  E2 = (FE row 2, det F_P)   read by the force kernel and G2P
+//     Q0..Q2 = rows of F_P (.w unused)     touched only by particles whose return mapping changed a singular value
+//     K  = (m, id, -, -)                   constants: never written after the upload
+//   grid arrays, node index = k*sz + j*sy + i  (whole grid: (k*ny + j)*nx + i, RegularGrid.cpp:164-168)
+//     mp = (m, px, py, pz)   f = (fx, fy, fz, -)   vt = (v~x, v~y, v~z, s)  with v = s * v~  (s = 0 on sticking collider nodes)
+//   block flags: one byte per 8x8x8 node block, set by the scatters; grid passes run over the compact list of flagged blocks.
 //
 // Scatter strategy: shared-memory float atomics are CAS loops on sm_100 (ATOMS.CAST.SPIN) while global memory has native vector
 // reductions (REDG.E.ADD.F32x4).  So nothing is accumulated in shared memory: a half-warp walks a run of cell-sorted particles,
 // its 16 lanes own the 16 (j,k) rows of the 4x4x4 stencil and keep the 4 nodes of their row in registers while the particles
 // stay in one cell (and slide the 4-node window when the next cell is an x-neighbour); a node goes to L2 with one REDG.F32x4 when
-// it leaves the window.  Gather strategy: the (cells+3) x 4 x 4 node box of a warp's 32 particles is staged once in the warp's
-// own shared memory and every lane reads its 64 nodes from there.
+// it leaves the window.  Gather strategy: the (cells+3) x 4 x 4 node box of a half-warp's 16 particles is fetched by TMA into the
+// half-warp's own shared memory and every lane reads its 64 nodes from there.
 #pragma once
 #include <stdint.h>
 #include "aep_math.cuh"
@@ -26,11 +29,16 @@
 
 namespace aep {
 
-enum { PX = 0, PVM, PC0, PC1, PC2, PE0, PE1, PE2, PQ0, PQ1, PQ2, P_NARR };
+enum { PX = 0, PV, PC0, PC1, PE0, PE1, PE2, PQ0, PQ1, PQ2, PK, P_NARR };
 
 struct PartP {
     float4* a[P_NARR];
 };
+
+// rows of B from the packed (V.w, C0, C1)
+__device__ __forceinline__ void unpack_B(const float4& V, const float4& C0, const float4& C1, float4& b0, float4& b1, float4& b2) {
+    b0 = make_float4(V.w, C0.x, C0.y, 0.f); b1 = make_float4(C0.z, C0.w, C1.x, 0.f); b2 = make_float4(C1.y, C1.z, C1.w, 0.f);
+}
 
 // simulation clock + reductions, lives in device memory so that n substeps need no host round trip
 struct SimClock {
@@ -41,20 +49,34 @@ struct SimClock {
     long long substeps;
     unsigned long long escaped;        // particles that tried to leave the grid (clamped), sticky
     float vmax_last;
-    int pad;
+    int pad0;
     // adaptive re-sort (aep_config.sort_every == 0): particles that changed cell since the last physical sort, and the accumulated
-    // per-substep out-of-order fraction.  Reset together (16 bytes) when the particles are re-sorted.
+    // per-substep out-of-order fraction.  moved_since_sort + sort_cost are reset together (16 bytes) when the particles are re-sorted.
     unsigned long long moved_since_sort;
     float sort_cost;
+    int n_slots;                       // particle slots in use (live + dead).  Device-resident: migration changes it without the host
+    int n_dead;                        // slots whose particle migrated away since the last compaction
+    int comm_timeout;                  // a peer's flag did not arrive within the spin limit (sticky; the host fails loudly on it)
+    // aep_run_frames: the device stops itself.  halt 0 = running; 1 = the clock kernel has just completed the last requested frame,
+    // the rest of this substep (G2P ...) still runs; 2 = halted, every kernel returns at once.  Kernels ahead of the clock kernel in
+    // a substep return when halt >= 1, kernels behind it when halt >= 2 (the clock kernel turns 1 into 2 the next time it runs).
+    int halt;
+    int stop_frame;                    // halt when frame_no reaches this (-1: never)
+    long long stop_substep;            // ... or when `substeps` reaches this (-1: never)
     int pad2;
+    unsigned long long mig_dropped;    // leavers / arrivals that did not fit the migration buffers (sticky; the host fails loudly on it)
+    float vmax_mass_floor;             // 0 = the reference rule.  > 0 (opt-in, NOT the reference): nodes lighter than this do not enter max|v|
+    int pad1;
 };
+#define AEP_HALT_PRE(clk)  do { if ((clk)->halt >= 1) return; } while (0)
+#define AEP_HALT_POST(clk) do { if ((clk)->halt >= 2) return; } while (0)
 
 // slab decomposition: G2P appends the slots of particles whose new cell left [lo, hi) along `axis` to per-side index lists, so
 // that the migration step touches only the leavers instead of scanning every particle (axis < 0: not a slab / lists not bound)
 struct MigList {
     int axis, lo, hi, cap;
     unsigned int* list[2];
-    unsigned long long* counts;        // [2] (low, high), caller-owned device memory
+    unsigned long long* counts;        // [2] (low, high), device memory
 };
 
 __device__ __forceinline__ int cell_i(int c) { return c & 1023; }
@@ -62,19 +84,21 @@ __device__ __forceinline__ int cell_j(int c) { return (c >> 10) & 1023; }
 __device__ __forceinline__ int cell_k(int c) { return (c >> 20) & 1023; }
 __device__ __forceinline__ int cell_pack(int i, int j, int k) { return i | (j << 10) | (k << 20); }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 // CTA index of a grid pass -> block coordinates inside the run range, and the flat block index (flags)
 __device__ __forceinline__ int run_block(const GridP& G, int r, int& bx, int& by, int& bz) {
     bx = G.rb0[0] + r % G.rbn[0]; by = G.rb0[1] + (r / G.rbn[0]) % G.rbn[1]; bz = G.rb0[2] + r / (G.rbn[0] * G.rbn[1]);
     return (bz * G.nby + by) * G.nbx + bx;
 }
+// does this context hold node (i,j,k)?  (whole-grid contexts: the grid; slab contexts: the slab's reach)
+__device__ __forceinline__ bool node_held(const GridP& G, int i, int j, int k) {
+    return i >= G.a0[0] && i < G.a1[0] && j >= G.a0[1] && j < G.a1[1] && k >= G.a0[2] && k < G.a1[2];
+}
 
 // ================================================================================================ sort keys
-// Particles are ordered by 4x4x4-cell brick (x fastest), then by cell inside the brick (x fastest).  A CTA of 256 consecutive
-// particles at 8 per cell is then a 4x4x2 slab of cells whose stencils share a 7x7x5 node box (245 nodes, 3.9 KB) instead of the
-// 35x4x4 = 560 nodes of 32 cells in a row: the grid gathers of one CTA hit in L1 instead of going to L2.  The scatters only
-// need particles of one cell to be adjacent, which any cell-granular order provides.
+// Particles are ordered by cell (x fastest) -- or, with sort_bricks, by 4x4x4-cell brick and then by cell inside the brick.  The
+// scatters only need particles of one cell to be adjacent, which any cell-granular order provides; the gathers want the 16
+// particles of a half-warp in one row of cells.  Keys are built from the positions when a re-sort is due (not by G2P: that cost
+// 8 B per particle and substep for something needed every ~30 substeps).
 __device__ __forceinline__ unsigned sort_key(int ci, int cj, int ck, const GridP& G) {
     if (!G.bricks) return (unsigned)((ck * G.ny + cj) * G.nx + ci);
     const unsigned brick = (unsigned)(((ck >> 2) * G.nqy + (cj >> 2)) * G.nqx + (ci >> 2));
@@ -103,9 +127,10 @@ __global__ void __launch_bounds__(256) k_reorder(PartP src, PartP dst, const uns
 
 // ================================================================================================ grid passes
 // Compact list of the flagged 8^3 blocks (run indices, see run_block).  The dam break occupies 7 % of the 512^3 grid: launching
-// one CTA per block of the whole grid cost each pass ~0.2 ms of CTAs that only read a zero flag (0.77 ms of a 16.4 ms substep for
-// the three passes); with the list a pass is a persistent grid over the occupied blocks and runs at memory speed.
-__global__ void __launch_bounds__(256) k_list_blocks(GridP G, int nrun, unsigned int* __restrict__ list, unsigned int* __restrict__ count) {
+// one CTA per block of the whole grid cost each pass ~0.2 ms of CTAs that only read a zero flag; with the list a pass is a
+// persistent grid over the occupied blocks and runs at memory speed.  The caller zeroes the count first.
+__global__ void __launch_bounds__(256) k_list_blocks(GridP G, int nrun, unsigned int* __restrict__ list, unsigned int* __restrict__ count, const SimClock* __restrict__ clk) {
+    if (clk) AEP_HALT_PRE(clk);
     const int r = blockIdx.x * 256 + threadIdx.x;
     bool on = false;
     if (r < nrun) { int bx, by, bz; on = G.flags[run_block(G, r, bx, by, bz)] != 0; }
@@ -118,6 +143,22 @@ __global__ void __launch_bounds__(256) k_list_blocks(GridP G, int nrun, unsigned
     if (on) list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)r;
 }
 
+__device__ __forceinline__ bool node_valid(const GridP& G, int i, int j, int k) {
+    return i >= G.v0[0] && i < G.v1[0] && j >= G.v0[1] && j < G.v1[1] && k >= G.v0[2] && k < G.v1[2];
+}
+// node (i,j,k) of thread t (two per thread) of block (bx,by,bz); false outside the held range.  valid: inside the range whose sums
+// are complete (everything for a whole-grid context)
+__device__ __forceinline__ bool block_node(const GridP& G, int bx, int by, int bz, int t, size_t& n, bool& valid) {
+    const int i = bx * 8 + (t & 7), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t >> 6);
+    if (!node_held(G, i, j, k)) return false;
+    n = nidx(G, i, j, k);
+    valid = node_valid(G, i, j, k);
+    return true;
+}
+__device__ __forceinline__ bool block_node(const GridP& G, int bx, int by, int bz, int t, size_t& n) {
+    bool valid; return block_node(G, bx, by, bz, t, n, valid);
+}
+
 // zero (m,p) and f of every block that the previous P2G touched, and drop its flag
 __global__ void __launch_bounds__(256) k_clear_blocks(GridP G, const unsigned int* __restrict__ list, const unsigned int* __restrict__ count) {
     const unsigned nb = *count;
@@ -127,12 +168,8 @@ __global__ void __launch_bounds__(256) k_clear_blocks(GridP G, const unsigned in
         const int b = run_block(G, (int)list[q], bx, by, bz);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int t = threadIdx.x + 256 * h;
-            const int i = bx * 8 + (t & 7), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t >> 6);
-            if (i < G.nx && j < G.ny && k < G.nz) {
-                const size_t n = ((size_t)k * G.ny + j) * G.nx + i;
-                G.mp[n] = z; G.f[n] = z;
-            }
+            size_t n;
+            if (block_node(G, bx, by, bz, threadIdx.x + 256 * h, n)) { G.mp[n] = z; G.f[n] = z; }
         }
         if (threadIdx.x == 0) G.flags[b] = 0;
     }
@@ -157,14 +194,14 @@ __global__ void __launch_bounds__(256) k_vmax_from_mp(GridP G, SimClock* clk) {
     int bx, by, bz;
     const int b = run_block(G, blockIdx.x, bx, by, bz);
     if (!G.flags[b]) return;
+    const float floor_m = clk->vmax_mass_floor;
     float vm = 0.0f;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int t = threadIdx.x + 256 * h;
-        const int i = bx * 8 + (t & 7), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t >> 6);
-        if (i < G.nx && j < G.ny && k < G.nz) {
-            const float4 mp = G.mp[((size_t)k * G.ny + j) * G.nx + i];
-            if (mp.x > 0.0f) {
+        size_t n; bool valid;
+        if (block_node(G, bx, by, bz, threadIdx.x + 256 * h, n, valid) && valid) {
+            const float4 mp = G.mp[n];
+            if (mp.x > floor_m) {
                 const float im = 1.0f / mp.x;
                 const float vx = mp.y * im, vy = mp.z * im, vz = mp.w * im;
                 vm = fmaxf(vm, sqrtf(vx * vx + vy * vy + vz * vz));
@@ -174,75 +211,146 @@ __global__ void __launch_bounds__(256) k_vmax_from_mp(GridP G, SimClock* clk) {
     block_max_to_clock(vm, clk);
 }
 
+// Collider description for k_grid_update.  Static colliders (the reference: HS:484) are sampled once on the host into a byte code
+// per node (+ normals); a moving collider (opt-in, aep_set_collider_motion) is an analytic level set evaluated at the node, translated
+// by its velocity times the simulated time, and the projection works on the velocity relative to the collider.
+struct ColliderP {
+    int moving;                 // 0: sampled codes (G.ls_code / G.ls_nrm); 1: analytic, evaluated per node
+    int kind;                   // AEP_LS_* of the analytic form
+    float par[8];
+    float vel[3];               // collider velocity
+    float off[3];               // translation at the start of this substep (vel * t), refreshed by the clock kernel
+    int coulomb;                // 0: the reference's stick-or-slide (HS:494-502, the reduction at :501 is a no-op); 1: opt-in Coulomb friction
+};
+// analytic level sets on the device (same formulas as LevelSet.cpp:8-42 and the host sampler in aep_engine.cu): true inside (phi <= 0)
+__device__ __forceinline__ bool collider_eval(const ColliderP& C, float x, float y, float z, float& nx_, float& ny_, float& nz_) {
+    x -= C.off[0]; y -= C.off[1]; z -= C.off[2];
+    nx_ = 0.f; ny_ = 0.f; nz_ = 1.f;
+    switch (C.kind) {
+    case 1: return z - C.par[0] <= 0.0f;                                                   // ground
+    case 2: {                                                                               // wall corner + ground
+        const float dz = z - C.par[2], dx = C.par[0] - x, dy = C.par[1] - y;
+        if (fminf(fminf(dz, dx), dy) > 0.0f) return false;
+        const float az = fabsf(dz), ax = fabsf(dx), ay = fabsf(dy);
+        if (az <= ax && az <= ay) { } else if (ay <= ax) { ny_ = -1.f; nz_ = 0.f; } else { nx_ = -1.f; nz_ = 0.f; }
+        return true;
+    }
+    case 3: case 6: {                                                                       // sphere (+ ground for kind 3)
+        const float dx = x - C.par[0], dy = y - C.par[1], dz = z - C.par[2];
+        const float r = sqrtf(dx * dx + dy * dy + dz * dz);
+        const float ps = r - C.par[3], pg = C.kind == 3 ? z - C.par[4] : 1e30f;
+        if (fminf(ps, pg) > 0.0f) return false;
+        if (ps <= pg && r > 0.0f) { const float ir = 1.0f / r; nx_ = dx * ir; ny_ = dy * ir; nz_ = dz * ir; }
+        return true;
+    }
+    case 4: {                                                                               // box (inside is free)
+        const float d[6] = { z - C.par[2], C.par[5] - z, x - C.par[0], C.par[3] - x, y - C.par[1], C.par[4] - y };
+        int best = 0;
+#pragma unroll
+        for (int f = 1; f < 6; ++f) if (d[f] < d[best]) best = f;
+        if (d[best] > 0.0f) return false;
+        nx_ = best == 2 ? 1.f : (best == 3 ? -1.f : 0.f); ny_ = best == 4 ? 1.f : (best == 5 ? -1.f : 0.f); nz_ = best == 0 ? 1.f : (best == 1 ? -1.f : 0.f);
+        return true;
+    }
+    default: return false;
+    }
+}
+
 // updateGridVelocities_ (HybridSolver.cpp:725-737) + gravity (:457) + max|v| (RegularGrid.cpp:188-200)
 // + gridCollisionHandling_ level-set part (:467-511), one coalesced float4 pass over the active blocks.
-__global__ void __launch_bounds__(256) k_grid_update(GridP G, SimClock* clk, const unsigned int* __restrict__ list, const unsigned int* __restrict__ count) {
+// CLEAR (the fused substep): (m,p) and f are dead once v~ is written -- zero them and drop the block flag here, so that the
+// fused G2P+P2G kernel scatters into a clean grid without a separate clearing pass.
+template <bool CLEAR>
+__global__ void __launch_bounds__(256) k_grid_update(GridP G, const ColliderP* __restrict__ Cp, SimClock* clk, const unsigned int* __restrict__ list,
+                                                     const unsigned int* __restrict__ count) {
+    if (CLEAR) AEP_HALT_PRE(clk);
+    __shared__ ColliderP C;
+    if (threadIdx.x == 0) C = *Cp;
+    __syncthreads();
     const unsigned nb = *count;
     const float dt = clk->dt;
+    const float floor_m = clk->vmax_mass_floor;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float vm = 0.0f;
     for (unsigned q = blockIdx.x; q < nb; q += gridDim.x) {
-    int bx, by, bz;
-    run_block(G, (int)list[q], bx, by, bz);
+        int bx, by, bz;
+        const int b = run_block(G, (int)list[q], bx, by, bz);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int t = threadIdx.x + 256 * h;
-        const int i = bx * 8 + (t & 7), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t >> 6);
-        if (i < G.nx && j < G.ny && k < G.nz) {
-            const size_t n = ((size_t)k * G.ny + j) * G.nx + i;
+        for (int h = 0; h < 2; ++h) {
+            const int t = threadIdx.x + 256 * h;
+            size_t n; bool valid;
+            if (!block_node(G, bx, by, bz, t, n, valid)) continue;
             const float4 mp = G.mp[n];
             float vx = 0.f, vy = 0.f, vz = 0.f, s = 1.0f;
-            if (mp.x > 0.0f) {
+            if (valid && mp.x > 0.0f) {
                 const float4 f = G.f[n];
                 const float im = 1.0f / mp.x;
                 vx = fmaf(dt, f.x * im, mp.y * im);
                 vy = fmaf(dt, f.y * im, mp.z * im);
                 vz = fmaf(dt, fmaf(-G.gravity, mp.x, f.z) * im, mp.w * im);
-                vm = fmaxf(vm, sqrtf(vx * vx + vy * vy + vz * vz));
-                const int code = G.ls_code ? G.ls_code[n] : 0;
-                if (code) {
-                    float nx_, ny_, nz_;
+                if (mp.x > floor_m) vm = fmaxf(vm, sqrtf(vx * vx + vy * vy + vz * vz));
+                bool inside = false; float nx_ = 0.f, ny_ = 0.f, nz_ = 1.f;
+                if (C.moving) {
+                    const int i = bx * 8 + (t & 7), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t >> 6);
+                    inside = collider_eval(C, fmaf((float)i, G.hx, G.mnx), fmaf((float)j, G.hy, G.mny), fmaf((float)k, G.hz, G.mnz), nx_, ny_, nz_);
+                } else {
+                    const int code = G.ls_code ? G.ls_code[n] : 0;
+                    inside = code != 0;
                     if (code == 7) { const float4 nn = G.ls_nrm[n]; nx_ = nn.x; ny_ = nn.y; nz_ = nn.z; }
-                    else {
+                    else if (code) {
                         nx_ = (code == 1) ? 1.f : (code == 2 ? -1.f : 0.f);
                         ny_ = (code == 3) ? 1.f : (code == 4 ? -1.f : 0.f);
                         nz_ = (code == 5) ? 1.f : (code == 6 ? -1.f : 0.f);
                     }
-                    const float vn = vx * nx_ + vy * ny_ + vz * nz_;                 // HybridSolver.cpp:486
-                    if (vn < 0.0f) {                                                 // :488 approaching
-                        vx = fmaf(-vn, nx_, vx); vy = fmaf(-vn, ny_, vy); vz = fmaf(-vn, nz_, vz);   // :490-492
-                        const float vt = sqrtf(vx * vx + vy * vy + vz * vz);
-                        // :494-502 stick test; the Coulomb reduction at :501 is a no-op expression statement
-                        s = (vt < -G.friction * vn) ? 0.0f : 1.0f;
+                }
+                if (inside) {
+                    const float cvx = C.moving ? C.vel[0] : 0.f, cvy = C.moving ? C.vel[1] : 0.f, cvz = C.moving ? C.vel[2] : 0.f;   // HS:484: static
+                    float rx_ = vx - cvx, ry_ = vy - cvy, rz_ = vz - cvz;
+                    const float vn = rx_ * nx_ + ry_ * ny_ + rz_ * nz_;                  // HybridSolver.cpp:486
+                    if (vn < 0.0f) {                                                     // :488 approaching
+                        rx_ = fmaf(-vn, nx_, rx_); ry_ = fmaf(-vn, ny_, ry_); rz_ = fmaf(-vn, nz_, rz_);   // :490-492
+                        const float vtn = sqrtf(rx_ * rx_ + ry_ * ry_ + rz_ * rz_);
+                        // :494-502 stick test; the Coulomb reduction at :501 is a no-op expression statement.  Opt-in Coulomb: |v_t|
+                        // shrinks by mu |v_n| (what :500-501 set out to do), stored as v = s v~ with 0 <= s <= 1
+                        if (!C.coulomb) s = (vtn < -G.friction * vn) ? 0.0f : 1.0f;
+                        else s = (vtn <= -G.friction * vn) ? 0.0f : 1.0f + G.friction * vn / vtn;
+                        vx = rx_ + cvx; vy = ry_ + cvy; vz = rz_ + cvz;
                     }
                 }
             }
             G.vt[n] = make_float4(vx, vy, vz, s);
+            if (CLEAR) { G.mp[n] = z4; G.f[n] = z4; }
         }
-    }
+        if (CLEAR && threadIdx.x == 0) G.flags[b] = 0;
     }
     block_max_to_clock(vm, clk);
 }
 
 // dt rule + frame clipping of HybridSolver.cpp:878-892, one thread, all in double like the reference
-__global__ void k_advance_clock(SimClock* clk, int fixed_dt, int n) {
+__global__ void k_advance_clock(SimClock* clk, int fixed_dt, ColliderP* col) {
+    if (clk->halt >= 1) { clk->halt = 2; return; }
     const float vmax = __uint_as_float(clk->vmax_bits);
     clk->vmax_last = vmax; clk->vmax_bits = 0u;
     if (fixed_dt == 2) return;                                   // stage-level API: only latch max|v|
-    clk->sort_cost += (float)clk->moved_since_sort / (float)max(n, 1);
+    clk->sort_cost += (float)clk->moved_since_sort / (float)max(clk->n_slots, 1);
     if (fixed_dt == 1) {                                         // pinned dt (aep_set_fixed_dt): plain time accumulation
         clk->inner_t += (double)clk->dt; clk->frame_flag = 0;
         if (clk->inner_t >= clk->frame_dt) { clk->inner_t -= clk->frame_dt; clk->t += clk->frame_dt; clk->frame_flag = 1; clk->frame_no += 1; }
-        clk->substeps += 1;
-        return;
-    }
-    double dt = clk->cfl / fmax(clk->rate_floor, (double)vmax / clk->hmin);
-    if (clk->inner_t + dt >= clk->frame_dt) {
-        dt = clk->frame_dt - clk->inner_t; clk->t += clk->frame_dt; clk->inner_t = 0.0; clk->frame_flag = 1; clk->frame_no += 1;
     } else {
-        clk->inner_t += dt; clk->frame_flag = 0;
+        double dt = clk->cfl / fmax(clk->rate_floor, (double)vmax / clk->hmin);
+        if (clk->inner_t + dt >= clk->frame_dt) {
+            dt = clk->frame_dt - clk->inner_t; clk->t += clk->frame_dt; clk->inner_t = 0.0; clk->frame_flag = 1; clk->frame_no += 1;
+        } else {
+            clk->inner_t += dt; clk->frame_flag = 0;
+        }
+        clk->dt = (float)dt;
     }
-    clk->dt = (float)dt;
     clk->substeps += 1;
+    if ((clk->stop_frame >= 0 && clk->frame_no >= clk->stop_frame) || (clk->stop_substep >= 0 && clk->substeps >= clk->stop_substep)) clk->halt = 1;   // G2P of this substep still runs
+    if (col && col->moving) {                                    // where the collider is when the next grid update runs
+        const double tt = clk->t + clk->inner_t;
+        for (int a = 0; a < 3; ++a) col->off[a] = (float)(col->vel[a] * tt);
+    }
 }
 __global__ void k_initial_dt(SimClock* clk) {                      // HybridSolver.cpp:860
     const float vmax = __uint_as_float(clk->vmax_bits);
@@ -251,16 +359,20 @@ __global__ void k_initial_dt(SimClock* clk) {                      // HybridSolv
 }
 
 // ================================================================================================ scatter machinery
-// Both scatters (P2G, force) run in two phases per warp of 32 cell-sorted particles:
+// Both scatters (P2G, force) run in two phases per round of 16 cell-sorted particles per half-warp:
 //   phase A  thread-per-particle: everything that depends on the particle only (1-D weights, affine / stress matrices)
-//            goes to a per-warp shared-memory record;
+//            goes to a per-half-warp shared-memory record;
 //   phase B  one HALF-WARP per particle, 16 lanes = the 16 (j,k) rows of the 4x4x4 stencil, each lane owns the 4 nodes
 //            along x of its row and accumulates in registers (packed fp32x2, aep_pack.cuh) over the run of particles that share
 //            a cell.  No atomics and no shuffles in the inner loop.
 // Sliding window along x: when the next particle's cell is d = 1..3 cells further along x in the same (j,k) row of cells, only the
 // d nodes that fall out of the 4-node window are reduced to memory and the accumulators shift; x-adjacent cells share 3 of their
-// 4 nodes per row, so a sorted row of C cells costs C+3 reductions per lane instead of 4C.  slide_row_pk returns false when the window
-// cannot slide (the caller then flushes all four nodes with flush_row_pk).
+// 4 nodes per row, so a sorted row of C cells costs C+3 reductions per lane instead of 4C.  A half-warp keeps its window open over
+// ROUNDS x 16 consecutive particles: every flush costs one LSU wavefront per lane and node (the 16 rows of a half-warp lie in 16
+// different cache lines), and the scatters are bound by exactly those wavefronts plus the shared-memory record reads.
+// Run STARTS (not ends) drive the window: phase A ballots "my cell differs from the cell of the particle before me" (the half-warp's
+// last cell of the round before for its first lane), so nothing has to be known about particles that are not processed yet -- the
+// fused G2P+P2G kernel only learns a particle's new cell when it has advected it.
 
 // CTA -> chunk of the sorted particle order for the scatter kernels.  Consecutive CTAs run concurrently; if they also worked on
 // consecutive chunks, neighbouring rows and planes of cells would reduce into the same grid nodes at the same time and the L2
@@ -281,17 +393,15 @@ __host__ __device__ __forceinline__ int strided_grid(int nchunks, int strips) {
 __device__ __forceinline__ void flush_nodes(const GridP& G, float4* __restrict__ dst, int cell, int oi, int oj, int ok,
                                             const float4& a0, const float4& a1, bool mark) {
     const int ni = cell_i(cell) - 1 + oi, nj = cell_j(cell) - 1 + oj, nk0 = cell_k(cell) - 1 + ok, nk1 = nk0 + 2;
-    const bool inij = (ni >= 0) && (ni < G.nx) && (nj >= 0) && (nj < G.ny);
-    if (inij && nk0 >= 0 && nk0 < G.nz) {
-        atomicAdd(dst + (((size_t)nk0 * G.ny + nj) * G.nx + ni), a0);
+    if (node_held(G, ni, nj, nk0)) {
+        atomicAdd(dst + nidx(G, ni, nj, nk0), a0);
         if (mark) G.flags[((nk0 >> 3) * G.nby + (nj >> 3)) * G.nbx + (ni >> 3)] = 1;
     }
-    if (inij && nk1 >= 0 && nk1 < G.nz) {
-        atomicAdd(dst + (((size_t)nk1 * G.ny + nj) * G.nx + ni), a1);
+    if (node_held(G, ni, nj, nk1)) {
+        atomicAdd(dst + nidx(G, ni, nj, nk1), a1);
         if (mark) G.flags[((nk1 >> 3) * G.nby + (nj >> 3)) * G.nbx + (ni >> 3)] = 1;
     }
 }
-
 
 // ---- packed accumulators: AccRow (aep_scatter.cuh)
 // same, but pinned behind the reductions that consumed the old values (volatile): see slide_row_pk
@@ -309,32 +419,37 @@ __device__ __forceinline__ float4 requad(float4* slot, f32x2 lo, f32x2 hi) {
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "l"(lo), "l"(hi) : "memory");
     return v;
 }
+// rows that this context does not hold never receive anything (outside the grid: the weights are masked, HS:44-46; outside a slab's
+// reach: a particle can only get there after it has left the slab, and its new owner scatters it)
+__device__ __forceinline__ bool row_held(const GridP& G, int nj, int nk) {
+    return nj >= G.a0[1] && nj < G.a1[1] && nk >= G.a0[2] && nk < G.a1[2];
+}
 __device__ __forceinline__ void flush_row_pk(const GridP& G, float4* __restrict__ dst, float4* slot, int cell, int j, int k, const AccRow& a, bool mark) {
     const int ni0 = cell_i(cell) - 1, nj = cell_j(cell) - 1 + j, nk = cell_k(cell) - 1 + k;
-    if (nj < 0 || nj >= G.ny || nk < 0 || nk >= G.nz) return;
-    float4* row = dst + ((size_t)nk * G.ny + nj) * G.nx;
+    if (!row_held(G, nj, nk)) return;
+    float4* row = dst + nidx(G, 0, nj, nk);
     unsigned char* frow = G.flags + ((nk >> 3) * G.nby + (nj >> 3)) * G.nbx;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int ni = ni0 + i;
-        if (ni >= 0 && ni < G.nx) {
+        if (ni >= G.a0[0] && ni < G.a1[0]) {
             atomicAdd(row + ni, requad(slot, a.lo[i], a.hi[i]));
             // block flags: the first node of the window in the grid, and the last one when it sits in another 8-block
-            if (mark && (i == 0 || ni == 0 || ((i == 3 || ni == G.nx - 1) && (ni >> 3) != (max(ni0, 0) >> 3)))) frow[ni >> 3] = 1;
+            if (mark && (i == 0 || ni == G.a0[0] || ((i == 3 || ni == G.a1[0] - 1) && (ni >> 3) != (max(ni0, G.a0[0]) >> 3)))) frow[ni >> 3] = 1;
         }
     }
 }
-// sliding window along x (see slide_row): reduce the d nodes that leave the window, shift the rest
+// sliding window along x: reduce the d nodes that leave the window, shift the rest
 __device__ __forceinline__ bool slide_row_pk(const GridP& G, float4* __restrict__ dst, float4* slot, int cur, int next, int j, int k, AccRow& a, bool mark) {
     const int d = next - cur;
     if (d <= 0 || d >= 4 || (next & 1023) - (cur & 1023) != d) return false;
     const int nj = cell_j(cur) - 1 + j, nk = cell_k(cur) - 1 + k;
-    const bool in_jk = nj >= 0 && nj < G.ny && nk >= 0 && nk < G.nz;
-    float4* row = dst + ((size_t)nk * G.ny + nj) * G.nx;
-    unsigned char* frow = G.flags + ((nk >> 3) * G.nby + (nj >> 3)) * G.nbx;
+    const bool in_jk = row_held(G, nj, nk);
+    float4* row = dst + (in_jk ? nidx(G, 0, nj, nk) : 0);
+    unsigned char* frow = G.flags + (in_jk ? ((nk >> 3) * G.nby + (nj >> 3)) * G.nbx : 0);
     int ni = cell_i(cur) - 1;
     for (int s = 0; s < d; ++s, ++ni) {
-        if (in_jk && ni >= 0 && ni < G.nx) {
+        if (in_jk && ni >= G.a0[0] && ni < G.a1[0]) {
             atomicAdd(row + ni, requad(slot, a.lo[0], a.hi[0]));
             // a node that slides out marks its block only when it is the block's last one: a block the window has left behind saw
             // its last node slide out, and the blocks under the window are marked by the flush that ends the run
@@ -349,42 +464,60 @@ __device__ __forceinline__ bool slide_row_pk(const GridP& G, float4* __restrict_
     }
     return true;
 }
+// a run of same-cell particles starts at this record: move the window from cell `prev` (-1: nothing accumulated yet) to cell `cur`
+__device__ __forceinline__ void window_move(const GridP& G, float4* __restrict__ dst, float4* slot, int prev, int cur, int j, int k, AccRow& a, bool mark) {
+    if (prev < 0) return;
+    if (!slide_row_pk(G, dst, slot, prev, cur, j, k, a, mark)) {
+        flush_row_pk(G, dst, slot, prev, j, k, a, mark);
+        acc_zero_ordered(a);
+    }
+}
+// phase A of a round: which records of the half-warp start a run (bit s of the result, already shifted to the caller's half-warp),
+// the cell before each lane's (`prev`), and the half-warp's last cell (`wcell`, carried to the next round; -1 before the first)
+__device__ __forceinline__ unsigned run_starts(int cell, int& wcell, int& prev) {
+    const int lane = threadIdx.x & 31;
+    prev = __shfl_up_sync(0xffffffffu, cell, 1);
+    if ((lane & 15) == 0) prev = wcell;
+    const unsigned starts = __ballot_sync(0xffffffffu, cell != prev);
+    wcell = __shfl_sync(0xffffffffu, cell, (lane & 16) | 15);
+    return starts >> (lane & 16);
+}
 
-// ================================================================================================ P2G
+// ================================================================================================ P2G (stand-alone)
 // particleToGrid_ (HybridSolver.cpp:113-231): m_i = sum w m ; p_i = sum w m (v + (3/h^2) B (x_i - x_p)).
 // Per particle the momentum of node offset (i,j,k) is q0 + Qm (i,j,k)^T with Qm = m (3/h^2) B diag(h), q0 = m v - Qm (1+f).
 // Phase-A record of one particle: see p2g_make_record (aep_scatter.cuh).
-// Phase B is bound by shared-memory wavefronts as much as by issue slots (profiles/README.md, v9): every LDS of the two half-warps
-// costs one wavefront per half-warp, so the record holds plain scalars (FFMA2 takes a broadcast .F32 operand) and the end of a
-// run of same-cell particles comes from a ballot of phase A instead of a per-particle load of the cell index.
+// Used for the first transfer (HS:854), restarts, mesh points and the stage-level API; inside a substep the same phase B runs at
+// the end of the fused kernel (aep_particle.cuh) on records made from registers.
 #define P2G_HW_PAD 2
 #define P2G_HW_F4 (16 * P2G_STRIDE + P2G_HW_PAD)
-// bit l of the result: the run of same-cell particles ends with the particle of lane l
-__device__ __forceinline__ unsigned run_ends(int cell) {
-    const int lane = threadIdx.x & 31;
-    const int nxt = __shfl_down_sync(0xffffffffu, cell, 1);
-    return __ballot_sync(0xffffffffu, nxt != cell || (lane & 15) == 15);
+// one round of phase B: the half-warp's 16 records into the window
+__device__ __forceinline__ void p2g_phase_b(const GridP& G, const float4* __restrict__ recs, unsigned starts, float4* slot, int j, int k, int yoff, int zoff,
+                                            f32x2 J, f32x2 K, AccRow& acc) {
+#pragma unroll 1
+    for (int it = 0; it < 16; ++it) {
+        const float4* r = recs + it * P2G_STRIDE;
+        if ((starts >> it) & 1u) {                                            // a run of particles sharing a cell starts here
+            const float2 cn = *reinterpret_cast<const float2*>(r + 7);
+            window_move(G, G.mp, slot, __float_as_int(cn.y), __float_as_int(cn.x), j, k, acc, true);
+        }
+        p2g_row_accumulate(r, yoff, zoff, J, K, acc);
+    }
 }
-// Every flush costs one LSU wavefront per lane and node (the 16 rows of a half-warp lie in 16 different cache lines), and P2G is
-// bound by exactly those wavefronts plus the shared-memory reads (l1tex data-pipe 97 % busy, profiles/r1_v9c).  A half-warp
-// therefore keeps its window open over P2G_ROUNDS x 16 consecutive particles instead of 16: with 8 particles per cell the
-// reductions per lane drop from 5 per 16 particles to 19 per 128 (measured: 3.77 ms at 1 round, 3.05 at 4, 2.95 at 8, 2.91 at 16).  Round r of a warp loads, per half-warp h, the particles
-// base + h*16*ROUNDS + r*16 + (lane & 15), so each half-warp walks one contiguous piece of the sorted order.
-#ifndef P2G_ROUNDS
-#define P2G_ROUNDS 8
-#endif
-#define P2G_CTA_PARTICLES (256 * P2G_ROUNDS)
-__global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
+// ROUNDS x 16 consecutive particles per half-warp: 8 for large scenes (fewest reductions), less when that would leave SMs idle
+template <int ROUNDS>
+__global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n, const SimClock* __restrict__ clk) {
+    if (clk) AEP_HALT_POST(clk);                                              // inside a substep (mesh points); nullptr: stage-level call
     __shared__ float4 stage[8][2][P2G_HW_F4];
     __shared__ float4 bounce[256];                                            // lane-private slots of requad()
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float4* slot = bounce + threadIdx.x;
-    const int chunk = strided_chunk(blockIdx.x, (n + P2G_CTA_PARTICLES - 1) / P2G_CTA_PARTICLES, G.strips);
+    const int cta_particles = 256 * ROUNDS;
+    const int chunk = strided_chunk(blockIdx.x, (n + cta_particles - 1) / cta_particles, G.strips);
     if (chunk < 0) return;
     const int hw = lane >> 4, s = lane & 15, j = s & 3, k = s >> 2;
-    const int hbase = chunk * P2G_CTA_PARTICLES + wib * (32 * P2G_ROUNDS) + hw * (16 * P2G_ROUNDS);      // first particle of this half-warp
-    if (chunk * P2G_CTA_PARTICLES + wib * (32 * P2G_ROUNDS) >= n) return;    // warp-uniform; no block-level barrier below
-    const int hend = hbase + 16 * P2G_ROUNDS;                                // one past its last particle (may exceed n)
+    const int hbase = chunk * cta_particles + wib * (32 * ROUNDS) + hw * (16 * ROUNDS);      // first particle of this half-warp
+    if (chunk * cta_particles + wib * (32 * ROUNDS) >= n) return;             // warp-uniform; no block-level barrier below
     float fj = (float)j, fk = (float)k;
     int yoff = 16 + 4 * j, zoff = 32 + 4 * k;                                 // byte offsets of Ny[j], Nz[k] inside a record
     // lane constants: ptxas re-derives them from %tid on every trip (8 instructions) unless they come out of something it cannot
@@ -394,44 +527,34 @@ __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n) {
     const f32x2 J = pk1(fj), K = pk1(fk);
     AccRow acc; acc_zero(acc);
     const float4* recs = &stage[wib][hw][0];
+    int wcell = -1;
 #pragma unroll 1
-    for (int round = 0; round < P2G_ROUNDS; ++round) {
-        unsigned ends;
+    for (int round = 0; round < ROUNDS; ++round) {
+        unsigned starts;
         {   // ---- phase A: thread per particle
             const int q = hbase + round * 16 + s;                            // may lie past the end: such lanes repeat the last particle with zero mass
             const int p = min(q, n - 1);
-            const float4 X = ldg4(P.a[PX] + p), VM = ldg4(P.a[PVM] + p);
-            const float4 c0 = ldg4(P.a[PC0] + p), c1 = ldg4(P.a[PC1] + p), c2 = ldg4(P.a[PC2] + p);
-            // cell of the half-warp's next particle (-1 behind its last one): the lines are the ones the neighbouring lanes load
-            const int ncell = (q + 1 < hend) ? __float_as_int(__ldg(&P.a[PX][min(q + 1, n - 1)].w)) : -1;
-            const float m = (q < n) ? VM.w : 0.0f;
+            const float4 X = ldg4(P.a[PX] + p), V = ldg4(P.a[PV] + p), C0 = ldg4(P.a[PC0] + p), C1 = ldg4(P.a[PC1] + p);
+            const float m = (q < n) ? __ldg(&P.a[PK][p].x) : 0.0f;
+            float4 b0, b1, b2; unpack_B(V, C0, C1, b0, b1, b2);
+            int prev;
+            starts = run_starts(__float_as_int(X.w), wcell, prev);
             __syncwarp();                                                    // phase B of the round before is done with the records
-            p2g_make_record(&stage[wib][hw][s * P2G_STRIDE], X, VM, c0, c1, c2, m, G.apic, G.hx, G.hy, G.hz, __int_as_float(ncell));
-            ends = __ballot_sync(0xffffffffu, ncell != __float_as_int(X.w));
+            p2g_make_record(&stage[wib][hw][s * P2G_STRIDE], X, make_float4(V.x, V.y, V.z, m), b0, b1, b2, m, G.apic, G.hx, G.hy, G.hz, __int_as_float(prev));
         }
         __syncwarp();
         // ---- phase B: half-warp per particle, lane = (j,k) row of the stencil, 4 nodes along x in packed accumulators
-        ends >>= hw * 16;
-#pragma unroll 1
-        for (int it = 0; it < 16; ++it) {
-            const float4* r = recs + it * P2G_STRIDE;
-            p2g_row_accumulate(r, yoff, zoff, J, K, acc);
-            if ((ends >> it) & 1u) {                                          // the run of particles sharing this cell ends here
-                const float2 cn = *reinterpret_cast<const float2*>(r + 7);
-                const int cur = __float_as_int(cn.x), nxt = __float_as_int(cn.y);
-                if (!slide_row_pk(G, G.mp, slot, cur, nxt, j, k, acc, true)) {
-                    flush_row_pk(G, G.mp, slot, cur, j, k, acc, true);
-                    acc_zero_ordered(acc);
-                }
-            }
-        }
+        p2g_phase_b(G, recs, starts, slot, j, k, yoff, zoff, J, K, acc);
     }
+    if (wcell >= 0) flush_row_pk(G, G.mp, slot, wcell, j, k, acc, true);
 }
 
-// launch helper shared by the engine, the slab arrivals and the mesh transfers
-inline void p2g_launch(cudaStream_t st, const PartP& P, const GridP& G, long long n) {
-    const int chunks = (int)((n + P2G_CTA_PARTICLES - 1) / P2G_CTA_PARTICLES);
-    k_p2g<<<strided_grid(chunks, G.strips), 256, 0, st>>>(P, G, (int)n);
+// launch helper shared by the engine and the mesh transfers
+inline void p2g_launch(cudaStream_t st, const PartP& P, const GridP& G, long long n, const SimClock* clk = nullptr) {
+    if (n <= 0) return;
+    if (n >= (1ll << 22)) { const int chunks = (int)((n + 2047) / 2048); k_p2g<8><<<strided_grid(chunks, G.strips), 256, 0, st>>>(P, G, (int)n, clk); }
+    else if (n >= (1ll << 19)) { const int chunks = (int)((n + 511) / 512); k_p2g<2><<<strided_grid(chunks, G.strips), 256, 0, st>>>(P, G, (int)n, clk); }
+    else { const int chunks = (int)((n + 255) / 256); k_p2g<1><<<strided_grid(chunks, G.strips), 256, 0, st>>>(P, G, (int)n, clk); }
 }
 
 // first P2G only: rho_p = sum_i w m_i / (hx hy hz), V_p = m_p / rho_p           HybridSolver.cpp:242-249
@@ -450,482 +573,37 @@ __global__ void __launch_bounds__(256) k_init_volumes(PartP P, GridP G, int n) {
         for (int j = 0; j < 4; ++j) {
             const int nj = clampi(ay.n0 + j, 0, G.ny - 1);
             const float wjk = ay.N[j] * az.N[k];
-            const size_t row = ((size_t)nk * G.ny + nj) * G.nx;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int ni = clampi(ax.n0 + i, 0, G.nx - 1);
-                dens = fmaf(ax.N[i] * wjk, ldg4(G.mp + row + ni).x, dens);
+                dens = fmaf(ax.N[i] * wjk, ldg4(G.mp + nidx(G, ni, nj, nk)).x, dens);
             }
         }
     }
     dens *= G.inv_cell_vol;
-    const float m = P.a[PVM][p].w;
+    const float m = P.a[PK][p].x;
     float4 e0 = P.a[PE0][p]; e0.w = m * (1.0f / dens); P.a[PE0][p] = e0;
 }
 
 // v_i = p_i / m_i where m_i > 0 (HybridSolver.cpp:233-240) for every active node, into the vt array (free between P2G and
 // the grid update), so that the force gather below does 64 loads and no divisions per particle.
-__global__ void __launch_bounds__(256) k_grid_normalise(GridP G, const unsigned int* __restrict__ list, const unsigned int* __restrict__ count) {
+__global__ void __launch_bounds__(256) k_grid_normalise(GridP G, const SimClock* __restrict__ clk, const unsigned int* __restrict__ list, const unsigned int* __restrict__ count) {
+    AEP_HALT_PRE(clk);
     const unsigned nb = *count;
     for (unsigned q = blockIdx.x; q < nb; q += gridDim.x) {
-    int bx, by, bz;
-    run_block(G, (int)list[q], bx, by, bz);
+        int bx, by, bz;
+        run_block(G, (int)list[q], bx, by, bz);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int t = threadIdx.x + 256 * h;
-        const int i = bx * 8 + (t & 7), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t >> 6);
-        if (i < G.nx && j < G.ny && k < G.nz) {
-            const size_t n = ((size_t)k * G.ny + j) * G.nx + i;
+        for (int h = 0; h < 2; ++h) {
+            size_t n;
+            if (!block_node(G, bx, by, bz, threadIdx.x + 256 * h, n)) continue;
             const float4 mp = G.mp[n];
             const float im = mp.x > 0.0f ? 1.0f / mp.x : 0.0f;
             G.vt[n] = make_float4(mp.y * im, mp.z * im, mp.w * im, 1.0f);
         }
     }
-    }
 }
 
-// ================================================================================================ shared grid tile for the gathers
-// A warp of 32 cell-sorted particles normally sits in one row of cells (same j,k; 4 cells along x at 8 particles per cell), so the
-// 64-node stencils of its particles live in a (cells+3) x 4 x 4 node box.  The warp stages that box of G.vt in its own slice of
-// shared memory with coalesced loads (all in flight at once) and every lane then gathers with LDS.128 instead of 64 dependent
-// L1/L2 round trips.  Warp-private tiles need no block barrier, so the warps of a CTA drift apart and overlap each other's load
-// and compute phases.  A warp whose particles do not fit the box (row wrap, sparse or unsorted particles, domain faces) takes
-// the global-memory path.
-#ifndef AEP_USE_TILE
-#define AEP_USE_TILE 1
-#endif
-struct TileRef {
-    int ox0, j0, k0;                    // node coordinates of tile[0]
-};
-// warp-uniform: decide whether the tile path applies and, if so, fill the warp's tile.  cell/complete describe the lane's particle.
-__device__ __forceinline__ bool stage_tile(const GridP& G, float4* __restrict__ tile, TileRef& T, int cell, bool complete) {
-    if (!AEP_USE_TILE) return false;
-    const int lane = threadIdx.x & 31;
-    const int cref = __shfl_sync(0xffffffffu, cell, 0);
-    T.ox0 = cell_i(cref) - 1 - TILE_SLACK; T.j0 = cell_j(cref) - 1; T.k0 = cell_k(cref) - 1;
-    const int ci = cell_i(cell);
-    const bool fits = complete && ((cell ^ cref) >> 10) == 0 && (ci - 1) >= T.ox0 && (ci + 2) < T.ox0 + TILE_W;
-    if (!__all_sync(0xffffffffu, fits)) return false;
-    // rows j0..j0+3, k0..k0+3 are inside the grid because every particle of the warp is `complete`; x is clipped to the grid
-#pragma unroll
-    for (int q = 0; q < TILE_F4 / 32; ++q) {
-        const int idx = lane + 32 * q;
-        const int r = idx / TILE_W, x = idx - r * TILE_W, gx = T.ox0 + x;
-        if (gx >= 0 && gx < G.nx) tile[idx] = ldg4(G.vt + ((size_t)(T.k0 + (r >> 2)) * G.ny + (T.j0 + (r & 3))) * G.nx + gx);
-    }
-    __syncwarp();
-    return true;
-}
-
-// asynchronous version of stage_tile: the warp's grid tile is fetched with cp.async (no registers, no wait) for a chunk whose X
-// records are already in registers, so that the copy flies behind the arithmetic of the chunk before.  Warp-uniform result.
-__device__ __forceinline__ void cp_async16(float4* smem_dst, const float4* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async16_stream(float4* smem_dst, const float4* gsrc) {      // L2 only: streaming particle data stays out of L1
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }   // all but the N most recent groups
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ bool tile_issue(const GridP& G, float4* __restrict__ tile, TileRef& T, int cell) {
-    if (!AEP_USE_TILE) return false;
-    const int lane = threadIdx.x & 31;
-    const int ci = cell_i(cell), cj = cell_j(cell), ck = cell_k(cell);
-    const bool complete = ci >= 1 && ci + 2 < G.nx && cj >= 1 && cj + 2 < G.ny && ck >= 1 && ck + 2 < G.nz;     // == axis_setup's
-    const int cref = __shfl_sync(0xffffffffu, cell, 0);
-    T.ox0 = cell_i(cref) - 1 - TILE_SLACK; T.j0 = cell_j(cref) - 1; T.k0 = cell_k(cref) - 1;
-    const bool fits = complete && ((cell ^ cref) >> 10) == 0 && (ci - 1) >= T.ox0 && (ci + 2) < T.ox0 + TILE_W;
-    if (!__all_sync(0xffffffffu, fits)) return false;
-#pragma unroll
-    for (int q = 0; q < TILE_F4 / 32; ++q) {
-        const int idx = lane + 32 * q;
-        const int r = idx / TILE_W, x = idx - r * TILE_W, gx = T.ox0 + x;
-        if (gx >= 0 && gx < G.nx) cp_async16(tile + idx, G.vt + ((size_t)(T.k0 + (r >> 2)) * G.ny + (T.j0 + (r & 3))) * G.nx + gx);
-    }
-    return true;
-}
-
-// ================================================================================================ forces
-// computeGridForces_, particle part (HybridSolver.cpp:252-368).  Phase A (thread per particle): gather
-// grad v = sum_i v_i (grad w_i)^T, Fhat = (I + dt grad v) FE, SVD, stress, A = V_p P FE^T.  Phase B (half-warp per particle):
-// f_i -= A grad w_ip.
-// Phase-A record of one particle for the force scatter: see frc_make_record (aep_scatter.cuh).
-// The warp's grid tile of phase A lives in the same shared memory: it is dead once the gather is done.
-#define FRC_NT 128
-#define FRC_HW_PAD 2
-#define FRC_WARP_F4 (2 * (16 * FRC_STRIDE + FRC_HW_PAD))
-static_assert(FRC_WARP_F4 >= TILE_F4, "the gather tile is aliased onto the warp's record area");
-#ifndef FRC_MIN_CTAS
-#define FRC_MIN_CTAS 6
-#endif
-// One CTA per 128 particles.  A persistent-warp build with cp.async prefetch of X / F_E and an early tile request (the recipe that
-// gained 7 % in k_g2p) was measured at 7.73 ms against 6.53 ms here: the tile shares its memory with the records of phase B, so
-// it cannot be fetched ahead, and the loop costs more than the two remaining waits (profiles/README.md, v10d).
-__global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP G, MatParams mpar, const SimClock* __restrict__ clk, int n) {
-    __shared__ float4 stage[FRC_NT / 32][FRC_WARP_F4];
-    __shared__ float4 bounce[FRC_NT];                                          // lane-private slots of requad()
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    float4* slot = bounce + threadIdx.x;
-    float4* tile = stage[wib];
-    const int base = blockIdx.x * FRC_NT + wib * 32;        // consecutive chunks: the gather of phase A lives on L1/L2 locality (strided: 2% slower)
-    if (base >= n) return;                                                       // warp-uniform; no block-level barrier below
-    const int cnt = min(32, n - base);
-    const float dt = clk->dt;
-    unsigned ends;
-    {   // ---- phase A
-        const int p = base + min(lane, cnt - 1);
-        const float4 X = ldg4(P.a[PX] + p);
-        const float4 e0 = ldg4(P.a[PE0] + p), e1 = ldg4(P.a[PE1] + p), e2 = ldg4(P.a[PE2] + p);
-        const int cell = __float_as_int(X.w);
-        Axis ax, ay, az;
-        bool complete = axis_setup(ax, X.x, cell_i(cell), G.nx, G.ihx);
-        complete &= axis_setup(ay, X.y, cell_j(cell), G.ny, G.ihy);
-        complete &= axis_setup(az, X.z, cell_k(cell), G.nz, G.ihz);
-        float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        TileRef T;
-        if (stage_tile(G, tile, T, cell, complete)) gather_grad<2>(G, ax, ay, az, tile, ax.n0 - T.ox0, g);
-        else gather_grad<AEP_FALLBACK_MODE>(G, ax, ay, az, tile, 0, g);           // rare: row ends, freshly moved particles, domain faces
-        const float FE[9] = { e0.x, e0.y, e0.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z };
-        float GF[9], Fh[9], A[9];
-        mat_mul(g, FE, GF);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Fh[i] = fmaf(dt, GF[i], FE[i]);              // HybridSolver.cpp:306
-        stress_times_FEt(mpar, Fh, FE, (lane < cnt) ? -e0.w : 0.0f, e2.w, A);    // A := -V_p P FE^T (sign of :356-366 folded in); padding lanes: zero volume
-        __syncwarp();                                                            // every lane is done with the tile: reuse it for the records
-        float4* rec = stage[wib] + (lane >> 4) * (16 * FRC_STRIDE + FRC_HW_PAD) + (lane & 15) * FRC_STRIDE;
-        frc_make_record(rec, ax.N, ax.D, ay.N, ay.D, az.N, az.D, A, X.w);
-        ends = run_ends(cell);
-    }
-    __syncwarp();
-    // ---- phase B: f_i += A grad w_i  with  grad w_i = (Dx_i Ny Nz, Nx_i Dy Nz, Nx_i Ny Dz)   (HybridSolver.cpp:356-366)
-    //      = Dx_i U + Nx_i V,  U = A[:,0] Ny Nz,  V = A[:,1] Dy Nz + A[:,2] Ny Dz  per (j,k) row
-    const int hw = lane >> 4, s = lane & 15, j = s & 3, k = s >> 2;
-    int yoff = 32 + 8 * j, zoff = 64 + 8 * k;                                 // byte offsets of (Ny,Dy)[j], (Nz,Dz)[k] inside a record
-    asm volatile("" : "+r"(yoff), "+r"(zoff));                                // lane constants: keep them in registers
-    ends >>= hw * 16;
-    AccRow acc; acc_zero(acc);
-    const float4* recs = stage[wib] + hw * (16 * FRC_STRIDE + FRC_HW_PAD);
-#pragma unroll 1
-    for (int it = 0; it < 16; ++it) {
-        const float4* r = recs + it * FRC_STRIDE;
-        frc_row_accumulate(r, yoff, zoff, acc);
-        if ((ends >> it) & 1u) {                                              // the run of particles sharing this cell ends here
-            const int cur = __float_as_int(r[9].x);
-            const int nxt = (it == 15) ? -1 : __float_as_int(r[FRC_STRIDE + 9].x);
-            if (!slide_row_pk(G, G.f, slot, cur, nxt, j, k, acc, false)) {
-                flush_row_pk(G, G.f, slot, cur, j, k, acc, false);
-                acc_zero_ordered(acc);
-            }
-        }
-    }
-}
-
-inline void forces_launch(cudaStream_t st, int sm_count, const PartP& P, const GridP& G, const MatParams& mat, const SimClock* clk, long long n) {
-    (void)sm_count;
-    k_forces<<<(unsigned)((n + FRC_NT - 1) / FRC_NT), FRC_NT, 0, st>>>(P, G, mat, clk, (int)n);
-}
-
-// ================================================================================================ G2P
-// Two builds of the G2P kernel: the default, persistent warps that software-pipeline every memory round trip of a chunk behind the
-// arithmetic of the chunk before, and -DAEP_G2P_PIPE=0, one CTA per 128 particles with a register-staged tile.  While the
-// kernel was 3800-4200 SASS instructions the pipelined form lost 5-8 % to instruction-cache misses and loop overhead
-// (profiles/README.md, v9b / v9d); on the slimmed kernel (2700-3000 instructions) it wins 7 % (6.20 -> 5.76 ms, v10c).
-#ifndef AEP_G2P_PIPE
-#define AEP_G2P_PIPE 1
-#endif
-#if AEP_G2P_PIPE
-// updateParticleVelocities_ (HybridSolver.cpp:739-745), updateAffineMomenta_ with damp 0 (:760-825, :908-917),
-// advection x = sum w (x_i + dt v~_i) (:942-945), updateDeformationGradient_ (:553-578), updatePlasticity_
-// (:612-681), all in registers, one thread per particle.  Writes the new sort key.
-//
-// Persistent warps: G2P_CTAS_PER_SM CTAs per SM, every warp walks chunks of 32 cell-sorted particles with a grid stride.  A chunk
-// used to open with two dependent memory round trips (X from DRAM, then the grid tile whose position X decides) and to wait
-// again for F_E / F_P after the gather: 20 % of the kernel's stall samples at 4 warps per scheduler
-// (profiles/r1_v8_k_g2p_sass_summary.txt).  Everything a chunk needs now arrives by cp.async while the chunk before it computes --
-// X two chunks ahead, F_E / F_P one chunk ahead, the grid tile as soon as the gather of the current chunk is done with the
-// buffer -- into the warp's own shared memory, so no prefetched value ever occupies a register (a register-staged variant
-// spilled the prefetched X at once and stalled on the spill store: profiles/README.md, v9b).
-#define G2P_NT 128
-#ifndef G2P_CTAS_PER_SM
-#define G2P_CTAS_PER_SM 4
-#endif
-struct G2PWarpSmem {
-    float4 tile[TILE_F4];
-    float4 x[2][32];
-    float4 eq[6][32];
-};
-__global__ void __launch_bounds__(G2P_NT, G2P_CTAS_PER_SM) k_g2p(PartP P, GridP G, MatParams mpar, SimClock* __restrict__ clk,
-                                             unsigned int* __restrict__ keys, unsigned int* __restrict__ vals, int n, MigList ML) {
-    __shared__ G2PWarpSmem wsm[G2P_NT / 32];
-    const int lane = threadIdx.x & 31;
-    G2PWarpSmem& W = wsm[threadIdx.x >> 5];
-    float4* tile = W.tile;
-    const int nchunks = (n + 31) >> 5, wstride = gridDim.x * (G2P_NT / 32);
-    int chunk = blockIdx.x * (G2P_NT / 32) + (threadIdx.x >> 5);            // the warps of a CTA take neighbouring chunks (shared L1 lines)
-    if (chunk >= nchunks) return;
-    const float dt = clk->dt;
-    TileRef T;
-    bool use_tile;
-    int buf = 0;
-    {   // prologue: X of the first chunk (waited for), then its tile, its F_E / F_P and the X of the second chunk in flight
-        const int p = min(chunk * 32 + lane, n - 1);
-        cp_async16_stream(&W.x[0][lane], P.a[PX] + p);
-        cp_async_wait_all();
-        use_tile = tile_issue(G, tile, T, __float_as_int(W.x[0][lane].w));
-        cp_async_commit();                                                  // group "tile"
-#pragma unroll
-        for (int a = 0; a < 6; ++a) cp_async16_stream(&W.eq[a][lane], P.a[PE0 + a] + p);
-        if (chunk + wstride < nchunks) cp_async16_stream(&W.x[1][lane], P.a[PX] + min((chunk + wstride) * 32 + lane, n - 1));
-        cp_async_commit();                                                  // group "particle data"
-    }
-    for (;;) {
-        const int p_raw = chunk * 32 + lane;
-        const bool live = p_raw < n;                                        // tail lanes recompute the last particle and write nothing:
-        const int p = live ? p_raw : n - 1;                                 // the warp stays converged for the votes below
-        const int next = chunk + wstride;
-        const bool more = next < nchunks;                                   // warp-uniform
-        cp_async_wait_group<1>();                                           // the tile has landed; this chunk's F_E / F_P and the next X may still fly
-        __syncwarp();
-        const float4 X = W.x[buf][lane];
-        const int cell = __float_as_int(X.w);
-        int ci = cell_i(cell), cj = cell_j(cell), ck = cell_k(cell);
-        Axis ax, ay, az;
-        bool complete = axis_setup(ax, X.x, ci, G.nx, G.ihx);
-        complete &= axis_setup(ay, X.y, cj, G.ny, G.ihy);
-        complete &= axis_setup(az, X.z, ck, G.nz, G.ihz);
-        float rx[4], ry[4], rz[4];                                              // x_i - x_p per axis: h (o - 1 - f)
-#pragma unroll
-        for (int o = 0; o < 4; ++o) { rx[o] = G.hx * ((float)(o - 1) - X.x); ry[o] = G.hy * ((float)(o - 1) - X.y); rz[o] = G.hz * ((float)(o - 1) - X.z); }
-        float nrx[4];
-#pragma unroll
-        for (int o = 0; o < 4; ++o) nrx[o] = ax.N[o] * rx[o];
-        G2PSums S;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { S.vc[i] = 0.f; S.va[i] = 0.f; }
-#pragma unroll
-        for (int i = 0; i < 9; ++i) { S.B[i] = 0.f; S.g[i] = 0.f; }
-        S.smin = 1.0f;
-        if (use_tile) { g2p_gather<2>(G, ax, ay, az, nrx, rx, ry, rz, tile, ax.n0 - T.ox0, S); if (S.smin == 0.0f) g2p_stick_correction<2>(G, ax, ay, az, rx, ry, rz, tile, ax.n0 - T.ox0, S); }
-        else { g2p_gather<0>(G, ax, ay, az, nrx, rx, ry, rz, tile, 0, S); if (S.smin == 0.0f) g2p_stick_correction<0>(G, ax, ay, az, rx, ry, rz, tile, 0, S); }
-        cp_async_wait_group<0>();                                           // F_E / F_P of this chunk, X of the next
-        __syncwarp();                                                       // every lane is done with the tile
-        if (more) use_tile = tile_issue(G, tile, T, __float_as_int(W.x[buf ^ 1][lane].w));
-        cp_async_commit();                                                  // group "tile" of the next chunk
-        float (&va)[3] = S.va; float (&B)[9] = S.B; float (&g)[9] = S.g;
-        const float vp[3] = { S.va[0] + S.vc[0], S.va[1] + S.vc[1], S.va[2] + S.vc[2] };       // sum w s v~ = sum w v~ - sum_{s=0} w v~
-        // ---- advection (HybridSolver.cpp:944): x' = sum w (x_i + dt v~_i) = x + [sum w (x_i - x)] + (sum w - 1) x + dt sum w v~
-        // the bracket and (sum w - 1) vanish unless the stencil is truncated by the domain boundary (:44-46); both are separable.
-        float dxp = dt * va[0], dyp = dt * va[1], dzp = dt * va[2];
-        if (!complete) {
-            const float sx = ax.N[0] + ax.N[1] + ax.N[2] + ax.N[3], sy = ay.N[0] + ay.N[1] + ay.N[2] + ay.N[3], sz = az.N[0] + az.N[1] + az.N[2] + az.N[3];
-            const float mx = nrx[0] + nrx[1] + nrx[2] + nrx[3];
-            const float my = ay.N[0] * ry[0] + ay.N[1] * ry[1] + ay.N[2] * ry[2] + ay.N[3] * ry[3];
-            const float mz = az.N[0] * rz[0] + az.N[1] * rz[1] + az.N[2] * rz[2] + az.N[3] * rz[3];
-            const float s0 = sx * sy * sz;
-            const float xw = fmaf((float)ci + X.x, G.hx, G.mnx), yw = fmaf((float)cj + X.y, G.hy, G.mny), zw = fmaf((float)ck + X.z, G.hz, G.mnz);
-            dxp += mx * sy * sz + (s0 - 1.0f) * xw; dyp += sx * my * sz + (s0 - 1.0f) * yw; dzp += sx * sy * mz + (s0 - 1.0f) * zw;
-        }
-        float nfx = fmaf(dxp, G.ihx, X.x), nfy = fmaf(dyp, G.ihy, X.y), nfz = fmaf(dzp, G.ihz, X.z);
-        {
-            const float flx = floorf(nfx), fly = floorf(nfy), flz = floorf(nfz);
-            nfx -= flx; nfy -= fly; nfz -= flz; ci += (int)flx; cj += (int)fly; ck += (int)flz;
-            nfx = fminf(nfx, 0.99999994f); nfy = fminf(nfy, 0.99999994f); nfz = fminf(nfz, 0.99999994f);
-            const int cci = clampi(ci, 0, G.nx - 1), ccj = clampi(cj, 0, G.ny - 1), cck = clampi(ck, 0, G.nz - 1);
-            const bool nan = !(nfx == nfx) || !(nfy == nfy) || !(nfz == nfz);
-            if (cci != ci || ccj != cj || cck != ck || nan) {
-                if (live) atomicAdd(&clk->escaped, 1ull);
-                if (!(nfx == nfx)) nfx = 0.5f;
-                if (!(nfy == nfy)) nfy = 0.5f;
-                if (!(nfz == nfz)) nfz = 0.5f;
-            }
-            ci = cci; cj = ccj; ck = cck;
-        }
-        // ---- deformation gradient + plasticity
-        const float4 e0 = W.eq[0][lane], e1 = W.eq[1][lane], e2 = W.eq[2][lane];
-        const float4 q0 = W.eq[3][lane], q1 = W.eq[4][lane], q2 = W.eq[5][lane];
-        float FE[9] = { e0.x, e0.y, e0.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z };
-        float FP[9] = { q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z };
-        float GF[9], Fh[9];
-        mat_mul(g, FE, GF);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Fh[i] = fmaf(dt, GF[i], FE[i]);                  // HybridSolver.cpp:575
-        float q = e1.w;
-        return_map(mpar, Fh, FE, FP, q);
-        const float Jp = mat_det(FP);
-        // ---- write back
-        const int ncell = cell_pack(ci, cj, ck);
-        {   // particles that left their cell are out of order until the next physical sort
-            const unsigned mv = __ballot_sync(0xffffffffu, live && ncell != cell);
-            if ((threadIdx.x & 31) == 0 && mv) atomicAdd(&clk->moved_since_sort, (unsigned long long)__popc(mv));
-        }
-        if (live) {
-            P.a[PX][p] = make_float4(nfx, nfy, nfz, __int_as_float(ncell));
-            P.a[PVM][p] = make_float4(vp[0], vp[1], vp[2], q1.w);
-            P.a[PC0][p] = make_float4(B[0], B[1], B[2], 0.f);
-            P.a[PC1][p] = make_float4(B[3], B[4], B[5], 0.f);
-            P.a[PC2][p] = make_float4(B[6], B[7], B[8], 0.f);
-            P.a[PE0][p] = make_float4(FE[0], FE[1], FE[2], e0.w);
-            P.a[PE1][p] = make_float4(FE[3], FE[4], FE[5], q);
-            P.a[PE2][p] = make_float4(FE[6], FE[7], FE[8], Jp);
-            P.a[PQ0][p] = make_float4(FP[0], FP[1], FP[2], q0.w);
-            P.a[PQ1][p] = make_float4(FP[3], FP[4], FP[5], q1.w);
-            P.a[PQ2][p] = make_float4(FP[6], FP[7], FP[8], q2.w);
-            keys[p] = sort_key(ci, cj, ck, G);
-            vals[p] = (unsigned)p;
-            if (ML.axis >= 0 && q1.w != 0.0f) {                                     // live particle of a slab context: did it leave the slab?
-                const int ca = ML.axis == 0 ? ci : (ML.axis == 1 ? cj : ck);
-                if (ca < ML.lo || ca >= ML.hi) {
-                    const int side = ca < ML.lo ? 0 : 1;
-                    const unsigned long long slot = atomicAdd(ML.counts + side, 1ull);
-                    if (slot < (unsigned long long)ML.cap) (side == 0 ? ML.list[0] : ML.list[1])[slot] = (unsigned)p;
-                }
-            }
-        }
-        if (!more) break;
-        // F_E / F_P of the next chunk and X of the one after it: this lane's slots were consumed above
-        {
-            const int pn = min(next * 32 + lane, n - 1);
-#pragma unroll
-            for (int a = 0; a < 6; ++a) cp_async16_stream(&W.eq[a][lane], P.a[PE0 + a] + pn);
-            if (next + wstride < nchunks) cp_async16_stream(&W.x[buf][lane], P.a[PX] + min((next + wstride) * 32 + lane, n - 1));
-            cp_async_commit();                                              // group "particle data" of the next chunk
-        }
-        chunk = next; buf ^= 1;
-    }
-}
-
-inline void g2p_launch(cudaStream_t st, int sm_count, const PartP& P, const GridP& G, const MatParams& mat, SimClock* clk, unsigned int* keys,
-                       unsigned int* vals, long long n, const MigList& ML) {
-    const long long chunks = (n + 31) / 32, per_cta = G2P_NT / 32;
-    const int grid = (int)std::min<long long>((chunks + per_cta - 1) / per_cta, (long long)sm_count * G2P_CTAS_PER_SM);
-    k_g2p<<<grid, G2P_NT, 0, st>>>(P, G, mat, clk, keys, vals, (int)n, ML);
-}
-
-#else
-// updateParticleVelocities_ (HybridSolver.cpp:739-745), updateAffineMomenta_ with damp 0 (:760-825, :908-917),
-// advection x = sum w (x_i + dt v~_i) (:942-945), updateDeformationGradient_ (:553-578), updatePlasticity_
-// (:612-681), all in registers, one thread per particle.  The 64-node gather sums along x first (per (j,k) row:
-// a = sum v~ Nx, b = sum v~ Dx, c = sum s v~ Nx, d = sum s v~ Nx rx), then combines rows.  Writes the new sort key.
-#define G2P_NT 128
-__global__ void __launch_bounds__(G2P_NT, 4) k_g2p(PartP P, GridP G, MatParams mpar, SimClock* __restrict__ clk,
-                                             unsigned int* __restrict__ keys, unsigned int* __restrict__ vals, int n, MigList ML) {
-    __shared__ float4 tiles[G2P_NT / 32][TILE_F4];
-    float4* tile = tiles[threadIdx.x >> 5];
-    const int p_raw = blockIdx.x * G2P_NT + threadIdx.x;
-    if ((p_raw & ~31) >= n) return;                                         // whole warp past the end
-    const bool live = p_raw < n;                                            // tail lanes recompute the last particle and write nothing:
-    const int p = live ? p_raw : n - 1;                                     // the warp stays converged for the votes below
-    // the deformation gradients are needed only after the gather: pull their lines towards the SM now
-    prefetch_l1(P.a[PE0] + p); prefetch_l1(P.a[PE1] + p); prefetch_l1(P.a[PE2] + p);
-    prefetch_l1(P.a[PQ0] + p); prefetch_l1(P.a[PQ1] + p); prefetch_l1(P.a[PQ2] + p);
-    const float dt = clk->dt;
-    const float4 X = ldg4(P.a[PX] + p);
-    const int cell = __float_as_int(X.w);
-    int ci = cell_i(cell), cj = cell_j(cell), ck = cell_k(cell);
-    Axis ax, ay, az;
-    bool complete = axis_setup(ax, X.x, ci, G.nx, G.ihx);
-    complete &= axis_setup(ay, X.y, cj, G.ny, G.ihy);
-    complete &= axis_setup(az, X.z, ck, G.nz, G.ihz);
-    float rx[4], ry[4], rz[4];                                              // x_i - x_p per axis: h (o - 1 - f)
-#pragma unroll
-    for (int o = 0; o < 4; ++o) { rx[o] = G.hx * ((float)(o - 1) - X.x); ry[o] = G.hy * ((float)(o - 1) - X.y); rz[o] = G.hz * ((float)(o - 1) - X.z); }
-    float nrx[4];
-#pragma unroll
-    for (int o = 0; o < 4; ++o) nrx[o] = ax.N[o] * rx[o];
-    G2PSums S;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { S.vc[i] = 0.f; S.va[i] = 0.f; }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { S.B[i] = 0.f; S.g[i] = 0.f; }
-    S.smin = 1.0f;
-    TileRef T;
-    if (stage_tile(G, tile, T, cell, complete)) {
-        g2p_gather<2>(G, ax, ay, az, nrx, rx, ry, rz, tile, ax.n0 - T.ox0, S);
-        if (S.smin == 0.0f) g2p_stick_correction<2>(G, ax, ay, az, rx, ry, rz, tile, ax.n0 - T.ox0, S);
-    } else {                                                                 // rare: row ends, freshly moved particles, domain faces
-        g2p_gather<AEP_FALLBACK_MODE>(G, ax, ay, az, nrx, rx, ry, rz, tile, 0, S);
-        if (S.smin == 0.0f) g2p_stick_correction<0>(G, ax, ay, az, rx, ry, rz, tile, 0, S);
-    }
-    float (&va)[3] = S.va; float (&B)[9] = S.B; float (&g)[9] = S.g;
-    const float vp[3] = { S.va[0] + S.vc[0], S.va[1] + S.vc[1], S.va[2] + S.vc[2] };       // sum w s v~ = sum w v~ - sum_{s=0} w v~
-    // ---- advection (HybridSolver.cpp:944): x' = sum w (x_i + dt v~_i) = x + [sum w (x_i - x)] + (sum w - 1) x + dt sum w v~
-    // the bracket and (sum w - 1) vanish unless the stencil is truncated by the domain boundary (:44-46); both are separable.
-    float dxp = dt * va[0], dyp = dt * va[1], dzp = dt * va[2];
-    if (!complete) {
-        const float sx = ax.N[0] + ax.N[1] + ax.N[2] + ax.N[3], sy = ay.N[0] + ay.N[1] + ay.N[2] + ay.N[3], sz = az.N[0] + az.N[1] + az.N[2] + az.N[3];
-        const float mx = nrx[0] + nrx[1] + nrx[2] + nrx[3];
-        const float my = ay.N[0] * ry[0] + ay.N[1] * ry[1] + ay.N[2] * ry[2] + ay.N[3] * ry[3];
-        const float mz = az.N[0] * rz[0] + az.N[1] * rz[1] + az.N[2] * rz[2] + az.N[3] * rz[3];
-        const float s0 = sx * sy * sz;
-        const float xw = fmaf((float)ci + X.x, G.hx, G.mnx), yw = fmaf((float)cj + X.y, G.hy, G.mny), zw = fmaf((float)ck + X.z, G.hz, G.mnz);
-        dxp += mx * sy * sz + (s0 - 1.0f) * xw; dyp += sx * my * sz + (s0 - 1.0f) * yw; dzp += sx * sy * mz + (s0 - 1.0f) * zw;
-    }
-    float nfx = fmaf(dxp, G.ihx, X.x), nfy = fmaf(dyp, G.ihy, X.y), nfz = fmaf(dzp, G.ihz, X.z);
-    {
-        const float flx = floorf(nfx), fly = floorf(nfy), flz = floorf(nfz);
-        nfx -= flx; nfy -= fly; nfz -= flz; ci += (int)flx; cj += (int)fly; ck += (int)flz;
-        nfx = fminf(nfx, 0.99999994f); nfy = fminf(nfy, 0.99999994f); nfz = fminf(nfz, 0.99999994f);
-        const int cci = clampi(ci, 0, G.nx - 1), ccj = clampi(cj, 0, G.ny - 1), cck = clampi(ck, 0, G.nz - 1);
-        const bool nan = !(nfx == nfx) || !(nfy == nfy) || !(nfz == nfz);
-        if (cci != ci || ccj != cj || cck != ck || nan) {
-            if (live) atomicAdd(&clk->escaped, 1ull);
-            if (!(nfx == nfx)) nfx = 0.5f;
-            if (!(nfy == nfy)) nfy = 0.5f;
-            if (!(nfz == nfz)) nfz = 0.5f;
-        }
-        ci = cci; cj = ccj; ck = cck;
-    }
-    // ---- deformation gradient + plasticity
-    const float4 e0 = ldg4(P.a[PE0] + p), e1 = ldg4(P.a[PE1] + p), e2 = ldg4(P.a[PE2] + p);
-    const float4 q0 = ldg4(P.a[PQ0] + p), q1 = ldg4(P.a[PQ1] + p), q2 = ldg4(P.a[PQ2] + p);
-    float FE[9] = { e0.x, e0.y, e0.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z };
-    float FP[9] = { q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z };
-    float GF[9], Fh[9];
-    mat_mul(g, FE, GF);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) Fh[i] = fmaf(dt, GF[i], FE[i]);                  // HybridSolver.cpp:575
-    float q = e1.w;
-    return_map(mpar, Fh, FE, FP, q);
-    const float Jp = mat_det(FP);
-    // ---- write back
-    const int ncell = cell_pack(ci, cj, ck);
-    {   // particles that left their cell are out of order until the next physical sort
-        const unsigned mv = __ballot_sync(0xffffffffu, live && ncell != cell);
-        if ((threadIdx.x & 31) == 0 && mv) atomicAdd(&clk->moved_since_sort, (unsigned long long)__popc(mv));
-    }
-    if (!live) return;
-    P.a[PX][p] = make_float4(nfx, nfy, nfz, __int_as_float(ncell));
-    P.a[PVM][p] = make_float4(vp[0], vp[1], vp[2], q1.w);
-    P.a[PC0][p] = make_float4(B[0], B[1], B[2], 0.f);
-    P.a[PC1][p] = make_float4(B[3], B[4], B[5], 0.f);
-    P.a[PC2][p] = make_float4(B[6], B[7], B[8], 0.f);
-    P.a[PE0][p] = make_float4(FE[0], FE[1], FE[2], e0.w);
-    P.a[PE1][p] = make_float4(FE[3], FE[4], FE[5], q);
-    P.a[PE2][p] = make_float4(FE[6], FE[7], FE[8], Jp);
-    P.a[PQ0][p] = make_float4(FP[0], FP[1], FP[2], q0.w);
-    P.a[PQ1][p] = make_float4(FP[3], FP[4], FP[5], q1.w);
-    P.a[PQ2][p] = make_float4(FP[6], FP[7], FP[8], q2.w);
-    keys[p] = sort_key(ci, cj, ck, G);
-    vals[p] = (unsigned)p;
-    if (ML.axis >= 0 && q1.w != 0.0f) {                                     // live particle of a slab context: did it leave the slab?
-        const int ca = ML.axis == 0 ? ci : (ML.axis == 1 ? cj : ck);
-        if (ca < ML.lo || ca >= ML.hi) {
-            const int side = ca < ML.lo ? 0 : 1;
-            const unsigned long long slot = atomicAdd(ML.counts + side, 1ull);
-            if (slot < (unsigned long long)ML.cap) (side == 0 ? ML.list[0] : ML.list[1])[slot] = (unsigned)p;
-        }
-    }
-}
-
-inline void g2p_launch(cudaStream_t st, int sm_count, const PartP& P, const GridP& G, const MatParams& mat, SimClock* clk, unsigned int* keys,
-                       unsigned int* vals, long long n, const MigList& ML) {
-    (void)sm_count;
-    k_g2p<<<(unsigned)((n + G2P_NT - 1) / G2P_NT), G2P_NT, 0, st>>>(P, G, mat, clk, keys, vals, (int)n, ML);
-}
-
-#endif  // AEP_G2P_PIPE
 // ================================================================================================ host <-> device
 // fp64 reference layouts -> packed fp32 records.  `st` is a staged chunk: columns of length cnt, in the order
 // x(3) v(3) B1(3) B2(3) B3(3) m vol q, then FE (cnt x 9, column-major per particle), FP likewise.
@@ -952,10 +630,9 @@ __global__ void k_upload_convert(PartP P, GridP G, const double* __restrict__ st
     const int d = dst0 + i;
     const float m = (float)col(15);
     P.a[PX][d] = make_float4(fr[0], fr[1], fr[2], __int_as_float(cell_pack(ce[0], ce[1], ce[2])));
-    P.a[PVM][d] = make_float4((float)col(3), (float)col(4), (float)col(5), m);
-    P.a[PC0][d] = make_float4((float)col(6), (float)col(7), (float)col(8), 0.f);
-    P.a[PC1][d] = make_float4((float)col(9), (float)col(10), (float)col(11), 0.f);
-    P.a[PC2][d] = make_float4((float)col(12), (float)col(13), (float)col(14), 0.f);
+    P.a[PV][d] = make_float4((float)col(3), (float)col(4), (float)col(5), (float)col(6));
+    P.a[PC0][d] = make_float4((float)col(7), (float)col(8), (float)col(9), (float)col(10));
+    P.a[PC1][d] = make_float4((float)col(11), (float)col(12), (float)col(13), (float)col(14));
     const double* fe = st + (size_t)18 * cnt + (size_t)9 * i;    // column-major 3x3: (r,c) at 3c + r
     const double* fp = st + (size_t)27 * cnt + (size_t)9 * i;
     float FP[9];
@@ -966,69 +643,80 @@ __global__ void k_upload_convert(PartP P, GridP G, const double* __restrict__ st
     P.a[PE0][d] = make_float4((float)fe[0], (float)fe[3], (float)fe[6], (float)col(16));
     P.a[PE1][d] = make_float4((float)fe[1], (float)fe[4], (float)fe[7], (float)col(17));
     P.a[PE2][d] = make_float4((float)fe[2], (float)fe[5], (float)fe[8], mat_det(FP));
-    P.a[PQ0][d] = make_float4(FP[0], FP[1], FP[2], __int_as_float((int)(id0 + i)));
-    P.a[PQ1][d] = make_float4(FP[3], FP[4], FP[5], m);
+    P.a[PQ0][d] = make_float4(FP[0], FP[1], FP[2], 0.f);
+    P.a[PQ1][d] = make_float4(FP[3], FP[4], FP[5], 0.f);
     P.a[PQ2][d] = make_float4(FP[6], FP[7], FP[8], 0.f);
+    P.a[PK][d] = make_float4(m, __int_as_float((int)(id0 + i)), 0.f, 0.f);
 }
 
-// packed records [s0, s0+cnt) -> staged fp64 chunk for original ids [id0, id0+cnt_ids): scatter by id.
+// one particle's state as the fp64 staging columns (shared by the id-ordered and the slot-ordered download)
 // out columns: x(3) v(3) B1(3) B2(3) B3(3) vol q, then FE, FP (9 each, column-major per particle)
-__global__ void k_download_convert(PartP P, GridP G, double* __restrict__ st, int n, long long id0, int cnt_ids,
-                                   double mnx, double mny, double mnz, double hx, double hy, double hz) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const float4 q0 = P.a[PQ0][s];
-    const long long id = (long long)__float_as_int(q0.w) - id0;
-    if (id < 0 || id >= cnt_ids) return;
-    const size_t i = (size_t)id, cnt = (size_t)cnt_ids;
-    const float4 X = P.a[PX][s], VM = P.a[PVM][s], c0 = P.a[PC0][s], c1 = P.a[PC1][s], c2 = P.a[PC2][s];
-    const float4 e0 = P.a[PE0][s], e1 = P.a[PE1][s], e2 = P.a[PE2][s], q1 = P.a[PQ1][s], q2 = P.a[PQ2][s];
+__device__ __forceinline__ void download_one(const PartP& P, int s, double* __restrict__ st, size_t i, size_t cnt,
+                                             double mnx, double mny, double mnz, double hx, double hy, double hz) {
+    const float4 X = P.a[PX][s], V = P.a[PV][s], C0 = P.a[PC0][s], C1 = P.a[PC1][s];
+    const float4 e0 = P.a[PE0][s], e1 = P.a[PE1][s], e2 = P.a[PE2][s], q0 = P.a[PQ0][s], q1 = P.a[PQ1][s], q2 = P.a[PQ2][s];
     const int cell = __float_as_int(X.w);
     st[0 * cnt + i] = mnx + ((double)cell_i(cell) + (double)X.x) * hx;
     st[1 * cnt + i] = mny + ((double)cell_j(cell) + (double)X.y) * hy;
     st[2 * cnt + i] = mnz + ((double)cell_k(cell) + (double)X.z) * hz;
-    st[3 * cnt + i] = VM.x; st[4 * cnt + i] = VM.y; st[5 * cnt + i] = VM.z;
-    st[6 * cnt + i] = c0.x; st[7 * cnt + i] = c0.y; st[8 * cnt + i] = c0.z;
-    st[9 * cnt + i] = c1.x; st[10 * cnt + i] = c1.y; st[11 * cnt + i] = c1.z;
-    st[12 * cnt + i] = c2.x; st[13 * cnt + i] = c2.y; st[14 * cnt + i] = c2.z;
+    st[3 * cnt + i] = V.x; st[4 * cnt + i] = V.y; st[5 * cnt + i] = V.z;
+    st[6 * cnt + i] = V.w; st[7 * cnt + i] = C0.x; st[8 * cnt + i] = C0.y;
+    st[9 * cnt + i] = C0.z; st[10 * cnt + i] = C0.w; st[11 * cnt + i] = C1.x;
+    st[12 * cnt + i] = C1.y; st[13 * cnt + i] = C1.z; st[14 * cnt + i] = C1.w;
     st[15 * cnt + i] = e0.w; st[16 * cnt + i] = e1.w;
     double* fe = st + 17 * cnt + 9 * i; double* fp = st + 26 * cnt + 9 * i;
     fe[0] = e0.x; fe[3] = e0.y; fe[6] = e0.z; fe[1] = e1.x; fe[4] = e1.y; fe[7] = e1.z; fe[2] = e2.x; fe[5] = e2.y; fe[8] = e2.z;
     fp[0] = q0.x; fp[3] = q0.y; fp[6] = q0.z; fp[1] = q1.x; fp[4] = q1.y; fp[7] = q1.z; fp[2] = q2.x; fp[5] = q2.y; fp[8] = q2.z;
 }
+// packed records [0, n) -> staged fp64 chunk for original ids [id0, id0+cnt_ids): scatter by id.
+__global__ void k_download_convert(PartP P, double* __restrict__ st, int n, long long id0, int cnt_ids,
+                                   double mnx, double mny, double mnz, double hx, double hy, double hz) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const float4 kk = P.a[PK][s];
+    const long long id = (long long)__float_as_int(kk.y) - id0;
+    if (id < 0 || id >= cnt_ids) return;
+    download_one(P, s, st, (size_t)id, (size_t)cnt_ids, mnx, mny, mnz, hx, hy, hz);
+}
 
-__global__ void k_download_positions_f32(PartP P, GridP G, float* __restrict__ out, int n, int by_slot) {
+// positions only.  by_slot: out[3*slot]; else out[3*(id - id_base)] with a bounds check (ids of a context are id_base + 0..n_ids)
+__global__ void k_download_positions_f32(PartP P, GridP G, float* __restrict__ out, int n, int by_slot, long long id_base, long long n_ids) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const float4 X = P.a[PX][s];
-    const int id = by_slot ? s : __float_as_int(P.a[PQ0][s].w);
+    long long id = s;
+    if (!by_slot) { id = (long long)__float_as_int(P.a[PK][s].y) - id_base; if (id < 0 || id >= n_ids) return; }
     const int cell = __float_as_int(X.w);
     out[3 * (size_t)id + 0] = fmaf((float)cell_i(cell) + X.x, G.hx, G.mnx);
     out[3 * (size_t)id + 1] = fmaf((float)cell_j(cell) + X.y, G.hy, G.mny);
     out[3 * (size_t)id + 2] = fmaf((float)cell_k(cell) + X.z, G.hz, G.mnz);
 }
 
-// grid -> fp64 reference layout (Ng x 3 column-major).  mode 0: after P2G (v = p/m); mode 1: after grid update
-// (v = s v~, vt = v~).  Forces get the gravity term the reference folds in at HybridSolver.cpp:457.
+// grid -> fp64 reference layout (Ng x 3 column-major, node index (k*ny + j)*nx + i).  mode 0: after P2G (v = p/m); mode 1: after
+// grid update (v = s v~, vt = v~).  Forces get the gravity term the reference folds in at HybridSolver.cpp:457.  Nodes that a slab
+// context does not hold come back as zeros.
 __global__ void k_download_grid(GridP G, double* __restrict__ m, double* __restrict__ v, double* __restrict__ f,
-                                double* __restrict__ vt, long long n0, long long cnt, long long Ng, int mode) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cnt) return;
-    const size_t n = (size_t)(n0 + i);
-    const float4 mp = G.mp[n], ff = G.f[n];
-    if (m) m[i] = mp.x;
-    if (f) { f[i] = ff.x; f[cnt + i] = ff.y; f[2 * cnt + i] = (double)ff.z - (double)G.gravity * (double)mp.x; }
-    const int b = (((int)(n / ((size_t)G.nx * G.ny)) >> 3) * G.nby + ((int)((n / G.nx) % G.ny) >> 3)) * G.nbx + ((int)(n % G.nx) >> 3);
-    const bool act = G.flags[b] != 0;
+                                double* __restrict__ vt, long long n0, long long cnt, int mode) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    const long long g = n0 + t;
+    const int i = (int)(g % G.nx), j = (int)((g / G.nx) % G.ny), k = (int)(g / ((long long)G.nx * G.ny));
+    float4 mp = make_float4(0.f, 0.f, 0.f, 0.f), ff = mp, tv = mp;
+    const bool held = node_held(G, i, j, k);
+    const size_t n = held ? nidx(G, i, j, k) : 0;
+    if (held) { mp = G.mp[n]; ff = G.f[n]; }
+    if (m) m[t] = mp.x;
+    if (f) { f[t] = ff.x; f[cnt + t] = ff.y; f[2 * cnt + t] = (double)ff.z - (double)G.gravity * (double)mp.x; }
+    const bool act = held && G.flags[((k >> 3) * G.nby + (j >> 3)) * G.nbx + (i >> 3)] != 0;
     if (mode == 0) {
         if (v) {
             const double im = mp.x > 0.0f ? 1.0 / (double)mp.x : 0.0;
-            v[i] = mp.y * im; v[cnt + i] = mp.z * im; v[2 * cnt + i] = mp.w * im;
+            v[t] = mp.y * im; v[cnt + t] = mp.z * im; v[2 * cnt + t] = mp.w * im;
         }
     } else {
-        const float4 t = act ? G.vt[n] : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (v) { v[i] = t.w * t.x; v[cnt + i] = t.w * t.y; v[2 * cnt + i] = t.w * t.z; }
-        if (vt) { vt[i] = t.x; vt[cnt + i] = t.y; vt[2 * cnt + i] = t.z; }
+        if (act) tv = G.vt[n];
+        if (v) { v[t] = tv.w * tv.x; v[cnt + t] = tv.w * tv.y; v[2 * cnt + t] = tv.w * tv.z; }
+        if (vt) { vt[t] = tv.x; vt[cnt + t] = tv.y; vt[2 * cnt + t] = tv.z; }
     }
 }
 
@@ -1040,9 +728,8 @@ __global__ void __launch_bounds__(256) k_count_active(GridP G, unsigned long lon
     int cnt = 0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int t = threadIdx.x + 256 * h;
-        const int i = bx * 8 + (t & 7), j = by * 8 + ((t >> 3) & 7), k = bz * 8 + (t >> 6);
-        if (i < G.nx && j < G.ny && k < G.nz) cnt += G.mp[((size_t)k * G.ny + j) * G.nx + i].x > 0.0f;
+        size_t n; bool valid;
+        if (block_node(G, bx, by, bz, threadIdx.x + 256 * h, n, valid) && valid) cnt += G.mp[n].x > 0.0f;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -1050,26 +737,28 @@ __global__ void __launch_bounds__(256) k_count_active(GridP G, unsigned long lon
     if (threadIdx.x == 0) atomicAdd(out2, 1ull);
 }
 
-// bulk statistics (double accumulation): sum m x (3), sum 0.5 m v^2, sum det FP, sum m
-__global__ void __launch_bounds__(256) k_stats(PartP P, GridP G, double* __restrict__ out6, int n) {
-    double acc[6] = {0, 0, 0, 0, 0, 0};
+// bulk statistics (double accumulation): sum m x (3), sum 0.5 m v^2, sum det FP, sum m, live particles
+__global__ void __launch_bounds__(256) k_stats(PartP P, GridP G, double* __restrict__ out7, const SimClock* __restrict__ clk) {
+    const int n = clk->n_slots;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
-        const float4 X = P.a[PX][s], VM = P.a[PVM][s];
+        const float4 X = P.a[PX][s], V = P.a[PV][s];
         const int cell = __float_as_int(X.w);
-        const double m = VM.w;
+        const double m = P.a[PK][s].x;
         acc[0] += m * ((double)G.mnx + ((double)cell_i(cell) + X.x) * (double)G.hx);
         acc[1] += m * ((double)G.mny + ((double)cell_j(cell) + X.y) * (double)G.hy);
         acc[2] += m * ((double)G.mnz + ((double)cell_k(cell) + X.z) * (double)G.hz);
-        acc[3] += 0.5 * m * ((double)VM.x * VM.x + (double)VM.y * VM.y + (double)VM.z * VM.z);
+        acc[3] += 0.5 * m * ((double)V.x * V.x + (double)V.y * V.y + (double)V.z * V.z);
         acc[4] += m > 0.0 ? (double)P.a[PE2][s].w : 0.0;          // dead slots of a slab context carry no mass and are not counted
         acc[5] += m;
+        acc[6] += m > 0.0 ? 1.0 : 0.0;
     }
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < 7; ++k) {
         double v = acc[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(out6 + k, v);
+        if ((threadIdx.x & 31) == 0) atomicAdd(out7 + k, v);
     }
 }
 

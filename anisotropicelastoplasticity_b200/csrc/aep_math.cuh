@@ -180,6 +180,11 @@ struct MatParams {
     int material;              // 0 snow, 1 sand
 };
 
+// ln s for a singular value s of an elastic deformation gradient (s ~ 1): s - 1 is exact in fp32 for s in [1/2, 2], and log1p keeps
+// full relative accuracy of the *strain*, which is what the stress and the yield function see (logf(s) alone rounds s to 6e-8
+// relative first, i.e. 1e-4 of a 1e-3 strain).
+__device__ __forceinline__ float hencky(float s) { return log1pf(s - 1.0f); }
+
 // First Piola stress times F_E^T times volume:  A = V_p * P(Fhat) * FE^T       HybridSolver.cpp:314-339
 __device__ __forceinline__ void stress_times_FEt(const MatParams& mp, const float (&Fh)[9], const float (&FE)[9],
                                                  float vol, float Jp, float (&A)[9]) {
@@ -199,7 +204,7 @@ __device__ __forceinline__ void stress_times_FEt(const MatParams& mp, const floa
         for (int i = 0; i < 9; ++i) P[i] = fmaf(k, cof[i], P[i]);
     } else {
         // sand, Hencky strain:  P = U diag(2 mu ln s / s + lambda tr(ln s) / s) V^T
-        const float l0 = logf(sv.S[0]), l1 = logf(sv.S[1]), l2 = logf(sv.S[2]);
+        const float l0 = hencky(sv.S[0]), l1 = hencky(sv.S[1]), l2 = hencky(sv.S[2]);
         const float tr = l0 + l1 + l2;
         const float d[3] = { (2.0f * mp.mu0 * l0 + mp.lambda0 * tr) / sv.S[0], (2.0f * mp.mu0 * l1 + mp.lambda0 * tr) / sv.S[1],
                              (2.0f * mp.mu0 * l2 + mp.lambda0 * tr) / sv.S[2] };
@@ -210,12 +215,15 @@ __device__ __forceinline__ void stress_times_FEt(const MatParams& mp, const floa
     for (int i = 0; i < 9; ++i) A[i] = vol * T[i];
 }
 
-// Plastic return mapping on the candidate Fhat (in: Fh, FP, q; out: FE, FP, q).      HybridSolver.cpp:612-681
+// Plastic return mapping on the candidate Fhat, in two parts so that the caller touches F_P only for particles that yield:
+//   return_map_project   SVD of Fhat, projection of the singular values (snow clamp / Drucker-Prager), hardening state q;
+//                        returns whether any singular value changed                                 HybridSolver.cpp:612-673
+//   return_map_apply     FE = U S' V^T,  FP = V S'^-1 U^T Fhat FP                                   HybridSolver.cpp:618-619, 675-677
 // When the projection leaves the singular values untouched the reference's U S V^T / V S^-1 U^T Ftot round trip
 // is the identity in exact arithmetic, so FE = Fhat and FP is left alone (closest to the fp64 reference).
-__device__ __forceinline__ void return_map(const MatParams& mp, const float (&Fh)[9], float (&FE)[9], float (&FP)[9], float& q) {
-    Svd3 sv; svd3(Fh, sv);
-    float sn[3] = { sv.S[0], sv.S[1], sv.S[2] };
+__device__ __forceinline__ bool return_map_project(const MatParams& mp, const float (&Fh)[9], Svd3& sv, float (&sn)[3], float& q) {
+    svd3(Fh, sv);
+    sn[0] = sv.S[0]; sn[1] = sv.S[1]; sn[2] = sv.S[2];
     bool changed = false;
     if (mp.material == 0) {
 #pragma unroll
@@ -228,7 +236,7 @@ __device__ __forceinline__ void return_map(const MatParams& mp, const float (&Fh
         const float phi = (mp.h0 + (mp.h1 * q - mp.h3) * expf(-mp.h2 * q)) * (PI_F / 180.0f);      // HybridSolver.cpp:646-647
         const float sp = sinf(phi);
         const float alpha = 0.81649658092772603f * 2.0f * sp / (3.0f - sp);                          // sqrt(2/3), :649-650
-        const float l0 = logf(sn[0]), l1 = logf(sn[1]), l2 = logf(sn[2]);
+        const float l0 = hencky(sn[0]), l1 = hencky(sn[1]), l2 = hencky(sn[2]);
         const float tr = l0 + l1 + l2;
         const float m3 = tr * (1.0f / 3.0f);
         const float d0 = l0 - m3, d1 = l1 - m3, d2 = l2 - m3;
@@ -244,16 +252,24 @@ __device__ __forceinline__ void return_map(const MatParams& mp, const float (&Fh
             q += dg; changed = true;
         }
     }
-    if (!changed) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) FE[i] = Fh[i];
-        return;
-    }
+    return changed;
+}
+__device__ __forceinline__ void return_map_apply(const Svd3& sv, const float (&sn)[3], const float (&Fh)[9], float (&FE)[9], float (&FP)[9]) {
     float Ftot[9]; mat_mul(Fh, FP, Ftot);                                            // :618-619
     usvt(sv.U, sn, sv.V, FE);                                                        // :675
     const float inv[3] = { 1.0f / sn[0], 1.0f / sn[1], 1.0f / sn[2] };
     float Mi[9]; usvt(sv.V, inv, sv.U, Mi);                                          // V S^-1 U^T
     mat_mul(Mi, Ftot, FP);                                                           // :676-677
+}
+// both parts (in: Fh, FP, q; out: FE, FP, q)
+__device__ __forceinline__ void return_map(const MatParams& mp, const float (&Fh)[9], float (&FE)[9], float (&FP)[9], float& q) {
+    Svd3 sv; float sn[3];
+    if (!return_map_project(mp, Fh, sv, sn, q)) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) FE[i] = Fh[i];
+        return;
+    }
+    return_map_apply(sv, sn, Fh, FE, FP);
 }
 
 // ------------------------------------------------------------------------------------------------ QR (cloth)

@@ -20,11 +20,12 @@
 
 namespace aep {
 
+// Mesh points use the particle layout of aep_kernels.cuh for what the transfers touch: X, V = (v, B00), C0, C1 (rest of B), K = (m, -, -, -).
 struct MeshDev {
     // vertices
-    float4 *VX, *VVM, *VC0, *VC1, *VC2, *VF;       // VF: in-plane force accumulator
+    float4 *VX, *VV, *VC0, *VC1, *VK, *VKe, *VF;   // VF: in-plane force accumulator; VKe: K with the mass zeroed for points of other ranks
     // elements (one per face)
-    float4 *EX, *EVM, *EC0, *EC1, *EC2;
+    float4 *EX, *EV, *EC0, *EC1, *EK, *EKe;
     float4 *ED1, *ED2, *ED3;                       // current directions; ED3.w = element volume
     float4 *RD1, *RD2, *RD3;                       // rest directions
     float4* PK;                                    // (pk00, pk01, pk11, -) = invRest * P   LagrangianMesh.cpp:446
@@ -32,12 +33,27 @@ struct MeshDev {
     int* fixed_ids;
     float mu, lambda, gamma, kstiff, cf;
 };
+// Slab decomposition of the cloth (SURVEY 8e "Cloth"): every rank holds the whole mesh state; a rank transfers (scatters, gathers,
+// advects) only the points whose cell lies in its slab and receives the others' results from their owners.  In-plane forces are
+// computed redundantly by everyone (a pure function of the replicated state).  axis < 0: this context owns every point.
+struct MeshOwn {
+    int axis, lo, hi;
+};
+__device__ __forceinline__ bool mesh_owned(const MeshOwn& O, int cell) {
+    if (O.axis < 0) return true;
+    const int c = O.axis == 0 ? (cell & 1023) : (O.axis == 1 ? ((cell >> 10) & 1023) : ((cell >> 20) & 1023));
+    return c >= O.lo && c < O.hi;
+}
 
 struct MeshState {
     long long nv = 0, nf = 0;
     int n_fixed = 0;
     MeshDev d{};
-    std::vector<void*> allocs;
+    MeshOwn own{-1, 0, 0};
+    void* block = nullptr; size_t block_bytes = 0;  // every array above lives in this one allocation (peers map it with one IPC handle)
+    size_t sync_v_off = 0, sync_v_bytes = 0;        // byte range of the per-vertex / per-element arrays that G2P rewrites (owner -> peers)
+    size_t sync_e_off = 0, sync_e_bytes = 0;
+    unsigned char *owner_v = nullptr, *owner_e = nullptr;   // 1 where this rank did the G2P of the point in the current substep
     double mn[3]{}, h[3]{};
 };
 
@@ -85,7 +101,7 @@ __device__ __forceinline__ void point_gather(const GridP& G, const float4& X, Po
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int nj = clampi(ay.n0 + j, 0, G.ny - 1);
-            const size_t row = ((size_t)nk * G.ny + nj) * G.nx;
+            const size_t row = nidx(G, 0, nj, nk);
             const float nn = ay.N[j] * az.N[k], dn = ay.D[j] * az.N[k], nd = ay.N[j] * az.D[k];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -143,8 +159,24 @@ __device__ __forceinline__ void warp_scatter_stress(const GridP& G, float fx, fl
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
+// ownership snapshot of a substep (slab contexts only): flags + the masses the P2G of this substep sees (0 for points of other ranks)
+__global__ void __launch_bounds__(256) k_mesh_own(MeshDev M, MeshOwn O, const SimClock* __restrict__ clk, unsigned char* __restrict__ owner_v,
+                                                  unsigned char* __restrict__ owner_e, float4* __restrict__ VKe, float4* __restrict__ EKe, int nv, int nf) {
+    AEP_HALT_PRE(clk);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nv) {
+        const bool o = mesh_owned(O, __float_as_int(M.VX[t].w));
+        owner_v[t] = o ? 1 : 0; float4 kk = M.VK[t]; if (!o) kk.x = 0.f; VKe[t] = kk;
+    } else if (t - nv < nf) {
+        const int f = t - nv;
+        const bool o = mesh_owned(O, __float_as_int(M.EX[f].w));
+        owner_e[f] = o ? 1 : 0; float4 kk = M.EK[f]; if (!o) kk.x = 0.f; EKe[f] = kk;
+    }
+}
+
 // LagrangianMesh::computeVertexInPlaneForces (LagrangianMesh.cpp:382-460), one thread per face
-__global__ void __launch_bounds__(128) k_cloth_inplane(MeshDev M, int nf) {
+__global__ void __launch_bounds__(128) k_cloth_inplane(MeshDev M, const SimClock* __restrict__ clk, int nf) {
+    AEP_HALT_PRE(clk);
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nf) return;
     const float4 e1 = M.ED1[f], e2 = M.ED2[f], e3 = M.ED3[f], r1 = M.RD1[f], r2 = M.RD2[f], r3 = M.RD3[f];
@@ -177,7 +209,8 @@ __global__ void __launch_bounds__(128) k_cloth_inplane(MeshDev M, int nf) {
 }
 
 // forces += vertexOmegas^T * vertexInPlaneForces  (HybridSolver.cpp:378), warp-cooperative, run length 1
-__global__ void __launch_bounds__(256) k_vertex_force_scatter(MeshDev M, GridP G, int nv) {
+__global__ void __launch_bounds__(256) k_vertex_force_scatter(MeshDev M, GridP G, const SimClock* __restrict__ clk, const unsigned char* __restrict__ owner, int nv) {
+    AEP_HALT_PRE(clk);
     const int lane = threadIdx.x & 31;
     const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
     if (base >= nv) return;
@@ -186,13 +219,15 @@ __global__ void __launch_bounds__(256) k_vertex_force_scatter(MeshDev M, GridP G
     float fx = 0.f, fy = 0.f, fz = 0.f, Fx = 0.f, Fy = 0.f, Fz = 0.f; int cell = 0;
     if (lane < cnt) {
         const float4 X = M.VX[base + lane], F = M.VF[base + lane];
-        fx = X.x; fy = X.y; fz = X.z; cell = __float_as_int(X.w); Fx = F.x; Fy = F.y; Fz = F.z;
+        fx = X.x; fy = X.y; fz = X.z; cell = __float_as_int(X.w);
+        if (!owner || owner[base + lane]) { Fx = F.x; Fy = F.y; Fz = F.z; }                      // points of other ranks add nothing here
     }
     const int oi = lane & 3, oj = (lane >> 2) & 3, ok = lane >> 4;
     for (int p = 0; p < cnt; ++p) {
         const int c = __shfl_sync(FULL, cell, p);
         const float pfx = __shfl_sync(FULL, fx, p), pfy = __shfl_sync(FULL, fy, p), pfz = __shfl_sync(FULL, fz, p);
         const float ax = __shfl_sync(FULL, Fx, p), ay = __shfl_sync(FULL, Fy, p), az = __shfl_sync(FULL, Fz, p);
+        if (ax == 0.f && ay == 0.f && az == 0.f) continue;
         float wx, wy, wz0, wz1, d;
         bspline_lane(pfx, oi, wx, d); bspline_lane(pfy, oj, wy, d); bspline_lane(pfz, ok, wz0, d); bspline_lane(pfz, ok + 2, wz1, d);
         const float w0 = wx * wy * wz0, w1 = wx * wy * wz1;
@@ -201,14 +236,15 @@ __global__ void __launch_bounds__(256) k_vertex_force_scatter(MeshDev M, GridP G
 }
 
 // normal / shear part of computeGridForces_ (HybridSolver.cpp:389-455)
-__global__ void __launch_bounds__(128) k_cloth_normal(MeshDev M, GridP G, int nf) {
+__global__ void __launch_bounds__(128) k_cloth_normal(MeshDev M, GridP G, const SimClock* __restrict__ clk, const unsigned char* __restrict__ owner, int nf) {
+    AEP_HALT_PRE(clk);
     const int lane = threadIdx.x & 31;
     const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
     if (base >= nf) return;
     const int cnt = min(32, nf - base);
     float fx = 0.f, fy = 0.f, fz = 0.f; int cell = 0;
     float A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (lane < cnt) {
+    if (lane < cnt && (!owner || owner[base + lane])) {
         const int f = base + lane;
         const float4 X = M.EX[f]; fx = X.x; fy = X.y; fz = X.z; cell = __float_as_int(X.w);
         const float4 e1 = M.ED1[f], e2 = M.ED2[f], e3 = M.ED3[f], pk = M.PK[f];
@@ -242,7 +278,8 @@ __global__ void __launch_bounds__(128) k_cloth_normal(MeshDev M, GridP G, int nf
 
 // pinned vertices: zero v and v~ in the 3x3x3 node block around every stencil node (HybridSolver.cpp:513-550).
 // Per-axis indices are NOT range checked, only the flat index (:538-539) -- reproduced, including the row wrap.
-__global__ void k_mesh_pin(MeshDev M, GridP G, int n_fixed) {
+__global__ void k_mesh_pin(MeshDev M, GridP G, const SimClock* __restrict__ clk, int n_fixed) {
+    AEP_HALT_PRE(clk);
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_fixed * 64) return;
     const int v = M.fixed_ids[t >> 6], e = t & 63;
@@ -256,37 +293,41 @@ __global__ void k_mesh_pin(MeshDev M, GridP G, int n_fixed) {
     if (ri < 0 || ri >= G.nx || rj < 0 || rj >= G.ny || rk < 0 || rk >= G.nz) return;
     const long long Ng = (long long)G.nx * G.ny * G.nz;
     for (int i = ri - 1; i <= ri + 1; ++i) for (int j = rj - 1; j <= rj + 1; ++j) for (int k = rk - 1; k <= rk + 1; ++k) {
-        const long long index = ((long long)k * G.ny + j) * G.nx + i;
-        if (index >= 0 && index < Ng) G.vt[index] = make_float4(0.f, 0.f, 0.f, 1.f);
+        const long long index = ((long long)k * G.ny + j) * G.nx + i;                            // the reference's flat index
+        if (index < 0 || index >= Ng) continue;
+        const int wi = (int)(index % G.nx), wj = (int)((index / G.nx) % G.ny), wk = (int)(index / ((long long)G.nx * G.ny));
+        if (node_held(G, wi, wj, wk)) G.vt[nidx(G, wi, wj, wk)] = make_float4(0.f, 0.f, 0.f, 1.f);
     }
 }
 
 // vertices: velocity, affine (damp 1), advection        HybridSolver.cpp:748, 920-926, 948
-__global__ void __launch_bounds__(128) k_vertex_g2p(MeshDev M, GridP G, const SimClock* __restrict__ clk, int nv) {
+__global__ void __launch_bounds__(128) k_vertex_g2p(MeshDev M, GridP G, const SimClock* __restrict__ clk, const unsigned char* __restrict__ owner, int nv) {
+    AEP_HALT_POST(clk);
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= nv) return;
+    if (v >= nv || (owner && !owner[v])) return;
     const float dt = clk->dt;
     const float4 X = M.VX[v];
     PointGather pg; point_gather(G, X, pg);
     skew_part(pg.B);
-    M.VVM[v] = make_float4(pg.vp[0], pg.vp[1], pg.vp[2], M.VVM[v].w);
-    M.VC0[v] = make_float4(pg.B[0], pg.B[1], pg.B[2], 0.f); M.VC1[v] = make_float4(pg.B[3], pg.B[4], pg.B[5], 0.f); M.VC2[v] = make_float4(pg.B[6], pg.B[7], pg.B[8], 0.f);
+    M.VV[v] = make_float4(pg.vp[0], pg.vp[1], pg.vp[2], pg.B[0]);
+    M.VC0[v] = make_float4(pg.B[1], pg.B[2], pg.B[3], pg.B[4]); M.VC1[v] = make_float4(pg.B[5], pg.B[6], pg.B[7], pg.B[8]);
     M.VX[v] = pos_offset(G, X, fmaf(dt, pg.va[0], pg.corr[0]), fmaf(dt, pg.va[1], pg.corr[1]), fmaf(dt, pg.va[2], pg.corr[2]));
 }
 
 // elements: mean vertex velocity (:749-756), affine at the OLD centroid (:927-933), d1/d2 from advected vertices and
 // d3 += dt grad v~ d3 (:584-606), cone return mapping (:684-722), new centroid (LagrangianMesh.cpp:371-380)
-__global__ void __launch_bounds__(128) k_element_g2p(MeshDev M, GridP G, const SimClock* __restrict__ clk, int nf) {
+__global__ void __launch_bounds__(128) k_element_g2p(MeshDev M, GridP G, const SimClock* __restrict__ clk, const unsigned char* __restrict__ owner, int nf) {
+    AEP_HALT_POST(clk);
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nf) return;
+    if (f >= nf || (owner && !owner[f])) return;
     const float dt = clk->dt;
     const float4 X = M.EX[f];
     PointGather pg; point_gather(G, X, pg);
     skew_part(pg.B);
     const int4 fa = M.faces[f];
-    const float4 va = M.VVM[fa.x], vb = M.VVM[fa.y], vc = M.VVM[fa.z];
-    M.EVM[f] = make_float4((va.x + vb.x + vc.x) / 3.0f, (va.y + vb.y + vc.y) / 3.0f, (va.z + vb.z + vc.z) / 3.0f, M.EVM[f].w);
-    M.EC0[f] = make_float4(pg.B[0], pg.B[1], pg.B[2], 0.f); M.EC1[f] = make_float4(pg.B[3], pg.B[4], pg.B[5], 0.f); M.EC2[f] = make_float4(pg.B[6], pg.B[7], pg.B[8], 0.f);
+    const float4 va = M.VV[fa.x], vb = M.VV[fa.y], vc = M.VV[fa.z];
+    M.EV[f] = make_float4((va.x + vb.x + vc.x) / 3.0f, (va.y + vb.y + vc.y) / 3.0f, (va.z + vb.z + vc.z) / 3.0f, pg.B[0]);
+    M.EC0[f] = make_float4(pg.B[1], pg.B[2], pg.B[3], pg.B[4]); M.EC1[f] = make_float4(pg.B[5], pg.B[6], pg.B[7], pg.B[8]);
     const float4 xa = M.VX[fa.x], xb = M.VX[fa.y], xc = M.VX[fa.z];
     float d1[3], d2[3]; pos_diff(G, xa, xb, d1); pos_diff(G, xa, xc, d2);                        // :591-594
     const float4 e3 = M.ED3[f];
@@ -308,21 +349,21 @@ __global__ void __launch_bounds__(128) k_element_g2p(MeshDev M, GridP G, const S
 }
 
 // packed -> fp64 staging for download: per point x(3) v(3) B rows(9) [ + d1 d2 d3 (9) for elements ]
-__global__ void k_mesh_download(const float4* X, const float4* VM, const float4* C0, const float4* C1, const float4* C2,
+__global__ void k_mesh_download(const float4* X, const float4* V, const float4* C0, const float4* C1,
                                 const float4* D1, const float4* D2, const float4* D3, double* out, int n,
                                 double mnx, double mny, double mnz, double hx, double hy, double hz) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const size_t N = (size_t)n;
-    const float4 x = X[i], v = VM[i], c0 = C0[i], c1 = C1[i], c2 = C2[i];
+    const float4 x = X[i], v = V[i], c0 = C0[i], c1 = C1[i];
     const int cell = __float_as_int(x.w);
     out[0 * N + i] = mnx + ((double)cell_i(cell) + (double)x.x) * hx;
     out[1 * N + i] = mny + ((double)cell_j(cell) + (double)x.y) * hy;
     out[2 * N + i] = mnz + ((double)cell_k(cell) + (double)x.z) * hz;
     out[3 * N + i] = v.x; out[4 * N + i] = v.y; out[5 * N + i] = v.z;
-    out[6 * N + i] = c0.x; out[7 * N + i] = c0.y; out[8 * N + i] = c0.z;
-    out[9 * N + i] = c1.x; out[10 * N + i] = c1.y; out[11 * N + i] = c1.z;
-    out[12 * N + i] = c2.x; out[13 * N + i] = c2.y; out[14 * N + i] = c2.z;
+    out[6 * N + i] = v.w; out[7 * N + i] = c0.x; out[8 * N + i] = c0.y;
+    out[9 * N + i] = c0.z; out[10 * N + i] = c0.w; out[11 * N + i] = c1.x;
+    out[12 * N + i] = c1.y; out[13 * N + i] = c1.z; out[14 * N + i] = c1.w;
     if (D1) {
         const float4 a = D1[i], b = D2[i], c = D3[i];
         out[15 * N + i] = a.x; out[16 * N + i] = a.y; out[17 * N + i] = a.z;
@@ -333,17 +374,8 @@ __global__ void k_mesh_download(const float4* X, const float4* VM, const float4*
 
 // ------------------------------------------------------------------------------------------------ host side
 inline void mesh_free(MeshState& m) {
-    for (void* p : m.allocs) cudaFree(p);
-    m.allocs.clear(); m.nv = m.nf = 0; m.n_fixed = 0;
-}
-
-template <typename T>
-inline cudaError_t mesh_alloc_copy(MeshState& m, T** dst, const std::vector<T>& src, cudaStream_t s) {
-    cudaError_t e = cudaMalloc((void**)dst, std::max<size_t>(src.size(), 1) * sizeof(T));
-    if (e != cudaSuccess) return e;
-    m.allocs.push_back(*dst);
-    if (!src.empty()) e = cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, s);
-    return e;
+    if (m.block) cudaFree(m.block);
+    m.block = nullptr; m.block_bytes = 0; m.nv = m.nf = 0; m.n_fixed = 0; m.owner_v = m.owner_e = nullptr;
 }
 
 inline float4 host_pack_pos(const MeshState& m, const GridP& G, double x, double y, double z) {
@@ -363,6 +395,9 @@ inline float4 host_pack_pos(const MeshState& m, const GridP& G, double x, double
     return make_float4(fr[0], fr[1], fr[2], w);
 }
 
+// Everything in ONE device allocation, laid out identically on every rank (the layout depends on nv, nf and the number of pinned
+// vertices only), so that a peer maps it with one IPC handle and addresses any array by the same offset.  The arrays that G2P
+// rewrites come first and are contiguous per point kind: [VX VV VC0 VC1] and [EX EV EC0 EC1 ED1 ED2 ED3].
 inline int mesh_upload(MeshState& m, const GridP& G, const double* mn, const double* h, int64_t nv, int64_t nf, const double* vx,
                        const double* vv, const double* vm, const double* vvol, const double* vB, const int32_t* faces,
                        const double* ev, const double* em, const double* evol, const double* eB, const double* ed, const double* eD,
@@ -372,26 +407,44 @@ inline int mesh_upload(MeshState& m, const GridP& G, const double* mn, const dou
     mesh_free(m);
     for (int a = 0; a < 3; ++a) { m.mn[a] = mn[a]; m.h[a] = h[a]; }
     const size_t NV = (size_t)nv, NF = (size_t)nf;
-    std::vector<float4> VX(NV), VVM(NV), VC0(NV), VC1(NV), VC2(NV), VF(NV, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<int> fixed;
+    if (fixedv) for (size_t i = 0; i < NV; ++i) if (fixedv[i] != 0.0) fixed.push_back((int)i);      // LagrangianMesh.cpp:462-481
+    // layout (float4 units)
+    const size_t nVarr = 7, nEarr = 15;                       // VX VV VC0 VC1 | VK VKe VF ;  EX EV EC0 EC1 ED1 ED2 ED3 | EK EKe RD1 RD2 RD3 PK + faces(int4)
+    const size_t f4 = nVarr * NV + nEarr * NF;
+    const size_t bytes = f4 * 16 + ((fixed.size() * 4 + 15) & ~(size_t)15) + ((NV + NF + 255) & ~(size_t)255);
+    if (cudaMalloc(&m.block, bytes) != cudaSuccess) return -3;
+    m.block_bytes = bytes;
+    std::vector<float4> H(f4, make_float4(0.f, 0.f, 0.f, 0.f));
+    float4* base = (float4*)m.block; size_t off = 0;
+    auto take = [&](float4*& dev, size_t n) { dev = base + off; float4* hp = H.data() + off; off += n; return hp; };
+    MeshDev& d = m.d;
+    float4 *VX = take(d.VX, NV), *VV = take(d.VV, NV), *VC0 = take(d.VC0, NV), *VC1 = take(d.VC1, NV);
+    m.sync_v_off = 0; m.sync_v_bytes = 4 * NV * 16;
+    float4 *EX = take(d.EX, NF), *EV = take(d.EV, NF), *EC0 = take(d.EC0, NF), *EC1 = take(d.EC1, NF), *ED1 = take(d.ED1, NF), *ED2 = take(d.ED2, NF), *ED3 = take(d.ED3, NF);
+    m.sync_e_off = 4 * NV * 16; m.sync_e_bytes = 7 * NF * 16;
+    float4* VKe_dev; float4* EKe_dev;
+    float4 *VK = take(d.VK, NV), *VKe = take(VKe_dev, NV); take(d.VF, NV);
+    float4 *EK = take(d.EK, NF), *EKe = take(EKe_dev, NF), *RD1 = take(d.RD1, NF), *RD2 = take(d.RD2, NF), *RD3 = take(d.RD3, NF);
+    take(d.PK, NF);
+    float4* FAh = take(*reinterpret_cast<float4**>(&d.faces), NF);
     for (size_t i = 0; i < NV; ++i) {
         VX[i] = host_pack_pos(m, G, vx[i], vx[NV + i], vx[2 * NV + i]);
-        VVM[i] = make_float4((float)vv[i], (float)vv[NV + i], (float)vv[2 * NV + i], (float)vm[i]);
-        VC0[i] = make_float4((float)vB[i], (float)vB[NV + i], (float)vB[2 * NV + i], 0.f);
-        VC1[i] = make_float4((float)vB[3 * NV + i], (float)vB[4 * NV + i], (float)vB[5 * NV + i], 0.f);
-        VC2[i] = make_float4((float)vB[6 * NV + i], (float)vB[7 * NV + i], (float)vB[8 * NV + i], 0.f);
+        VV[i] = make_float4((float)vv[i], (float)vv[NV + i], (float)vv[2 * NV + i], (float)vB[i]);
+        VC0[i] = make_float4((float)vB[NV + i], (float)vB[2 * NV + i], (float)vB[3 * NV + i], (float)vB[4 * NV + i]);
+        VC1[i] = make_float4((float)vB[5 * NV + i], (float)vB[6 * NV + i], (float)vB[7 * NV + i], (float)vB[8 * NV + i]);
+        VK[i] = make_float4((float)vm[i], 0.f, 0.f, 0.f); VKe[i] = VK[i];
     }
-    std::vector<float4> EX(NF), EVM(NF), EC0(NF), EC1(NF), EC2(NF), ED1(NF), ED2(NF), ED3(NF), RD1(NF), RD2(NF), RD3(NF), PK(NF, make_float4(0.f, 0.f, 0.f, 0.f));
-    std::vector<int4> FA(NF);
     for (size_t f = 0; f < NF; ++f) {
         const int a = faces[f], b = faces[NF + f], c = faces[2 * NF + f];
-        if (a < 0 || b < 0 || c < 0 || a >= nv || b >= nv || c >= nv) return -1;
-        FA[f] = make_int4(a, b, c, 0);
+        if (a < 0 || b < 0 || c < 0 || a >= nv || b >= nv || c >= nv) { mesh_free(m); return -1; }
+        const int4 fa = make_int4(a, b, c, 0); std::memcpy(&FAh[f], &fa, 16);
         // element centroid = mean of its vertices (LagrangianMesh.cpp:371-380, called from the ctor :185)
         EX[f] = host_pack_pos(m, G, (vx[a] + vx[b] + vx[c]) / 3.0, (vx[NV + a] + vx[NV + b] + vx[NV + c]) / 3.0, (vx[2 * NV + a] + vx[2 * NV + b] + vx[2 * NV + c]) / 3.0);
-        EVM[f] = make_float4((float)ev[f], (float)ev[NF + f], (float)ev[2 * NF + f], (float)em[f]);
-        EC0[f] = make_float4((float)eB[f], (float)eB[NF + f], (float)eB[2 * NF + f], 0.f);
-        EC1[f] = make_float4((float)eB[3 * NF + f], (float)eB[4 * NF + f], (float)eB[5 * NF + f], 0.f);
-        EC2[f] = make_float4((float)eB[6 * NF + f], (float)eB[7 * NF + f], (float)eB[8 * NF + f], 0.f);
+        EV[f] = make_float4((float)ev[f], (float)ev[NF + f], (float)ev[2 * NF + f], (float)eB[f]);
+        EC0[f] = make_float4((float)eB[NF + f], (float)eB[2 * NF + f], (float)eB[3 * NF + f], (float)eB[4 * NF + f]);
+        EC1[f] = make_float4((float)eB[5 * NF + f], (float)eB[6 * NF + f], (float)eB[7 * NF + f], (float)eB[8 * NF + f]);
+        EK[f] = make_float4((float)em[f], 0.f, 0.f, 0.f); EKe[f] = EK[f];
         ED1[f] = make_float4((float)ed[f], (float)ed[NF + f], (float)ed[2 * NF + f], 0.f);
         ED2[f] = make_float4((float)ed[3 * NF + f], (float)ed[4 * NF + f], (float)ed[5 * NF + f], 0.f);
         ED3[f] = make_float4((float)ed[6 * NF + f], (float)ed[7 * NF + f], (float)ed[8 * NF + f], (float)evol[f]);
@@ -399,50 +452,63 @@ inline int mesh_upload(MeshState& m, const GridP& G, const double* mn, const dou
         RD2[f] = make_float4((float)eD[3 * NF + f], (float)eD[4 * NF + f], (float)eD[5 * NF + f], 0.f);
         RD3[f] = make_float4((float)eD[6 * NF + f], (float)eD[7 * NF + f], (float)eD[8 * NF + f], 0.f);
     }
-    std::vector<int> fixed;
-    if (fixedv) for (size_t i = 0; i < NV; ++i) if (fixedv[i] != 0.0) fixed.push_back((int)i);      // LagrangianMesh.cpp:462-481
-    MeshDev& d = m.d;
-#define MC(field, vec) if (mesh_alloc_copy(m, &d.field, vec, s) != cudaSuccess) return -2
-    MC(VX, VX); MC(VVM, VVM); MC(VC0, VC0); MC(VC1, VC1); MC(VC2, VC2); MC(VF, VF);
-    MC(EX, EX); MC(EVM, EVM); MC(EC0, EC0); MC(EC1, EC1); MC(EC2, EC2); MC(ED1, ED1); MC(ED2, ED2); MC(ED3, ED3);
-    MC(RD1, RD1); MC(RD2, RD2); MC(RD3, RD3); MC(PK, PK); MC(faces, FA); MC(fixed_ids, fixed);
-#undef MC
+    d.VKe = VKe_dev; d.EKe = EKe_dev;
+    unsigned char* tail = (unsigned char*)(base + f4);
+    d.fixed_ids = (int*)tail; tail += (fixed.size() * 4 + 15) & ~(size_t)15;
+    m.owner_v = tail; m.owner_e = tail + NV;
+    if (cudaMemcpyAsync(base, H.data(), f4 * 16, cudaMemcpyHostToDevice, s) != cudaSuccess) return -2;
+    if (!fixed.empty() && cudaMemcpyAsync(d.fixed_ids, fixed.data(), fixed.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) return -2;
+    if (cudaMemsetAsync(m.owner_v, 1, NV + NF, s) != cudaSuccess) return -2;
     d.mu = (float)mu; d.lambda = (float)lambda; d.gamma = (float)shear; d.kstiff = (float)stiff; d.cf = (float)fric;
     if (cudaStreamSynchronize(s) != cudaSuccess) return -2;
     m.nv = nv; m.nf = nf; m.n_fixed = (int)fixed.size();
     return 0;
 }
 
-inline int mesh_p2g(MeshState& m, const GridP& G, cudaStream_t s, long long* launches) {
-    PartP pv{}, pe{};
-    pv.a[PX] = m.d.VX; pv.a[PVM] = m.d.VVM; pv.a[PC0] = m.d.VC0; pv.a[PC1] = m.d.VC1; pv.a[PC2] = m.d.VC2;
-    pe.a[PX] = m.d.EX; pe.a[PVM] = m.d.EVM; pe.a[PC0] = m.d.EC0; pe.a[PC1] = m.d.EC1; pe.a[PC2] = m.d.EC2;
-    p2g_launch(s, pv, G, m.nv);
-    p2g_launch(s, pe, G, m.nf);
-    *launches += 2;
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
-}
+inline bool mesh_sliced(const MeshState& m) { return m.own.axis >= 0; }
 
-inline int mesh_forces(MeshState& m, const GridP& G, cudaStream_t s, long long* launches) {
-    cudaMemsetAsync(m.d.VF, 0, (size_t)m.nv * sizeof(float4), s);
-    k_cloth_inplane<<<(int)((m.nf + 127) / 128), 128, 0, s>>>(m.d, (int)m.nf);
-    k_vertex_force_scatter<<<(int)((m.nv + 255) / 256), 256, 0, s>>>(m.d, G, (int)m.nv);
-    k_cloth_normal<<<(int)((m.nf + 127) / 128), 128, 0, s>>>(m.d, G, (int)m.nf);
-    *launches += 3;
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
-}
-
-inline int mesh_pin(MeshState& m, const GridP& G, cudaStream_t s, long long* launches) {
-    const int n = m.n_fixed * 64;
-    k_mesh_pin<<<(n + 127) / 128, 128, 0, s>>>(m.d, G, m.n_fixed);
+inline int mesh_own_snapshot(MeshState& m, const SimClock* clk, cudaStream_t s, long long* launches) {
+    if (!mesh_sliced(m)) return 0;
+    k_mesh_own<<<(int)((m.nv + m.nf + 255) / 256), 256, 0, s>>>(m.d, m.own, clk, m.owner_v, m.owner_e, m.d.VKe, m.d.EKe, (int)m.nv, (int)m.nf);
     *launches += 1;
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-inline int mesh_g2p(MeshState& m, const GridP& G, SimClock* clk, cudaStream_t s, long long* launches) {
-    k_vertex_g2p<<<(int)((m.nv + 127) / 128), 128, 0, s>>>(m.d, G, clk, (int)m.nv);
-    k_element_g2p<<<(int)((m.nf + 127) / 128), 128, 0, s>>>(m.d, G, clk, (int)m.nf);
+inline int mesh_p2g(MeshState& m, const GridP& G, const SimClock* clk, cudaStream_t s, long long* launches) {
+    PartP pv{}, pe{};
+    pv.a[PX] = m.d.VX; pv.a[PV] = m.d.VV; pv.a[PC0] = m.d.VC0; pv.a[PC1] = m.d.VC1; pv.a[PK] = m.d.VKe;
+    pe.a[PX] = m.d.EX; pe.a[PV] = m.d.EV; pe.a[PC0] = m.d.EC0; pe.a[PC1] = m.d.EC1; pe.a[PK] = m.d.EKe;
+    p2g_launch(s, pv, G, m.nv, clk);
+    p2g_launch(s, pe, G, m.nf, clk);
     *launches += 2;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+inline int mesh_forces(MeshState& m, const GridP& G, const SimClock* clk, cudaStream_t s, long long* launches) {
+    const unsigned char* ov = mesh_sliced(m) ? m.owner_v : nullptr; const unsigned char* oe = mesh_sliced(m) ? m.owner_e : nullptr;
+    cudaMemsetAsync(m.d.VF, 0, (size_t)m.nv * sizeof(float4), s);
+    k_cloth_inplane<<<(int)((m.nf + 127) / 128), 128, 0, s>>>(m.d, clk, (int)m.nf);
+    k_vertex_force_scatter<<<(int)((m.nv + 255) / 256), 256, 0, s>>>(m.d, G, clk, ov, (int)m.nv);
+    k_cloth_normal<<<(int)((m.nf + 127) / 128), 128, 0, s>>>(m.d, G, clk, oe, (int)m.nf);
+    *launches += 3;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+inline int mesh_pin(MeshState& m, const GridP& G, const SimClock* clk, cudaStream_t s, long long* launches) {
+    const int n = m.n_fixed * 64;
+    k_mesh_pin<<<(n + 127) / 128, 128, 0, s>>>(m.d, G, clk, m.n_fixed);
+    *launches += 1;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+inline int mesh_g2p_vertices(MeshState& m, const GridP& G, SimClock* clk, cudaStream_t s, long long* launches) {
+    k_vertex_g2p<<<(int)((m.nv + 127) / 128), 128, 0, s>>>(m.d, G, clk, mesh_sliced(m) ? m.owner_v : nullptr, (int)m.nv);
+    *launches += 1;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+inline int mesh_g2p_elements(MeshState& m, const GridP& G, SimClock* clk, cudaStream_t s, long long* launches) {
+    k_element_g2p<<<(int)((m.nf + 127) / 128), 128, 0, s>>>(m.d, G, clk, mesh_sliced(m) ? m.owner_e : nullptr, (int)m.nf);
+    *launches += 1;
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -452,13 +518,13 @@ inline int mesh_download(MeshState& m, double* vx, double* vv, double* vB, doubl
     double* st = nullptr;
     if (cudaMalloc((void**)&st, std::max(NV * 15, NF * 24) * sizeof(double)) != cudaSuccess) return -3;
     int rc = 0;
-    k_mesh_download<<<(int)((NV + 255) / 256), 256, 0, s>>>(m.d.VX, m.d.VVM, m.d.VC0, m.d.VC1, m.d.VC2, nullptr, nullptr, nullptr, st, (int)NV,
+    k_mesh_download<<<(int)((NV + 255) / 256), 256, 0, s>>>(m.d.VX, m.d.VV, m.d.VC0, m.d.VC1, nullptr, nullptr, nullptr, st, (int)NV,
                                                           m.mn[0], m.mn[1], m.mn[2], m.h[0], m.h[1], m.h[2]);
     if (vx) cudaMemcpyAsync(vx, st, 3 * NV * sizeof(double), cudaMemcpyDeviceToHost, s);
     if (vv) cudaMemcpyAsync(vv, st + 3 * NV, 3 * NV * sizeof(double), cudaMemcpyDeviceToHost, s);
     if (vB) cudaMemcpyAsync(vB, st + 6 * NV, 9 * NV * sizeof(double), cudaMemcpyDeviceToHost, s);
     if (cudaStreamSynchronize(s) != cudaSuccess) rc = -2;
-    k_mesh_download<<<(int)((NF + 255) / 256), 256, 0, s>>>(m.d.EX, m.d.EVM, m.d.EC0, m.d.EC1, m.d.EC2, m.d.ED1, m.d.ED2, m.d.ED3, st, (int)NF,
+    k_mesh_download<<<(int)((NF + 255) / 256), 256, 0, s>>>(m.d.EX, m.d.EV, m.d.EC0, m.d.EC1, m.d.ED1, m.d.ED2, m.d.ED3, st, (int)NF,
                                                           m.mn[0], m.mn[1], m.mn[2], m.h[0], m.h[1], m.h[2]);
     if (ex) cudaMemcpyAsync(ex, st, 3 * NF * sizeof(double), cudaMemcpyDeviceToHost, s);
     if (ev) cudaMemcpyAsync(ev, st + 3 * NF, 3 * NF * sizeof(double), cudaMemcpyDeviceToHost, s);

@@ -24,10 +24,10 @@ __device__ __forceinline__ void acc_zero(AccRow& a) {
 //   r0 Nx[4]    r1 Ny[4] (read as float [j])    r2 Nz[4] (float [k])
 //   r3 (m, q0x | q0y, q0z)      (mass, momentum) of node offset (0,0,0)
 //   r4 r5 r6  (0, Qm[0][c] | Qm[1][c], Qm[2][c]) for c = 0,1,2: what one step along i, j, k adds to (m, p)
-//   r7 (cell, cell of the half-warp's next particle, -, -)      (read on the flush path only)
+//   r7 (cell, cell of the particle before it, -, -)             (read when a run starts only)
 #define P2G_STRIDE 9
 __device__ __forceinline__ void p2g_make_record(float4* __restrict__ rec, const float4& X, const float4& VM, const float4& c0, const float4& c1,
-                                                const float4& c2, float m, float apic, float hx, float hy, float hz, float ncell_bits) {
+                                                const float4& c2, float m, float apic, float hx, float hy, float hz, float prev_bits) {
     float Nx[4], Ny[4], Nz[4], D[4];
     bspline4(X.x, Nx, D); bspline4(X.y, Ny, D); bspline4(X.z, Nz, D);
     const float km = m * apic;
@@ -40,7 +40,7 @@ __device__ __forceinline__ void p2g_make_record(float4* __restrict__ rec, const 
     rec[0] = make_float4(Nx[0], Nx[1], Nx[2], Nx[3]); rec[1] = make_float4(Ny[0], Ny[1], Ny[2], Ny[3]); rec[2] = make_float4(Nz[0], Nz[1], Nz[2], Nz[3]);
     rec[3] = make_float4(m, q0x, q0y, q0z);
     rec[4] = make_float4(0.f, Q[0], Q[3], Q[6]); rec[5] = make_float4(0.f, Q[1], Q[4], Q[7]); rec[6] = make_float4(0.f, Q[2], Q[5], Q[8]);
-    rec[7] = make_float4(X.w, ncell_bits, 0.f, 0.f);
+    rec[7] = make_float4(X.w, prev_bits, 0.f, 0.f);
 }
 // one particle into the 4 nodes of row (j,k): yoff / zoff = byte offsets of Ny[j] / Nz[k] in the record, J = (j,j), K = (k,k)
 __device__ __forceinline__ void p2g_row_accumulate(const float4* __restrict__ r, int yoff, int zoff, f32x2 J, f32x2 K, AccRow& acc) {
@@ -64,15 +64,15 @@ __device__ __forceinline__ void p2g_row_accumulate(const float4* __restrict__ r,
 //      = Dx_i U + Nx_i V,  U = A[:,0] Ny Nz,  V = A[:,1] Dy Nz + A[:,2] Ny Dz  per (j,k) row.
 // Record (FRC_STRIDE float4, odd stride: conflict-free STS.128):
 //   r0 Nx[4]   r1 Dx[4]   r2 r3 (Ny_j, Dy_j) pairs, read as float2 [j]   r4 r5 (Nz_k, Dz_k), float2 [k]
-//   r6 r7 r8  columns of A:  (A[0][c], A[1][c] | A[2][c], 0)            r9.x  packed cell index (flush path only)
+//   r6 r7 r8  columns of A:  (A[0][c], A[1][c] | A[2][c], 0)            r9 (cell, cell of the particle before it, -, -)   (run starts only)
 #define FRC_STRIDE 11
 __device__ __forceinline__ void frc_make_record(float4* __restrict__ rec, const float (&Nx)[4], const float (&Dx)[4], const float (&Ny)[4], const float (&Dy)[4],
-                                                const float (&Nz)[4], const float (&Dz)[4], const float (&A)[9], float cell_bits) {
+                                                const float (&Nz)[4], const float (&Dz)[4], const float (&A)[9], float cell_bits, float prev_bits = 0.f) {
     rec[0] = make_float4(Nx[0], Nx[1], Nx[2], Nx[3]); rec[1] = make_float4(Dx[0], Dx[1], Dx[2], Dx[3]);
     rec[2] = make_float4(Ny[0], Dy[0], Ny[1], Dy[1]); rec[3] = make_float4(Ny[2], Dy[2], Ny[3], Dy[3]);
     rec[4] = make_float4(Nz[0], Dz[0], Nz[1], Dz[1]); rec[5] = make_float4(Nz[2], Dz[2], Nz[3], Dz[3]);
     rec[6] = make_float4(A[0], A[3], A[6], 0.f); rec[7] = make_float4(A[1], A[4], A[7], 0.f); rec[8] = make_float4(A[2], A[5], A[8], 0.f);
-    rec[9].x = cell_bits;
+    rec[9] = make_float4(cell_bits, prev_bits, 0.f, 0.f);
 }
 // yoff / zoff = byte offsets of (Ny,Dy)[j] / (Nz,Dz)[k] in the record
 __device__ __forceinline__ void frc_row_accumulate(const float4* __restrict__ r, int yoff, int zoff, AccRow& acc) {

@@ -152,16 +152,68 @@ class GpuSlabBackend:
         self.stream = None
 
     def particles_local(self):
-        from .scenes import from_colmajor, mats_from_colmajor
-        n = self.e.n_particles
-        ids = np.empty(n, np.int64); b = {k: np.empty(3 * n) for k in ("x", "v", "B1", "B2", "B3")}
-        FE = np.empty(9 * n); FP = np.empty(9 * n); vol = np.empty(n); q = np.empty(n)
-        dp = self.capi.dp
-        P = lambda a: a.ctypes.data_as(dp)
-        self._ck(self.L.aep_download_particles_local(self.h, ids.ctypes.data_as(self.capi.i64p), P(b["x"]), P(b["v"]), P(b["B1"]), P(b["B2"]), P(b["B3"]),
-                                                     P(FE), P(FP), P(vol), P(q)))
-        B = np.stack([from_colmajor(b["B1"], n), from_colmajor(b["B2"], n), from_colmajor(b["B3"], n)], axis=1)
-        return dict(ids=ids, x=from_colmajor(b["x"], n), v=from_colmajor(b["v"], n), B=B, FE=mats_from_colmajor(FE, n), FP=mats_from_colmajor(FP, n), vol=vol, q=q)
+        return download_local(self.e)
+
+
+def download_local(engine):
+    """Particles a slab context currently holds, in its own order, with their global ids (dead slots dropped)."""
+    from . import capi
+    from .scenes import from_colmajor, mats_from_colmajor
+    n = engine.n_particles
+    ids = np.empty(n, np.int64); b = {k: np.empty(3 * n) for k in ("x", "v", "B1", "B2", "B3")}
+    FE = np.empty(9 * n); FP = np.empty(9 * n); vol = np.empty(n); q = np.empty(n)
+    P = lambda a: a.ctypes.data_as(capi.dp)
+    capi.check(engine.L.aep_download_particles_local(engine.h, ids.ctypes.data_as(capi.i64p), P(b["x"]), P(b["v"]), P(b["B1"]), P(b["B2"]), P(b["B3"]),
+                                                     P(FE), P(FP), P(vol), P(q)), engine.h)
+    B = np.stack([from_colmajor(b["B1"], n), from_colmajor(b["B2"], n), from_colmajor(b["B3"], n)], axis=1)
+    return dict(ids=ids, x=from_colmajor(b["x"], n), v=from_colmajor(b["v"], n), B=B, FE=mats_from_colmajor(FE, n), FP=mats_from_colmajor(FP, n), vol=vol, q=q)
+
+
+# ------------------------------------------------------------------------------------------------ peer-memory exchange
+class PeerSlabGroup:
+    """Several slab contexts of ONE process, connected by plain device pointers and stepped in lockstep by the library
+    (aep_comm_connect_local / aep_group_init / aep_group_run): the same kernels and the same flag protocol as the multi-process
+    path, where the pointers are CUDA IPC mappings (connect_ranks below).  One GPU or several."""
+
+    def __init__(self, engines: List, migrate_capacity: int = 1 << 14):
+        from . import capi
+        self.capi = capi; self.engs = list(engines); self.L = engines[0].L
+        self.world = len(engines)
+        self.arr = (C.c_void_p * self.world)(*[e.h for e in engines])
+        capi.check(self.L.aep_comm_connect_local(self.arr, self.world, int(migrate_capacity)), engines[0].h)
+
+    def _ck(self, rc):
+        if rc != 0:
+            msgs = [self.L.aep_last_error(e.h) for e in self.engs]
+            raise self.capi.AepError(f"libaep_b200 error {rc}: " + " | ".join(m.decode() for m in msgs if m))
+
+    def init(self): self._ck(self.L.aep_group_init(self.arr, self.world))
+    def run(self, n): self._ck(self.L.aep_group_run(self.arr, self.world, int(n)))
+    def substep(self): self.run(1)
+
+    def gather_particles(self):
+        parts = [download_local(e) for e in self.engs]
+        ids = np.concatenate([p["ids"] for p in parts]); order = np.argsort(ids)
+        out = {k: np.concatenate([p[k] for p in parts], axis=0)[order] for k in parts[0] if k != "ids"}
+        out["ids"] = ids[order]
+        return out
+
+
+def connect_ranks(engine, rank: int, world: int, migrate_capacity: int, group=None):
+    """One process per GPU: export this rank's communication block, all-gather the 256-byte blobs over torch.distributed (the only
+    thing the process group is used for besides timing), connect.  From then on engine.init()/run() exchange over peer memory."""
+    import torch
+    import torch.distributed as dist
+    from . import capi
+    blob = (C.c_ubyte * capi.COMM_BLOB_BYTES)()
+    capi.check(engine.L.aep_comm_export(engine.h, C.cast(blob, C.c_void_p), int(migrate_capacity)), engine.h)
+    dev = torch.device("cuda", engine.cfg.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(bytes(blob)), dtype=torch.uint8).to(dev)
+    allb = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allb, mine, group=group)
+    raw = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allb)
+    buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+    capi.check(engine.L.aep_comm_connect(engine.h, int(rank), int(world), C.cast(buf, C.c_void_p)), engine.h)
 
 
 # ------------------------------------------------------------------------------------------------ per-rank driver
@@ -427,7 +479,7 @@ def split_scene_particles(scene, plan: SlabPlan, rank: int):
     return np.nonzero(plan.owner_of_cells(cells) == rank)[0]
 
 
-def make_gpu_slab_engine(scene, plan: SlabPlan, rank: int, device: int, capacity_factor: float = 1.3, dt_rate_floor=None, ids=None):
+def make_gpu_slab_engine(scene, plan: SlabPlan, rank: int, device: int, capacity_factor: float = 1.3, dt_rate_floor=None, ids=None, **engine_kw):
     """Engine holding only `rank`'s particles of `scene` (global ids preserved when the slab is a contiguous id range or ids given)."""
     import copy
     from .engine import Engine
@@ -438,7 +490,7 @@ def make_gpu_slab_engine(scene, plan: SlabPlan, rank: int, device: int, capacity
                       E=p.E, nu=p.nu, thetaC=p.thetaC, thetaS=p.thetaS)
     shell = copy.copy(scene); shell.particles = None
     cap = int(max(1024, capacity_factor * len(idx) + 4096))
-    eng = Engine(shell, device=device, particle_capacity=cap, slab=plan.slab(rank), dt_rate_floor=dt_rate_floor)
+    eng = Engine(shell, device=device, particle_capacity=cap, slab=plan.slab(rank), dt_rate_floor=dt_rate_floor, **engine_kw)
     return eng, local, idx
 
 

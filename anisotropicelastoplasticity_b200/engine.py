@@ -20,7 +20,8 @@ def _p(a):
 
 
 class Engine:
-    def __init__(self, scene: Scene, device: int = 0, particle_capacity: int = 0, slab=None, dt_rate_floor=None, sort_every=None, sort_bricks=None, scatter_strips=None):
+    def __init__(self, scene: Scene, device: int = 0, particle_capacity: int = 0, slab=None, dt_rate_floor=None, sort_every=None, sort_bricks=None, scatter_strips=None,
+                 vmax_min_mass_fraction=None, coulomb_friction=None, use_graph=None):
         self.L = capi.load()
         cfg = capi.Config(); capi.check(self.L.aep_default_config(C.byref(cfg)))
         g = scene.grid
@@ -36,6 +37,12 @@ class Engine:
             cfg.scatter_strips = int(scatter_strips)
         if sort_bricks is not None:
             cfg.sort_bricks = int(sort_bricks)
+        if vmax_min_mass_fraction is not None:
+            cfg.vmax_min_mass_fraction = float(vmax_min_mass_fraction)      # opt-in, NOT the reference's dt rule
+        if coulomb_friction is not None:
+            cfg.coulomb_friction = int(coulomb_friction)                    # opt-in, NOT the reference's collider
+        if use_graph is not None:
+            cfg.use_graph = int(use_graph)
         if slab is not None:
             cfg.slab_axis, cfg.slab_lo, cfg.slab_hi = slab
         self.cfg = cfg
@@ -90,6 +97,15 @@ class Engine:
                                           _p(np.ascontiguousarray(m.em, np.float64)), _p(np.ascontiguousarray(m.evol, np.float64)), _p(eB), _p(ed), _p(eD),
                                           _p(fixed), m.mu, m.lam, m.shear, m.stiff, m.fric), self.h)
 
+    def set_collider_motion(self, velocity):
+        v = None if velocity is None else np.ascontiguousarray(velocity, np.float64)
+        capi.check(self.L.aep_set_collider_motion(self.h, _p(v)), self.h)
+
+    def counters(self):
+        a = [C.c_int64() for _ in range(4)]
+        capi.check(self.L.aep_get_counters(self.h, *[C.byref(x) for x in a]), self.h)
+        return dict(sorts=a[0].value, slots=a[1].value, dead=a[2].value, moved_since_sort=a[3].value)
+
     def set_levelset_samples(self, inside, normal):
         inside = np.ascontiguousarray(inside, np.uint8); normal = colmajor(normal)
         capi.check(self.L.aep_set_levelset_samples(self.h, inside.ctypes.data_as(C.POINTER(C.c_uint8)), _p(normal)), self.h)
@@ -116,7 +132,7 @@ class Engine:
     def checkpoint(self):
         """Everything needed to continue this run elsewhere: particle and mesh state in the reference's layouts + the clock."""
         c = self.clock()
-        out = dict(clock=np.array([c["dt"], c["t"], c["inner_t"], c["frame"], c["substeps"]], np.float64))
+        out = dict(clock=np.array([c["dt"], c["t"], c["inner_t"], c["frame"], c["substeps"], c["escaped"]], np.float64))
         if self.n_particles:
             out.update({"p_" + k: v for k, v in self.particles().items()})
         if self.nv:
@@ -137,8 +153,11 @@ class Engine:
             m.vx, m.vv, m.vB, m.ev, m.eB, m.ed = (np.array(ckpt["m_" + k]) for k in ("vx", "vv", "vB", "ev", "eB", "ed"))
         e = cls(s, **kw)
         capi.check(e.L.aep_resume(e.h), e.h)
-        dt, t, inner_t, frame, substeps = (float(v) for v in np.asarray(ckpt["clock"]))
+        ck = [float(v) for v in np.asarray(ckpt["clock"])]
+        dt, t, inner_t, frame, substeps = ck[:5]
         capi.check(e.L.aep_set_clock(e.h, dt, t, inner_t, int(frame), int(substeps)), e.h)
+        if len(ck) > 5 and ck[5] > 0:
+            capi.check(e.L.aep_set_escaped(e.h, int(ck[5])), e.h)
         return e
 
     def clock(self):

@@ -37,7 +37,8 @@ UNIT = "particle-substeps/s"
 BYTES_PARTICLE = {sc.SAND: 340.0, sc.SNOW: 376.0}
 BYTES_NODE = 172.0
 # per-stage split of the same model (sand; snow adds 36 B to forces)
-STAGE_BYTES = {"forces": (52.0, 24.0), "g2p": (224.0, 24.0), "p2g": (64.0, 44.0), "grid": (0.0, 52.0), "sort": (0.0, 0.0)}
+# the fused kernel of a substep does the G2P of this substep and the P2G of the next: its algorithmic bytes are the sum of the two rows
+STAGE_BYTES = {"forces": (52.0, 24.0), "g2p": (224.0, 24.0), "p2g": (64.0, 44.0), "g2p2g": (288.0, 68.0), "grid": (0.0, 52.0), "sort": (0.0, 0.0)}
 
 
 def ncu_traffic(kernel, particles):
@@ -260,7 +261,7 @@ def workload_config(args, res_override=None, note=None, n_particles=None):
 def transfers_roofline(stage_ms, n, nodes, peak):
     """The two transfers BASELINE.json's north star singles out ("P2G+G2P at 50% or more of the HBM roofline per GPU"): their
     algorithmic bytes (SURVEY.md 8d split) over the sum of their stage times."""
-    ms = stage_ms.get("p2g", 0.0) + stage_ms.get("g2p", 0.0)
+    ms = stage_ms.get("p2g", 0.0) + stage_ms.get("g2p", 0.0) + stage_ms.get("g2p2g", 0.0)     # one fused kernel per substep since round 2
     b = sum(STAGE_BYTES[k][0] * n + STAGE_BYTES[k][1] * nodes for k in ("p2g", "g2p"))
     gbs = b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     return {"algorithmic_bytes": b, "ms": ms, "achieved_gbs": gbs, "frac": gbs / peak if peak else None}
@@ -313,15 +314,15 @@ def run_engine(args):
     stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in tm.items()}
     # dominant kernel = the stage that costs most PER SUBSTEP; the re-sort (5.6 ms when the policy fires, every ~30th substep,
     # no algorithmic bytes) is overhead inside `value`, not a candidate
-    dom = max(("forces", "g2p", "p2g", "grid"), key=lambda k: stage_ms.get(k, 0.0))
+    dom = max(("forces", "g2p2g", "g2p", "p2g", "grid"), key=lambda k: stage_ms.get(k, 0.0))
     bp, bn = STAGE_BYTES[dom]
     dom_bytes = bp * n + bn * nodes
     achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
     sub_bytes = BYTES_PARTICLE[sc.SAND] * n + BYTES_NODE * nodes
     sub_gbs = sub_bytes / (ms * 1e-3 / args.steps) / 1e9
-    roofline = {"bound": "hbm", "kernel": {"forces": "k_forces", "g2p": "k_g2p", "p2g": "k_p2g", "grid": "k_grid_update", "sort": "cub radix sort + k_reorder"}[dom],
+    roofline = {"bound": "hbm", "kernel": {"forces": "k_forces", "g2p2g": "k_g2p2g", "g2p": "k_g2p2g<scatter off>", "p2g": "k_p2g", "grid": "k_grid_update", "sort": "cub radix sort + k_reorder"}[dom],
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth, MEASURED_PEAKS.json", "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic({"forces": "k_forces", "g2p": "k_g2p", "p2g": "k_p2g"}.get(dom, ""), n),
+                "frac": achieved / peak, "traffic": ncu_traffic({"forces": "k_forces", "g2p2g": "k_g2p2g", "p2g": "k_p2g"}.get(dom, ""), n),
                 "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom],
                 "stage_ms": stage_ms,
                 "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes, "active_blocks": blocks},

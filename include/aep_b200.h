@@ -53,6 +53,7 @@ extern "C" {
 #define AEP_LS_SPHERE_GROUND 3  /* params: cx, cy, cz, radius, groundZ              */
 #define AEP_LS_BOX 4            /* params: x0, y0, z0, x1, y1, z1 (inside is free)  */
 #define AEP_LS_SAMPLED 5
+#define AEP_LS_SPHERE 6         /* params: cx, cy, cz, radius  (no ground: a free, possibly moving, ball) */
 
 typedef struct aep_ctx aep_ctx;
 
@@ -87,6 +88,13 @@ typedef struct aep_config {
     int32_t scatter_strips;    /* 64: concurrently running P2G CTAs are spread over this many far-apart parts of the sorted particle
                                   order so that they do not reduce into the same grid nodes at the same time (L2 atomic contention) */
     double sort_cost_threshold; /* 0.5: the extra scatter work of unsorted particles has about paid for one re-sort       */
+    /* --- opt-in departures from the reference (all default to the reference's behaviour) --- */
+    double vmax_min_mass_fraction; /* 0: the reference's dt rule, max |v_i| over EVERY node with m_i > 0 (RegularGrid.cpp:188-200), which at
+                                  nearly massless stencil-edge nodes is rounding noise of p/m and can cut dt by orders of magnitude.
+                                  > 0 (NOT the reference): nodes lighter than this fraction of one particle's mass do not enter max |v_i| */
+    int32_t coulomb_friction;  /* 0: the reference's stick-or-slide collider (HS:494-502; the Coulomb reduction at :500-501 is a no-op
+                                  expression).  1: |v_t| is reduced by mu |v_n| as those lines set out to do                          */
+    int32_t use_graph;         /* 1 (default): a substep is replayed from a CUDA graph -- one host launch.  0: launch kernel by kernel */
 } aep_config;
 
 AEP_API int aep_default_config(aep_config* cfg);
@@ -116,6 +124,11 @@ AEP_API int aep_upload_mesh(aep_ctx* ctx, int64_t nv, int64_t nf, const double* 
 /* HybridSolver::setLevelSet (HybridSolver.h:89).  Colliders are static (HS:484) and only sampled at nodes.  */
 AEP_API int aep_set_levelset_analytic(aep_ctx* ctx, int kind, const double* params8);
 AEP_API int aep_set_levelset_samples(aep_ctx* ctx, const uint8_t* inside /*Ng*/, const double* normal /*Ng x 3*/);
+/* Moving collider (not in the reference, whose colliders are static: HS:484 sets the collider velocity to zero).  The analytic level
+ * set given to aep_set_levelset_analytic translates rigidly with `velocity3`; it is then evaluated at the grid nodes on the device
+ * every substep at its current position, and the projection of HS:486-502 works on the velocity relative to the collider.
+ * NULL or a zero vector: back to the static, host-sampled collider.                                                          */
+AEP_API int aep_set_collider_motion(aep_ctx* ctx, const double* velocity3);
 
 /* ---- stepping ------------------------------------------------------------------------------------------- */
 /* HS:830-860: bin particles, first particleToGrid_ (computes volumes, HS:242-249), initial dt.             */
@@ -124,11 +137,15 @@ AEP_API int aep_init(aep_ctx* ctx);
 AEP_API int aep_init_begin(aep_ctx* ctx);
 AEP_API int aep_init_volumes(aep_ctx* ctx);
 AEP_API int aep_init_dt(aep_ctx* ctx);
+AEP_API int aep_init_dt_async(aep_ctx* ctx);      /* the same without the final stream synchronisation */
 /* One iteration of the while loop HS:867-1032 with the reference's dt rule evaluated on the device.        */
 AEP_API int aep_substep(aep_ctx* ctx);
 /* n iterations back to back, no host synchronisation in between.                                           */
 AEP_API int aep_run(aep_ctx* ctx, int n_substeps);
-/* Run until `n_frames` more 1/60 s frames have completed (HS:880-892); returns the substeps taken.         */
+/* Run until `n_frames` more 1/60 s frames have completed (HS:880-892) or `max_substeps` substeps were taken; returns the substeps
+ * taken.  The stop condition is evaluated on the device (the clock kernel halts the context, substeps queued behind the halt return
+ * at once), the host only polls every few substeps: the last substep of a frame is clipped exactly as at HS:880-884.
+ * Returns AEP_ERR_STATE when particles left the grid / became NaN (the state is then clamped garbage), or a peer timed out.   */
 AEP_API int aep_run_frames(aep_ctx* ctx, int n_frames, int max_substeps, int64_t* substeps_done);
 
 /* Stage-level entry points for the parity tests; same split as the reference's private methods.            */
@@ -155,6 +172,8 @@ AEP_API int aep_get_clock(aep_ctx* ctx, double* dt, double* t, double* inner_t, 
  * decomposition is restarted by re-partitioning the saved global state (distributed.py), not rank by rank.               */
 AEP_API int aep_resume(aep_ctx* ctx);
 AEP_API int aep_set_clock(aep_ctx* ctx, double dt, double t, double inner_t, int32_t frame_no, int64_t substeps);
+/* the sticky "particles left the grid" counter of aep_get_clock, so that a restart carries it on */
+AEP_API int aep_set_escaped(aep_ctx* ctx, int64_t escaped);
 
 /* ---- state download (original particle order, reference layouts; any pointer may be NULL) --------------- */
 AEP_API int64_t aep_num_particles(aep_ctx* ctx);
@@ -168,6 +187,11 @@ AEP_API int aep_download_mesh(aep_ctx* ctx, double* vx, double* vv, double* vB, 
 /* positions only, float32 x,y,z interleaved: the per-frame OBJ payload of HS:991-1007.  Original particle order; for a slab
  * context (ids are global there) the context's current order, aep_num_particles entries.                    */
 AEP_API int aep_download_positions_f32(aep_ctx* ctx, float* xyz);
+/* Asynchronous variant for a frame loop: begin snapshots the positions in stream order (behind everything queued so far) and copies
+ * them to `pinned_xyz` (cudaMallocHost / pinned memory, 3 floats per particle) on a second stream while the following substeps
+ * compute; wait blocks until the copy has landed.  One download can be in flight per context.                     */
+AEP_API int aep_frame_positions_begin(aep_ctx* ctx, float* pinned_xyz);
+AEP_API int aep_frame_positions_wait(aep_ctx* ctx);
 /* bulk statistics on the device: centre of mass (3), kinetic energy, mean det F_P, total mass.             */
 AEP_API int aep_stats(aep_ctx* ctx, double* com3, double* kinetic, double* mean_jp, double* mass);
 
@@ -188,7 +212,10 @@ AEP_API int aep_get_timers(aep_ctx* ctx, double* ms /*AEP_NUM_STAGES*/, int64_t*
 #define AEP_STAGE_G2P 4
 #define AEP_STAGE_MESH 5
 #define AEP_STAGE_HALO 6
+#define AEP_STAGE_G2P2G 7   /* the fused kernel of a substep: G2P of this substep + P2G of the next */
 #define AEP_NUM_STAGES 8
+/* physical re-sorts done so far, particle slots in use / dead (slab contexts), particles that changed cell since the last re-sort */
+AEP_API int aep_get_counters(aep_ctx* ctx, int64_t* sorts, int64_t* slots, int64_t* dead, int64_t* moved_since_sort);
 
 /* ---- multi-GPU slab decomposition -------------------------------------------------------------
  * The context owns the particles whose cell index along cfg.slab_axis lies in [slab_lo, slab_hi).  Their cubic
@@ -232,6 +259,27 @@ AEP_API int aep_set_particle_id_base(aep_ctx* ctx, int64_t id_base);
 /* download in the context's current (cell-sorted) order together with the global ids; arrays sized aep_num_particles */
 AEP_API int aep_download_particles_local(aep_ctx* ctx, int64_t* ids, double* x, double* v, double* B1, double* B2, double* B3,
                                          double* FE, double* FP, double* vol, double* q);
+
+
+/* ---- peer-memory exchange: the multi-GPU substep without the host in the loop --------------------------------------------------
+ * For y- or z-slab contexts (slab_axis 1 or 2; such a context allocates only the node planes of its slab, laid out with the slab
+ * axis slowest).  Every rank exports a 256-byte blob describing its communication block (a CUDA IPC handle between processes, a
+ * plain pointer inside one process); after aep_comm_connect with the blobs of ALL ranks (rank order = slab order along the axis),
+ * aep_init / aep_substep / aep_run / aep_run_frames carry out the whole exchange themselves: the kernels of a substep store halo planes
+ * (3 for f; 4 for (m,p) because the fused G2P+P2G scatters a particle that has just crossed the boundary before it migrates),
+ * migrating particles and max|v| into the neighbour's memory over NVLink and publish epoch flags; the receiving stream waits for the
+ * flag on the device.  No host synchronisation per substep, no collective-library call; particle counts live on the device.
+ * Cloth: every rank holds the whole mesh (upload it on every rank BEFORE aep_comm_export), transfers only the points in its slab and
+ * pushes what it advected to all ranks.  Device-side overflow (migration buffers, particle capacity) and peer timeouts are sticky and
+ * surface as AEP_ERR_STATE from aep_get_clock / aep_run_frames.                                                                     */
+#define AEP_COMM_BLOB_BYTES 256
+AEP_API int aep_comm_export(aep_ctx* ctx, void* blob256, int64_t migrate_capacity /* particles per side and substep */);
+AEP_API int aep_comm_connect(aep_ctx* ctx, int rank, int world, const void* blobs /* world x 256 bytes */);
+/* several slab contexts inside ONE process (tests; one GPU or several): connect them, initialise and step them in lockstep from one
+ * thread (a context's stream waits on the device for its neighbours, so their work must be queued before the host blocks).       */
+AEP_API int aep_comm_connect_local(aep_ctx** ctxs, int world, int64_t migrate_capacity);
+AEP_API int aep_group_init(aep_ctx** ctxs, int world);
+AEP_API int aep_group_run(aep_ctx** ctxs, int world, int n_substeps);
 
 #ifdef __cplusplus
 }

@@ -80,12 +80,13 @@ void h_frc_scatter(const float* f, const float* A, const float* h, float* out) {
         }
 }
 // ---- the two gathers, exactly as the kernels run them.  vt: nx*ny*nz nodes x (v~x, v~y, v~z, s), node index (k*ny + j)*nx + i.
-// use_tile = 1: the nodes are first staged like stage_tile / tile_issue do (the particle must have a complete stencil), MODE 2;
+// use_tile = 1: the nodes are first staged like the TMA box of hw_tile_issue (zeros outside the grid), MODE 2;
 // use_tile = 0: clamped loads from the grid, MODE 0 (stencils cut by a domain face).
 static GridP small_grid(int nx, int ny, int nz, const float* vt, const float* h) {
     GridP G{}; G.nx = nx; G.ny = ny; G.nz = nz; G.hx = h[0]; G.hy = h[1]; G.hz = h[2];
     G.ihx = 1.0f / h[0]; G.ihy = 1.0f / h[1]; G.ihz = 1.0f / h[2];
     G.vt = reinterpret_cast<float4*>(const_cast<float*>(vt));
+    G.sy = nx; G.sz = (long long)nx * ny; G.a1[0] = G.v1[0] = nx; G.a1[1] = G.v1[1] = ny; G.a1[2] = G.v1[2] = nz;
     return G;
 }
 static int fill_tile(const GridP& G, const int* cell, std::vector<float4>& tile) {      // returns xoff of the particle's first node
@@ -93,7 +94,9 @@ static int fill_tile(const GridP& G, const int* cell, std::vector<float4>& tile)
     tile.assign(TILE_F4, make_float4(1e30f, 1e30f, 1e30f, 1.0f));                       // poison: entries outside the box must not be read
     for (int idx = 0; idx < TILE_F4; ++idx) {
         const int r = idx / TILE_W, x = idx - r * TILE_W, gx = ox0 + x;
-        if (gx >= 0 && gx < G.nx) tile[idx] = G.vt[((size_t)(k0 + (r >> 2)) * G.ny + (j0 + (r & 3))) * G.nx + gx];
+        const int gy = j0 + (r & 3), gz = k0 + (r >> 2);
+        if (gx >= 0 && gx < G.nx && gy >= 0 && gy < G.ny && gz >= 0 && gz < G.nz) tile[idx] = G.vt[nidx(G, gx, gy, gz)];
+        else tile[idx] = make_float4(0.f, 0.f, 0.f, 0.f);                                  // TMA zero fill outside the tensor
     }
     return (cell[0] - 1) - ox0;
 }
@@ -123,10 +126,10 @@ void h_g2p_gather(int nx, int ny, int nz, const float* vt, const int* cell, cons
     if (use_tile) {
         const int xoff = fill_tile(G, cell, tile);
         g2p_gather<2>(G, ax, ay, az, nrx, rx, ry, rz, tile.data(), xoff, S);
-        if (S.smin == 0.0f) g2p_stick_correction<2>(G, ax, ay, az, rx, ry, rz, tile.data(), xoff, S);
+        if (S.smin < 1.0f) g2p_stick_correction<2>(G, ax, ay, az, rx, ry, rz, tile.data(), xoff, S);
     } else {
         g2p_gather<0>(G, ax, ay, az, nrx, rx, ry, rz, nullptr, 0, S);
-        if (S.smin == 0.0f) g2p_stick_correction<0>(G, ax, ay, az, rx, ry, rz, nullptr, 0, S);
+        if (S.smin < 1.0f) g2p_stick_correction<0>(G, ax, ay, az, rx, ry, rz, nullptr, 0, S);
     }
     std::memcpy(va, S.va, 12); std::memcpy(vc, S.vc, 12); std::memcpy(B, S.B, 36); std::memcpy(g, S.g, 36); *smin = S.smin;
 }
