@@ -22,28 +22,41 @@ inline float4* plane_ptr(aep_ctx* c, float4* arr, int p0) {
     return arr + (a == 1 ? nidx(c->G, 0, p0, 0) : nidx(c->G, 0, 0, p0));
 }
 
-int peer_halo(aep_ctx* c, int what, int halt_class) {
+struct HaloGeom { int np; int send0[2], recv0[2]; long long n_f4; int ctas; };
+// (m,p): 4 planes per side -- what I scattered into the neighbour's reach, including the scratch plane that catches particles about
+// to migrate; f: the 3 planes both sides share.  Send range / receive range per side (0 = low neighbour, 1 = high).
+inline HaloGeom halo_geom(aep_ctx* c, int what) {
+    HaloGeom g; const int lo = c->cfg.slab_lo, hi = c->cfg.slab_hi;
+    g.np = what == 0 ? 4 : 3;
+    g.send0[0] = what == 0 ? lo - 2 : lo - 1; g.send0[1] = hi - 1;
+    g.recv0[0] = lo - 1; g.recv0[1] = what == 0 ? hi - 2 : hi - 1;
+    g.n_f4 = (long long)g.np * c->comm.plane_nodes;
+    g.ctas = (int)std::min<long long>((g.n_f4 + 255) / 256, c->sm_count * 4);
+    return g;
+}
+int peer_halo_send(aep_ctx* c, int what, int halt_class) {
     StageTimer T(c, AEP_STAGE_HALO);
     Comm& m = c->comm;
     const int a = c->cfg.slab_axis, nres = c->cfg.res[a];
     float4* arr = what == 0 ? c->G.mp : c->G.f;
-    // (m,p): 4 planes per side -- what I scattered into the neighbour's reach, including the scratch plane that catches particles about
-    // to migrate; f: the 3 planes both sides share.  Send range / receive range per side (0 = low neighbour, 1 = high):
-    const int np = what == 0 ? 4 : 3;
-    const int lo = c->cfg.slab_lo, hi = c->cfg.slab_hi;
-    const int send0[2] = { what == 0 ? lo - 2 : lo - 1, hi - 1 };
-    const int recv0[2] = { lo - 1, what == 0 ? hi - 2 : hi - 1 };
-    const long long n_f4 = (long long)np * m.plane_nodes;
-    const int ctas = (int)std::min<long long>((n_f4 + 255) / 256, c->sm_count * 4);
+    const HaloGeom g = halo_geom(c, what);
     for (int side = 0; side < 2; ++side) {
         if (!m.peers.halo_in[what][side]) continue;
-        if (send0[side] < 0 || send0[side] + np > nres) return fail(c, AEP_ERR_INVALID, "slab too close to the domain face for the halo planes");
+        if (g.send0[side] < 0 || g.send0[side] + g.np > nres) return fail(c, AEP_ERR_INVALID, "slab too close to the domain face for the halo planes");
         const int nb = side == 0 ? m.rank - 1 : m.rank + 1;
-        k_peer_halo_send<<<ctas, 256, 0, c->stream>>>(plane_ptr(c, arr, send0[side]), n_f4, m.peers.halo_in[what][side],
+        k_peer_halo_send<<<g.ctas, 256, 0, c->stream>>>(plane_ptr(c, arr, g.send0[side]), g.n_f4, m.peers.halo_in[what][side],
                                                       &m.peers.head[nb]->halo_flag[what][1 - side], &m.d_local->halo_epoch[what][side],
                                                       &m.d_local->done[what * 2 + side], c->d_clk, halt_class);
         LAUNCH_OK("k_peer_halo_send");
     }
+    return AEP_OK;
+}
+int peer_halo_recv(aep_ctx* c, int what, int halt_class) {
+    StageTimer T(c, AEP_STAGE_HALO);
+    Comm& m = c->comm;
+    const int a = c->cfg.slab_axis;
+    float4* arr = what == 0 ? c->G.mp : c->G.f;
+    const HaloGeom g = halo_geom(c, what);
     CommHead* me = m.peers.head[m.rank];
     const bool has0 = m.peers.halo_in[what][0] != nullptr, has1 = m.peers.halo_in[what][1] != nullptr;
     if (has0 || has1) {
@@ -54,24 +67,33 @@ int peer_halo(aep_ctx* c, int what, int halt_class) {
     for (int side = 0; side < 2; ++side) {
         if (!m.peers.halo_in[what][side]) continue;
         float4* buf = reinterpret_cast<float4*>(m.block + m.halo_off[what][side]);
-        k_peer_halo_add<<<ctas, 256, 0, c->stream>>>(plane_ptr(c, arr, recv0[side]), buf, n_f4, c->G, a, recv0[side], m.plane_nodes, c->d_clk, halt_class);
+        k_peer_halo_add<<<g.ctas, 256, 0, c->stream>>>(plane_ptr(c, arr, g.recv0[side]), buf, g.n_f4, c->G, a, g.recv0[side], m.plane_nodes, c->d_clk, halt_class);
         LAUNCH_OK("k_peer_halo_add");
     }
     return AEP_OK;
 }
 
-int peer_vmax(aep_ctx* c, int halt_class) {
+int peer_vmax_share(aep_ctx* c, int halt_class) {
     Comm& m = c->comm;
     k_peer_vmax_share<<<1, 32, 0, c->stream>>>(m.peers, m.d_local, c->d_clk, halt_class); LAUNCH_OK("k_peer_vmax_share");
+    return AEP_OK;
+}
+int peer_vmax_reduce(aep_ctx* c, int halt_class) {
+    Comm& m = c->comm;
     k_peer_vmax_reduce<<<1, 1, 0, c->stream>>>(m.peers, m.d_local, c->d_clk, halt_class); LAUNCH_OK("k_peer_vmax_reduce");
     return AEP_OK;
 }
 
-int peer_migrate(aep_ctx* c) {
+int peer_migrate_send(aep_ctx* c) {
     StageTimer T(c, AEP_STAGE_HALO);
     Comm& m = c->comm;
     k_peer_migrate_send<<<2 * cdiv(c->mig.cap, 256), 256, 0, c->stream>>>(c->P[c->cur], c->mig, m.peers, m.d_local, c->d_clk, 2);
     LAUNCH_OK("k_peer_migrate_send");
+    return AEP_OK;
+}
+int peer_migrate_recv(aep_ctx* c) {
+    StageTimer T(c, AEP_STAGE_HALO);
+    Comm& m = c->comm;
     CommHead* me = m.peers.head[m.rank];
     const bool has0 = m.rank > 0, has1 = m.rank < m.world - 1;
     if (has0 || has1) {
@@ -84,8 +106,8 @@ int peer_migrate(aep_ctx* c) {
     return AEP_OK;
 }
 
-// cloth: what this rank advanced (0: vertices, 1: elements) -> every rank's copy, then wait for everybody else's
-int peer_mesh_sync(aep_ctx* c, int which) {
+// cloth: what this rank advanced (0: vertices, 1: elements) -> every rank's copy ... then wait for everybody else's
+int peer_mesh_push(aep_ctx* c, int which) {
     Comm& m = c->comm;
     if (m.world < 2 || !c->mesh.nv) return AEP_OK;
     const MeshState& ms = c->mesh;
@@ -94,8 +116,27 @@ int peer_mesh_sync(aep_ctx* c, int which) {
     dim3 grid((unsigned)std::min(cdiv(n, 256), c->sm_count * 2), (unsigned)m.world);
     k_peer_mesh_push<<<grid, 256, 0, c->stream>>>(m.peers, m.d_local, which == 0 ? ms.owner_v : ms.owner_e, off, narr, n, which, c->d_clk, 2);
     LAUNCH_OK("k_peer_mesh_push");
+    return AEP_OK;
+}
+int peer_mesh_wait(aep_ctx* c, int which) {
+    Comm& m = c->comm;
+    if (m.world < 2 || !c->mesh.nv) return AEP_OK;
     k_peer_mesh_wait<<<1, 1, 0, c->stream>>>(m.peers, m.d_local, which, c->d_clk, 2);
     LAUNCH_OK("k_peer_mesh_wait");
+    return AEP_OK;
+}
+
+// inside one process the members' streams are ordered by events (see Comm::group): a phase waits for the phase before it of every member
+int phase_begin(aep_ctx* c, int phase) {
+    Comm& m = c->comm;
+    if (m.group.empty() || phase == 0) return AEP_OK;
+    for (aep_ctx* g : m.group) if (g != c) CU(cudaStreamWaitEvent(c->stream, g->comm.ev_phase[phase - 1], 0));
+    return AEP_OK;
+}
+int phase_end(aep_ctx* c, int phase) {
+    Comm& m = c->comm;
+    if (m.group.empty()) return AEP_OK;
+    CU(cudaEventRecord(m.ev_phase[phase], c->stream));
     return AEP_OK;
 }
 
@@ -191,6 +232,11 @@ int aep_comm_connect_local(aep_ctx** ctxs, int world, int64_t migrate_capacity) 
     std::vector<CommBlob> blobs((size_t)world);
     for (int r = 0; r < world; ++r) { int rc = aep_comm_export(ctxs[r], &blobs[r], migrate_capacity); if (rc) return rc; }
     for (int r = 0; r < world; ++r) { int rc = aep_comm_connect(ctxs[r], r, world, blobs.data()); if (rc) return rc; }
+    for (int r = 0; r < world; ++r) {
+        aep_ctx* c = ctxs[r]; cudaSetDevice(c->device);
+        c->comm.group.assign(ctxs, ctxs + world);
+        for (int i = 0; i < 8; ++i) if (!c->comm.ev_phase[i]) CU(cudaEventCreateWithFlags(&c->comm.ev_phase[i], cudaEventDisableTiming));
+    }
     return AEP_OK;
 }
 // ... and step them in lockstep from one host thread: a context's stream waits (on the device) for flags its neighbours raise in the
@@ -207,13 +253,10 @@ int aep_group_run(aep_ctx** ctxs, int world, int n_substeps) {
     int rc;
     for (int r = 0; r < world; ++r) if ((rc = require_init(ctxs[r]))) return rc;
     for (int s = 0; s < n_substeps; ++s) {
-        // launches of every context first, then the (possibly host-synchronising) re-sort decisions
-        for (int r = 0; r < world; ++r) {
-            aep_ctx* c = ctxs[r]; cudaSetDevice(c->device);
-            const bool was = c->use_graph; c->use_graph = false;            // a sort inside do_substep would synchronise: split it
-            rc = enqueue_substep(c); c->use_graph = was;
-            if (rc) return rc;
-        }
+        // phase by phase over the members (a phase waits on events the members record at the end of the phase before), then the
+        // (possibly host-synchronising) re-sort decisions
+        for (int ph = 0; ph < SUBSTEP_PHASES; ++ph)
+            for (int r = 0; r < world; ++r) { cudaSetDevice(ctxs[r]->device); if ((rc = enqueue_phase(ctxs[r], ph))) return rc; }
         for (int r = 0; r < world; ++r) { cudaSetDevice(ctxs[r]->device); if ((rc = maybe_sort(ctxs[r]))) return rc; }
     }
     return AEP_OK;

@@ -53,6 +53,11 @@ struct Comm {
     CommLocal* d_local = nullptr;
     CommPeers peers{};
     std::vector<void*> opened;                               // cudaIpcOpenMemHandle mappings to close
+    // several slab contexts inside ONE process (aep_comm_connect_local): a device-side spin on a flag that another stream of the same
+    // GPU must raise can starve (streams may share a hardware queue), so inside a process the phases of a substep are ordered by
+    // CUDA events between the members' streams; the flag protocol runs all the same and finds its flags already raised
+    std::vector<aep_ctx*> group;
+    cudaEvent_t ev_phase[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 }  // namespace
@@ -105,6 +110,7 @@ struct aep_ctx {
     // lagged, non-blocking readback of the telemetry
     static constexpr int RING = 4, LAG = 2;
     Telemetry* h_ring = nullptr; cudaEvent_t ring_ev[RING] = {nullptr, nullptr, nullptr, nullptr};
+    SimClock* h_clk = nullptr; cudaEvent_t clk_ev[2] = {nullptr, nullptr};     // aep_run_frames polls the device clock through these
     long long step_counter = 0, last_sort_step = -1;
     long long sorts = 0;
 
@@ -370,24 +376,27 @@ int do_clock(aep_ctx* c) {
     return AEP_OK;
 }
 
-int peer_mesh_sync(aep_ctx* c, int which);
+int peer_mesh_push(aep_ctx* c, int which);
+int peer_mesh_wait(aep_ctx* c, int which);
 
-// scatter: the fused kernel (G2P + P2G of the next substep); otherwise G2P alone (stage-level API, caller-driven slab path)
+// particles: the fused kernel (G2P + P2G of the next substep), or G2P alone (stage-level API, caller-driven slab path)
+int do_g2p_particles(aep_ctx* c, bool scatter) {
+    if (!n_launch(c)) return AEP_OK;
+    StageTimer T(c, scatter ? AEP_STAGE_G2P2G : AEP_STAGE_G2P);
+    if (c->mig.axis >= 0 && !peer_mode(c)) cudaMemsetAsync(c->mig.counts, 0, 2 * sizeof(unsigned long long), c->stream);
+    cudaError_t e = scatter ? g2p2g_launch<true>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig)
+                            : g2p2g_launch<false>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig);
+    if (e != cudaSuccess) return fail(c, AEP_ERR_CUDA, "k_g2p2g: %s", cudaGetErrorString(e));
+    LAUNCH_OK("k_g2p2g");
+    return AEP_OK;
+}
+// whole G2P of a context without peers (mesh included)
 int do_g2p(aep_ctx* c, bool scatter) {
-    if (n_launch(c)) {
-        StageTimer T(c, scatter ? AEP_STAGE_G2P2G : AEP_STAGE_G2P);
-        if (c->mig.axis >= 0 && !peer_mode(c)) cudaMemsetAsync(c->mig.counts, 0, 2 * sizeof(unsigned long long), c->stream);
-        cudaError_t e = scatter ? g2p2g_launch<true>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig)
-                                : g2p2g_launch<false>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig);
-        if (e != cudaSuccess) return fail(c, AEP_ERR_CUDA, "k_g2p2g: %s", cudaGetErrorString(e));
-        LAUNCH_OK("k_g2p2g");
-    }
+    if (int r = do_g2p_particles(c, scatter)) return r;
     if (c->mesh.nv) {
         StageTimer T(c, AEP_STAGE_MESH);
         if (mesh_g2p_vertices(c->mesh, c->G, c->d_clk, c->stream, &c->launches)) return fail(c, AEP_ERR_CUDA, "mesh_g2p failed");
-        if (peer_mode(c)) { if (int r = peer_mesh_sync(c, 0)) return r; }          // elements read the advected vertices of every rank
         if (mesh_g2p_elements(c->mesh, c->G, c->d_clk, c->stream, &c->launches)) return fail(c, AEP_ERR_CUDA, "mesh_g2p failed");
-        if (peer_mode(c)) { if (int r = peer_mesh_sync(c, 1)) return r; }
         if (scatter) { if (mesh_p2g(c->mesh, c->G, c->d_clk, c->stream, &c->launches)) return fail(c, AEP_ERR_CUDA, "mesh_p2g failed"); }
     }
     if (scatter) c->grid_mode = 0;
@@ -425,24 +434,71 @@ int compact_slab(aep_ctx* c) {
     return do_sort(c);
 }
 
-int peer_halo(aep_ctx* c, int what, int halt_class);
-int peer_vmax(aep_ctx* c, int halt_class);
-int peer_migrate(aep_ctx* c);
+int peer_halo_send(aep_ctx* c, int what, int halt_class);
+int peer_halo_recv(aep_ctx* c, int what, int halt_class);
+int peer_vmax_share(aep_ctx* c, int halt_class);
+int peer_vmax_reduce(aep_ctx* c, int halt_class);
+int peer_migrate_send(aep_ctx* c);
+int peer_migrate_recv(aep_ctx* c);
+int phase_begin(aep_ctx* c, int phase);
+int phase_end(aep_ctx* c, int phase);
 
+// One substep in phases.  A phase ends where this rank has stored something into its neighbours' memory and begins with waiting for
+// what they stored (on the device: flags between processes, stream events inside one process).  Without peers the phases simply run
+// back to back: forces | grid update | clock, G2P+P2G (mesh: vertices | elements | P2G) | migration | halo of (m,p).
+enum { SUBSTEP_PHASES = 7 };
+int enqueue_phase(aep_ctx* c, int ph) {
+    int r;
+    const bool peer = peer_mode(c), mesh = c->mesh.nv != 0;
+    if (peer && (r = phase_begin(c, ph))) return r;
+    switch (ph) {
+    case 0:
+        if (mesh && mesh_own_snapshot(c->mesh, c->d_clk, c->stream, &c->launches)) return fail(c, AEP_ERR_CUDA, "mesh ownership snapshot failed");
+        if ((r = do_forces(c, true))) return r;                    // HS:873  (dt of the previous iteration)
+        if (peer && (r = peer_halo_send(c, 1, 1))) return r;
+        break;
+    case 1:
+        if (peer && (r = peer_halo_recv(c, 1, 1))) return r;
+        if ((r = do_grid(c, true))) return r;                      // HS:877, 899
+        if (peer && (r = peer_vmax_share(c, 1))) return r;
+        break;
+    case 2:
+        if (peer && (r = peer_vmax_reduce(c, 1))) return r;
+        if ((r = do_clock(c))) return r;                           // HS:878-892
+        if ((r = do_g2p_particles(c, true))) return r;             // HS:903-959 and, fused, HS:987 (the order of HS:963-983 never affects results)
+        c->grid_mode = 0;
+        if (mesh) {
+            if (mesh_g2p_vertices(c->mesh, c->G, c->d_clk, c->stream, &c->launches)) return fail(c, AEP_ERR_CUDA, "mesh_g2p failed");
+            if (peer && (r = peer_mesh_push(c, 0))) return r;       // elements read the advected vertices of every rank
+        }
+        break;
+    case 3:
+        if (mesh) {
+            if (peer && (r = peer_mesh_wait(c, 0))) return r;
+            if (mesh_g2p_elements(c->mesh, c->G, c->d_clk, c->stream, &c->launches)) return fail(c, AEP_ERR_CUDA, "mesh_g2p failed");
+            if (peer && (r = peer_mesh_push(c, 1))) return r;
+        }
+        break;
+    case 4:
+        if (mesh) {
+            if (peer && (r = peer_mesh_wait(c, 1))) return r;
+            if (mesh_p2g(c->mesh, c->G, c->d_clk, c->stream, &c->launches)) return fail(c, AEP_ERR_CUDA, "mesh_p2g failed");
+        }
+        if (peer && (r = peer_migrate_send(c))) return r;
+        break;
+    case 5:
+        if (peer) { if ((r = peer_migrate_recv(c))) return r; if ((r = peer_halo_send(c, 0, 2))) return r; }
+        break;
+    case 6:
+        if (peer && (r = peer_halo_recv(c, 0, 2))) return r;
+        break;
+    }
+    if (peer && (r = phase_end(c, ph))) return r;
+    return AEP_OK;
+}
 // one substep, launches only (what the graph captures)
 int enqueue_substep(aep_ctx* c) {
-    int r;
-    if (c->mesh.nv && mesh_own_snapshot(c->mesh, c->d_clk, c->stream, &c->launches)) return fail(c, AEP_ERR_CUDA, "mesh ownership snapshot failed");
-    if ((r = do_forces(c, true))) return r;                    // HS:873  (dt of the previous iteration)
-    if (peer_mode(c) && (r = peer_halo(c, 1, 1))) return r;
-    if ((r = do_grid(c, true))) return r;                      // HS:877, 899
-    if (peer_mode(c) && (r = peer_vmax(c, 1))) return r;
-    if ((r = do_clock(c))) return r;                           // HS:878-892
-    if ((r = do_g2p(c, true))) return r;                       // HS:903-959 and, fused, HS:987 (the order of HS:963-983 never affects results)
-    if (peer_mode(c)) {
-        if ((r = peer_migrate(c))) return r;
-        if ((r = peer_halo(c, 0, 2))) return r;
-    }
+    for (int ph = 0; ph < SUBSTEP_PHASES; ++ph) if (int r = enqueue_phase(c, ph)) return r;
     return AEP_OK;
 }
 
@@ -631,6 +687,8 @@ int aep_create(aep_ctx** out, const aep_config* cfg) {
     CUC(cudaEventCreateWithFlags(&ctx->frame_ev, cudaEventDisableTiming));
     CUC(cudaMallocHost((void**)&ctx->h_ring, aep_ctx::RING * sizeof(Telemetry)));
     for (int i = 0; i < aep_ctx::RING; ++i) { ctx->h_ring[i] = Telemetry{0.f, 0, 0, 0}; CUC(cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming)); }
+    CUC(cudaMallocHost((void**)&ctx->h_clk, 2 * sizeof(SimClock)));
+    for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&ctx->clk_ev[i], cudaEventDisableTiming));
     {   // sort keys: (brick << 6) | cell-in-brick, see sort_key()
         const size_t nkeys = (size_t)G.nqx * G.nqy * ((G.nz + 3) / 4) * 64;
         ctx->key_bits = 1; while (((size_t)1 << ctx->key_bits) < nkeys) ctx->key_bits++;
@@ -650,6 +708,7 @@ int aep_destroy(aep_ctx* c) {
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->graph) cudaGraphExecDestroy(c->graph);
     for (void* p : c->comm.opened) cudaIpcCloseMemHandle(p);
+    for (int i = 0; i < 8; ++i) if (c->comm.ev_phase[i]) cudaEventDestroy(c->comm.ev_phase[i]);
     if (c->comm.block) cudaFree(c->comm.block);
     if (c->comm.d_local) cudaFree(c->comm.d_local);
     for (void* p : c->dev_allocs) cudaFree(p);
@@ -658,6 +717,8 @@ int aep_destroy(aep_ctx* c) {
     if (c->d_sort_tmp) cudaFree(c->d_sort_tmp);
     mesh_free(c->mesh);
     if (c->h_ring) cudaFreeHost(c->h_ring);
+    if (c->h_clk) cudaFreeHost(c->h_clk);
+    for (int i = 0; i < 2; ++i) if (c->clk_ev[i]) cudaEventDestroy(c->clk_ev[i]);
     for (int i = 0; i < aep_ctx::RING; ++i) if (c->ring_ev[i]) cudaEventDestroy(c->ring_ev[i]);
     if (c->tm.ev[0]) cudaEventDestroy(c->tm.ev[0]);
     if (c->tm.ev[1]) cudaEventDestroy(c->tm.ev[1]);
@@ -806,18 +867,20 @@ int aep_init_begin(aep_ctx* c) {
     int r;
     if ((r = do_sort(c))) return r;
     if ((r = do_p2g(c, false))) return r;                                   // HS:854 (mass / momentum part)
-    if (peer_mode(c) && (r = peer_halo(c, 0, 3))) return r;
+    if (peer_mode(c)) { if ((r = peer_halo_send(c, 0, 3))) return r; if ((r = phase_end(c, 0))) return r; }
     return AEP_OK;
 }
 int aep_init_volumes(aep_ctx* c) {
     int r = require_init(c); if (r) return r;
+    if (peer_mode(c)) { if ((r = phase_begin(c, 1))) return r; if ((r = peer_halo_recv(c, 0, 3))) return r; }
     if (c->n) { k_init_volumes<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->P[c->cur], c->G, (int)c->n); LAUNCH_OK("k_init_volumes"); }   // HS:242-249
     k_vmax_from_mp<<<c->nrun, 256, 0, c->stream>>>(c->G, c->d_clk); LAUNCH_OK("k_vmax_from_mp");
-    if (peer_mode(c) && (r = peer_vmax(c, 3))) return r;
+    if (peer_mode(c)) { if ((r = peer_vmax_share(c, 3))) return r; if ((r = phase_end(c, 1))) return r; }
     return AEP_OK;
 }
 int aep_init_dt_async(aep_ctx* c) {
     int r = require_init(c); if (r) return r;
+    if (peer_mode(c)) { if ((r = phase_begin(c, 2))) return r; if ((r = peer_vmax_reduce(c, 3))) return r; }
     k_initial_dt<<<1, 1, 0, c->stream>>>(c->d_clk); LAUNCH_OK("k_initial_dt");  // HS:860
     return AEP_OK;
 }
@@ -853,13 +916,18 @@ int aep_run_frames(aep_ctx* c, int n_frames, int max_substeps, int64_t* substeps
     static_assert(offsetof(SimClock, stop_substep) - offsetof(SimClock, halt) == 8, "halt, stop_frame, stop_substep are contiguous");
     CU(cudaMemcpyAsync(&c->d_clk->halt, &stop, sizeof stop, cudaMemcpyHostToDevice, c->stream));
     // a frame takes >= 1/(60 dt_max) = 5 substeps (dt <= cfl/rate_floor): poll the device clock every BURST substeps, one burst late
+    // (the clock of burst i is read while burst i+1 is already queued: the device never waits for the host; what was queued behind the
+    // halt costs a few empty launches)
     const int BURST = 8;
     bool done = n_frames == 0 || max_substeps == 0;
-    long long queued = 0;
+    long long queued = 0; int pending = -1;
     while (!done) {
         for (int s = 0; s < BURST; ++s) { if ((r = do_substep(c))) return r; ++queued; }
-        CU(cudaMemcpyAsync(&clk, c->d_clk, sizeof clk, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
-        done = clk.halt != 0 || clk.comm_timeout;
+        const int slot = (int)((queued / BURST) & 1);
+        CU(cudaMemcpyAsync(&c->h_clk[slot], c->d_clk, sizeof(SimClock), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaEventRecord(c->clk_ev[slot], c->stream));
+        if (pending >= 0) { CU(cudaEventSynchronize(c->clk_ev[pending])); done = c->h_clk[pending].halt != 0 || c->h_clk[pending].comm_timeout != 0; }
+        pending = slot;
         if (queued > (long long)max_substeps + 2 * BURST) done = true;
     }
     CU(cudaMemcpyAsync(&clk, c->d_clk, sizeof clk, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
@@ -1013,6 +1081,9 @@ int aep_frame_positions_begin(aep_ctx* c, float* pinned_xyz) {
     c->frame_pending = true;
     return AEP_OK;
 }
+// page-locked host memory for the asynchronous downloads (the host layer is plain C++ and has no CUDA runtime of its own)
+void* aep_host_alloc(int64_t bytes) { void* p = nullptr; return (bytes > 0 && cudaMallocHost(&p, (size_t)bytes) == cudaSuccess) ? p : nullptr; }
+void aep_host_free(void* p) { if (p) cudaFreeHost(p); }
 int aep_frame_positions_wait(aep_ctx* c) {
     if (!c) return AEP_ERR_INVALID;
     cudaSetDevice(c->device);

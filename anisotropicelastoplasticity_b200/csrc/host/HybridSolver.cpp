@@ -235,7 +235,10 @@ struct BlobReader {
 }  // namespace
 
 void HybridSolver::writeStateFile(const std::string& path, const ParticleSystem* ps, const LagrangianMesh* mesh, const double clock5[5]) {
-    BlobWriter w(path);
+    // written next to the target and renamed over it: a crash in the middle of the write leaves the previous restart file intact
+    const std::string tmp = path + ".tmp";
+    {
+    BlobWriter w(tmp);
     const double version = 1.0;
     w.put("aep_checkpoint", &version, 1); w.put("clock", clock5, 5);                      // dt, t, inner_t, frame_no, substeps
     if (ps) {
@@ -255,6 +258,8 @@ void HybridSolver::writeStateFile(const std::string& path, const ParticleSystem*
         const std::vector<double> ed = stack3(m.elementDirections_1, m.elementDirections_2, m.elementDirections_3);
         w.put("m_vB", vB.data(), (int64_t)vB.size()); w.put("m_eB", eB.data(), (int64_t)eB.size()); w.put("m_ed", ed.data(), (int64_t)ed.size());
     }
+    }   // BlobWriter's destructor finalises and closes the file
+    if (std::rename(tmp.c_str(), path.c_str()) != 0) throw std::runtime_error("cannot move " + tmp + " over " + path);
 }
 
 void HybridSolver::readStateFile(const std::string& path, ParticleSystem* ps, LagrangianMesh* mesh, double clock5[5]) {
@@ -319,19 +324,70 @@ void HybridSolver::writeFrame_(int frameNo) {                                   
 }
 
 // alpha (FLIP blend) is accepted and ignored, exactly as in the reference (HybridSolver.cpp:739: pure APIC/PIC).
+// Frame pipeline: the positions of frame N are snapshotted on the device the moment the frame completes and travel to page-locked
+// host memory on a second stream while frame N+1 computes; particle_N.obj is written by a helper thread while frame N+2 computes.
+// aep_run_frames fails loudly (AEP_ERR_STATE -> exception) when particles left the grid or became NaN: no plausible-looking
+// frames of a blown-up simulation are written.
 void HybridSolver::solve(double CFL, double maxt, double /*alpha*/) {
     begin(CFL);
     if (write_frames_) {                                                        // HybridSolver.cpp:857-858 (system("mkdir ..."))
         ::mkdir(out_dir_.c_str(), 0777); ::mkdir((out_dir_ + "/particle").c_str(), 0777); ::mkdir((out_dir_ + "/mesh").c_str(), 0777);
     }
-    double t = 0.0; int frameNo = 0;
-    while (t <= maxt) {                                                         // HybridSolver.cpp:867; t advances by 1/60 per finished frame (:883)
-        const int n = advanceFrames(1);
-        t += 1.0 / 60.0;
-        fetchPositions();
-        if (write_frames_) writeFrame_(frameNo);
-        if (verbose_) std::clog << "frame " << frameNo << ": time " << t << ", " << n << " substeps" << std::endl;
-        ++frameNo;
+    const size_t np = ps_ ? (size_t)ps_->masses.size() : 0;
+    float* pin[2] = { nullptr, nullptr };
+    if (np) for (int b = 0; b < 2; ++b) {
+        pin[b] = static_cast<float*>(aep_host_alloc((int64_t)(np * 3 * sizeof(float))));
+        if (!pin[b]) { if (pin[0]) aep_host_free(pin[0]); throw std::runtime_error("HybridSolver::solve: cannot allocate page-locked frame buffers"); }
     }
+    std::thread writer; std::exception_ptr werr;
+    auto finish_frame = [&](int frame, int buf, double tt, int nsub) {          // frame's positions have landed in pin[buf]
+        if (np) {
+            std::lock_guard<std::mutex> lk(mtx_);                               // the render thread reads positions (main.cpp:19-24)
+            for (size_t p = 0; p < np; ++p) for (int a = 0; a < 3; ++a) ps_->positions((std::ptrdiff_t)p, a) = pin[buf][3 * p + a];
+        }
+        if (write_frames_) writeFrame_(frame);
+        if (verbose_) std::clog << "frame " << frame << ": time " << tt << ", " << nsub << " substeps" << std::endl;
+    };
+    struct Pending { int frame = -1, buf = 0, n = 0; double t = 0.0; } pend;
+    auto flush_pending = [&](bool in_background) {                              // the copy of pend.frame has had a whole frame of compute to land
+        if (pend.frame < 0) return;
+        ck(aep_frame_positions_wait(ctx_), ctx_, "aep_frame_positions_wait");
+        if (writer.joinable()) writer.join();                                   // the frame before it is on disk; its buffer is free again
+        if (werr) std::rethrow_exception(werr);
+        const Pending p = pend; pend.frame = -1;
+        if (in_background) writer = std::thread([&, p]() { try { finish_frame(p.frame, p.buf, p.t, p.n); } catch (...) { werr = std::current_exception(); } });
+        else finish_frame(p.frame, p.buf, p.t, p.n);
+    };
+    double t = 0.0; int frameNo = 0;
+    try {
+        while (t <= maxt) {                                                     // HybridSolver.cpp:867; t advances by 1/60 per finished frame (:883)
+            const int n = advanceFrames(1);
+            t += 1.0 / 60.0;
+            if (np && !mesh_) {
+                flush_pending(true);
+                ck(aep_frame_positions_begin(ctx_, pin[frameNo & 1]), ctx_, "aep_frame_positions_begin");
+                pend.frame = frameNo; pend.buf = frameNo & 1; pend.n = n; pend.t = t;
+            } else {                                                            // with a mesh (small scenes): frame by frame
+                if (mesh_) {
+                    std::lock_guard<std::mutex> lk(mtx_);
+                    ck(aep_download_mesh(ctx_, mesh_->vertexPositions.data(), nullptr, nullptr, mesh_->elementPositions.data(), nullptr, nullptr, nullptr), ctx_, "aep_download_mesh");
+                }
+                if (np) {
+                    ck(aep_frame_positions_begin(ctx_, pin[0]), ctx_, "aep_frame_positions_begin");
+                    ck(aep_frame_positions_wait(ctx_), ctx_, "aep_frame_positions_wait");
+                }
+                finish_frame(frameNo, 0, t, n);
+            }
+            ++frameNo;
+        }
+        flush_pending(false);
+        if (writer.joinable()) writer.join();
+        if (werr) std::rethrow_exception(werr);
+    } catch (...) {
+        if (writer.joinable()) writer.join();
+        for (int b = 0; b < 2; ++b) if (pin[b]) aep_host_free(pin[b]);
+        throw;
+    }
+    for (int b = 0; b < 2; ++b) if (pin[b]) aep_host_free(pin[b]);
     finish();
 }

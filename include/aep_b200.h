@@ -192,6 +192,9 @@ AEP_API int aep_download_positions_f32(aep_ctx* ctx, float* xyz);
  * compute; wait blocks until the copy has landed.  One download can be in flight per context.                     */
 AEP_API int aep_frame_positions_begin(aep_ctx* ctx, float* pinned_xyz);
 AEP_API int aep_frame_positions_wait(aep_ctx* ctx);
+/* page-locked host memory for the asynchronous download (NULL on failure); plain host code needs no CUDA runtime of its own      */
+AEP_API void* aep_host_alloc(int64_t bytes);
+AEP_API void aep_host_free(void* p);
 /* bulk statistics on the device: centre of mass (3), kinetic energy, mean det F_P, total mass.             */
 AEP_API int aep_stats(aep_ctx* ctx, double* com3, double* kinetic, double* mean_jp, double* mass);
 

@@ -124,6 +124,15 @@ int aep_download_grid(aep_ctx* c, double* m, double* v, double* f, double* vt) {
     if (vt) for (int64_t i = 0; i < 3 * Ng; ++i) vt[i] = 14.0;
     return AEP_OK;
 }
+// the asynchronous per-frame download: float32 xyz per particle, same pattern as aep_download_particles(x)
+int aep_frame_positions_begin(aep_ctx* c, float* xyz) {
+    c->calls.push_back("aep_frame_positions_begin");
+    for (int64_t p = 0; p < c->n; ++p) for (int a = 0; a < 3; ++a) xyz[3 * p + a] = (float)(c->x[(size_t)(a * c->n + p)] + 0.01 * c->frames);
+    return AEP_OK;
+}
+int aep_frame_positions_wait(aep_ctx* c) { c->calls.push_back("aep_frame_positions_wait"); return AEP_OK; }
+void* aep_host_alloc(int64_t bytes) { return bytes > 0 ? std::malloc((size_t)bytes) : nullptr; }
+void aep_host_free(void* p) { std::free(p); }
 int aep_set_fixed_dt(aep_ctx* c, double) { c->calls.push_back("aep_set_fixed_dt"); return AEP_OK; }
 int aep_resume(aep_ctx* c) { c->calls.push_back("aep_resume"); return AEP_OK; }
 int aep_set_clock(aep_ctx* c, double, double, double, int32_t fr, int64_t ss) { c->calls.push_back("aep_set_clock"); c->frames = fr; c->substeps = ss; return AEP_OK; }

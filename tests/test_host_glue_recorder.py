@@ -75,9 +75,13 @@ def test_solve_plumbing(binding, recorder_dir, tmp_path, request):
     head = ["aep_create", "aep_upload_particles", "aep_upload_mesh", "aep_set_levelset_samples", "aep_init"]
     assert calls[:5] == head and calls[-1] == "aep_destroy"
     assert calls.count("aep_run_frames") == n_frames == int(rec["cfg"][11])
-    per_frame = calls[5:5 + 3 * n_frames]
-    assert per_frame == ["aep_run_frames", "aep_download_particles(x)", "aep_download_mesh(x)"] * n_frames          # positions only, once per frame
-    assert calls[5 + 3 * n_frames:-1] == ["aep_download_particles(all)", "aep_download_mesh(all)", "aep_download_grid"]
+    # positions only, once per frame: binding A through the pinned float32 frame download, binding B through the fp64 download
+    frame_calls = (["aep_run_frames", "aep_download_mesh(x)", "aep_frame_positions_begin", "aep_frame_positions_wait"] if binding == "A"
+                   else ["aep_run_frames", "aep_download_particles(x)", "aep_download_mesh(x)"])
+    nfc = len(frame_calls)
+    per_frame = calls[5:5 + nfc * n_frames]
+    assert per_frame == frame_calls * n_frames
+    assert calls[5 + nfc * n_frames:-1] == ["aep_download_particles(all)", "aep_download_mesh(all)", "aep_download_grid"]
     # ---- configuration: the grid of the RegularGrid, CFL, SAND (HS:873)
     assert rec["cfg"][0] == 1 and rec["cfg"][1] == scene.cfl and np.allclose(rec["cfg"][2:8], np.concatenate([g.mn, g.mx])) and list(rec["cfg"][8:11]) == list(g.res)
     # ---- what reached the ABI: the containers' arrays in the reference's layouts
