@@ -45,7 +45,7 @@ SYMBOLS = (
     "aep_halo_pack", "aep_halo_add", "aep_vmax_get", "aep_vmax_set", "aep_step_forces", "aep_step_grid", "aep_step_g2p",
     "aep_step_p2g", "aep_migrate_extract", "aep_migrate_insert", "aep_migrate_bind", "aep_migrate_extract_begin", "aep_migrate_extract_end",
     "aep_step_p2g_arrivals", "aep_set_particle_id_base", "aep_download_particles_local", "aep_resume", "aep_set_clock",
-    "aep_set_escaped", "aep_host_alloc", "aep_host_free", "aep_set_collider_motion", "aep_init_dt_async", "aep_frame_positions_begin", "aep_frame_positions_wait", "aep_get_counters",
+    "aep_set_escaped", "aep_host_alloc", "aep_host_free", "aep_set_collider_motion", "aep_init_dt_async", "aep_frame_positions_begin", "aep_frame_positions_wait", "aep_get_counters", "aep_get_migration",
     "aep_comm_export", "aep_comm_connect", "aep_comm_connect_local", "aep_group_init", "aep_group_run",
 )
 COMM_BLOB_BYTES = 256
@@ -105,6 +105,7 @@ def load():
     L.aep_set_collider_motion.argtypes = [vp, dp]
     L.aep_frame_positions_begin.argtypes = [vp, C.POINTER(C.c_float)]
     L.aep_get_counters.argtypes = [vp, i64p, i64p, i64p, i64p]
+    L.aep_get_migration.argtypes = [vp, i64p, i64p]
     L.aep_comm_export.argtypes = [vp, vp, C.c_int64]
     L.aep_comm_connect.argtypes = [vp, C.c_int, C.c_int, vp]
     L.aep_comm_connect_local.argtypes = [C.POINTER(vp), C.c_int, C.c_int64]

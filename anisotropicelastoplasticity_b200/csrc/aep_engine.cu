@@ -1006,6 +1006,15 @@ int aep_get_counters(aep_ctx* c, int64_t* sorts, int64_t* slots, int64_t* dead, 
     return AEP_OK;
 }
 
+int aep_get_migration(aep_ctx* c, int64_t* sent, int64_t* received) {
+    if (!c) return AEP_ERR_INVALID;
+    cudaSetDevice(c->device);
+    SimClock clk;
+    CU(cudaMemcpyAsync(&clk, c->d_clk, sizeof clk, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
+    if (sent) *sent = (int64_t)clk.mig_sent; if (received) *received = (int64_t)clk.mig_received;
+    return AEP_OK;
+}
+
 int64_t aep_num_particles(aep_ctx* c) {      // live particles (dead slots of a slab context excluded)
     if (!c) return -1;
     if (peer_mode(c)) {

@@ -153,7 +153,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
 }
 // one thread waits until *flag >= want; a flag that never arrives is reported (comm_timeout), not waited for forever
-#define AEP_SPIN_LIMIT (1u << 22)
+#define AEP_SPIN_LIMIT (1u << 24)                                     // x (256 ns sleep + one system-scope load): several seconds
 __device__ __forceinline__ void spin_until(const unsigned long long* flag, unsigned long long want, SimClock* clk) {
     if (clk->comm_timeout) return;                                          // sticky: after one timeout nothing waits any more
     for (unsigned spin = 0; ld_acquire_sys(flag) < want; ++spin) {
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256) k_peer_migrate_send(PartP P, MigList ML, 
             } else if (c) clk->mig_dropped += c;                             // left through a domain face: cannot happen (positions are clamped)
             ML.counts[sd] = 0ull;
         }
-        clk->n_dead += (int)tot;
+        clk->n_dead += (int)tot; clk->mig_sent += tot;
     }
 }
 // append what the neighbours stored (counts from my block's head)
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256) k_peer_migrate_insert(PartP P, const floa
     __syncthreads();
     if (threadIdx.x == 0 && atomicAdd(done, 1u) == gridDim.x - 1) {
         *done = 0u;
-        clk->n_slots = n_old + take;
+        clk->n_slots = n_old + take; clk->mig_received += (unsigned long long)take;
         clk->moved_since_sort += (unsigned long long)take;                  // arrivals sit unsorted at the tail
         if (take < c0 + c1) clk->mig_dropped += (unsigned long long)(c0 + c1 - take);
         head->mig_count[0] = 0ull; head->mig_count[1] = 0ull;

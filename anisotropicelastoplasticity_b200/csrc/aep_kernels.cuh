@@ -67,6 +67,7 @@ struct SimClock {
     unsigned long long mig_dropped;    // leavers / arrivals that did not fit the migration buffers (sticky; the host fails loudly on it)
     float vmax_mass_floor;             // 0 = the reference rule.  > 0 (opt-in, NOT the reference): nodes lighter than this do not enter max|v|
     int pad1;
+    unsigned long long mig_sent, mig_received;   // particles this context handed to / took from its neighbours (peer exchange), cumulative
 };
 #define AEP_HALT_PRE(clk)  do { if ((clk)->halt >= 1) return; } while (0)
 #define AEP_HALT_POST(clk) do { if ((clk)->halt >= 2) return; } while (0)

@@ -317,10 +317,25 @@ class SlabSolver:
         b.step_p2g_arrivals(bufs[0].shape[0] + bufs[1].shape[0])
         self.stats["migrated"] += out[0].shape[0] + out[1].shape[0]
 
+    def _on_stream(self):
+        """torch.distributed orders its sends / receives against torch's CURRENT stream, the engine's kernels (halo pack / add,
+        migration gather, max|v|) run on the context's own non-blocking stream: every exchange must be issued with that stream
+        current, or halves of a halo travel before they are packed.  Entered here, so that no caller can get it wrong."""
+        st = getattr(self.b, "stream", None)
+        if st is None:
+            import contextlib
+            return contextlib.nullcontext()
+        return self.b.torch.cuda.stream(st)
+
     def init(self):
-        self.b.init_begin(); self.halo(0); self.b.init_volumes(); self.allreduce_vmax(); self.b.init_dt()
+        with self._on_stream():
+            self.b.init_begin(); self.halo(0); self.b.init_volumes(); self.allreduce_vmax(); self.b.init_dt()
 
     def substep(self):
+        with self._on_stream():
+            self._substep()
+
+    def _substep(self):
         b = self.b
         b.step_forces(); self.halo(1)
         b.step_grid(); self.allreduce_vmax()
@@ -495,12 +510,28 @@ def make_gpu_slab_engine(scene, plan: SlabPlan, rank: int, device: int, capacity
 
 
 # ------------------------------------------------------------------------------------------------ bench (N > 1)
+class PeerRank:
+    """One rank of the peer-memory decomposition (one process per GPU): after connect_ranks the engine's own init / run exchange halo
+    planes, migrating particles and max|v| through the neighbours' memory; nothing per substep happens in Python or on the host."""
+
+    def __init__(self, engine, rank, world, migrate_capacity):
+        self.e = engine; self.rank = rank; self.world = world
+        connect_ranks(engine, rank, world, migrate_capacity)
+
+    def init(self): self.e.init()
+    def run(self, n): self.e.run(n)
+    def sync(self): self.e.sync()
+    def close(self): self.e.sync()
+
+
 def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, UNIT):
-    """Strong scaling of the C5 dam break over `world` GPUs (one process per GPU, launched by torchrun)."""
+    """Strong scaling of the C5 dam break over `world` GPUs (one process per GPU, launched by torchrun).  Every rank generates its
+    rows of the SAME scene the one-GPU run holds (bench.dam_break_positions: one random stream per lattice row)."""
     import torch
     import torch.distributed as dist
     import bench as B
     from . import scenes as sc
+    from . import capi
     from .engine import Engine
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
@@ -513,93 +544,109 @@ def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, U
     bounds = [0] + [lo_c + round(r * (hi_c - lo_c) / world) for r in range(1, world)] + [res]
     plan = SlabPlan(1, bounds)
     h = 1.0 / res
-    y0, y1 = plan.bounds[rank] * h, plan.bounds[rank + 1] * h
     t_gen = time.perf_counter()
-    x = B.dam_break_positions(res, seed=5 + 1000 * rank, y_range=(y0, y1))
+    x, id_base = B.dam_break_positions(res, y_cells=(plan.bounds[rank], plan.bounds[rank + 1]))
     n_local = x.shape[0]
     counts = torch.zeros(world, dtype=torch.int64, device="cuda"); counts[rank] = n_local
-    dist.all_reduce(counts); counts = counts.cpu().numpy(); n_total = int(counts.sum()); id_base = int(counts[:rank].sum())
+    dist.all_reduce(counts); counts = counts.cpu().numpy(); n_total = int(counts.sum())
+    assert id_base == int(counts[:rank].sum())
     mass = sc.SAND_RHO * h ** 3 / 8.0
     arrs, keep = B.packed_rest_state(x, mass, pinned=True); del x
+    B.set_state(arrs, args)
     t_gen = time.perf_counter() - t_gen
     shell = B.make_shell_scene(res)
     rate_floor = B.rate_floor_for(res)
+    peer = args.exchange == "peer"
+    mig_cap = max(1 << 16, n_local // 20)
 
-    def create():
-        """context + communication buffers (setup: allocation, no data)"""
-        eng = Engine(shell, device=local, particle_capacity=int(1.25 * n_local + 65536), slab=plan.slab(rank), dt_rate_floor=rate_floor,
-                     sort_every=args.sort_every)
-        from . import capi
-        capi.check(eng.L.aep_set_particle_id_base(eng.h, id_base), eng.h)
-        return eng
+    # context + communication buffers (setup: allocation, no data), created once; every leg uploads into it
+    eng = Engine(shell, device=local, particle_capacity=int(1.25 * n_local + 65536), slab=plan.slab(rank), dt_rate_floor=rate_floor, sort_every=args.sort_every)
+    capi.check(eng.L.aep_set_particle_id_base(eng.h, id_base), eng.h)
+    if peer:
+        solver = PeerRank(eng, rank, world, mig_cap); be = None
+        stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+    else:
+        be = GpuSlabBackend(eng, migrate_capacity=mig_cap); solver = SlabSolver(be, plan, rank); stream = be.stream
 
-    def load(eng):
-        """host fp64 state -> device, slab solver around it"""
+    def load():
         eng.upload_packed(n_local, arrs, sc.SAND_E, sc.SAND_NU, 2.5e-2, 7.5e-3)
-        be = GpuSlabBackend(eng, migrate_capacity=max(1 << 16, n_local // 50))
-        return be, SlabSolver(be, plan, rank)
 
-    eng = create()
-    be, solver = load(eng)
-    with torch.cuda.stream(be.stream):
+    load()
+    dist.barrier()                                                         # the ranks start together: a peer's flag is waited for on the device, for seconds at most
+    with torch.cuda.stream(stream):
         solver.init()
         solver.run(args.warmup)
-        be.sync(); dist.barrier(); torch.cuda.synchronize()
+        eng.sync(); dist.barrier(); torch.cuda.synchronize()
         sampler = ClockSampler(local) if rank == 0 else None
-        l0 = eng.kernel_launches
+        l0 = eng.kernel_launches; c0 = eng.counters(); k0 = eng.clock(); m0 = eng.migration()
+        dist.barrier(); torch.cuda.synchronize()
         ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-        ev0.record(be.stream)
+        ev0.record(stream)
         solver.run(args.steps)
-        ev1.record(be.stream); torch.cuda.synchronize()
+        ev1.record(stream); torch.cuda.synchronize()
         ms_local = ev0.elapsed_time(ev1)
         dist.barrier()
     t = torch.tensor([ms_local], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     clocks = sampler.stop() if sampler else None
     launches = eng.kernel_launches - l0
-    nodes_t = torch.tensor([eng.grid_activity()[1]], dtype=torch.int64, device="cuda"); dist.all_reduce(nodes_t); nodes = int(nodes_t.item())
-    nloc_t = torch.tensor([eng.n_particles], dtype=torch.int64, device="cuda"); dist.all_reduce(nloc_t)
-    assert int(nloc_t.item()) == n_total, "particles were lost in migration"
-    clk = eng.clock()
+    c1 = eng.counters(); clk = eng.clock(); m1 = eng.migration()
+    mig_local = (m1["sent"] - m0["sent"]) if peer else solver.stats["migrated"]
+    agg = torch.tensor([eng.grid_activity()[1], eng.n_particles, mig_local, c1["sorts"] - c0["sorts"]], dtype=torch.int64, device="cuda"); dist.all_reduce(agg)
+    nodes, n_now, migrated, sorts_all = (int(v) for v in agg.tolist())
+    assert n_now == n_total, f"particles were lost in migration: {n_now} of {n_total}"
     value = n_total * args.steps / (ms * 1e-3)
-    # per-stage time on this rank (profiled pass)
-    with torch.cuda.stream(be.stream):
-        eng.profile(True); solver.run(3); be.sync(); tm = eng.timers(); eng.profile(False)
+    sim_s = (clk["t"] + clk["inner_t"]) - (k0["t"] + k0["inner_t"])
+    # per-stage time on this rank (profiled pass: every stage fenced by events, so waiting for the neighbours shows up under "halo")
+    with torch.cuda.stream(stream):
+        eng.profile(True); solver.run(3); eng.sync(); tm = eng.timers(); eng.profile(False)
+    dist.barrier()
     stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in tm.items()}
     peak, peak_kind = measured_peak_gbs()
-    dom = max(("forces", "g2p", "p2g", "grid", "sort"), key=lambda k: stage_ms.get(k, 0.0))
+    dom = max(("forces", "g2p2g", "g2p", "p2g", "grid"), key=lambda k: stage_ms.get(k, 0.0))
     bp, bn = B.STAGE_BYTES[dom]
     dom_bytes = bp * eng.n_particles + bn * eng.grid_activity()[1]
     achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
     sub_bytes = B.BYTES_PARTICLE[sc.SAND] * n_total + B.BYTES_NODE * nodes
     sub_gbs = sub_bytes / (ms * 1e-3 / args.steps) / 1e9 / world
-    roofline = {"bound": "hbm", "kernel": {"forces": "k_forces", "g2p": "k_g2p", "p2g": "k_p2g", "grid": "k_grid_update", "sort": "cub radix sort + k_reorder"}[dom],
+    kernels = {"forces": "k_forces", "g2p2g": "k_g2p2g", "g2p": "k_g2p2g<scatter off>", "p2g": "k_p2g", "grid": "k_grid_update"}
+    roofline = {"bound": "hbm", "kernel": kernels[dom],
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth, MEASURED_PEAKS.json", "unit": "GB/s", "frac": achieved / peak,
-                "traffic": B.ncu_traffic({"forces": "k_forces", "g2p": "k_g2p", "p2g": "k_p2g"}.get(dom, ""), eng.n_particles), "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom], "stage_ms": stage_ms, "rank": 0,
-                "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs_per_gpu": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes}}
-    halo_bytes = solver.stats["halo_bytes"]; migrated = solver.stats["migrated"]
-    # e2e: fresh contexts, upload from pinned host memory + init + K substeps + f32 positions back, wall clock max over ranks
-    be.close(); del solver, be; eng.close(); del eng
+                "traffic": B.ncu_traffic(kernels[dom], eng.n_particles), "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom], "stage_ms": stage_ms, "rank": 0,
+                "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs_per_gpu": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes},
+                "p2g_g2p": B.transfers_roofline(stage_ms, eng.n_particles, eng.grid_activity()[1], peak)}
+    plane_bytes = res * res * 16
+    halo_bytes = (2 if 0 < rank < world - 1 else 1) * (4 + 3) * plane_bytes if peer else solver.stats["halo_bytes"] / max(1, args.steps + args.warmup + 3 + 1)
+    # e2e: upload from pinned host memory + init + K substeps + f32 positions back, wall clock max over ranks
     out_t = torch.empty((int(1.25 * n_local + 65536), 3), dtype=torch.float32, pin_memory=True)
-    eng = create()
-    dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
-    be, solver = load(eng)
-    with torch.cuda.stream(be.stream):
+    eng.sync(); dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    load()
+    dist.barrier()
+    with torch.cuda.stream(stream):
         solver.init(); solver.run(args.steps)
-    from . import capi
     capi.check(eng.L.aep_download_positions_f32(eng.h, C.cast(out_t.data_ptr(), C.POINTER(C.c_float))), eng.h)
     torch.cuda.synchronize(); dist.barrier()
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda"); dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e = {"value": n_total * args.steps / float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": 36 * 8 * n_total / args.steps,
            "d2h_bytes_per_step": 12 * n_total / args.steps, "seconds": float(t_e2e.item()),
-           "what": "per rank, on a context created (and sized) beforehand: aep_upload_particles(fp64 host, pinned) + init + K substeps (halo/migration over NCCL) + f32 positions"}
-    be.close(); del solver, be; eng.close()
+           "what": "per rank, on a context created (and sized) beforehand: aep_upload_particles(fp64 host, pinned) + init + K substeps (halo / migration / max|v| exchange included) + f32 positions"}
+    eng.sync(); dist.barrier()
+    solver.close()
+    if be is not None:
+        be.close()
+    del solver, be
     if rank == 0:
+        exch = ("peer memory: the engine's kernels store halo planes (4 + 3 node planes per side and substep), migrating particles and max|v| into the neighbours' "
+                "memory (CUDA IPC mappings over NVLink) and publish epoch flags; one CUDA-graph launch per substep, no host synchronisation, no NCCL on the data path"
+                if peer else "NCCL send/recv driven from Python: 2 halo exchanges (3 node planes per side) + 1 four-byte all-reduce(max) + particle migration per substep")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(args, n_particles=n_total), decomposition=f"{world} y-slabs, bounds {plan.bounds}",
-                               exchange="NCCL send/recv: 2 halo exchanges (3 node planes per side) + 1 four-byte all-reduce(max) + particle migration per substep"),
+                "config": dict(workload_config(args, n_particles=n_total), decomposition=f"{world} y-slabs, bounds {plan.bounds}", exchange=exch),
                 "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "comm": {"halo_bytes_per_step_per_rank": halo_bytes / max(1, args.steps + args.warmup + 3 + 1), "migrated_particles_rank0": migrated},
+                "comm": {"halo_bytes_per_step_per_rank": halo_bytes, "migrated_particles": migrated, "migrated_particles_rank0": int(mig_local)},
+                "running": {"state": args.state, "sorts_in_timed_region_all_ranks": sorts_all, "migrated_particles_in_timed_region": migrated,
+                            "amortised_sort_ms": (c1["sorts"] - c0["sorts"]) * stage_ms.get("sort", 0.0) / args.steps,
+                            "simulated_seconds_per_wall_second": sim_s / (ms * 1e-3) if ms > 0 else 0.0},
                 "sim": {"dt": clk["dt"], "t": clk["t"] + clk["inner_t"], "escaped": clk["escaped"], "vmax": clk["vmax"]}, "setup_s": {"generate": t_gen}}
         print(json.dumps(line))
+    eng.close()
     dist.destroy_process_group()

@@ -106,6 +106,11 @@ class Engine:
         capi.check(self.L.aep_get_counters(self.h, *[C.byref(x) for x in a]), self.h)
         return dict(sorts=a[0].value, slots=a[1].value, dead=a[2].value, moved_since_sort=a[3].value)
 
+    def migration(self):
+        a = [C.c_int64() for _ in range(2)]
+        capi.check(self.L.aep_get_migration(self.h, *[C.byref(x) for x in a]), self.h)
+        return dict(sent=a[0].value, received=a[1].value)
+
     def set_levelset_samples(self, inside, normal):
         inside = np.ascontiguousarray(inside, np.uint8); normal = colmajor(normal)
         capi.check(self.L.aep_set_levelset_samples(self.h, inside.ctypes.data_as(C.POINTER(C.c_uint8)), _p(normal)), self.h)

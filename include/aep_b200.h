@@ -219,6 +219,9 @@ AEP_API int aep_get_timers(aep_ctx* ctx, double* ms /*AEP_NUM_STAGES*/, int64_t*
 #define AEP_NUM_STAGES 8
 /* physical re-sorts done so far, particle slots in use / dead (slab contexts), particles that changed cell since the last re-sort */
 AEP_API int aep_get_counters(aep_ctx* ctx, int64_t* sorts, int64_t* slots, int64_t* dead, int64_t* moved_since_sort);
+/* peer-memory exchange: particles this context has handed to / taken from its neighbours so far (HybridSolver.cpp:940-951 moves
+ * particles across slab boundaries; the counts live on the device)                                                               */
+AEP_API int aep_get_migration(aep_ctx* ctx, int64_t* sent, int64_t* received);
 
 /* ---- multi-GPU slab decomposition -------------------------------------------------------------
  * The context owns the particles whose cell index along cfg.slab_axis lies in [slab_lo, slab_hi).  Their cubic

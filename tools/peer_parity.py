@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Parity of the MULTI-PROCESS peer-memory slab exchange (CUDA IPC mappings, device-side epoch flags) on real GPUs:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/peer_parity.py [--same-device] [--res 128]
+
+Every rank holds one y-slab of a C5-like scene (sand column at `res`^3, sheared so that particles cross the slab boundaries in both
+directions), connected with distributed.connect_ranks; pinned dt, `--steps` substeps.  Rank 0 gathers all particles by global id and
+compares them with (a) ONE whole-domain context on its GPU and (b) the CPU oracle (small res only).  `--same-device` puts every rank
+on GPU 0 (gloo for the blob exchange): the cross-process protocol on a one-GPU box.  Prints one JSON line; exit code 1 on mismatch."""
+import argparse, json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def scene_for(res, seed=5):
+    """C5 at `res`^3 (bench's dam break), every particle moving: v_x = 2 z/H, v_y = +-1.5 m/s by height (both directions across every slab boundary)"""
+    from anisotropicelastoplasticity_b200 import scenes as sc
+    s = sc.c5_dam_break(res=res, seed=seed)
+    p = s.particles
+    sc.perturb_state(p, np.random.default_rng(7), strain=3e-3, vel=0.1, affine=0.3)
+    p.v[:, 0] += 2.0 * p.x[:, 2] / 0.25; p.v[:, 1] += 1.5 * np.sin(2 * np.pi * p.x[:, 2] / 0.25)
+    order = np.argsort(p.x[:, 1], kind="stable")                     # contiguous global ids per slab
+    for k in ("x", "v", "B", "FE", "FP", "m", "vol", "q"):
+        setattr(p, k, getattr(p, k)[order])
+    return s
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--res", type=int, default=128); ap.add_argument("--steps", type=int, default=24); ap.add_argument("--dt", type=float, default=1e-4)
+    ap.add_argument("--same-device", action="store_true"); ap.add_argument("--oracle", action="store_true"); ap.add_argument("--adaptive", action="store_true")
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    import torch, torch.distributed as dist
+    from anisotropicelastoplasticity_b200 import capi
+    from anisotropicelastoplasticity_b200.engine import Engine
+    from anisotropicelastoplasticity_b200.distributed import SlabPlan, make_gpu_slab_engine, connect_ranks, download_local
+    world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local = 0 if a.same_device else int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if a.same_device: dist.init_process_group("gloo")
+    else: dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    scene = scene_for(a.res)
+    n = scene.particles.n
+    cells = np.floor(scene.particles.x[:, 1] * a.res).astype(np.int64)
+    plan = SlabPlan.balanced(cells, a.res, world, axis=1)
+    rf = 300.0 * a.res / 32.0
+    eng, localp, idx = make_gpu_slab_engine(scene, plan, rank, device=local, dt_rate_floor=rf)
+    assert (np.diff(idx) == 1).all()
+    capi.check(eng.L.aep_set_particle_id_base(eng.h, int(idx[0])), eng.h)
+    eng.upload_particles(localp)
+    connect_ranks(eng, rank, world, migrate_capacity=max(4096, len(idx) // 10))
+    dt = float(np.float32(a.dt))
+    dist.barrier(); t0 = time.perf_counter()
+    eng.init()
+    if not a.adaptive: eng.set_fixed_dt(dt)
+    dist.barrier()
+    n0 = eng.n_particles
+    eng.run(a.steps); eng.sync()
+    t_run = time.perf_counter() - t0
+    clk = eng.clock(); mig = eng.migration(); cnt = eng.counters()
+    part = download_local(eng)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object({"part": part, "mig": mig, "n0": n0, "n1": eng.n_particles, "dt": clk["dt"], "escaped": clk["escaped"], "sorts": cnt["sorts"]}, gathered, dst=0)
+    ok = True; out = {}
+    if rank == 0:
+        ids = np.concatenate([g["part"]["ids"] for g in gathered]); order = np.argsort(ids)
+        got = {k: np.concatenate([g["part"][k] for g in gathered], axis=0)[order] for k in ("x", "v", "FE", "FP", "q", "B")}
+        out = {"world": world, "same_device": a.same_device, "res": a.res, "particles": int(n), "steps": a.steps, "adaptive_dt": a.adaptive,
+               "bounds": plan.bounds, "n_start": [g["n0"] for g in gathered], "n_end": [g["n1"] for g in gathered],
+               "migrated_sent": [g["mig"]["sent"] for g in gathered], "migrated_received": [g["mig"]["received"] for g in gathered],
+               "sorts": [g["sorts"] for g in gathered], "dt_per_rank": [g["dt"] for g in gathered], "escaped": [g["escaped"] for g in gathered], "wall_s": t_run}
+        ok &= bool((ids[order] == np.arange(n)).all()); out["nobody_lost_or_duplicated"] = bool((ids[order] == np.arange(n)).all())
+        ok &= sum(out["migrated_sent"]) > 0 and sum(out["migrated_sent"]) == sum(out["migrated_received"])
+        ok &= len(set(out["dt_per_rank"])) == 1                                            # the dt rule saw the GLOBAL max|v|
+        whole = Engine(scene, device=local, dt_rate_floor=rf); whole.init()
+        if not a.adaptive: whole.set_fixed_dt(dt)
+        whole.run(a.steps); pw = whole.particles(); out["dt_whole"] = whole.clock()["dt"]; whole.close()
+        tol = {"x": 2e-6, "v": 5e-5, "FE": 2e-5, "FP": 2e-5, "q": 2e-4} if not a.adaptive else {"x": 1e-4, "v": 1e-2, "FE": 1e-3, "FP": 1e-3, "q": 1e-1}
+        out["vs_whole_context"] = {k: relerr(got[k], pw[k]) for k in tol}
+        ok &= all(out["vs_whole_context"][k] < tol[k] for k in tol)
+        if a.oracle and not a.adaptive:
+            from oracle.oracle_py import Oracle
+            o = Oracle(scene, threads=0, rate_floor=rf); o.init()
+            for _ in range(a.steps):
+                o.stage_forces(dt); o.stage_grid_update(dt); o.stage_collide(); o.stage_g2p(dt); o.rebuild_weights(); o.p2g(False)
+            po = o.particles(); tolo = {"x": 1e-5, "v": 1e-4, "FE": 2e-5, "FP": 2e-5}
+            out["vs_oracle"] = {k: relerr(got[k], po[k]) for k in tolo}
+            ok &= all(out["vs_oracle"][k] < tolo[k] for k in tolo)
+        out["ok"] = bool(ok)
+        line = json.dumps(out); print(line)
+        if a.out:
+            with open(a.out, "w") as f: f.write(line + "\n")
+    flag = torch.tensor([1 if ok else 0]); dist.broadcast(flag, src=0) if a.same_device else None
+    eng.close(); dist.barrier() if a.same_device else None
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
