@@ -86,6 +86,7 @@ struct aep_ctx {
     long long n = 0, cap = 0;                   // slots in use as the host knows them (exact, except with peer communication: see n_launch)
     PartP P[2]{}; int cur = 0;
     unsigned int *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr};
+    DeferP defer{nullptr, nullptr};             // particles that do not fit their half-warp's gather box (aep_particle.cuh)
     void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     int key_bits = 0;
     MatParams mat{};
@@ -345,9 +346,9 @@ int do_forces(aep_ctx* c, bool in_substep) {
     }
     if (n_launch(c)) {
         StageTimer T(c, AEP_STAGE_FORCES);
-        cudaError_t e = forces_launch(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c));
+        cudaError_t e = forces_launch(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->defer);
         if (e != cudaSuccess) return fail(c, AEP_ERR_CUDA, "k_forces: %s", cudaGetErrorString(e));
-        LAUNCH_OK("k_forces");
+        LAUNCH_OK("k_forces"); c->launches++;                                 // + the launch over the deferred list
     }
     if (c->mesh.nv) {
         StageTimer T(c, AEP_STAGE_MESH);
@@ -384,10 +385,10 @@ int do_g2p_particles(aep_ctx* c, bool scatter) {
     if (!n_launch(c)) return AEP_OK;
     StageTimer T(c, scatter ? AEP_STAGE_G2P2G : AEP_STAGE_G2P);
     if (c->mig.axis >= 0 && !peer_mode(c)) cudaMemsetAsync(c->mig.counts, 0, 2 * sizeof(unsigned long long), c->stream);
-    cudaError_t e = scatter ? g2p2g_launch<true>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig)
-                            : g2p2g_launch<false>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig);
+    cudaError_t e = scatter ? g2p2g_launch<true>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig, c->defer)
+                            : g2p2g_launch<false>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig, c->defer);
     if (e != cudaSuccess) return fail(c, AEP_ERR_CUDA, "k_g2p2g: %s", cudaGetErrorString(e));
-    LAUNCH_OK("k_g2p2g");
+    LAUNCH_OK("k_g2p2g"); c->launches++;                                      // + the launch over the deferred list
     return AEP_OK;
 }
 // whole G2P of a context without peers (mesh included)
@@ -574,6 +575,7 @@ static int ensure_particle_capacity(aep_ctx* c, long long cap) {
     for (int b = 0; b < 2; ++b)
         for (int a = 0; a < P_NARR; ++a) CU(dalloc(c, &c->P[b].a[a], (size_t)cap));
     for (int b = 0; b < 2; ++b) { CU(dalloc(c, &c->d_keys[b], (size_t)cap)); CU(dalloc(c, &c->d_vals[b], (size_t)cap)); }
+    CU(dalloc(c, &c->defer.list, (size_t)cap)); CU(dalloc(c, &c->defer.count, 1));
     size_t tmp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], (int)cap, 0, c->key_bits + 2, c->stream);
     CU(cudaMalloc(&c->d_sort_tmp, tmp)); c->sort_tmp_bytes = tmp;

@@ -560,7 +560,8 @@ def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, U
     mig_cap = max(1 << 16, n_local // 20)
 
     # context + communication buffers (setup: allocation, no data), created once; every leg uploads into it
-    eng = Engine(shell, device=local, particle_capacity=int(1.25 * n_local + 65536), slab=plan.slab(rank), dt_rate_floor=rate_floor, sort_every=args.sort_every)
+    eng = Engine(shell, device=local, particle_capacity=int(1.25 * n_local + 65536), slab=plan.slab(rank), dt_rate_floor=rate_floor, sort_every=args.sort_every,
+                 sort_cost_threshold=getattr(args, "sort_threshold", None))
     capi.check(eng.L.aep_set_particle_id_base(eng.h, id_base), eng.h)
     if peer:
         solver = PeerRank(eng, rank, world, mig_cap); be = None
@@ -630,9 +631,10 @@ def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, U
            "d2h_bytes_per_step": 12 * n_total / args.steps, "seconds": float(t_e2e.item()),
            "what": "per rank, on a context created (and sized) beforehand: aep_upload_particles(fp64 host, pinned) + init + K substeps (halo / migration / max|v| exchange included) + f32 positions"}
     eng.sync(); dist.barrier()
-    solver.close()
     if be is not None:
         be.close()
+    else:
+        solver.close()
     del solver, be
     if rank == 0:
         exch = ("peer memory: the engine's kernels store halo planes (4 + 3 node planes per side and substep), migrating particles and max|v| into the neighbours' "

@@ -21,7 +21,7 @@ def _p(a):
 
 class Engine:
     def __init__(self, scene: Scene, device: int = 0, particle_capacity: int = 0, slab=None, dt_rate_floor=None, sort_every=None, sort_bricks=None, scatter_strips=None,
-                 vmax_min_mass_fraction=None, coulomb_friction=None, use_graph=None):
+                 vmax_min_mass_fraction=None, coulomb_friction=None, use_graph=None, sort_cost_threshold=None):
         self.L = capi.load()
         cfg = capi.Config(); capi.check(self.L.aep_default_config(C.byref(cfg)))
         g = scene.grid
@@ -43,6 +43,8 @@ class Engine:
             cfg.coulomb_friction = int(coulomb_friction)                    # opt-in, NOT the reference's collider
         if use_graph is not None:
             cfg.use_graph = int(use_graph)
+        if sort_cost_threshold is not None:
+            cfg.sort_cost_threshold = float(sort_cost_threshold)
         if slab is not None:
             cfg.slab_axis, cfg.slab_lo, cfg.slab_hi = slab
         self.cfg = cfg

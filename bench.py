@@ -354,9 +354,12 @@ def run_engine(args):
     rate_floor = rate_floor_for(res)
     mat = (sc.SAND_E, sc.SAND_NU, 2.5e-2, 7.5e-3)
     # one context, created and sized once (23 GB of cudaMalloc is setup, not a step); every leg below uploads into it
-    eng = Engine(shell, device=local, particle_capacity=n, dt_rate_floor=rate_floor, sort_every=args.sort_every, sort_bricks=args.sort_bricks)
+    eng = Engine(shell, device=local, particle_capacity=n, dt_rate_floor=rate_floor, sort_every=args.sort_every, sort_bricks=args.sort_bricks,
+                 sort_cost_threshold=args.sort_threshold)
     stream = torch.cuda.ExternalStream(eng.stream, device=local)
     eng.upload_packed(n, arrs, *mat); eng.init()
+    if args.pin_dt:
+        eng.set_fixed_dt(0.3 / rate_floor)
     # ---- timed region: K substeps of the developed state, device events on the engine's stream
     sampler = ClockSampler(local)
     tr = timed_run(eng, stream, args, n)
@@ -469,6 +472,8 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: peer = halo / migration / max|v| stored into the neighbours' memory by the engine's own kernels (CUDA IPC over NVLink); nccl = torch.distributed send/recv driven from Python (the baseline)")
     ap.add_argument("--perturb", type=float, default=0.0, help="development: random strain scale added to the rest state (0 = the named workload)")
     ap.add_argument("--sort-bricks", type=int, default=0, help="1: brick-major particle order (aep_config.sort_bricks), 0: cell-index order")
+    ap.add_argument("--pin-dt", action="store_true", help="development: pin dt at cfl / rate_floor (the largest step the rule takes) so that runs are comparable; the headline uses the reference rule")
+    ap.add_argument("--sort-threshold", type=float, default=None, help="development: aep_config.sort_cost_threshold of the adaptive re-sort (default: the library's)")
     ap.add_argument("--sort-every", type=int, default=0, help="physical re-sort period in substeps (aep_config.sort_every); 0 = adaptive (default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -41,6 +41,13 @@ void h_stress(int material, double E, double nu, const float* Fh, const float* F
     float fh[9], fe[9], a[9]; std::memcpy(fh, Fh, 36); std::memcpy(fe, FE, 36);
     stress_times_FEt(M, fh, fe, vol, Jp, a); std::memcpy(A, a, 36);
 }
+// the SVD path alone (what round 1 shipped): the series path must be at least as close to the fp64 reference
+void h_stress_svd(int material, double E, double nu, const float* Fh, const float* FE, float vol, float Jp, float* A) {
+    MatParams M = mk(material, E, nu, 2.5e-2, 7.5e-3);
+    float fh[9], fe[9], a[9]; std::memcpy(fh, Fh, 36); std::memcpy(fe, FE, 36);
+    stress_times_FEt_svd(M, fh, fe, vol, Jp, a); std::memcpy(A, a, 36);
+}
+int h_small_strain(const float* Fh) { float fh[9]; std::memcpy(fh, Fh, 36); Sym3 E; return left_cauchy_green_minus_one(fh, E) < AEP_SMALL_E2 ? 1 : 0; }
 void h_return_map(int material, double E, double nu, double thetaC, double thetaS, const float* Fh, float* FE, float* FP, float* q) {
     MatParams M = mk(material, E, nu, thetaC, thetaS);
     float fh[9], fe[9], fp[9]; std::memcpy(fh, Fh, 36); std::memcpy(fp, FP, 36);

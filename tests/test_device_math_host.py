@@ -91,6 +91,53 @@ def test_stress_and_return_map_vs_oracle(H, mat, E, nu):
         assert worst / amax < 3e-7 / strain + 1e-6, (strain, worst / amax)
 
 
+def test_sand_series_path_vs_svd_path_vs_oracle(H):
+    """Sand at the strains a stiff granular material really sees (1e-4 .. 3e-3): the SVD-free series path (aep_math.cuh, "sand
+    without the SVD") against the fp64 oracle (HybridSolver.cpp:326-339, 646-677 through Eigen-style SVD) and against round 1's
+    Jacobi path.  It must take the series branch, be at least as accurate as the SVD path in the stress, and reproduce all three
+    branches of the Drucker-Prager projection (elastic, tensile apex, cone) to fp32 rounding."""
+    L = op.lib()
+    L.orc_particle_stress.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, dp, dp, dp, C.c_double, dp]
+    L.orc_particle_return_map.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp, dp, dp]
+    H.h_stress_svd.argtypes = H.h_stress.argtypes; H.h_small_strain.argtypes = [fp]; H.h_small_strain.restype = C.c_int
+    rng = np.random.default_rng(12)
+    cm = lambda M: np.ascontiguousarray(M.T).ravel()
+    E_, nu = 3.537e5, 0.3
+    branches = {"elastic": 0, "apex": 0, "cone": 0}
+    for strain in (1e-4, 1e-3, 3e-3):
+        e_series = e_svd = amax = 0.0
+        for trial in range(400):
+            R = np.linalg.qr(rng.standard_normal((3, 3)))[0]                                  # any rotation: nothing may depend on it
+            kind = trial % 4
+            S = np.eye(3) + strain * rng.standard_normal((3, 3))
+            if kind == 1: S = S - 2.0 * strain * np.eye(3)                                   # compressed: elastic or cone
+            if kind == 2: S = S + 2.0 * strain * np.eye(3)                                   # stretched: the tensile apex
+            if kind == 3: S = (1.0 - 2.0 * strain) * np.eye(3) + 0.05 * strain * rng.standard_normal((3, 3))   # nearly hydrostatic compression: elastic
+            Fh = f32(R @ S); FE = f32(Fh - 0.3 * strain * rng.standard_normal((3, 3)))
+            assert H.h_small_strain(P(Fh.ravel())) == 1
+            FPm = f32(np.eye(3) + 0.02 * rng.standard_normal((3, 3))); vol = 1e-6; q0 = float(np.float32(abs(rng.standard_normal()) * 0.3))
+            A = np.zeros(9, np.float32); H.h_stress(1, E_, nu, P(Fh.ravel()), P(FE.ravel()), C.c_float(vol), C.c_float(1.0), P(A))
+            As = np.zeros(9, np.float32); H.h_stress_svd(1, E_, nu, P(Fh.ravel()), P(FE.ravel()), C.c_float(vol), C.c_float(1.0), P(As))
+            A64 = np.zeros(9)
+            L.orc_particle_stress(1, E_, nu, 10.0, D(cm(Fh.astype(np.float64))), D(cm(FE.astype(np.float64))), D(cm(FPm.astype(np.float64))), vol, D(A64))
+            A64 = A64.reshape(3, 3).T
+            e_series = max(e_series, np.abs(A.reshape(3, 3) - A64).max()); e_svd = max(e_svd, np.abs(As.reshape(3, 3) - A64).max()); amax = max(amax, np.abs(A64).max())
+            FEo = np.zeros(9, np.float32); FPo = FPm.copy().ravel(); q = C.c_float(q0)
+            H.h_return_map(1, E_, nu, 2.5e-2, 7.5e-3, P(Fh.ravel()), P(FEo), P(FPo), C.byref(q))
+            FE9 = np.zeros(9); FP9 = cm(FPm.astype(np.float64)).copy(); q64 = C.c_double(q0)
+            L.orc_particle_return_map(1, E_, nu, 2.5e-2, 7.5e-3, D(cm(Fh.astype(np.float64))), D(FE9), D(FP9), C.byref(q64))
+            FE64 = FE9.reshape(3, 3).T
+            assert np.abs(FEo.reshape(3, 3) - FE64).max() < 4e-7, (strain, kind)
+            assert np.abs(FPo.reshape(3, 3) - FP9.reshape(3, 3).T).max() < 6e-7, (strain, kind)
+            assert abs(q.value - q64.value) < 2e-7 + 1e-6 * abs(q64.value - q0), (strain, kind)
+            if np.abs(FE64 - Fh).max() < 1e-12: branches["elastic"] += 1
+            elif abs(np.linalg.det(FE64) - 1.0) < 1e-9 and np.abs(np.linalg.svd(FE64)[1] - 1.0).max() < 1e-9: branches["apex"] += 1
+            else: branches["cone"] += 1
+        assert e_series <= 1.2 * e_svd + 1e-7 * amax, (strain, e_series / amax, e_svd / amax)
+        assert e_series / amax < 2e-7 / strain + 1e-6, (strain, e_series / amax)
+    assert min(branches.values()) >= 100, branches
+
+
 def _weights64(f):
     """cubic B-spline values of the 4 stencil nodes of a particle at cell fraction f, fp64, straight from interpolation.cpp:9-16
     via the oracle: node o sits at signed distance u = f + 1 - o (in cells)."""

@@ -102,3 +102,54 @@ def test_peer_slabs_z_axis_and_resort():
     whole = Engine(s, sort_every=7); whole.init(); whole.set_fixed_dt(dt); whole.run(nsteps); pw = whole.particles()
     for k, tol in (("x", 2e-6), ("v", 1e-4), ("FE", 3e-5)):
         assert relerr(got[k], pw[k]) < tol, (k, relerr(got[k], pw[k]))
+
+
+def _coupling_scene(res=48, cloth_n=40):
+    """configs[3] in small: sand block over a cloth pinned at two corners; the sheet spans the whole y range (every slab owns a strip
+    of it), the sand is lowered onto it and everything drifts along +y so that particles AND cloth points change their owner."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_zzx_configs_at_size import deform_cloth
+    from anisotropicelastoplasticity_b200 import scenes as sc
+    s = sc.c4_coupling(res=res, cloth_n=cloth_n)
+    rng = np.random.default_rng(17)
+    s.particles.x[:, 2] -= 0.05 - 1.5 / res
+    sc.perturb_state(s.particles, rng, strain=5e-3, vel=0.2, affine=0.5)
+    s.particles.v[:, 1] += 2.5; s.particles.v[:, 2] -= 1.0
+    deform_cloth(s.mesh, rng, amp=0.01, vel=0.3)
+    s.mesh.vv[:, 1] += 5.0; s.mesh.ev[:, 1] += 5.0                                 # a row of vertices crosses the slab boundary within 20 substeps
+    p = s.particles; order = np.argsort(p.x[:, 1], kind="stable")
+    for k in ("x", "v", "B", "FE", "FP", "m", "vol", "q"):
+        setattr(p, k, getattr(p, k)[order])
+    return s
+
+
+@pytest.mark.parametrize("nslabs", [2, 4])
+def test_peer_slabs_cloth_sand_coupling_matches_single_context(nslabs):
+    """Cloth in slab contexts (SURVEY 8e "Cloth", BASELINE configs[3] "1/2/4 B200"): every rank holds the whole mesh state, transfers
+    the vertices / elements whose cell lies in its slab (HS:121-125, 137-141, 378, 444-454), computes the in-plane forces redundantly,
+    and pushes the points it advanced into every other rank's copy.  Gate: the slabs' union equals the whole-domain context."""
+    from anisotropicelastoplasticity_b200.engine import Engine
+    scene = _coupling_scene()
+    dt = float(np.float32(1e-4)); nsteps = 20
+    ycell = np.floor(scene.mesh.vx[:, 1] * scene.grid.res[1]).astype(int)
+    grp, engs, n0, plan = _peer_group(scene, nslabs)
+    owners0 = plan.owner_of_cells(ycell)
+    assert len(set(owners0.tolist())) == nslabs                                    # the sheet lies in every slab
+    grp.init()
+    for e in engs:
+        e.set_fixed_dt(dt)
+    grp.run(nsteps)
+    got = grp.gather_particles()
+    assert (got["ids"] == np.arange(scene.particles.n)).all()
+    assert any(e.n_particles != n for e, n in zip(engs, n0)), "no particle migrated: test is vacuous"
+    whole = Engine(scene); whole.init(); whole.set_fixed_dt(dt); whole.run(nsteps); pw = whole.particles(); mw = whole.mesh()
+    ycell1 = np.floor(mw["vx"][:, 1] * scene.grid.res[1]).astype(int)
+    assert (plan.owner_of_cells(ycell1) != owners0).any(), "no cloth vertex changed its owner: test is vacuous"
+    for k, tol in (("x", 2e-6), ("v", 5e-5), ("FE", 2e-5), ("FP", 2e-5)):
+        assert relerr(got[k], pw[k]) < tol, ("particles vs whole", k, relerr(got[k], pw[k]))
+    for r, e in enumerate(engs):                                                     # every rank's copy of the mesh is complete and current
+        me = e.mesh()
+        for k, tol in (("vx", 2e-6), ("vv", 1e-4), ("ex", 2e-6), ("ev", 1e-4), ("ed", 5e-5)):
+            assert relerr(me[k], mw[k]) < tol, ("mesh vs whole", r, k, relerr(me[k], mw[k]))
+    assert all(e.clock()["escaped"] == 0 for e in engs)

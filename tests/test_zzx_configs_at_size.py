@@ -35,7 +35,12 @@ def deform_cloth(mesh, rng, amp=0.02, vel=0.3):
     F = mesh.faces
     d1 = V[F[:, 1]] - V[F[:, 0]]; d2 = V[F[:, 2]] - V[F[:, 0]]
     n = np.cross(d1, d2); n /= np.linalg.norm(n, axis=1)[:, None]
-    d3 = n * (1.0 + 0.05 * rng.standard_normal((nf, 1))) + 0.05 * rng.standard_normal((nf, 3))
+    # third directors shorter than the normal (r33 in ~[0.8, 0.98]) and tilted: the return mapping HS:684-722 stays on its continuous
+    # branch.  r33 > 1 (d3 := unit normal, r13 = r23 = 0) is a jump of |(r13, r23)| with the scenes' zero shear stiffness; an element that
+    # was clamped once sits exactly on that jump afterwards and takes either side on rounding -- in the reference's own fp64 arithmetic
+    # too (two oracle runs whose inputs differ by float32 rounding disagree by 2e-3 on such elements after two substeps).  Both branches
+    # are pinned on the small fixtures (tests/golden/ref_cloth_*.npz, tests/test_reference_pin.py::test_random_cloth_scenes_oracle_vs_reference).
+    d3 = n * (0.88 + 0.04 * rng.uniform(-1.0, 1.0, (nf, 1))) + 0.02 * rng.standard_normal((nf, 3))
     mesh.ed = np.stack([d1, d2, d3], axis=0)
     mesh.vv = vel * np.stack([0.2 * np.sin(2 * np.pi * w), 0.2 * np.cos(2 * np.pi * u), -1.0 + 0.3 * np.sin(2 * np.pi * u)], axis=1) + 0.02 * vel * rng.standard_normal((nv, 3))
     mesh.ev = (mesh.vv[F[:, 0]] + mesh.vv[F[:, 1]] + mesh.vv[F[:, 2]]) / 3.0

@@ -22,7 +22,8 @@ def scene_for(res, seed=5):
     from anisotropicelastoplasticity_b200 import scenes as sc
     s = sc.c5_dam_break(res=res, seed=seed)
     p = s.particles
-    sc.perturb_state(p, np.random.default_rng(7), strain=3e-3, vel=0.1, affine=0.3)
+    # APIC matrices B such that the velocity gradient C = 3 B / h^2 is ~20 /s at every resolution (B itself scales with h^2)
+    sc.perturb_state(p, np.random.default_rng(7), strain=2e-3, vel=0.05, affine=20.0 / (3.0 * res * res))
     p.v[:, 0] += 2.0 * p.x[:, 2] / 0.25; p.v[:, 1] += 1.5 * np.sin(2 * np.pi * p.x[:, 2] / 0.25)
     order = np.argsort(p.x[:, 1], kind="stable")                     # contiguous global ids per slab
     for k in ("x", "v", "B", "FE", "FP", "m", "vol", "q"):
