@@ -5,6 +5,17 @@
 // slab context include the exchanges: halo planes, migrating particles, max|v| and the cloth's advected points are STORED INTO THE
 // NEIGHBOUR'S MEMORY by the kernels of the substep (NVLink peer stores; CUDA IPC mappings between processes), completion travels
 // as an epoch flag, and the receiving stream waits for it with a one-thread kernel.  Nothing returns to the host.
+//
+// Why a receive buffer is never overwritten before it was consumed (phases of enqueue_phase in aep_engine.cu; A, B neighbours):
+//   f planes:   A sends f of substep s+1 in its phase 0.  That follows A's phase 6 of substep s (stream order), which waited for B's
+//               (m,p) flag of substep s, raised in B's phase 5 -- after B's phase 1 of substep s, where B consumed A's f of substep s.
+//   (m,p):      A sends (m,p) of substep s in phase 5, after its phase 1 of s, which waited for B's f flag of s (B's phase 0 of s),
+//               raised after B's phase 6 of s-1, where B consumed A's (m,p) of s-1.
+//   migrants:   A's phase 4 of s follows its phase 1 of s -> B's phase 0 of s -> B's phase 5 of s-1, where B appended A's migrants of s-1.
+//   max|v|:     slots alternate by epoch parity; A rewrites a slot in phase 1 of s+2, after its phase 6 of s+1 -> B's phase 5 of s+1,
+//               after B's phase 2 of s, where B read it.
+// The sender fences every thread's peer stores (__threadfence_system) before its CTA counts itself done; the last CTA fences again and
+// raises the flag with st.release.sys; the waiting thread reads it with ld.acquire.sys and the consumer is a LATER kernel of the stream.
 namespace {
 
 struct CommBlob {                       // what a rank tells the others (AEP_COMM_BLOB_BYTES)

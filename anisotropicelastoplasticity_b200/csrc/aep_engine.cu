@@ -593,7 +593,7 @@ int aep_default_config(aep_config* cfg) {
     cfg->cfl = 0.3; cfg->gravity = 9.8; cfg->collider_friction = 0.2; cfg->snow_hardening = 10.0;
     cfg->sand_h[0] = 35.0; cfg->sand_h[1] = 9.0; cfg->sand_h[2] = 0.2; cfg->sand_h[3] = 10.0;
     cfg->dt_rate_floor = 3e2; cfg->frame_dt = 1.0 / 60.0;
-    cfg->particle_capacity = 0; cfg->slab_axis = -1; cfg->slab_lo = 0; cfg->slab_hi = 0; cfg->sort_every = 0; cfg->sort_bricks = 0; cfg->sort_cost_threshold = 0.5; cfg->scatter_strips = 64;
+    cfg->particle_capacity = 0; cfg->slab_axis = -1; cfg->slab_lo = 0; cfg->slab_hi = 0; cfg->sort_every = 0; cfg->sort_bricks = 0; cfg->sort_cost_threshold = 0.06; cfg->scatter_strips = 64;
     cfg->vmax_min_mass_fraction = 0.0; cfg->coulomb_friction = 0; cfg->use_graph = 1;
     return AEP_OK;
 }
@@ -848,6 +848,7 @@ int aep_set_collider_motion(aep_ctx* c, const double* velocity3) {
     if (moving && (c->col.kind < AEP_LS_GROUND || c->col.kind == AEP_LS_SAMPLED)) return fail(c, AEP_ERR_INVALID, "a moving collider needs an analytic level set (aep_set_levelset_analytic first)");
     c->col.moving = moving ? 1 : 0;
     for (int a = 0; a < 3; ++a) { c->col.vel[a] = moving ? (float)velocity3[a] : 0.f; }
+    c->G.cvx = c->col.vel[0]; c->G.cvy = c->col.vel[1]; c->G.cvz = c->col.vel[2]; c->graph_dirty = true;    // GridP travels by value in the launches
     // keep the device's current offset (the clock kernel maintains it); only velocity / mode change
     ColliderP tmp = c->col;
     CU(cudaMemcpyAsync(&c->d_col->moving, &tmp.moving, sizeof(int), cudaMemcpyHostToDevice, c->stream));

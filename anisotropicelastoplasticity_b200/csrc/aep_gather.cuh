@@ -27,6 +27,7 @@ struct GridP {
     float apic;                        // 3 / hmin^2                       HybridSolver.cpp:175-177
     float inv_cell_vol;                // 1 / (hx hy hz)                   HybridSolver.cpp:246
     float gravity, friction;
+    float cvx, cvy, cvz;               // velocity of a moving collider (0 for the reference's static ones, HS:484): a sticking node moves with it
     long long sy, sz;                  // element strides of the node index along y and z (x is contiguous): node = k*sz + j*sy + i.
                                        // Whole-grid contexts: sy = nx, sz = nx*ny (RegularGrid.cpp:164-168).  A slab context allocates only
                                        // its own node planes and makes the slab axis the slowest one; the array pointers are then biased
@@ -236,9 +237,10 @@ __device__ __forceinline__ void g2p_stick_correction(const GridP& G, const Axis&
         if (MODE == 2) t = tile[xoff + (k * 4 + j) * TILE_W + i];
         else t = ldg4(G.vt + nidx(G, clampi(ax.n0 + i, 0, G.nx - 1), clampi(ay.n0 + j, 0, G.ny - 1), clampi(az.n0 + k, 0, G.nz - 1)));
         if (t.w == 1.0f) continue;
-        // v = s v~: s = 0 on sticking nodes (the reference, HS:494-502); 0 < s < 1 only with the opt-in Coulomb friction
+        // v = c + s (v~ - c), c = the collider's velocity (0: the reference's static colliders): s = 0 on sticking nodes (HS:494-502);
+        // 0 < s < 1 only with the opt-in Coulomb friction
         const float w = (t.w - 1.0f) * sel4(ax.N, i) * sel4(ay.N, j) * sel4(az.N, k);
-        const float cx = w * t.x, cy = w * t.y, cz = w * t.z;
+        const float cx = w * (t.x - G.cvx), cy = w * (t.y - G.cvy), cz = w * (t.z - G.cvz);
         const float rxi = sel4(rx, i), ryj = sel4(ry, j), rzk = sel4(rz, k);
         S.vc[0] += cx; S.vc[1] += cy; S.vc[2] += cz;
         S.B[0] = fmaf(cx, rxi, S.B[0]); S.B[1] = fmaf(cx, ryj, S.B[1]); S.B[2] = fmaf(cx, rzk, S.B[2]);

@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256) k_grid_update(GridP G, const ColliderP* _
                         rx_ = fmaf(-vn, nx_, rx_); ry_ = fmaf(-vn, ny_, ry_); rz_ = fmaf(-vn, nz_, rz_);   // :490-492
                         const float vtn = sqrtf(rx_ * rx_ + ry_ * ry_ + rz_ * rz_);
                         // :494-502 stick test; the Coulomb reduction at :501 is a no-op expression statement.  Opt-in Coulomb: |v_t|
-                        // shrinks by mu |v_n| (what :500-501 set out to do), stored as v = s v~ with 0 <= s <= 1
+                        // shrinks by mu |v_n| (what :500-501 set out to do), stored as v = c + s (v~ - c) with 0 <= s <= 1 (c: collider velocity)
                         if (!C.coulomb) s = (vtn < -G.friction * vn) ? 0.0f : 1.0f;
                         else s = (vtn <= -G.friction * vn) ? 0.0f : 1.0f + G.friction * vn / vtn;
                         vx = rx_ + cvx; vy = ry_ + cvy; vz = rz_ + cvz;
@@ -716,7 +716,7 @@ __global__ void k_download_grid(GridP G, double* __restrict__ m, double* __restr
         }
     } else {
         if (act) tv = G.vt[n];
-        if (v) { v[t] = tv.w * tv.x; v[cnt + t] = tv.w * tv.y; v[2 * cnt + t] = tv.w * tv.z; }
+        if (v) { v[t] = G.cvx + tv.w * (tv.x - G.cvx); v[cnt + t] = G.cvy + tv.w * (tv.y - G.cvy); v[2 * cnt + t] = G.cvz + tv.w * (tv.z - G.cvz); }
         if (vt) { vt[t] = tv.x; vt[cnt + t] = tv.y; vt[2 * cnt + t] = tv.z; }
     }
 }

@@ -109,8 +109,8 @@ __device__ __forceinline__ void point_gather(const GridP& G, const float4& X, Po
                 const float w = ax.N[i] * nn;
                 const float4 t = ldg4(G.vt + row + ni);
                 const float dwx = ax.D[i] * nn, dwy = ax.N[i] * dn, dwz = ax.N[i] * nd;
-                const float ws = w * t.w;
-                const float ux = ws * t.x, uy = ws * t.y, uz = ws * t.z;
+                // post-friction velocity v = c + s (v~ - c), c = collider velocity (0 for the reference's static colliders: v = s v~)
+                const float ux = w * fmaf(t.w, t.x - G.cvx, G.cvx), uy = w * fmaf(t.w, t.y - G.cvy, G.cvy), uz = w * fmaf(t.w, t.z - G.cvz, G.cvz);
                 o.vp[0] += ux; o.vp[1] += uy; o.vp[2] += uz;
                 o.va[0] = fmaf(w, t.x, o.va[0]); o.va[1] = fmaf(w, t.y, o.va[1]); o.va[2] = fmaf(w, t.z, o.va[2]);
                 o.B[0] = fmaf(ux, rx[i], o.B[0]); o.B[1] = fmaf(ux, ry[j], o.B[1]); o.B[2] = fmaf(ux, rz[k], o.B[2]);

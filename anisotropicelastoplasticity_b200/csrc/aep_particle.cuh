@@ -68,7 +68,6 @@ struct DeferP {
 };
 struct HwTile {
     int ox0;                            // x node coordinate of tile column 0
-    int cref;                           // the cell the box is built around
 };
 __device__ __forceinline__ bool cell_fits(int cell, int cref) {
     const int ox0 = cell_i(cref) - 1 - TILE_SLACK, ci = cell_i(cell);
@@ -76,18 +75,25 @@ __device__ __forceinline__ bool cell_fits(int cell, int cref) {
 }
 // issues the box of the half-warp's 16 particles (always: the reference lane fits its own box); `fits` = this lane's particle lies in it.
 // The reference cell is the first lane's -- or the ninth lane's, when that one has more of the half-warp with it (the first lane
-// may be the stray one).
-__device__ __forceinline__ void hw_tile_issue(const CUtensorMap* tm, const GridP& G, float4* tile, unsigned long long* bar, HwTile& T, int cell, bool& fits) {
-    const int lane = threadIdx.x & 31, h0 = lane & 16;
+// may be the stray one).  `cell` comes back as the cell the lane works on: its own, or -- a stray's stand-in -- the cell of the nearest
+// fitting lane before it (after it, if there is none), so that the stand-in neither leaves the box nor breaks the run of same-cell
+// particles it sits in.
+__device__ __forceinline__ void hw_tile_issue(const CUtensorMap* tm, const GridP& G, float4* tile, unsigned long long* bar, HwTile& T, int& cell, bool& fits) {
+    const int lane = threadIdx.x & 31, h0 = lane & 16, s = lane & 15;
     const int c1 = __shfl_sync(0xffffffffu, cell, h0), c2 = __shfl_sync(0xffffffffu, cell, h0 | 8);
     const bool f1 = cell_fits(cell, c1), f2 = cell_fits(cell, c2);
     const unsigned b1 = (__ballot_sync(0xffffffffu, f1) >> h0) & 0xffffu, b2 = (__ballot_sync(0xffffffffu, f2) >> h0) & 0xffffu;
     const bool second = __popc(b2) > __popc(b1);
-    T.cref = second ? c2 : c1; fits = second ? f2 : f1;
-    T.ox0 = cell_i(T.cref) - 1 - TILE_SLACK;
-    if ((lane & 15) == 0) {
+    const int cref = second ? c2 : c1; fits = second ? f2 : f1;
+    const unsigned fm = second ? b2 : b1;                                   // never 0: the reference lane fits
+    T.ox0 = cell_i(cref) - 1 - TILE_SLACK;
+    const unsigned below = fm & ((1u << s) - 1u);
+    const int src = below ? 31 - __clz(below) : __ffs(fm) - 1;
+    const int sub = __shfl_sync(0xffffffffu, cell, h0 | src);
+    cell = fits ? cell : sub;
+    if (s == 0) {
         mbar_expect_tx(bar, TILE_F4 * 16);
-        tma_load_4d(tile, tm, bar, 0, T.ox0 - G.a0[0], cell_j(T.cref) - 1 - G.a0[1], cell_k(T.cref) - 1 - G.a0[2]);
+        tma_load_4d(tile, tm, bar, 0, T.ox0 - G.a0[0], cell_j(cref) - 1 - G.a0[1], cell_k(cref) - 1 - G.a0[2]);
     }
 }
 // the lanes of `defer` append their particle slots to the list (one atomic per warp)
@@ -150,13 +156,15 @@ __global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP 
         const int wbase = chunk * cta_particles + (threadIdx.x >> 5) * (32 * ROUNDS);
         if (wbase >= n) break;                                                // warp-uniform; no block-level barrier below
         const int hbase = wbase + hw * (16 * ROUNDS);
-        HwTile T, Tn; T.ox0 = 0; T.cref = 0; Tn = T;
+        HwTile T, Tn; T.ox0 = 0; Tn = T;
         bool fit = true, fit_n = true;
+        int cuse, cuse_n = 0;                                                 // the cell a lane works on (a stray's stand-in: see hw_tile_issue)
         {   // prologue: X of round 0 (waited for), then its tile, its F_E and the X of round 1 in flight
             const int p0 = slot_of(hbase + s);
             cp_async16_stream(&W.x[0][lane], P.a[PX] + p0);
             cp_async_commit(); cp_async_wait_all();
-            if (!LIST) hw_tile_issue(&tm, G, tile, bar, T, __float_as_int(W.x[0][lane].w), fit);
+            cuse = __float_as_int(W.x[0][lane].w);
+            if (!LIST) hw_tile_issue(&tm, G, tile, bar, T, cuse, fit);
 #pragma unroll
             for (int a = 0; a < 3; ++a) cp_async16_stream(&W.e[a][lane], P.a[PE0 + a] + p0);
             if (ROUNDS > 1) cp_async16_stream(&W.x[1][lane], P.a[PX] + slot_of(hbase + 16 + s));
@@ -173,7 +181,7 @@ __global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP 
                 const int q = hbase + round * 16 + s;
                 const bool act = q < n && fit;                                 // padding lanes and deferred strays: zero volume, at the reference cell
                 if (!LIST) defer_append(D, q < n && !fit, q);
-                const int cell = fit ? __float_as_int(X.w) : T.cref;
+                const int cell = cuse;
                 Axis ax, ay, az;
                 axis_setup(ax, X.x, cell_i(cell), G.nx, G.ihx); axis_setup(ay, X.y, cell_j(cell), G.ny, G.ihy); axis_setup(az, X.z, cell_k(cell), G.nz, G.ihz);
                 float g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -181,7 +189,7 @@ __global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP 
                 else gather_grad<0>(G, ax, ay, az, tile, 0, g);
                 cp_async_wait_all();                                           // F_E of this round, X of the next
                 __syncwarp();                                                  // every lane is done with the tile (and phase B of the round before with the records)
-                if (!LIST && more) hw_tile_issue(&tm, G, tile, bar, Tn, __float_as_int(W.x[(round + 1) & 1][lane].w), fit_n);
+                if (more) { cuse_n = __float_as_int(W.x[(round + 1) & 1][lane].w); if (!LIST) hw_tile_issue(&tm, G, tile, bar, Tn, cuse_n, fit_n); }
                 const float4 e0 = W.e[0][lane], e1 = W.e[1][lane], e2 = W.e[2][lane];
                 if (more) {                                                    // this lane's slots are consumed: next round's F_E, X of the round after
                     const int pn = slot_of(hbase + (round + 1) * 16 + s);
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP 
                 int prev;
                 starts = run_starts(cell, wcell, prev);
                 frc_make_record(W.rec[hw] + s * FRC_STRIDE, ax.N, ax.D, ay.N, ay.D, az.N, az.D, A, __int_as_float(cell), __int_as_float(prev));
-                T = Tn; fit = fit_n;
+                T = Tn; fit = fit_n; cuse = cuse_n;
             }
             __syncwarp();
             // ---- phase B: f_i += A grad w_i  with  grad w_i = (Dx_i Ny Nz, Nx_i Dy Nz, Nx_i Ny Dz)   (HybridSolver.cpp:356-366)
@@ -299,13 +307,15 @@ __global__ void __launch_bounds__(G2G_NT, G2G_MIN_CTAS) k_g2p2g(PartP P, GridP G
         const int wbase = chunk * cta_particles + (threadIdx.x >> 5) * (32 * ROUNDS);
         if (wbase >= n) break;                                                 // warp-uniform; no block-level barrier below
         const int hbase = wbase + hw * (16 * ROUNDS);
-        HwTile T, Tn; T.ox0 = 0; T.cref = 0; Tn = T;
+        HwTile T, Tn; T.ox0 = 0; Tn = T;
         bool fit = true, fit_n = true;
+        int cuse, cuse_n = 0;                                                  // the cell a lane works on (a stray's stand-in: see hw_tile_issue)
         {   // prologue: X of round 0 (waited for), then its tile, its F_E / constants and the X of round 1 in flight
             const int p0 = slot_of(hbase + s);
             cp_async16_stream(&W.x[0][lane], P.a[PX] + p0);
             cp_async_commit(); cp_async_wait_all();
-            if (!LIST) hw_tile_issue(&tm, G, tile, bar, T, __float_as_int(W.x[0][lane].w), fit);
+            cuse = __float_as_int(W.x[0][lane].w);
+            if (!LIST) hw_tile_issue(&tm, G, tile, bar, T, cuse, fit);
 #pragma unroll
             for (int a = 0; a < 3; ++a) cp_async16_stream(&W.e[a][lane], P.a[PE0 + a] + p0);
             cp_async16_stream(&W.e[3][lane], P.a[PK] + p0);
@@ -324,7 +334,7 @@ __global__ void __launch_bounds__(G2G_NT, G2G_MIN_CTAS) k_g2p2g(PartP P, GridP G
             unsigned starts = 0;
             {   // ---- phase A
                 const float4 X = W.x[round & 1][lane];
-                const int cell = fit ? __float_as_int(X.w) : T.cref;
+                const int cell = cuse;
                 int ci = cell_i(cell), cj = cell_j(cell), ck = cell_k(cell);
                 Axis ax, ay, az;
                 bool complete = axis_setup(ax, X.x, ci, G.nx, G.ihx);
@@ -352,7 +362,7 @@ __global__ void __launch_bounds__(G2G_NT, G2G_MIN_CTAS) k_g2p2g(PartP P, GridP G
                 }
                 cp_async_wait_all();                                            // F_E / constants of this round, X of the next
                 __syncwarp();                                                   // every lane is done with the tile
-                if (!LIST && more) hw_tile_issue(&tm, G, tile, bar, Tn, __float_as_int(W.x[(round + 1) & 1][lane].w), fit_n);
+                if (more) { cuse_n = __float_as_int(W.x[(round + 1) & 1][lane].w); if (!LIST) hw_tile_issue(&tm, G, tile, bar, Tn, cuse_n, fit_n); }
                 const float4 e0 = W.e[0][lane], e1 = W.e[1][lane], e2 = W.e[2][lane], kk = W.e[3][lane];
                 float (&va)[3] = S.va; float (&B)[9] = S.B; float (&g)[9] = S.g;
                 const float vp[3] = { S.va[0] + S.vc[0], S.va[1] + S.vc[1], S.va[2] + S.vc[2] };       // sum w s v~ = sum w v~ - sum w (1-s) v~
@@ -413,6 +423,9 @@ __global__ void __launch_bounds__(G2G_NT, G2G_MIN_CTAS) k_g2p2g(PartP P, GridP G
                         Svd3 sv; float sn[3];
                         if (return_map_project(mpar, Fh, sv, sn, qq) && live) { load_FP(); return_map_apply(sv, sn, Fh, FE, FP); yields = true; }
                     }
+                    // F_P is touched by yielding particles only: 48 B read + 48 B written that a particle at rest never pays.  (Fetching the
+                    // next round's rows ahead with cp.async while a warp's particles yield was tried: 21.06 against 20.91 ms per substep
+                    // in the flowing state, profiles/README.md -- the three dependent loads hide behind the other warps already.)
                     if (yields) {                                                             // yielding particle: F_P changes
                         Jp = mat_det(FP);
                         P.a[PQ0][p] = make_float4(FP[0], FP[1], FP[2], 0.f);
@@ -454,7 +467,7 @@ __global__ void __launch_bounds__(G2G_NT, G2G_MIN_CTAS) k_g2p2g(PartP P, GridP G
                     p2g_make_record(W.rec[hw] + s * P2G_STRIDE, Xn, make_float4(vp[0], vp[1], vp[2], m), make_float4(B[0], B[1], B[2], 0.f),
                                     make_float4(B[3], B[4], B[5], 0.f), make_float4(B[6], B[7], B[8], 0.f), m, G.apic, G.hx, G.hy, G.hz, __int_as_float(prev));
                 }
-                T = Tn; fit = fit_n;
+                T = Tn; fit = fit_n; cuse = cuse_n;
             }
             if (SCATTER) {
                 __syncwarp();

@@ -358,8 +358,8 @@ def run_engine(args):
                  sort_cost_threshold=args.sort_threshold)
     stream = torch.cuda.ExternalStream(eng.stream, device=local)
     eng.upload_packed(n, arrs, *mat); eng.init()
-    if args.pin_dt:
-        eng.set_fixed_dt(0.3 / rate_floor)
+    if args.pin_dt > 0.0:
+        eng.set_fixed_dt(args.pin_dt)
     # ---- timed region: K substeps of the developed state, device events on the engine's stream
     sampler = ClockSampler(local)
     tr = timed_run(eng, stream, args, n)
@@ -472,7 +472,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: peer = halo / migration / max|v| stored into the neighbours' memory by the engine's own kernels (CUDA IPC over NVLink); nccl = torch.distributed send/recv driven from Python (the baseline)")
     ap.add_argument("--perturb", type=float, default=0.0, help="development: random strain scale added to the rest state (0 = the named workload)")
     ap.add_argument("--sort-bricks", type=int, default=0, help="1: brick-major particle order (aep_config.sort_bricks), 0: cell-index order")
-    ap.add_argument("--pin-dt", action="store_true", help="development: pin dt at cfl / rate_floor (the largest step the rule takes) so that runs are comparable; the headline uses the reference rule")
+    ap.add_argument("--pin-dt", type=float, default=0.0, help="development: pin dt (s) so that runs are comparable -- the reference rule's dt follows rounding noise at near-massless nodes; the headline uses the reference rule")
     ap.add_argument("--sort-threshold", type=float, default=None, help="development: aep_config.sort_cost_threshold of the adaptive re-sort (default: the library's)")
     ap.add_argument("--sort-every", type=int, default=0, help="physical re-sort period in substeps (aep_config.sort_every); 0 = adaptive (default)")
     args = ap.parse_args()

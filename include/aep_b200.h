@@ -87,7 +87,8 @@ typedef struct aep_config {
                                   of the gathers, but the scatters of one CTA then contend for the same L2 lines: measured slower overall) */
     int32_t scatter_strips;    /* 64: concurrently running P2G CTAs are spread over this many far-apart parts of the sorted particle
                                   order so that they do not reduce into the same grid nodes at the same time (L2 atomic contention) */
-    double sort_cost_threshold; /* 0.5: the extra scatter work of unsorted particles has about paid for one re-sort       */
+    double sort_cost_threshold; /* 0.06: measured on the C5 dam break in flow (profiles/README.md, round 2): a particle that has left its
+                                  cell costs ~1.2 ms per % and substep (list pass + broken scatter runs), a re-sort 5.9 ms              */
     /* --- opt-in departures from the reference (all default to the reference's behaviour) --- */
     double vmax_min_mass_fraction; /* 0: the reference's dt rule, max |v_i| over EVERY node with m_i > 0 (RegularGrid.cpp:188-200), which at
                                   nearly massless stencil-edge nodes is rounding noise of p/m and can cut dt by orders of magnitude.

@@ -36,7 +36,7 @@ def test_config_struct_layout():
     assert cfg.collider_friction == pytest.approx(0.2) and cfg.snow_hardening == pytest.approx(10.0)         # HS:465, HS:267
     assert list(cfg.sand_h) == [35.0, 9.0, 0.2, 10.0] and cfg.dt_rate_floor == 300.0                         # HS:641-644, HS:860
     assert cfg.frame_dt == pytest.approx(1.0 / 60.0) and cfg.slab_axis == -1 and cfg.sort_every == 0
-    assert cfg.sort_bricks == 0 and cfg.scatter_strips == 64 and cfg.sort_cost_threshold == 0.5
+    assert cfg.sort_bricks == 0 and cfg.scatter_strips == 64 and cfg.sort_cost_threshold == 0.06
     # the opt-in departures from the reference are OFF by default; last field reached: layouts agree
     assert cfg.vmax_min_mass_fraction == 0.0 and cfg.coulomb_friction == 0 and cfg.use_graph == 1 and C.sizeof(capi.Config) == 208
 
