@@ -1,7 +1,7 @@
 // aep_engine.cu -- context management, stepping sequence and the C ABI (include/aep_b200.h) of libaep_b200.so.
 //
 // One aep_ctx = one GPU = one slab of the domain.  All work is enqueued on ctx->stream; a substep is
-//   forces -> grid update/collide (+max|v|) -> clock (dt rule) -> G2P/advect/F/plasticity + P2G of the next substep (one kernel)
+//   forces -> grid update/collide (+max|v|, clears what it consumed) -> clock (dt rule) -> G2P/advect/F/plasticity -> P2G of the next substep
 // (HybridSolver.cpp:867-1032) with no host synchronisation, dt and the particle count living in device memory.  The sequence
 // carries no changing launch arguments, so it is captured once into a CUDA graph and replayed: one host launch per substep.
 #include <cuda.h>
@@ -118,6 +118,9 @@ struct aep_ctx {
     // CUDA graph of one substep
     cudaGraphExec_t graph = nullptr; bool graph_dirty = true; long long graph_launches = 0;
     bool use_graph = true;
+    bool fused = false;                         // G2P and the next P2G as two kernels (default) or in one (k_g2p2g<SCATTER = true>; development:
+                                                // AEP_FUSED=1).  Measured on the same box, C5: 14.8 against 16.4 ms per substep at rest, 19.1 against 21.9
+                                                // in the flowing state (profiles/README.md, round 2): the scatter alone runs at 3x the occupancy
 
     Comm comm;
 
@@ -383,6 +386,13 @@ int peer_mesh_wait(aep_ctx* c, int which);
 // particles: the fused kernel (G2P + P2G of the next substep), or G2P alone (stage-level API, caller-driven slab path)
 int do_g2p_particles(aep_ctx* c, bool scatter) {
     if (!n_launch(c)) return AEP_OK;
+    if (scatter && !c->fused) {       // G2P, then the P2G of the next substep as its own kernel (same particles, same order, same result)
+        if (int r = do_g2p_particles(c, false)) return r;
+        StageTimer T(c, AEP_STAGE_P2G);
+        p2g_launch(c->stream, c->P[c->cur], c->G, n_launch(c), c->d_clk, peer_mode(c));
+        LAUNCH_OK("k_p2g");
+        return AEP_OK;
+    }
     StageTimer T(c, scatter ? AEP_STAGE_G2P2G : AEP_STAGE_G2P);
     if (c->mig.axis >= 0 && !peer_mode(c)) cudaMemsetAsync(c->mig.counts, 0, 2 * sizeof(unsigned long long), c->stream);
     cudaError_t e = scatter ? g2p2g_launch<true>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig, c->defer)
@@ -621,6 +631,7 @@ int aep_create(aep_ctx** out, const aep_config* cfg) {
     aep_ctx* ctx = new aep_ctx();
     ctx->cfg = *cfg; ctx->device = cfg->device; ctx->sm_count = prop.multiProcessorCount; ctx->mig.axis = -1;
     ctx->use_graph = cfg->use_graph != 0 && !getenv("AEP_NO_GRAPH");
+    if (const char* f = getenv("AEP_FUSED")) ctx->fused = atoi(f) != 0;
     c = ctx;
     auto bail = [&](int code) { std::string m = ctx->err; aep_destroy(ctx); g_create_error = m; return code; };
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, AEP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(e_ == cudaErrorMemoryAllocation ? AEP_ERR_ALLOC : AEP_ERR_CUDA); } } while (0)

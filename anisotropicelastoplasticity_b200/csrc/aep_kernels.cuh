@@ -492,6 +492,14 @@ __device__ __forceinline__ unsigned run_starts(int cell, int& wcell, int& prev) 
 // the end of the fused kernel (aep_particle.cuh) on records made from registers.
 #define P2G_HW_PAD 2
 #define P2G_HW_F4 (16 * P2G_STRIDE + P2G_HW_PAD)
+// A particle that has left its cell since the last physical sort sits alone between two stretches of its old cell's run:
+// ... A A A [B] A A A ...  Moving the window to B and back costs two flushes (up to 8 reductions per lane) and the window code twice;
+// instead such a SINGLETON goes to memory by itself (4 reductions per lane from a scratch row) and the window stays where it is.
+// Recognised where a run starts at record `it`, another one at `it + 1`, and that one returns to the cell before `it`.
+__device__ __forceinline__ bool singleton_at(const float4* __restrict__ cell_rec, int stride, unsigned starts, int it, int prev) {
+    if (it >= 15 || prev < 0 || !((starts >> (it + 1)) & 1u)) return false;
+    return __float_as_int(cell_rec[stride].x) == prev;                       // the next record's cell
+}
 // one round of phase B: the half-warp's 16 records into the window
 __device__ __forceinline__ void p2g_phase_b(const GridP& G, const float4* __restrict__ recs, unsigned starts, float4* slot, int j, int k, int yoff, int zoff,
                                             f32x2 J, f32x2 K, AccRow& acc) {
@@ -500,15 +508,24 @@ __device__ __forceinline__ void p2g_phase_b(const GridP& G, const float4* __rest
         const float4* r = recs + it * P2G_STRIDE;
         if ((starts >> it) & 1u) {                                            // a run of particles sharing a cell starts here
             const float2 cn = *reinterpret_cast<const float2*>(r + 7);
+            if (singleton_at(r + 7, P2G_STRIDE, starts, it, __float_as_int(cn.y))) {
+                AccRow one; acc_zero(one);
+                p2g_row_accumulate(r, yoff, zoff, J, K, one);
+                flush_row_pk(G, G.mp, slot, __float_as_int(cn.x), j, k, one, true);
+                starts &= ~(2u << it);                                        // the window never left the run that continues at it + 1
+                continue;
+            }
             window_move(G, G.mp, slot, __float_as_int(cn.y), __float_as_int(cn.x), j, k, acc, true);
         }
         p2g_row_accumulate(r, yoff, zoff, J, K, acc);
     }
 }
 // ROUNDS x 16 consecutive particles per half-warp: 8 for large scenes (fewest reductions), less when that would leave SMs idle
+// n < 0: the particle count lives on the device (clk->n_slots; the launch covers -n slots: slab contexts with peer communication)
 template <int ROUNDS>
 __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n, const SimClock* __restrict__ clk) {
-    if (clk) AEP_HALT_POST(clk);                                              // inside a substep (mesh points); nullptr: stage-level call
+    if (clk) AEP_HALT_POST(clk);                                              // inside a substep; nullptr: stage-level call
+    if (n < 0) n = clk->n_slots;
     __shared__ float4 stage[8][2][P2G_HW_F4];
     __shared__ float4 bounce[256];                                            // lane-private slots of requad()
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -551,11 +568,13 @@ __global__ void __launch_bounds__(256) k_p2g(PartP P, GridP G, int n, const SimC
 }
 
 // launch helper shared by the engine and the mesh transfers
-inline void p2g_launch(cudaStream_t st, const PartP& P, const GridP& G, long long n, const SimClock* clk = nullptr) {
+// device_count: the launch covers n slots, the kernel takes the count in use from the clock
+inline void p2g_launch(cudaStream_t st, const PartP& P, const GridP& G, long long n, const SimClock* clk = nullptr, bool device_count = false) {
     if (n <= 0) return;
-    if (n >= (1ll << 22)) { const int chunks = (int)((n + 2047) / 2048); k_p2g<8><<<strided_grid(chunks, G.strips), 256, 0, st>>>(P, G, (int)n, clk); }
-    else if (n >= (1ll << 19)) { const int chunks = (int)((n + 511) / 512); k_p2g<2><<<strided_grid(chunks, G.strips), 256, 0, st>>>(P, G, (int)n, clk); }
-    else { const int chunks = (int)((n + 255) / 256); k_p2g<1><<<strided_grid(chunks, G.strips), 256, 0, st>>>(P, G, (int)n, clk); }
+    const int na = device_count ? -(int)n : (int)n;
+    if (n >= (1ll << 22)) { const int chunks = (int)((n + 2047) / 2048); k_p2g<8><<<strided_grid(chunks, G.strips), 256, 0, st>>>(P, G, na, clk); }
+    else if (n >= (1ll << 19)) { const int chunks = (int)((n + 511) / 512); k_p2g<2><<<strided_grid(chunks, G.strips), 256, 0, st>>>(P, G, na, clk); }
+    else { const int chunks = (int)((n + 255) / 256); k_p2g<1><<<strided_grid(chunks, G.strips), 256, 0, st>>>(P, G, na, clk); }
 }
 
 // first P2G only: rho_p = sum_i w m_i / (hx hy hz), V_p = m_p / rho_p           HybridSolver.cpp:242-249

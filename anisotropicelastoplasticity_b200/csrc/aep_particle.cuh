@@ -9,11 +9,10 @@
 //   * the (cells+3) x 4 x 4 node box of the half-warp's 16 particles by TMA (cp.async.bulk.tensor, one lane issues, an mbarrier
 //     completes) -- no LSU wavefronts, no registers, zero fill outside the grid / the slab's reach;
 //   * the particle records (X two rounds ahead, F_E / constants one round ahead) by cp.async into the warp's shared memory.
-// Why fused G2P+P2G: G2P alone is bound by FP32 issue (74 %) with the LSU half idle, P2G alone by LSU wavefronts (95 %) with the
-// FMA pipe half idle (profiles/README.md, round 1); in one kernel the warps of an SM sit in different phases and the two pipes
-// overlap.  It also removes the 80 B / particle that G2P wrote only for P2G to read back, the P2G launch, and the clearing pass
-// (k_grid_update<true> zeroes what it has consumed).  A particle is scattered from where G2P left it, i.e. in the order of its OLD
-// cell: runs end a little earlier for the few % that changed cell, nothing else changes (the order never affects results).
+// SCATTER = true fuses the P2G of the next substep into the G2P kernel (records made from registers: V and B never travel through
+// memory, one launch and 80 B / particle less).  Built, measured, NOT the default: the fused kernel needs 128 registers and runs 16
+// warps per SM, where the scatter alone (k_p2g, 63 registers) runs 48: 14.8 against 16.4 ms per substep at rest and 19.1 against
+// 21.9 in the flowing state for two kernels against one (same box; profiles/README.md, round 2).  AEP_FUSED=1 selects it.
 #pragma once
 #include <cuda.h>
 #include "aep_kernels.cuh"
@@ -217,6 +216,13 @@ __global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP 
                 const float4* r = recs + it * FRC_STRIDE;
                 if ((starts >> it) & 1u) {                                      // a run of particles sharing a cell starts here
                     const float2 cn = *reinterpret_cast<const float2*>(r + 9);
+                    if (singleton_at(r + 9, FRC_STRIDE, starts, it, __float_as_int(cn.y))) {      // a lone mover inside a run (see p2g_phase_b)
+                        AccRow one; acc_zero(one);
+                        frc_row_accumulate(r, yoff, zoff, one);
+                        flush_row_pk(G, G.f, slot, __float_as_int(cn.x), j, k, one, false);
+                        starts &= ~(2u << it);
+                        continue;
+                    }
                     window_move(G, G.f, slot, __float_as_int(cn.y), __float_as_int(cn.x), j, k, acc, false);
                 }
                 frc_row_accumulate(r, yoff, zoff, acc);
@@ -263,21 +269,26 @@ inline cudaError_t forces_launch(cudaStream_t st, const PartP& P, const GridP& G
 // others the reference's F_P update is the identity (aep_math.cuh, return_map_project).
 #define G2G_NT 128
 #ifndef G2G_MIN_CTAS
-#define G2G_MIN_CTAS 4
+#define G2G_MIN_CTAS 4                  // fused kernel: 128 registers
 #endif
-struct __align__(128) G2GWarpSmem {
+#ifndef G2P_MIN_CTAS
+#define G2P_MIN_CTAS 5                  // G2P alone: 96 registers (8 B of spills), 20 warps per SM: 5.37 against 5.56 ms (C5, rest)
+#endif
+template <bool SCATTER>
+struct __align__(128) G2GWarpSmemT {
     float4 tile[2][TILE_F4];
-    float4 rec[2][P2G_HW_F4];
+    float4 rec[2][SCATTER ? P2G_HW_F4 : 1];   // the scatter's records: only the fused kernel has them
     float4 x[2][32];
     float4 e[4][32];                    // E0 E1 E2 K
     float4 bounce[32];
     unsigned long long bar[2];
 };
 template <int ROUNDS, bool SCATTER, bool LIST>
-__global__ void __launch_bounds__(G2G_NT, G2G_MIN_CTAS) k_g2p2g(PartP P, GridP G, const __grid_constant__ CUtensorMap tm, MatParams mpar,
+__global__ void __launch_bounds__(G2G_NT, SCATTER ? G2G_MIN_CTAS : G2P_MIN_CTAS) k_g2p2g(PartP P, GridP G, const __grid_constant__ CUtensorMap tm, MatParams mpar,
                                                                SimClock* __restrict__ clk, MigList ML, DeferP D) {
     AEP_HALT_POST(clk);
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    typedef G2GWarpSmemT<SCATTER> G2GWarpSmem;
     G2GWarpSmem& W = reinterpret_cast<G2GWarpSmem*>(smem_raw)[threadIdx.x >> 5];
     const int n = LIST ? (int)*D.count : clk->n_slots;                         // particles this launch walks
     const int lane = threadIdx.x & 31, hw = lane >> 4, s = lane & 15, j = s & 3, k = s >> 2;
@@ -484,7 +495,7 @@ __global__ void __launch_bounds__(G2G_NT, G2G_MIN_CTAS) k_g2p2g(PartP P, GridP G
 template <int ROUNDS, bool SCATTER>
 inline void g2p2g_launch_r(cudaStream_t st, const PartP& P, const GridP& G, const CUtensorMap& tm, const MatParams& mat, SimClock* clk,
                            long long n_hi, const MigList& ML, const DeferP& D) {
-    const int smem = (int)sizeof(G2GWarpSmem) * (G2G_NT / 32);
+    const int smem = (int)sizeof(G2GWarpSmemT<SCATTER>) * (G2G_NT / 32);
     const long long per_cta = (long long)G2G_NT * ROUNDS;
     const int chunks = (int)((n_hi + per_cta - 1) / per_cta);
     k_g2p2g<ROUNDS, SCATTER, false><<<SCATTER ? strided_grid(chunks, G.strips) : chunks, G2G_NT, smem, st>>>(P, G, tm, mat, clk, ML, D);
@@ -501,13 +512,13 @@ inline cudaError_t g2p2g_launch(cudaStream_t st, const PartP& P, const GridP& G,
     default: g2p2g_launch_r<1, SCATTER>(st, P, G, tm, mat, clk, n_hi, ML, D); break;
     }
     const long long list_ctas = std::min<long long>((n_hi + G2G_NT - 1) / G2G_NT, AEP_LIST_CTAS);
-    k_g2p2g<1, SCATTER, true><<<(unsigned)list_ctas, G2G_NT, (int)sizeof(G2GWarpSmem) * (G2G_NT / 32), st>>>(P, G, tm, mat, clk, ML, D);
+    k_g2p2g<1, SCATTER, true><<<(unsigned)list_ctas, G2G_NT, (int)sizeof(G2GWarpSmemT<SCATTER>) * (G2G_NT / 32), st>>>(P, G, tm, mat, clk, ML, D);
     return cudaGetLastError();
 }
 
 // dynamic shared memory above 48 KB needs an opt-in per kernel and device: aep_create calls this once
 inline cudaError_t particle_kernels_configure() {
-    const int fs = (int)sizeof(FrcWarpSmem) * (FRC_NT / 32), gs = (int)sizeof(G2GWarpSmem) * (G2G_NT / 32);
+    const int fs = (int)sizeof(FrcWarpSmem) * (FRC_NT / 32), gs = (int)sizeof(G2GWarpSmemT<true>) * (G2G_NT / 32);
     cudaError_t e;
 #define AEP_CFG(kern, bytes) if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e
     AEP_CFG((k_forces<8, false>), fs); AEP_CFG((k_forces<2, false>), fs); AEP_CFG((k_forces<1, false>), fs); AEP_CFG((k_forces<1, true>), fs);

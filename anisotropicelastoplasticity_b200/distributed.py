@@ -609,10 +609,10 @@ def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, U
     achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
     sub_bytes = B.BYTES_PARTICLE[sc.SAND] * n_total + B.BYTES_NODE * nodes
     sub_gbs = sub_bytes / (ms * 1e-3 / args.steps) / 1e9 / world
-    kernels = {"forces": "k_forces", "g2p2g": "k_g2p2g", "g2p": "k_g2p2g<scatter off>", "p2g": "k_p2g", "grid": "k_grid_update"}
+    kernels = {"forces": "k_forces", "g2p2g": "k_g2p2g", "g2p": "k_g2p2g<SCATTER=0> (G2P)", "p2g": "k_p2g", "grid": "k_grid_update"}
     roofline = {"bound": "hbm", "kernel": kernels[dom],
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth, MEASURED_PEAKS.json", "unit": "GB/s", "frac": achieved / peak,
-                "traffic": B.ncu_traffic(kernels[dom], eng.n_particles), "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom], "stage_ms": stage_ms, "rank": 0,
+                "traffic": B.ncu_traffic({"forces": "k_forces", "g2p2g": "k_g2p2g", "g2p": "k_g2p2g", "p2g": "k_p2g"}.get(dom, ""), eng.n_particles), "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom], "stage_ms": stage_ms, "rank": 0,
                 "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs_per_gpu": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes},
                 "p2g_g2p": B.transfers_roofline(stage_ms, eng.n_particles, eng.grid_activity()[1], peak)}
     plane_bytes = res * res * 16

@@ -379,9 +379,9 @@ def run_engine(args):
     achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
     sub_bytes = BYTES_PARTICLE[sc.SAND] * n + BYTES_NODE * nodes
     sub_gbs = sub_bytes / (ms * 1e-3 / args.steps) / 1e9
-    roofline = {"bound": "hbm", "kernel": {"forces": "k_forces", "g2p2g": "k_g2p2g", "g2p": "k_g2p2g<scatter off>", "p2g": "k_p2g", "grid": "k_grid_update", "sort": "cub radix sort + k_reorder"}[dom],
+    roofline = {"bound": "hbm", "kernel": {"forces": "k_forces", "g2p2g": "k_g2p2g", "g2p": "k_g2p2g<SCATTER=0> (G2P)", "p2g": "k_p2g", "grid": "k_grid_update", "sort": "cub radix sort + k_reorder"}[dom],
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth, MEASURED_PEAKS.json", "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic({"forces": "k_forces", "g2p2g": "k_g2p2g", "p2g": "k_p2g"}.get(dom, ""), n),
+                "frac": achieved / peak, "traffic": ncu_traffic({"forces": "k_forces", "g2p2g": "k_g2p2g", "g2p": "k_g2p2g", "p2g": "k_p2g"}.get(dom, ""), n),
                 "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom],
                 "stage_ms": stage_ms,
                 "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes, "active_blocks": blocks},

@@ -61,12 +61,14 @@ def main():
     if not a.adaptive: eng.set_fixed_dt(dt)
     dist.barrier()
     n0 = eng.n_particles
-    eng.run(a.steps); eng.sync()
+    if a.adaptive: eng.run_frames(1)                       # the reference dt rule, to a frame boundary: every rank halts on the same substep
+    else: eng.run(a.steps)
+    eng.sync()
     t_run = time.perf_counter() - t0
     clk = eng.clock(); mig = eng.migration(); cnt = eng.counters()
     part = download_local(eng)
     gathered = [None] * world if rank == 0 else None
-    dist.gather_object({"part": part, "mig": mig, "n0": n0, "n1": eng.n_particles, "dt": clk["dt"], "escaped": clk["escaped"], "sorts": cnt["sorts"]}, gathered, dst=0)
+    dist.gather_object({"part": part, "mig": mig, "n0": n0, "n1": eng.n_particles, "dt": clk["dt"], "escaped": clk["escaped"], "sorts": cnt["sorts"], "substeps": clk["substeps"]}, gathered, dst=0)
     ok = True; out = {}
     if rank == 0:
         ids = np.concatenate([g["part"]["ids"] for g in gathered]); order = np.argsort(ids)
@@ -80,10 +82,23 @@ def main():
         ok &= len(set(out["dt_per_rank"])) == 1                                            # the dt rule saw the GLOBAL max|v|
         whole = Engine(scene, device=local, dt_rate_floor=rf); whole.init()
         if not a.adaptive: whole.set_fixed_dt(dt)
-        whole.run(a.steps); pw = whole.particles(); out["dt_whole"] = whole.clock()["dt"]; whole.close()
-        tol = {"x": 2e-6, "v": 5e-5, "FE": 2e-5, "FP": 2e-5, "q": 2e-4} if not a.adaptive else {"x": 1e-4, "v": 1e-2, "FE": 1e-3, "FP": 1e-3, "q": 1e-1}
-        out["vs_whole_context"] = {k: relerr(got[k], pw[k]) for k in tol}
-        ok &= all(out["vs_whole_context"][k] < tol[k] for k in tol)
+        if a.adaptive: whole.run_frames(1)
+        else: whole.run(a.steps)
+        pw = whole.particles(); out["dt_whole"] = whole.clock()["dt"]; out["substeps_whole"] = whole.clock()["substeps"]; whole.close()
+        if not a.adaptive:
+            tol = {"x": 2e-6, "v": 5e-5, "FE": 2e-5, "FP": 2e-5, "q": 2e-4}
+            out["vs_whole_context"] = {k: relerr(got[k], pw[k]) for k in tol}
+            ok &= all(out["vs_whole_context"][k] < tol[k] for k in tol)
+        else:
+            # free running the dt rule follows rounding noise at near-massless nodes (tests/test_gpu_dt_rule_at_scale.py): slabs and the
+            # whole-domain context take different step sequences to the SAME simulated time (one frame); bulk statistics agree
+            from anisotropicelastoplasticity_b200.scenes import bulk_stats
+            m = scene.particles.m
+            cs, ks, js = bulk_stats(got["x"], got["v"], m, got["FP"]); cw, kw, jw = bulk_stats(pw["x"], pw["v"], m, pw["FP"])
+            out["bulk"] = {"com_rel": float(np.linalg.norm(cs - cw) / np.linalg.norm(cw)), "kinetic_rel": float(abs(ks - kw) / kw), "mean_det_FP_abs": float(abs(js - jw)),
+                           "substeps_slabs": [int(g["substeps"]) for g in gathered]}
+            ok &= out["bulk"]["com_rel"] < 1e-3 and out["bulk"]["kinetic_rel"] < 0.01 and out["bulk"]["mean_det_FP_abs"] < 1e-3
+            ok &= len(set(out["bulk"]["substeps_slabs"])) == 1
         if a.oracle and not a.adaptive:
             from oracle.oracle_py import Oracle
             o = Oracle(scene, threads=0, rate_floor=rf); o.init()
