@@ -87,6 +87,8 @@ struct aep_ctx {
     PartP P[2]{}; int cur = 0;
     unsigned int *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr};
     DeferP defer{nullptr, nullptr};             // particles that do not fit their half-warp's gather box (aep_particle.cuh)
+    ForceA forceA{{nullptr, nullptr, nullptr}}; // A = -V P F_E^T between the two force kernels (split_forces)
+    bool split_forces = true;                   // development: AEP_SPLIT_FORCES=0 -> gather and scatter of the forces in one kernel
     void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     int key_bits = 0;
     MatParams mat{};
@@ -349,9 +351,9 @@ int do_forces(aep_ctx* c, bool in_substep) {
     }
     if (n_launch(c)) {
         StageTimer T(c, AEP_STAGE_FORCES);
-        cudaError_t e = forces_launch(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->defer);
+        cudaError_t e = forces_launch(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->defer, c->forceA, c->split_forces, peer_mode(c));
         if (e != cudaSuccess) return fail(c, AEP_ERR_CUDA, "k_forces: %s", cudaGetErrorString(e));
-        LAUNCH_OK("k_forces"); c->launches++;                                 // + the launch over the deferred list
+        LAUNCH_OK("k_forces"); c->launches += c->split_forces ? 2 : 1;        // + the launch over the deferred list (+ the scatter kernel)
     }
     if (c->mesh.nv) {
         StageTimer T(c, AEP_STAGE_MESH);
@@ -586,6 +588,7 @@ static int ensure_particle_capacity(aep_ctx* c, long long cap) {
         for (int a = 0; a < P_NARR; ++a) CU(dalloc(c, &c->P[b].a[a], (size_t)cap));
     for (int b = 0; b < 2; ++b) { CU(dalloc(c, &c->d_keys[b], (size_t)cap)); CU(dalloc(c, &c->d_vals[b], (size_t)cap)); }
     CU(dalloc(c, &c->defer.list, (size_t)cap)); CU(dalloc(c, &c->defer.count, 1));
+    for (int a = 0; a < 3; ++a) CU(dalloc(c, &c->forceA.a[a], (size_t)cap));
     size_t tmp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], (int)cap, 0, c->key_bits + 2, c->stream);
     CU(cudaMalloc(&c->d_sort_tmp, tmp)); c->sort_tmp_bytes = tmp;
@@ -632,6 +635,7 @@ int aep_create(aep_ctx** out, const aep_config* cfg) {
     ctx->cfg = *cfg; ctx->device = cfg->device; ctx->sm_count = prop.multiProcessorCount; ctx->mig.axis = -1;
     ctx->use_graph = cfg->use_graph != 0 && !getenv("AEP_NO_GRAPH");
     if (const char* f = getenv("AEP_FUSED")) ctx->fused = atoi(f) != 0;
+    if (const char* f = getenv("AEP_SPLIT_FORCES")) ctx->split_forces = atoi(f) != 0;
     c = ctx;
     auto bail = [&](int code) { std::string m = ctx->err; aep_destroy(ctx); g_create_error = m; return code; };
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, AEP_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(e_ == cudaErrorMemoryAllocation ? AEP_ERR_ALLOC : AEP_ERR_CUDA); } } while (0)

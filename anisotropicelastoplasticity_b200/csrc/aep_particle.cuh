@@ -120,19 +120,28 @@ __device__ __forceinline__ void defer_append(const DeferP& D, bool defer, int p)
 #ifndef FRC_MIN_CTAS
 #define FRC_MIN_CTAS 4
 #endif
-struct __align__(128) FrcWarpSmem {
+#ifndef FRC_SPLIT_MIN_CTAS
+#define FRC_SPLIT_MIN_CTAS 5
+#endif
+// SPLIT: phase A only -- A = -V_p P F_E^T goes to memory (3 float4 per particle, `Aout`) and k_force_scatter does phase B as its own,
+// small-register kernel (the same reason G2P and P2G are two kernels: the scatter is bound by the LSU pipe and wants warps, the gather
+// by issue slots and wants registers).
+struct ForceA { float4* a[3]; };
+template <bool SPLIT>
+struct __align__(128) FrcWarpSmemT {
     float4 tile[2][TILE_F4];
-    float4 rec[2][FRC_HW_F4];
+    float4 rec[2][SPLIT ? 1 : FRC_HW_F4];
     float4 x[2][32];
     float4 e[3][32];
     float4 bounce[32];
     unsigned long long bar[2];
 };
-template <int ROUNDS, bool LIST>
-__global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP G, const __grid_constant__ CUtensorMap tm, MatParams mpar,
-                                                                  const SimClock* __restrict__ clk, DeferP D) {
+template <int ROUNDS, bool LIST, bool SPLIT>
+__global__ void __launch_bounds__(FRC_NT, SPLIT ? FRC_SPLIT_MIN_CTAS : FRC_MIN_CTAS) k_forces(PartP P, GridP G, const __grid_constant__ CUtensorMap tm, MatParams mpar,
+                                                                  const SimClock* __restrict__ clk, DeferP D, ForceA Aout) {
     AEP_HALT_PRE(clk);
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    typedef FrcWarpSmemT<SPLIT> FrcWarpSmem;
     FrcWarpSmem& W = reinterpret_cast<FrcWarpSmem*>(smem_raw)[threadIdx.x >> 5];
     const int n = LIST ? (int)*D.count : clk->n_slots;                        // particles this launch walks
     const int lane = threadIdx.x & 31, hw = lane >> 4, s = lane & 15, j = s & 3, k = s >> 2;
@@ -203,11 +212,20 @@ __global__ void __launch_bounds__(FRC_NT, FRC_MIN_CTAS) k_forces(PartP P, GridP 
 #pragma unroll
                 for (int i = 0; i < 9; ++i) Fh[i] = fmaf(dt, GF[i], FE[i]);      // HybridSolver.cpp:306
                 stress_times_FEt(mpar, Fh, FE, act ? -e0.w : 0.0f, e2.w, A);     // A := -V_p P FE^T (sign of :356-366 folded in)
-                int prev;
-                starts = run_starts(cell, wcell, prev);
-                frc_make_record(W.rec[hw] + s * FRC_STRIDE, ax.N, ax.D, ay.N, ay.D, az.N, az.D, A, __int_as_float(cell), __int_as_float(prev));
+                if (SPLIT) {
+                    if (act) {
+                        const int p = slot_of(q);
+                        Aout.a[0][p] = make_float4(A[0], A[1], A[2], 0.f); Aout.a[1][p] = make_float4(A[3], A[4], A[5], 0.f); Aout.a[2][p] = make_float4(A[6], A[7], A[8], 0.f);
+                    }
+                    starts = 0u;
+                } else {
+                    int prev;
+                    starts = run_starts(cell, wcell, prev);
+                    frc_make_record(W.rec[hw] + s * FRC_STRIDE, ax.N, ax.D, ay.N, ay.D, az.N, az.D, A, __int_as_float(cell), __int_as_float(prev));
+                }
                 T = Tn; fit = fit_n; cuse = cuse_n;
             }
+            if (SPLIT) continue;
             __syncwarp();
             // ---- phase B: f_i += A grad w_i  with  grad w_i = (Dx_i Ny Nz, Nx_i Dy Nz, Nx_i Ny Dz)   (HybridSolver.cpp:356-366)
             //      = Dx_i U + Nx_i V,  U = A[:,0] Ny Nz,  V = A[:,1] Dy Nz + A[:,2] Ny Dz  per (j,k) row
@@ -240,25 +258,109 @@ inline int rounds_for(long long n) {
     if (forced == 1 || forced == 2 || forced == 8) return forced;
     return n >= (1ll << 22) ? 8 : (n >= (1ll << 19) ? 2 : 1);
 }
+// ---- phase B alone: f_i += A grad w_ip from the A stored by k_forces<SPLIT> (HybridSolver.cpp:356-366).  Same mapping as k_p2g: 256
+// threads, a warp owns 32 x ROUNDS consecutive particles, window open over the rounds.  Strays need no list here: a particle
+// out of its cell order is just a run of length one (singleton_at).
+#define FRC_SCATTER_SMEM ((8 * 2 * FRC_HW_F4 + 256) * 16)
 template <int ROUNDS>
-inline cudaError_t forces_launch_r(cudaStream_t st, const PartP& P, const GridP& G, const CUtensorMap& tm, const MatParams& mat, const SimClock* clk, long long n_hi, const DeferP& D) {
-    const int smem = (int)sizeof(FrcWarpSmem) * (FRC_NT / 32);
+__global__ void __launch_bounds__(256) k_force_scatter(PartP P, GridP G, ForceA Ain, int n, const SimClock* __restrict__ clk) {
+    AEP_HALT_PRE(clk);
+    extern __shared__ __align__(128) unsigned char smem_raw[];                // 49.6 KB: above the static limit
+    float4 (*stage)[2][FRC_HW_F4] = reinterpret_cast<float4 (*)[2][FRC_HW_F4]>(smem_raw);
+    float4* bounce = reinterpret_cast<float4*>(smem_raw) + 8 * 2 * FRC_HW_F4;  // lane-private slots of requad()
+    if (n < 0) n = clk->n_slots;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float4* slot = bounce + threadIdx.x;
+    const int cta_particles = 256 * ROUNDS;
+    const int chunk = strided_chunk(blockIdx.x, (n + cta_particles - 1) / cta_particles, G.strips);
+    if (chunk < 0) return;
+    const int hw = lane >> 4, s = lane & 15, j = s & 3, k = s >> 2;
+    const int hbase = chunk * cta_particles + wib * (32 * ROUNDS) + hw * (16 * ROUNDS);
+    if (chunk * cta_particles + wib * (32 * ROUNDS) >= n) return;             // warp-uniform; no block-level barrier below
+    int yoff = 32 + 8 * j, zoff = 64 + 8 * k;                                 // byte offsets of (Ny,Dy)[j], (Nz,Dz)[k] inside a record
+    yoff = __shfl_sync(0xffffffffu, yoff, lane); zoff = __shfl_sync(0xffffffffu, zoff, lane);
+    AccRow acc; acc_zero(acc);
+    const float4* recs = &stage[wib][hw][0];
+    int wcell = -1;
+#pragma unroll 1
+    for (int round = 0; round < ROUNDS; ++round) {
+        unsigned starts;
+        {   // ---- phase A: thread per particle
+            const int q = hbase + round * 16 + s;                            // may lie past the end: such lanes repeat the last particle with A = 0
+            const int p = min(q, n - 1);
+            const float4 X = ldg4(P.a[PX] + p);
+            float4 a0 = ldg4(Ain.a[0] + p), a1 = ldg4(Ain.a[1] + p), a2 = ldg4(Ain.a[2] + p);
+            if (q >= n) { a0 = a1 = a2 = make_float4(0.f, 0.f, 0.f, 0.f); }
+            const int cell = __float_as_int(X.w);
+            Axis ax, ay, az;
+            axis_setup(ax, X.x, cell_i(cell), G.nx, G.ihx); axis_setup(ay, X.y, cell_j(cell), G.ny, G.ihy); axis_setup(az, X.z, cell_k(cell), G.nz, G.ihz);
+            const float A[9] = { a0.x, a0.y, a0.z, a1.x, a1.y, a1.z, a2.x, a2.y, a2.z };
+            int prev;
+            starts = run_starts(cell, wcell, prev);
+            __syncwarp();                                                    // phase B of the round before is done with the records
+            frc_make_record(&stage[wib][hw][s * FRC_STRIDE], ax.N, ax.D, ay.N, ay.D, az.N, az.D, A, X.w, __int_as_float(prev));
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int it = 0; it < 16; ++it) {
+            const float4* r = recs + it * FRC_STRIDE;
+            if ((starts >> it) & 1u) {                                        // a run of particles sharing a cell starts here
+                const float2 cn = *reinterpret_cast<const float2*>(r + 9);
+                if (singleton_at(r + 9, FRC_STRIDE, starts, it, __float_as_int(cn.y))) {
+                    AccRow one; acc_zero(one);
+                    frc_row_accumulate(r, yoff, zoff, one);
+                    flush_row_pk(G, G.f, slot, __float_as_int(cn.x), j, k, one, false);
+                    starts &= ~(2u << it);
+                    continue;
+                }
+                window_move(G, G.f, slot, __float_as_int(cn.y), __float_as_int(cn.x), j, k, acc, false);
+            }
+            frc_row_accumulate(r, yoff, zoff, acc);
+        }
+    }
+    if (wcell >= 0) flush_row_pk(G, G.f, slot, wcell, j, k, acc, false);
+}
+template <int ROUNDS>
+inline void force_scatter_launch_r(cudaStream_t st, const PartP& P, const GridP& G, const ForceA& A, long long n_hi, const SimClock* clk, bool device_count) {
+    const long long per_cta = 256ll * ROUNDS;
+    const int chunks = (int)((n_hi + per_cta - 1) / per_cta);
+    k_force_scatter<ROUNDS><<<strided_grid(chunks, G.strips), 256, FRC_SCATTER_SMEM, st>>>(P, G, A, device_count ? -(int)n_hi : (int)n_hi, clk);
+}
+
+template <int ROUNDS, bool SPLIT>
+inline cudaError_t forces_launch_r(cudaStream_t st, const PartP& P, const GridP& G, const CUtensorMap& tm, const MatParams& mat, const SimClock* clk, long long n_hi, const DeferP& D, const ForceA& A) {
+    const int smem = (int)sizeof(FrcWarpSmemT<SPLIT>) * (FRC_NT / 32);
     const long long per_cta = (long long)FRC_NT * ROUNDS;
-    k_forces<ROUNDS, false><<<(unsigned)((n_hi + per_cta - 1) / per_cta), FRC_NT, smem, st>>>(P, G, tm, mat, clk, D);
+    k_forces<ROUNDS, false, SPLIT><<<(unsigned)((n_hi + per_cta - 1) / per_cta), FRC_NT, smem, st>>>(P, G, tm, mat, clk, D, A);
     return cudaSuccess;
 }
-// the count of the deferred list is zeroed (stream order) before the main launch; the list launch follows it
-inline cudaError_t forces_launch(cudaStream_t st, const PartP& P, const GridP& G, const CUtensorMap& tm, const MatParams& mat, const SimClock* clk, long long n_hi, const DeferP& D) {
+// the count of the deferred list is zeroed (stream order) before the main launch; the list launch follows it; with SPLIT (A.a[0] set) the
+// scatter kernel comes last
+template <bool SPLIT>
+inline cudaError_t forces_launch_t(cudaStream_t st, const PartP& P, const GridP& G, const CUtensorMap& tm, const MatParams& mat, const SimClock* clk, long long n_hi, const DeferP& D,
+                                   const ForceA& A, bool device_count) {
     cudaError_t e = cudaMemsetAsync(D.count, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
-    switch (rounds_for(n_hi)) {
-    case 8: forces_launch_r<8>(st, P, G, tm, mat, clk, n_hi, D); break;
-    case 2: forces_launch_r<2>(st, P, G, tm, mat, clk, n_hi, D); break;
-    default: forces_launch_r<1>(st, P, G, tm, mat, clk, n_hi, D); break;
+    const int rounds = rounds_for(n_hi);
+    switch (rounds) {
+    case 8: forces_launch_r<8, SPLIT>(st, P, G, tm, mat, clk, n_hi, D, A); break;
+    case 2: forces_launch_r<2, SPLIT>(st, P, G, tm, mat, clk, n_hi, D, A); break;
+    default: forces_launch_r<1, SPLIT>(st, P, G, tm, mat, clk, n_hi, D, A); break;
     }
     const long long list_ctas = std::min<long long>((n_hi + FRC_NT - 1) / FRC_NT, AEP_LIST_CTAS);
-    k_forces<1, true><<<(unsigned)list_ctas, FRC_NT, (int)sizeof(FrcWarpSmem) * (FRC_NT / 32), st>>>(P, G, tm, mat, clk, D);
+    k_forces<1, true, SPLIT><<<(unsigned)list_ctas, FRC_NT, (int)sizeof(FrcWarpSmemT<SPLIT>) * (FRC_NT / 32), st>>>(P, G, tm, mat, clk, D, A);
+    if (SPLIT) {
+        switch (rounds) {
+        case 8: force_scatter_launch_r<8>(st, P, G, A, n_hi, clk, device_count); break;
+        case 2: force_scatter_launch_r<2>(st, P, G, A, n_hi, clk, device_count); break;
+        default: force_scatter_launch_r<1>(st, P, G, A, n_hi, clk, device_count); break;
+        }
+    }
     return cudaGetLastError();
+}
+inline cudaError_t forces_launch(cudaStream_t st, const PartP& P, const GridP& G, const CUtensorMap& tm, const MatParams& mat, const SimClock* clk, long long n_hi, const DeferP& D,
+                                 const ForceA& A, bool split, bool device_count) {
+    return split ? forces_launch_t<true>(st, P, G, tm, mat, clk, n_hi, D, A, device_count) : forces_launch_t<false>(st, P, G, tm, mat, clk, n_hi, D, A, device_count);
 }
 
 // ================================================================================================ G2P (+ P2G)
@@ -518,12 +620,14 @@ inline cudaError_t g2p2g_launch(cudaStream_t st, const PartP& P, const GridP& G,
 
 // dynamic shared memory above 48 KB needs an opt-in per kernel and device: aep_create calls this once
 inline cudaError_t particle_kernels_configure() {
-    const int fs = (int)sizeof(FrcWarpSmem) * (FRC_NT / 32), gs = (int)sizeof(G2GWarpSmemT<true>) * (G2G_NT / 32);
+    const int fs = (int)sizeof(FrcWarpSmemT<false>) * (FRC_NT / 32), gs = (int)sizeof(G2GWarpSmemT<true>) * (G2G_NT / 32);
     cudaError_t e;
 #define AEP_CFG(kern, bytes) if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e
-    AEP_CFG((k_forces<8, false>), fs); AEP_CFG((k_forces<2, false>), fs); AEP_CFG((k_forces<1, false>), fs); AEP_CFG((k_forces<1, true>), fs);
+    AEP_CFG((k_forces<8, false, false>), fs); AEP_CFG((k_forces<2, false, false>), fs); AEP_CFG((k_forces<1, false, false>), fs); AEP_CFG((k_forces<1, true, false>), fs);
+    AEP_CFG((k_forces<8, false, true>), fs); AEP_CFG((k_forces<2, false, true>), fs); AEP_CFG((k_forces<1, false, true>), fs); AEP_CFG((k_forces<1, true, true>), fs);
     AEP_CFG((k_g2p2g<8, true, false>), gs); AEP_CFG((k_g2p2g<2, true, false>), gs); AEP_CFG((k_g2p2g<1, true, false>), gs); AEP_CFG((k_g2p2g<1, true, true>), gs);
     AEP_CFG((k_g2p2g<8, false, false>), gs); AEP_CFG((k_g2p2g<2, false, false>), gs); AEP_CFG((k_g2p2g<1, false, false>), gs); AEP_CFG((k_g2p2g<1, false, true>), gs);
+    AEP_CFG(k_force_scatter<8>, FRC_SCATTER_SMEM); AEP_CFG(k_force_scatter<2>, FRC_SCATTER_SMEM); AEP_CFG(k_force_scatter<1>, FRC_SCATTER_SMEM);
 #undef AEP_CFG
     return cudaSuccess;
 }

@@ -557,7 +557,7 @@ def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, U
     shell = B.make_shell_scene(res)
     rate_floor = B.rate_floor_for(res)
     peer = args.exchange == "peer"
-    mig_cap = max(1 << 16, n_local // 20)
+    mig_cap = max(1 << 16, (n_total // world) // 20)               # the same on every rank: the peers' buffer layouts must agree
 
     # context + communication buffers (setup: allocation, no data), created once; every leg uploads into it
     eng = Engine(shell, device=local, particle_capacity=int(1.25 * n_local + 65536), slab=plan.slab(rank), dt_rate_floor=rate_floor, sort_every=args.sort_every,

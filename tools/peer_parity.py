@@ -54,7 +54,7 @@ def main():
     assert (np.diff(idx) == 1).all()
     capi.check(eng.L.aep_set_particle_id_base(eng.h, int(idx[0])), eng.h)
     eng.upload_particles(localp)
-    connect_ranks(eng, rank, world, migrate_capacity=max(4096, len(idx) // 10))
+    connect_ranks(eng, rank, world, migrate_capacity=max(4096, (n // world) // 10))     # the same on every rank
     dt = float(np.float32(a.dt))
     dist.barrier(); t0 = time.perf_counter()
     eng.init()
