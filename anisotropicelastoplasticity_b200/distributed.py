@@ -578,7 +578,7 @@ def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, U
         solver.init()
         solver.run(args.warmup)
         eng.sync(); dist.barrier(); torch.cuda.synchronize()
-        sampler = ClockSampler(local) if rank == 0 else None
+        sampler = ClockSampler(local) if rank == 0 else None             # NVML every 5 ms: the timed region of the 8-GPU run is ~50 ms
         l0 = eng.kernel_launches; c0 = eng.counters(); k0 = eng.clock(); m0 = eng.migration()
         dist.barrier(); torch.cuda.synchronize()
         ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
