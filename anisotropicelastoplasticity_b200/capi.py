@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AEP_B200_LIB") or os.path.join(_HERE, "libaep_b200.so")   # override: kernel-variant experiments only
 _LIB = None
 
-NUM_STAGES = 8
-STAGES = ("sort", "p2g", "forces", "grid", "g2p", "mesh", "halo", "g2p2g")
+NUM_STAGES = 11
+STAGES = ("sort", "p2g", "forces", "grid", "g2p", "mesh", "halo", "g2p2g", "force_scatter", "forces_list", "g2p_list")
 MIGRATE_FLOATS = 44
 
 dp = C.POINTER(C.c_double)

@@ -350,10 +350,21 @@ int do_forces(aep_ctx* c, bool in_substep) {
         LAUNCH_OK("k_grid_normalise");
     }
     if (n_launch(c)) {
-        StageTimer T(c, AEP_STAGE_FORCES);
-        cudaError_t e = forces_launch(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->defer, c->forceA, c->split_forces, peer_mode(c));
-        if (e != cudaSuccess) return fail(c, AEP_ERR_CUDA, "k_forces: %s", cudaGetErrorString(e));
-        LAUNCH_OK("k_forces"); c->launches += c->split_forces ? 2 : 1;        // + the launch over the deferred list (+ the scatter kernel)
+        cudaError_t e;
+        {   StageTimer T(c, AEP_STAGE_FORCES);
+            e = forces_main_launch(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->defer, c->forceA, c->split_forces);
+            if (e != cudaSuccess) return fail(c, AEP_ERR_CUDA, "k_forces: %s", cudaGetErrorString(e));
+            LAUNCH_OK("k_forces"); }
+        {   StageTimer T(c, AEP_STAGE_FORCES_LIST);
+            e = forces_list_launch(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->defer, c->forceA, c->split_forces);
+            if (e != cudaSuccess) return fail(c, AEP_ERR_CUDA, "k_forces<LIST>: %s", cudaGetErrorString(e));
+            LAUNCH_OK("k_forces<LIST>"); }
+        if (c->split_forces) {
+            StageTimer T(c, AEP_STAGE_FORCE_SCATTER);
+            e = force_scatter_launch(c->stream, c->P[c->cur], c->G, c->forceA, n_launch(c), c->d_clk, peer_mode(c));
+            if (e != cudaSuccess) return fail(c, AEP_ERR_CUDA, "k_force_scatter: %s", cudaGetErrorString(e));
+            LAUNCH_OK("k_force_scatter");
+        }
     }
     if (c->mesh.nv) {
         StageTimer T(c, AEP_STAGE_MESH);
@@ -395,12 +406,18 @@ int do_g2p_particles(aep_ctx* c, bool scatter) {
         LAUNCH_OK("k_p2g");
         return AEP_OK;
     }
-    StageTimer T(c, scatter ? AEP_STAGE_G2P2G : AEP_STAGE_G2P);
-    if (c->mig.axis >= 0 && !peer_mode(c)) cudaMemsetAsync(c->mig.counts, 0, 2 * sizeof(unsigned long long), c->stream);
-    cudaError_t e = scatter ? g2p2g_launch<true>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig, c->defer)
-                            : g2p2g_launch<false>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig, c->defer);
-    if (e != cudaSuccess) return fail(c, AEP_ERR_CUDA, "k_g2p2g: %s", cudaGetErrorString(e));
-    LAUNCH_OK("k_g2p2g"); c->launches++;                                      // + the launch over the deferred list
+    cudaError_t e;
+    {   StageTimer T(c, scatter ? AEP_STAGE_G2P2G : AEP_STAGE_G2P);
+        if (c->mig.axis >= 0 && !peer_mode(c)) cudaMemsetAsync(c->mig.counts, 0, 2 * sizeof(unsigned long long), c->stream);
+        e = scatter ? g2p2g_main_launch<true>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig, c->defer)
+                    : g2p2g_main_launch<false>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig, c->defer);
+        if (e != cudaSuccess) return fail(c, AEP_ERR_CUDA, "k_g2p2g: %s", cudaGetErrorString(e));
+        LAUNCH_OK("k_g2p2g"); }
+    {   StageTimer T(c, AEP_STAGE_G2P_LIST);
+        e = scatter ? g2p2g_list_launch<true>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig, c->defer)
+                    : g2p2g_list_launch<false>(c->stream, c->P[c->cur], c->G, c->tm_vt, c->mat, c->d_clk, n_launch(c), c->mig, c->defer);
+        if (e != cudaSuccess) return fail(c, AEP_ERR_CUDA, "k_g2p2g<LIST>: %s", cudaGetErrorString(e));
+        LAUNCH_OK("k_g2p2g<LIST>"); }
     return AEP_OK;
 }
 // whole G2P of a context without peers (mesh included)

@@ -121,7 +121,10 @@ __device__ __forceinline__ void defer_append(const DeferP& D, bool defer, int p)
 #define FRC_MIN_CTAS 4
 #endif
 #ifndef FRC_SPLIT_MIN_CTAS
-#define FRC_SPLIT_MIN_CTAS 5
+#define FRC_SPLIT_MIN_CTAS 8            // the gather / stress kernel alone fits 64 registers without spills: 32 warps per SM (2.86 ms against 3.06 at 5 CTAs,
+#endif                                  // C5 at rest); its list pass (global-memory gather) wants the registers: 5 CTAs (0.28 against 0.46 ms)
+#ifndef FRC_LIST_MIN_CTAS
+#define FRC_LIST_MIN_CTAS 5
 #endif
 // SPLIT: phase A only -- A = -V_p P F_E^T goes to memory (3 float4 per particle, `Aout`) and k_force_scatter does phase B as its own,
 // small-register kernel (the same reason G2P and P2G are two kernels: the scatter is bound by the LSU pipe and wants warps, the gather
@@ -133,11 +136,11 @@ struct __align__(128) FrcWarpSmemT {
     float4 rec[2][SPLIT ? 1 : FRC_HW_F4];
     float4 x[2][32];
     float4 e[3][32];
-    float4 bounce[32];
+    float4 bounce[SPLIT ? 1 : 32];      // SPLIT: 6.6 KB per warp, 8 CTAs of 4 warps fit an SM's 228 KB
     unsigned long long bar[2];
 };
 template <int ROUNDS, bool LIST, bool SPLIT>
-__global__ void __launch_bounds__(FRC_NT, SPLIT ? FRC_SPLIT_MIN_CTAS : FRC_MIN_CTAS) k_forces(PartP P, GridP G, const __grid_constant__ CUtensorMap tm, MatParams mpar,
+__global__ void __launch_bounds__(FRC_NT, SPLIT ? (LIST ? FRC_LIST_MIN_CTAS : FRC_SPLIT_MIN_CTAS) : FRC_MIN_CTAS) k_forces(PartP P, GridP G, const __grid_constant__ CUtensorMap tm, MatParams mpar,
                                                                   const SimClock* __restrict__ clk, DeferP D, ForceA Aout) {
     AEP_HALT_PRE(clk);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -334,33 +337,34 @@ inline cudaError_t forces_launch_r(cudaStream_t st, const PartP& P, const GridP&
     k_forces<ROUNDS, false, SPLIT><<<(unsigned)((n_hi + per_cta - 1) / per_cta), FRC_NT, smem, st>>>(P, G, tm, mat, clk, D, A);
     return cudaSuccess;
 }
-// the count of the deferred list is zeroed (stream order) before the main launch; the list launch follows it; with SPLIT (A.a[0] set) the
-// scatter kernel comes last
-template <bool SPLIT>
-inline cudaError_t forces_launch_t(cudaStream_t st, const PartP& P, const GridP& G, const CUtensorMap& tm, const MatParams& mat, const SimClock* clk, long long n_hi, const DeferP& D,
-                                   const ForceA& A, bool device_count) {
+// The three launches of the force stage, separately (the engine times them one by one in its profiled pass): main kernel over the
+// cell-sorted particles (zeroes the count of the deferred list first, in stream order), list pass over the strays, scatter (SPLIT).
+inline cudaError_t forces_main_launch(cudaStream_t st, const PartP& P, const GridP& G, const CUtensorMap& tm, const MatParams& mat, const SimClock* clk, long long n_hi, const DeferP& D,
+                                      const ForceA& A, bool split) {
     cudaError_t e = cudaMemsetAsync(D.count, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
     const int rounds = rounds_for(n_hi);
-    switch (rounds) {
-    case 8: forces_launch_r<8, SPLIT>(st, P, G, tm, mat, clk, n_hi, D, A); break;
-    case 2: forces_launch_r<2, SPLIT>(st, P, G, tm, mat, clk, n_hi, D, A); break;
-    default: forces_launch_r<1, SPLIT>(st, P, G, tm, mat, clk, n_hi, D, A); break;
-    }
-    const long long list_ctas = std::min<long long>((n_hi + FRC_NT - 1) / FRC_NT, AEP_LIST_CTAS);
-    k_forces<1, true, SPLIT><<<(unsigned)list_ctas, FRC_NT, (int)sizeof(FrcWarpSmemT<SPLIT>) * (FRC_NT / 32), st>>>(P, G, tm, mat, clk, D, A);
-    if (SPLIT) {
-        switch (rounds) {
-        case 8: force_scatter_launch_r<8>(st, P, G, A, n_hi, clk, device_count); break;
-        case 2: force_scatter_launch_r<2>(st, P, G, A, n_hi, clk, device_count); break;
-        default: force_scatter_launch_r<1>(st, P, G, A, n_hi, clk, device_count); break;
-        }
+    if (split) {
+        if (rounds == 8) forces_launch_r<8, true>(st, P, G, tm, mat, clk, n_hi, D, A); else if (rounds == 2) forces_launch_r<2, true>(st, P, G, tm, mat, clk, n_hi, D, A); else forces_launch_r<1, true>(st, P, G, tm, mat, clk, n_hi, D, A);
+    } else {
+        if (rounds == 8) forces_launch_r<8, false>(st, P, G, tm, mat, clk, n_hi, D, A); else if (rounds == 2) forces_launch_r<2, false>(st, P, G, tm, mat, clk, n_hi, D, A); else forces_launch_r<1, false>(st, P, G, tm, mat, clk, n_hi, D, A);
     }
     return cudaGetLastError();
 }
-inline cudaError_t forces_launch(cudaStream_t st, const PartP& P, const GridP& G, const CUtensorMap& tm, const MatParams& mat, const SimClock* clk, long long n_hi, const DeferP& D,
-                                 const ForceA& A, bool split, bool device_count) {
-    return split ? forces_launch_t<true>(st, P, G, tm, mat, clk, n_hi, D, A, device_count) : forces_launch_t<false>(st, P, G, tm, mat, clk, n_hi, D, A, device_count);
+inline cudaError_t forces_list_launch(cudaStream_t st, const PartP& P, const GridP& G, const CUtensorMap& tm, const MatParams& mat, const SimClock* clk, long long n_hi, const DeferP& D,
+                                      const ForceA& A, bool split) {
+    const long long list_ctas = std::min<long long>((n_hi + FRC_NT - 1) / FRC_NT, AEP_LIST_CTAS);
+    if (split) k_forces<1, true, true><<<(unsigned)list_ctas, FRC_NT, (int)sizeof(FrcWarpSmemT<true>) * (FRC_NT / 32), st>>>(P, G, tm, mat, clk, D, A);
+    else k_forces<1, true, false><<<(unsigned)list_ctas, FRC_NT, (int)sizeof(FrcWarpSmemT<false>) * (FRC_NT / 32), st>>>(P, G, tm, mat, clk, D, A);
+    return cudaGetLastError();
+}
+inline cudaError_t force_scatter_launch(cudaStream_t st, const PartP& P, const GridP& G, const ForceA& A, long long n_hi, const SimClock* clk, bool device_count) {
+    switch (rounds_for(n_hi)) {
+    case 8: force_scatter_launch_r<8>(st, P, G, A, n_hi, clk, device_count); break;
+    case 2: force_scatter_launch_r<2>(st, P, G, A, n_hi, clk, device_count); break;
+    default: force_scatter_launch_r<1>(st, P, G, A, n_hi, clk, device_count); break;
+    }
+    return cudaGetLastError();
 }
 
 // ================================================================================================ G2P (+ P2G)
@@ -602,10 +606,10 @@ inline void g2p2g_launch_r(cudaStream_t st, const PartP& P, const GridP& G, cons
     const int chunks = (int)((n_hi + per_cta - 1) / per_cta);
     k_g2p2g<ROUNDS, SCATTER, false><<<SCATTER ? strided_grid(chunks, G.strips) : chunks, G2G_NT, smem, st>>>(P, G, tm, mat, clk, ML, D);
 }
-// the count of the deferred list is zeroed (stream order) before the main launch; the list launch follows it
+// main kernel (zeroes the count of the deferred list first, in stream order) and list pass, separately (timed one by one when profiling)
 template <bool SCATTER>
-inline cudaError_t g2p2g_launch(cudaStream_t st, const PartP& P, const GridP& G, const CUtensorMap& tm, const MatParams& mat, SimClock* clk,
-                                long long n_hi, const MigList& ML, const DeferP& D) {
+inline cudaError_t g2p2g_main_launch(cudaStream_t st, const PartP& P, const GridP& G, const CUtensorMap& tm, const MatParams& mat, SimClock* clk,
+                                     long long n_hi, const MigList& ML, const DeferP& D) {
     cudaError_t e = cudaMemsetAsync(D.count, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
     switch (rounds_for(n_hi)) {
@@ -613,6 +617,11 @@ inline cudaError_t g2p2g_launch(cudaStream_t st, const PartP& P, const GridP& G,
     case 2: g2p2g_launch_r<2, SCATTER>(st, P, G, tm, mat, clk, n_hi, ML, D); break;
     default: g2p2g_launch_r<1, SCATTER>(st, P, G, tm, mat, clk, n_hi, ML, D); break;
     }
+    return cudaGetLastError();
+}
+template <bool SCATTER>
+inline cudaError_t g2p2g_list_launch(cudaStream_t st, const PartP& P, const GridP& G, const CUtensorMap& tm, const MatParams& mat, SimClock* clk,
+                                     long long n_hi, const MigList& ML, const DeferP& D) {
     const long long list_ctas = std::min<long long>((n_hi + G2G_NT - 1) / G2G_NT, AEP_LIST_CTAS);
     k_g2p2g<1, SCATTER, true><<<(unsigned)list_ctas, G2G_NT, (int)sizeof(G2GWarpSmemT<SCATTER>) * (G2G_NT / 32), st>>>(P, G, tm, mat, clk, ML, D);
     return cudaGetLastError();

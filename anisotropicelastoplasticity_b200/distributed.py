@@ -603,18 +603,13 @@ def bench_main(args, workload_config, ClockSampler, measured_peak_gbs, METRIC, U
     dist.barrier()
     stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in tm.items()}
     peak, peak_kind = measured_peak_gbs()
-    dom = max(("forces", "g2p2g", "g2p", "p2g", "grid"), key=lambda k: stage_ms.get(k, 0.0))
-    bp, bn = B.STAGE_BYTES[dom]
-    dom_bytes = bp * eng.n_particles + bn * eng.grid_activity()[1]
-    achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+    n_here = eng.n_particles; nodes_here = eng.grid_activity()[1]
+    dom, roofline = B.kernel_roofline(stage_ms, n_here, nodes_here, peak, peak_kind)
     sub_bytes = B.BYTES_PARTICLE[sc.SAND] * n_total + B.BYTES_NODE * nodes
     sub_gbs = sub_bytes / (ms * 1e-3 / args.steps) / 1e9 / world
-    kernels = {"forces": "k_forces", "g2p2g": "k_g2p2g", "g2p": "k_g2p2g<SCATTER=0> (G2P)", "p2g": "k_p2g", "grid": "k_grid_update"}
-    roofline = {"bound": "hbm", "kernel": kernels[dom],
-                "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " copy bandwidth, MEASURED_PEAKS.json", "unit": "GB/s", "frac": achieved / peak,
-                "traffic": B.ncu_traffic({"forces": "k_forces", "g2p2g": "k_g2p2g", "g2p": "k_g2p2g", "p2g": "k_p2g"}.get(dom, ""), eng.n_particles), "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom], "stage_ms": stage_ms, "rank": 0,
-                "substep": {"algorithmic_bytes": sub_bytes, "achieved_gbs_per_gpu": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes},
-                "p2g_g2p": B.transfers_roofline(stage_ms, eng.n_particles, eng.grid_activity()[1], peak)}
+    roofline["rank"] = 0
+    roofline["substep"] = {"algorithmic_bytes": sub_bytes, "achieved_gbs_per_gpu": sub_gbs, "frac": sub_gbs / peak, "active_nodes": nodes}
+    roofline["p2g_g2p"] = B.transfers_roofline(stage_ms, n_here, nodes_here, peak)
     plane_bytes = res * res * 16
     halo_bytes = (2 if 0 < rank < world - 1 else 1) * (4 + 3) * plane_bytes if peer else solver.stats["halo_bytes"] / max(1, args.steps + args.warmup + 3 + 1)
     # e2e: upload from pinned host memory + init + K substeps + f32 positions back, wall clock max over ranks

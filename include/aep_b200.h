@@ -216,8 +216,11 @@ AEP_API int aep_get_timers(aep_ctx* ctx, double* ms /*AEP_NUM_STAGES*/, int64_t*
 #define AEP_STAGE_G2P 4
 #define AEP_STAGE_MESH 5
 #define AEP_STAGE_HALO 6
-#define AEP_STAGE_G2P2G 7   /* the fused kernel of a substep: G2P of this substep + P2G of the next */
-#define AEP_NUM_STAGES 8
+#define AEP_STAGE_G2P2G 7   /* the fused kernel (development, AEP_FUSED=1): G2P of this substep + P2G of the next */
+#define AEP_STAGE_FORCE_SCATTER 8   /* k_force_scatter; AEP_STAGE_FORCES is the gather / stress kernel over the cell-sorted particles */
+#define AEP_STAGE_FORCES_LIST 9     /* the force kernel's pass over the deferred particles (strays) */
+#define AEP_STAGE_G2P_LIST 10       /* the G2P (or fused) kernel's pass over the deferred particles */
+#define AEP_NUM_STAGES 11
 /* physical re-sorts done so far, particle slots in use / dead (slab contexts), particles that changed cell since the last re-sort */
 AEP_API int aep_get_counters(aep_ctx* ctx, int64_t* sorts, int64_t* slots, int64_t* dead, int64_t* moved_since_sort);
 /* peer-memory exchange: particles this context has handed to / taken from its neighbours so far (HybridSolver.cpp:940-951 moves

@@ -5,6 +5,7 @@ mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_${TAG}_n${N}.txt 2>&1
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tools/peer_parity.py --res 128 --steps 24 --oracle --out gpurun_out/peer_parity_${TAG}_n${N}.json > gpurun_out/peer_parity_${TAG}_n${N}.log 2>&1; echo "peer parity rc=$?"
 tail -n 3 gpurun_out/peer_parity_${TAG}_n${N}.log | cut -c1-1500
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29535 tools/peer_parity.py --res 128 --steps 24 --exchange nccl --out gpurun_out/peer_parity_${TAG}_n${N}_nccl.json > gpurun_out/peer_parity_${TAG}_n${N}_nccl.log 2>&1; echo "nccl path parity rc=$?"; tail -n 1 gpurun_out/peer_parity_${TAG}_n${N}_nccl.log | cut -c1-800
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 tools/peer_parity.py --res 128 --steps 40 --adaptive --out gpurun_out/peer_parity_${TAG}_n${N}_adaptive.json > gpurun_out/peer_parity_${TAG}_n${N}_adaptive.log 2>&1; echo "peer parity adaptive rc=$?"
 tail -n 1 gpurun_out/peer_parity_${TAG}_n${N}_adaptive.log | cut -c1-1200
 for X in peer nccl; do

@@ -9,8 +9,9 @@ cut -c1-3000 gpurun_out/bench_${TAG}_1gpu.json; tail -n 3 gpurun_out/bench_${TAG
 timeout 600 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/bench_${TAG}_reference.json 2> gpurun_out/bench_${TAG}_reference.err; echo "reference rc=$?"
 cut -c1-600 gpurun_out/bench_${TAG}_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --quick > gpurun_out/ncu_launch_${TAG}.log 2>&1
-for K in k_forces k_g2p2g k_p2g; do
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 12 -c 1 -o gpurun_out/${TAG}_flow_$K -f python bench.py --steps 3 --warmup 5 --quick > gpurun_out/ncu_${TAG}_$K.log 2>&1
+for KS in k_forces:12 k_g2p2g:12 k_p2g:6 k_force_scatter:6; do
+K=${KS%%:*}; SK=${KS##*:}
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^$K\$|^$K<" -s $SK -c 1 -o gpurun_out/${TAG}_flow_$K -f python bench.py --steps 3 --warmup 5 --quick > gpurun_out/ncu_${TAG}_$K.log 2>&1
 ncu -i gpurun_out/${TAG}_flow_$K.ncu-rep --page raw --csv > gpurun_out/${TAG}_flow_${K}_raw.csv 2>/dev/null
 ncu -i gpurun_out/${TAG}_flow_$K.ncu-rep --page source --csv > gpurun_out/${TAG}_flow_${K}_src.csv 2>/dev/null
 rm -f gpurun_out/${TAG}_flow_$K.ncu-rep

@@ -35,12 +35,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--res", type=int, default=128); ap.add_argument("--steps", type=int, default=24); ap.add_argument("--dt", type=float, default=1e-4)
     ap.add_argument("--same-device", action="store_true"); ap.add_argument("--oracle", action="store_true"); ap.add_argument("--adaptive", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="nccl: the round-1 path (SlabSolver: torch.distributed send/recv driven from Python)")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     import torch, torch.distributed as dist
     from anisotropicelastoplasticity_b200 import capi
     from anisotropicelastoplasticity_b200.engine import Engine
-    from anisotropicelastoplasticity_b200.distributed import SlabPlan, make_gpu_slab_engine, connect_ranks, download_local
+    from anisotropicelastoplasticity_b200.distributed import SlabPlan, make_gpu_slab_engine, connect_ranks, download_local, GpuSlabBackend, SlabSolver
     world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local = 0 if a.same_device else int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if a.same_device: dist.init_process_group("gloo")
@@ -54,18 +55,28 @@ def main():
     assert (np.diff(idx) == 1).all()
     capi.check(eng.L.aep_set_particle_id_base(eng.h, int(idx[0])), eng.h)
     eng.upload_particles(localp)
-    connect_ranks(eng, rank, world, migrate_capacity=max(4096, (n // world) // 10))     # the same on every rank
+    mig_cap = max(4096, (n // world) // 10)                                             # the same on every rank
     dt = float(np.float32(a.dt))
-    dist.barrier(); t0 = time.perf_counter()
-    eng.init()
-    if not a.adaptive: eng.set_fixed_dt(dt)
-    dist.barrier()
-    n0 = eng.n_particles
-    if a.adaptive: eng.run_frames(1)                       # the reference dt rule, to a frame boundary: every rank halts on the same substep
-    else: eng.run(a.steps)
+    if a.exchange == "peer":
+        connect_ranks(eng, rank, world, migrate_capacity=mig_cap)
+        dist.barrier(); t0 = time.perf_counter()
+        eng.init()
+        if not a.adaptive: eng.set_fixed_dt(dt)
+        dist.barrier()
+        n0 = eng.n_particles
+        if a.adaptive: eng.run_frames(1)                   # the reference dt rule, to a frame boundary: every rank halts on the same substep
+        else: eng.run(a.steps)
+    else:
+        assert not a.adaptive and not a.same_device
+        be = GpuSlabBackend(eng, migrate_capacity=mig_cap); solver = SlabSolver(be, plan, rank)
+        dist.barrier(); t0 = time.perf_counter()
+        solver.init()                                      # enters the backend's stream itself (round-1 advisor finding)
+        eng.set_fixed_dt(dt)
+        n0 = eng.n_particles
+        solver.run(a.steps)
     eng.sync()
     t_run = time.perf_counter() - t0
-    clk = eng.clock(); mig = eng.migration(); cnt = eng.counters()
+    clk = eng.clock(); mig = eng.migration() if a.exchange == "peer" else {"sent": solver.stats["migrated"], "received": 0}; cnt = eng.counters()
     part = download_local(eng)
     gathered = [None] * world if rank == 0 else None
     dist.gather_object({"part": part, "mig": mig, "n0": n0, "n1": eng.n_particles, "dt": clk["dt"], "escaped": clk["escaped"], "sorts": cnt["sorts"], "substeps": clk["substeps"]}, gathered, dst=0)
@@ -73,12 +84,12 @@ def main():
     if rank == 0:
         ids = np.concatenate([g["part"]["ids"] for g in gathered]); order = np.argsort(ids)
         got = {k: np.concatenate([g["part"][k] for g in gathered], axis=0)[order] for k in ("x", "v", "FE", "FP", "q", "B")}
-        out = {"world": world, "same_device": a.same_device, "res": a.res, "particles": int(n), "steps": a.steps, "adaptive_dt": a.adaptive,
+        out = {"world": world, "exchange": a.exchange, "same_device": a.same_device, "res": a.res, "particles": int(n), "steps": a.steps, "adaptive_dt": a.adaptive,
                "bounds": plan.bounds, "n_start": [g["n0"] for g in gathered], "n_end": [g["n1"] for g in gathered],
                "migrated_sent": [g["mig"]["sent"] for g in gathered], "migrated_received": [g["mig"]["received"] for g in gathered],
                "sorts": [g["sorts"] for g in gathered], "dt_per_rank": [g["dt"] for g in gathered], "escaped": [g["escaped"] for g in gathered], "wall_s": t_run}
         ok &= bool((ids[order] == np.arange(n)).all()); out["nobody_lost_or_duplicated"] = bool((ids[order] == np.arange(n)).all())
-        ok &= sum(out["migrated_sent"]) > 0 and sum(out["migrated_sent"]) == sum(out["migrated_received"])
+        ok &= sum(out["migrated_sent"]) > 0 and (a.exchange == "nccl" or sum(out["migrated_sent"]) == sum(out["migrated_received"]))
         ok &= len(set(out["dt_per_rank"])) == 1                                            # the dt rule saw the GLOBAL max|v|
         whole = Engine(scene, device=local, dt_rate_floor=rf); whole.init()
         if not a.adaptive: whole.set_fixed_dt(dt)
@@ -114,6 +125,8 @@ def main():
         if a.out:
             with open(a.out, "w") as f: f.write(line + "\n")
     flag = torch.tensor([1 if ok else 0]); dist.broadcast(flag, src=0) if a.same_device else None
+    if a.exchange == "nccl":
+        be.close()
     eng.close(); dist.barrier() if a.same_device else None
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
