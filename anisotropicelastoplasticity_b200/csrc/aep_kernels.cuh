@@ -413,8 +413,16 @@ __device__ __forceinline__ void acc_zero_ordered(AccRow& a) {
 // The reduction wants its float4 in an aligned register quad while FFMA2 wants the accumulators in pairs that stay put across
 // the loop; asked for both, ptxas keeps the quads and pays ~20 MOVs per particle on the hot path to shuffle the pairs.  So the
 // (rare) flush bounces the pairs through a lane-private shared-memory slot: STS.64 x2 (pairs only) + LDS.128 into a fresh quad.
+#ifndef AEP_REQUAD_MOV
+#define AEP_REQUAD_MOV 1                // 1: register moves; 0: the shared-memory bounce below (round 1).  The scatters are bound by the LSU pipe (98 % in k_p2g in the
+                                        // flowing state), the moves ride on the ALU: 17.77 against 18.12 ms per substep (C5, flowing), 13.96 against 14.12 at rest
+#endif
 __device__ __forceinline__ float4 requad(float4* slot, f32x2 lo, f32x2 hi) {
     float4 v;
+#if AEP_REQUAD_MOV
+    asm volatile("mov.b64 {%0, %1}, %4;\n\tmov.b64 {%2, %3}, %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(lo), "l"(hi));
+    return v;
+#endif
     const unsigned a = (unsigned)__cvta_generic_to_shared(slot);
     asm volatile("st.shared.b64 [%4], %5;\n\tst.shared.b64 [%4+8], %6;\n\tld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "l"(lo), "l"(hi) : "memory");

@@ -31,10 +31,29 @@ def scene_for(res, seed=5):
     return s
 
 
+def scene_c4(res=256, cloth_n=256):
+    """BASELINE configs[3] at its stated size (4.04 M sand particles + 256 x 256 cloth on 256^3), the state of
+    tests/test_zzx_configs_at_size.py::test_c4 plus a drift along y: particles and cloth points change their owner"""
+    from anisotropicelastoplasticity_b200 import scenes as sc
+    from test_zzx_configs_at_size import deform_cloth
+    s = sc.c4_coupling(res=res, cloth_n=cloth_n)
+    s.particles.x[:, 2] -= 0.05 - 1.5 / res
+    rng = np.random.default_rng(41)
+    sc.perturb_state(s.particles, rng, strain=5e-3, vel=0.3, affine=20.0 / (3.0 * res * res))
+    s.particles.v[:, 2] -= 1.0; s.particles.v[:, 1] += 2.0
+    deform_cloth(s.mesh, rng, amp=0.004, vel=0.2)
+    s.mesh.vv[:, 1] += 2.0; s.mesh.ev[:, 1] += 2.0
+    p = s.particles; order = np.argsort(p.x[:, 1], kind="stable")
+    for k in ("x", "v", "B", "FE", "FP", "m", "vol", "q"):
+        setattr(p, k, getattr(p, k)[order])
+    return s
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--res", type=int, default=128); ap.add_argument("--steps", type=int, default=24); ap.add_argument("--dt", type=float, default=1e-4)
     ap.add_argument("--same-device", action="store_true"); ap.add_argument("--oracle", action="store_true"); ap.add_argument("--adaptive", action="store_true")
+    ap.add_argument("--scene", default="c5", choices=["c5", "c4"], help="c4: cloth-sand coupling at 256^3 (BASELINE configs[3], '1/2/4 B200'), cloth replicated on every rank")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="nccl: the round-1 path (SlabSolver: torch.distributed send/recv driven from Python)")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
@@ -46,7 +65,8 @@ def main():
     torch.cuda.set_device(local)
     if a.same_device: dist.init_process_group("gloo")
     else: dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    scene = scene_for(a.res)
+    scene = scene_for(a.res) if a.scene == "c5" else scene_c4()
+    if a.scene == "c4": a.res = 256
     n = scene.particles.n
     cells = np.floor(scene.particles.x[:, 1] * a.res).astype(np.int64)
     plan = SlabPlan.balanced(cells, a.res, world, axis=1)
@@ -76,10 +96,17 @@ def main():
         solver.run(a.steps)
     eng.sync()
     t_run = time.perf_counter() - t0
+    dist.barrier(); t1 = time.perf_counter()                # a second, timed stretch of the same length (everything is warm now)
+    if not a.adaptive and a.exchange == "peer":
+        eng.run(a.steps); eng.sync(); dist.barrier()
+    t_steady = time.perf_counter() - t1
+    if not a.adaptive and a.exchange == "peer":             # ... which the comparison below must not see: the whole context runs 2 x steps too
+        a.steps *= 2
     clk = eng.clock(); mig = eng.migration() if a.exchange == "peer" else {"sent": solver.stats["migrated"], "received": 0}; cnt = eng.counters()
     part = download_local(eng)
+    mesh_local = {k: v for k, v in eng.mesh().items() if k in ("vx", "vv", "ex", "ev", "ed")} if scene.mesh is not None else None
     gathered = [None] * world if rank == 0 else None
-    dist.gather_object({"part": part, "mig": mig, "n0": n0, "n1": eng.n_particles, "dt": clk["dt"], "escaped": clk["escaped"], "sorts": cnt["sorts"], "substeps": clk["substeps"]}, gathered, dst=0)
+    dist.gather_object({"part": part, "mesh": mesh_local, "mig": mig, "n0": n0, "n1": eng.n_particles, "dt": clk["dt"], "escaped": clk["escaped"], "sorts": cnt["sorts"], "substeps": clk["substeps"]}, gathered, dst=0)
     ok = True; out = {}
     if rank == 0:
         ids = np.concatenate([g["part"]["ids"] for g in gathered]); order = np.argsort(ids)
@@ -87,14 +114,18 @@ def main():
         out = {"world": world, "exchange": a.exchange, "same_device": a.same_device, "res": a.res, "particles": int(n), "steps": a.steps, "adaptive_dt": a.adaptive,
                "bounds": plan.bounds, "n_start": [g["n0"] for g in gathered], "n_end": [g["n1"] for g in gathered],
                "migrated_sent": [g["mig"]["sent"] for g in gathered], "migrated_received": [g["mig"]["received"] for g in gathered],
+               "slabs_ms_per_substep_steady": 2e3 * t_steady / max(1, a.steps) if (not a.adaptive and a.exchange == "peer") else None,
                "sorts": [g["sorts"] for g in gathered], "dt_per_rank": [g["dt"] for g in gathered], "escaped": [g["escaped"] for g in gathered], "wall_s": t_run}
         ok &= bool((ids[order] == np.arange(n)).all()); out["nobody_lost_or_duplicated"] = bool((ids[order] == np.arange(n)).all())
         ok &= sum(out["migrated_sent"]) > 0 and (a.exchange == "nccl" or sum(out["migrated_sent"]) == sum(out["migrated_received"]))
         ok &= len(set(out["dt_per_rank"])) == 1                                            # the dt rule saw the GLOBAL max|v|
         whole = Engine(scene, device=local, dt_rate_floor=rf); whole.init()
         if not a.adaptive: whole.set_fixed_dt(dt)
+        whole.sync(); tw = time.perf_counter()
         if a.adaptive: whole.run_frames(1)
         else: whole.run(a.steps)
+        whole.sync(); out["whole_context_ms_per_substep"] = 1e3 * (time.perf_counter() - tw) / max(1, whole.clock()["substeps"])
+        mw = whole.mesh() if scene.mesh is not None else None
         pw = whole.particles(); out["dt_whole"] = whole.clock()["dt"]; out["substeps_whole"] = whole.clock()["substeps"]; whole.close()
         if not a.adaptive:
             tol = {"x": 2e-6, "v": 5e-5, "FE": 2e-5, "FP": 2e-5, "q": 2e-4}
@@ -112,6 +143,12 @@ def main():
             # energy and +-2.5e-4 in mean det F_P over 4 frames (tests/test_gpu_parity.py::test_adaptive_dt_bulk_statistics)
             ok &= out["bulk"]["com_rel"] < 1e-3 and out["bulk"]["kinetic_rel"] < 0.05 and out["bulk"]["mean_det_FP_abs"] < 2e-3
             ok &= len(set(out["bulk"]["substeps_slabs"])) == 1
+        if scene.mesh is not None and not a.adaptive:                                     # every rank's copy of the cloth is complete and current
+            mtol = {"vx": 2e-6, "vv": 1e-4, "ex": 2e-6, "ev": 1e-4, "ed": 5e-5}
+            out["mesh_vs_whole_context_worst_rank"] = {k: max(relerr(g["mesh"][k], mw[k]) for g in gathered) for k in mtol}
+            ok &= all(out["mesh_vs_whole_context_worst_rank"][k] < mtol[k] for k in mtol)
+            ycell = np.floor(scene.mesh.vx[:, 1] * a.res).astype(int); ycell1 = np.floor(mw["vx"][:, 1] * a.res).astype(int)
+            out["cloth_vertices_that_changed_owner"] = int((plan.owner_of_cells(ycell1) != plan.owner_of_cells(ycell)).sum())
         if a.oracle and not a.adaptive:
             from oracle.oracle_py import Oracle
             o = Oracle(scene, threads=0, rate_floor=rf); o.init()

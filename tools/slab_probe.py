@@ -9,7 +9,7 @@ from anisotropicelastoplasticity_b200.engine import Engine
 res = 512; h = 1.0 / res
 import itertools
 for (lo, hi), strips in itertools.product(((0, 66), (0, 129), (0, 512)), (1, 64, 1024, 8192)):
-    x = B.dam_break_positions(res, seed=5, y_range=(lo * h, hi * h)); n = x.shape[0]
+    x, _ = B.dam_break_positions(res, seed=5, y_cells=(lo, hi)); n = x.shape[0]
     arrs, keep = B.packed_rest_state(x, sc.SAND_RHO * h ** 3 / 8.0, pinned=False); del x
     slab = None if (lo, hi) == (0, 512) else (1, lo, hi)
     e = Engine(B.make_shell_scene(res), device=0, particle_capacity=int(1.25 * n + 65536), slab=slab, dt_rate_floor=B.rate_floor_for(res), scatter_strips=strips)
