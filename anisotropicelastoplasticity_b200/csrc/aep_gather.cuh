@@ -96,14 +96,14 @@ __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, cons
                                             float (&g)[9]) {
     int ni[4], nj[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) { ni[o] = MODE == 2 ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = MODE == 2 ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
+    for (int o = 0; o < 4; ++o) { ni[o] = MODE == 2 ? o : clampi(ax.n0 + o, G.a0[0], G.a1[0] - 1); nj[o] = MODE == 2 ? ay.n0 + o : clampi(ay.n0 + o, G.a0[1], G.a1[1] - 1); }
     const float4* base = MODE == 2 ? tile + xoff : G.vt;
 #if AEP_GATHER_PK
     f32x2 g03 = pk(g[0], g[3]), g14 = pk(g[1], g[4]), g25 = pk(g[2], g[5]);     // rows 0 and 1 of grad v as pairs over the row index
 #endif
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
-        const int nk = MODE == 2 ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
+        const int nk = MODE == 2 ? az.n0 + k : clampi(az.n0 + k, G.a0[2], G.a1[2] - 1);
         const float nzk = sel4(az.N, k), dzk = sel4(az.D, k);
         const float4* plane = MODE == 2 ? base + k * 4 * TILE_W : base + (size_t)((long long)nk * G.sz);
 #pragma unroll
@@ -158,7 +158,7 @@ __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const
                                            G2PSums& S) {
     int ni[4], nj[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) { ni[o] = MODE == 2 ? o : clampi(ax.n0 + o, 0, G.nx - 1); nj[o] = MODE == 2 ? ay.n0 + o : clampi(ay.n0 + o, 0, G.ny - 1); }
+    for (int o = 0; o < 4; ++o) { ni[o] = MODE == 2 ? o : clampi(ax.n0 + o, G.a0[0], G.a1[0] - 1); nj[o] = MODE == 2 ? ay.n0 + o : clampi(ay.n0 + o, G.a0[1], G.a1[1] - 1); }
     const float4* base = MODE == 2 ? tile + xoff : G.vt;
 #if AEP_GATHER_PK
     f32x2 va01 = pk(S.va[0], S.va[1]);
@@ -167,7 +167,7 @@ __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const
 #endif
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
-        const int nk = MODE == 2 ? az.n0 + k : clampi(az.n0 + k, 0, G.nz - 1);
+        const int nk = MODE == 2 ? az.n0 + k : clampi(az.n0 + k, G.a0[2], G.a1[2] - 1);
         const float nzk = sel4(az.N, k), dzk = sel4(az.D, k), rzk = sel4(rz, k);
         const float4* plane = MODE == 2 ? base + k * 4 * TILE_W : base + (size_t)((long long)nk * G.sz);
 #pragma unroll
@@ -235,7 +235,7 @@ __device__ __forceinline__ void g2p_stick_correction(const GridP& G, const Axis&
         const int i = n & 3, j = (n >> 2) & 3, k = n >> 4;
         float4 t;
         if (MODE == 2) t = tile[xoff + (k * 4 + j) * TILE_W + i];
-        else t = ldg4(G.vt + nidx(G, clampi(ax.n0 + i, 0, G.nx - 1), clampi(ay.n0 + j, 0, G.ny - 1), clampi(az.n0 + k, 0, G.nz - 1)));
+        else t = ldg4(G.vt + nidx(G, clampi(ax.n0 + i, G.a0[0], G.a1[0] - 1), clampi(ay.n0 + j, G.a0[1], G.a1[1] - 1), clampi(az.n0 + k, G.a0[2], G.a1[2] - 1)));
         if (t.w == 1.0f) continue;
         // v = c + s (v~ - c), c = the collider's velocity (0: the reference's static colliders): s = 0 on sticking nodes (HS:494-502);
         // 0 < s < 1 only with the opt-in Coulomb friction

@@ -596,14 +596,14 @@ __global__ void __launch_bounds__(256) k_init_volumes(PartP P, GridP G, int n) {
     float dens = 0.0f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int nk = clampi(az.n0 + k, 0, G.nz - 1);
+        const int nk = clampi(az.n0 + k, G.a0[2], G.a1[2] - 1);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int nj = clampi(ay.n0 + j, 0, G.ny - 1);
+            const int nj = clampi(ay.n0 + j, G.a0[1], G.a1[1] - 1);
             const float wjk = ay.N[j] * az.N[k];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int ni = clampi(ax.n0 + i, 0, G.nx - 1);
+                const int ni = clampi(ax.n0 + i, G.a0[0], G.a1[0] - 1);
                 dens = fmaf(ax.N[i] * wjk, ldg4(G.mp + nidx(G, ni, nj, nk)).x, dens);
             }
         }

@@ -97,15 +97,15 @@ __device__ __forceinline__ void point_gather(const GridP& G, const float4& X, Po
     float s0 = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int nk = clampi(az.n0 + k, 0, G.nz - 1);
+        const int nk = clampi(az.n0 + k, G.a0[2], G.a1[2] - 1);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int nj = clampi(ay.n0 + j, 0, G.ny - 1);
+            const int nj = clampi(ay.n0 + j, G.a0[1], G.a1[1] - 1);
             const size_t row = nidx(G, 0, nj, nk);
             const float nn = ay.N[j] * az.N[k], dn = ay.D[j] * az.N[k], nd = ay.N[j] * az.D[k];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int ni = clampi(ax.n0 + i, 0, G.nx - 1);
+                const int ni = clampi(ax.n0 + i, G.a0[0], G.a1[0] - 1);
                 const float w = ax.N[i] * nn;
                 const float4 t = ldg4(G.vt + row + ni);
                 const float dwx = ax.D[i] * nn, dwy = ax.N[i] * dn, dwz = ax.N[i] * nd;

@@ -43,6 +43,7 @@ def scene_c4(res=256, cloth_n=256):
     s.particles.v[:, 2] -= 1.0; s.particles.v[:, 1] += 2.0
     deform_cloth(s.mesh, rng, amp=0.004, vel=0.2)
     s.mesh.vv[:, 1] += 2.0; s.mesh.ev[:, 1] += 2.0
+    s.mesh.fixed = None                                   # no pinned corners here: the whole sheet drifts with the sand (pins against a 2 m/s drift tear it)
     p = s.particles; order = np.argsort(p.x[:, 1], kind="stable")
     for k in ("x", "v", "B", "FE", "FP", "m", "vol", "q"):
         setattr(p, k, getattr(p, k)[order])
@@ -54,6 +55,7 @@ def main():
     ap.add_argument("--res", type=int, default=128); ap.add_argument("--steps", type=int, default=24); ap.add_argument("--dt", type=float, default=1e-4)
     ap.add_argument("--same-device", action="store_true"); ap.add_argument("--oracle", action="store_true"); ap.add_argument("--adaptive", action="store_true")
     ap.add_argument("--scene", default="c5", choices=["c5", "c4"], help="c4: cloth-sand coupling at 256^3 (BASELINE configs[3], '1/2/4 B200'), cloth replicated on every rank")
+    ap.add_argument("--c4-res", type=int, default=256); ap.add_argument("--c4-cloth", type=int, default=256)
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="nccl: the round-1 path (SlabSolver: torch.distributed send/recv driven from Python)")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
@@ -65,8 +67,8 @@ def main():
     torch.cuda.set_device(local)
     if a.same_device: dist.init_process_group("gloo")
     else: dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    scene = scene_for(a.res) if a.scene == "c5" else scene_c4()
-    if a.scene == "c4": a.res = 256
+    scene = scene_for(a.res) if a.scene == "c5" else scene_c4(a.c4_res, a.c4_cloth)
+    if a.scene == "c4": a.res = a.c4_res
     n = scene.particles.n
     cells = np.floor(scene.particles.x[:, 1] * a.res).astype(np.int64)
     plan = SlabPlan.balanced(cells, a.res, world, axis=1)
