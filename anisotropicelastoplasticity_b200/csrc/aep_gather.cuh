@@ -12,6 +12,12 @@
 #ifndef AEP_GATHER_PK
 #define AEP_GATHER_PK 0
 #endif
+#ifndef AEP_GATHER_PK_GRAD              // the force gather (gather_grad) and the G2P gather (g2p_gather) separately
+#define AEP_GATHER_PK_GRAD AEP_GATHER_PK
+#endif
+#ifndef AEP_GATHER_PK_G2P
+#define AEP_GATHER_PK_G2P AEP_GATHER_PK
+#endif
 
 namespace aep {
 
@@ -98,7 +104,7 @@ __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, cons
 #pragma unroll
     for (int o = 0; o < 4; ++o) { ni[o] = MODE == 2 ? o : clampi(ax.n0 + o, G.a0[0], G.a1[0] - 1); nj[o] = MODE == 2 ? ay.n0 + o : clampi(ay.n0 + o, G.a0[1], G.a1[1] - 1); }
     const float4* base = MODE == 2 ? tile + xoff : G.vt;
-#if AEP_GATHER_PK
+#if AEP_GATHER_PK_GRAD
     f32x2 g03 = pk(g[0], g[3]), g14 = pk(g[1], g[4]), g25 = pk(g[2], g[5]);     // rows 0 and 1 of grad v as pairs over the row index
 #endif
 #pragma unroll 1
@@ -109,7 +115,7 @@ __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, cons
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float4* row = MODE == 2 ? plane + j * TILE_W : plane + (size_t)((long long)nj[j] * G.sy);
-#if AEP_GATHER_PK
+#if AEP_GATHER_PK_GRAD
             const float nn = ay.N[j] * nzk, dn = ay.D[j] * nzk, nd = ay.N[j] * dzk;
             f32x2 axy = 0ull, azs = 0ull, bxy = 0ull, bzs = 0ull;
 #pragma unroll
@@ -137,7 +143,7 @@ __device__ __forceinline__ void gather_grad(const GridP& G, const Axis& ax, cons
 #endif
         }
     }
-#if AEP_GATHER_PK
+#if AEP_GATHER_PK_GRAD
     upk(g03, g[0], g[3]); upk(g14, g[1], g[4]); upk(g25, g[2], g[5]);
 #endif
 }
@@ -160,7 +166,7 @@ __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const
 #pragma unroll
     for (int o = 0; o < 4; ++o) { ni[o] = MODE == 2 ? o : clampi(ax.n0 + o, G.a0[0], G.a1[0] - 1); nj[o] = MODE == 2 ? ay.n0 + o : clampi(ay.n0 + o, G.a0[1], G.a1[1] - 1); }
     const float4* base = MODE == 2 ? tile + xoff : G.vt;
-#if AEP_GATHER_PK
+#if AEP_GATHER_PK_G2P
     f32x2 va01 = pk(S.va[0], S.va[1]);
     f32x2 g03 = pk(S.g[0], S.g[3]), g14 = pk(S.g[1], S.g[4]), g25 = pk(S.g[2], S.g[5]);
     f32x2 B03 = pk(S.B[0], S.B[3]), B14 = pk(S.B[1], S.B[4]), B25 = pk(S.B[2], S.B[5]);
@@ -173,7 +179,7 @@ __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float4* row = MODE == 2 ? plane + j * TILE_W : plane + (size_t)((long long)nj[j] * G.sy);
-#if AEP_GATHER_PK
+#if AEP_GATHER_PK_G2P
             const float nn = ay.N[j] * nzk, dn = ay.D[j] * nzk, nd = ay.N[j] * dzk;
             ulonglong2 q[4];
 #pragma unroll
@@ -219,7 +225,7 @@ __device__ __forceinline__ void g2p_gather(const GridP& G, const Axis& ax, const
 #endif
         }
     }
-#if AEP_GATHER_PK
+#if AEP_GATHER_PK_G2P
     upk(va01, S.va[0], S.va[1]);
     upk(g03, S.g[0], S.g[3]); upk(g14, S.g[1], S.g[4]); upk(g25, S.g[2], S.g[5]);
     upk(B03, S.B[0], S.B[3]); upk(B14, S.B[1], S.B[4]); upk(B25, S.B[2], S.B[5]);
