@@ -138,6 +138,58 @@ def test_sand_series_path_vs_svd_path_vs_oracle(H):
     assert min(branches.values()) >= 100, branches
 
 
+def _sym(v):
+    return np.array([[v[0], v[3], v[4]], [v[3], v[1], v[5]], [v[4], v[5], v[2]]], np.float64)
+
+
+def test_series_matrix_functions_vs_scipy(H):
+    """sym_half_log1p(E) = 1/2 logm(I + E) and sym_exp(X) = expm(X) for symmetric 3x3 arguments up to the size the fast path admits
+    (|E|_F < 0.05): the truncation (6 / 5 terms) stays below fp32 rounding of the result."""
+    from scipy.linalg import expm, logm
+    rng = np.random.default_rng(3)
+    for scale in (1e-4, 1e-3, 1e-2, 0.049):
+        for _ in range(100):
+            v = rng.standard_normal(6); M = _sym(v); M *= scale / np.linalg.norm(M)
+            v32 = f32(np.array([M[0, 0], M[1, 1], M[2, 2], M[0, 1], M[0, 2], M[1, 2]])); M32 = _sym(v32.astype(np.float64))
+            out = np.zeros(6, np.float32)
+            H.h_sym_half_log1p(P(v32), P(out))
+            ref = 0.5 * logm(np.eye(3) + M32).real
+            assert np.abs(_sym(out.astype(np.float64)) - ref).max() < 2.5e-7 * max(scale, 1e-3) / 1e-3 * 1e-3 + 6e-8 * scale, scale
+            H.h_sym_exp(P(v32), P(out))
+            assert np.abs(_sym(out.astype(np.float64)) - expm(M32)).max() < 1.3e-7, scale
+
+
+def test_series_and_svd_paths_agree_at_the_switch(H):
+    """A particle whose strain crosses |E|_F = 0.05 changes from the series to the SVD path: both must give the same stress and the
+    same projected F_E / F_P there (no jump in the material response), on every branch of the projection."""
+    H.h_stress_svd.argtypes = H.h_stress.argtypes; H.h_return_map_svd.argtypes = H.h_return_map.argtypes
+    H.h_small_strain.argtypes = [fp]; H.h_small_strain.restype = C.c_int
+    rng = np.random.default_rng(8)
+    E_, nu = 3.537e5, 0.3
+    seen = 0
+    for trial in range(600):
+        R = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+        S = np.eye(3) + 0.012 * rng.standard_normal((3, 3)) + (trial % 3 - 1) * 0.008 * np.eye(3)       # |E|_F around 0.03 .. 0.07
+        Fh = f32(R @ S)
+        if H.h_small_strain(P(Fh.ravel())) != 1:
+            continue
+        Em = Fh.astype(np.float64) @ Fh.astype(np.float64).T - np.eye(3)
+        if np.linalg.norm(Em) < 0.035:
+            continue                                                                                 # only the neighbourhood of the switch
+        seen += 1
+        FE = f32(Fh - 0.003 * rng.standard_normal((3, 3))); FPm = f32(np.eye(3) + 0.02 * rng.standard_normal((3, 3))); q0 = float(np.float32(abs(rng.standard_normal()) * 0.3))
+        A = np.zeros(9, np.float32); As = np.zeros(9, np.float32)
+        H.h_stress(1, E_, nu, P(Fh.ravel()), P(FE.ravel()), C.c_float(1e-6), C.c_float(1.0), P(A))
+        H.h_stress_svd(1, E_, nu, P(Fh.ravel()), P(FE.ravel()), C.c_float(1e-6), C.c_float(1.0), P(As))
+        assert np.abs(A - As).max() < 1e-4 * np.abs(As).max(), trial                                # both are fp32 evaluations: 4 digits in common, no jump
+        fe1 = np.zeros(9, np.float32); fp1 = FPm.copy().ravel(); q1 = C.c_float(q0)
+        fe2 = np.zeros(9, np.float32); fp2 = FPm.copy().ravel(); q2 = C.c_float(q0)
+        H.h_return_map(1, E_, nu, 2.5e-2, 7.5e-3, P(Fh.ravel()), P(fe1), P(fp1), C.byref(q1))
+        H.h_return_map_svd(1, E_, nu, 2.5e-2, 7.5e-3, P(Fh.ravel()), P(fe2), P(fp2), C.byref(q2))
+        assert np.abs(fe1 - fe2).max() < 2e-6 and np.abs(fp1 - fp2).max() < 3e-6 and abs(q1.value - q2.value) < 2e-6, trial
+    assert seen >= 100
+
+
 def _weights64(f):
     """cubic B-spline values of the 4 stencil nodes of a particle at cell fraction f, fp64, straight from interpolation.cpp:9-16
     via the oracle: node o sits at signed distance u = f + 1 - o (in cells)."""
