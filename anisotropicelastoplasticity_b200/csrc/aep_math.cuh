@@ -230,20 +230,32 @@ __device__ __forceinline__ float left_cauchy_green_minus_one(const float (&F)[9]
     E.yz = fmaf(D[3], D[6], fmaf(D[4], D[7], D[5] * D[8])) + (D[5] + D[7]);
     return sym_norm2(E);
 }
-// H = 1/2 ln(I + E) = 1/2 E (I - E/2 + E^2/3 - E^3/4 + E^4/5 - E^5/6), Horner in the matrix
-__device__ __forceinline__ Sym3 sym_half_log1p(const Sym3& E) {
-    Sym3 t = sym_axpi(-1.0f / 6.0f, E, 0.2f);
-    t = sym_axpi(1.0f, sym_mul(E, t), -0.25f);
-    t = sym_axpi(1.0f, sym_mul(E, t), 1.0f / 3.0f);
-    t = sym_axpi(1.0f, sym_mul(E, t), -0.5f);
+// H = 1/2 ln(I + E) = 1/2 E (I - E/2 + E^2/3 - E^3/4 + E^4/5 - E^5/6), Horner in the matrix.  e2 = |E|_F^2: below |E|_F = 4e-3 (the
+// strains a stiff granular material lives at) three terms are exact to fp32 (|E|^3 / 4 < 2e-8 relative): 2 products instead of 5
+#ifndef AEP_SHORT_E2
+#define AEP_SHORT_E2 1.6e-5f
+#endif
+__device__ __forceinline__ Sym3 sym_half_log1p(const Sym3& E, float e2) {
+    Sym3 t;
+    if (e2 < AEP_SHORT_E2) t = sym_axpi(1.0f / 3.0f, E, -0.5f);
+    else {
+        t = sym_axpi(-1.0f / 6.0f, E, 0.2f);
+        t = sym_axpi(1.0f, sym_mul(E, t), -0.25f);
+        t = sym_axpi(1.0f, sym_mul(E, t), 1.0f / 3.0f);
+        t = sym_axpi(1.0f, sym_mul(E, t), -0.5f);
+    }
     t = sym_axpi(1.0f, sym_mul(E, t), 1.0f);
     return sym_axpi(0.5f, sym_mul(E, t), 0.0f);
 }
-// exp(X) = I + X (I + X/2 (I + X/3 (I + X/4 (I + X/5))))
-__device__ __forceinline__ Sym3 sym_exp(const Sym3& X) {
-    Sym3 t = sym_axpi(0.2f, X, 1.0f);
-    t = sym_axpi(0.25f, sym_mul(X, t), 1.0f);
-    t = sym_axpi(1.0f / 3.0f, sym_mul(X, t), 1.0f);
+// exp(X) = I + X (I + X/2 (I + X/3 (I + X/4 (I + X/5)))); |X|_F < 4e-3: I + X (I + X/2 (I + X/3)) (|X|^4 / 24 < 1e-11)
+__device__ __forceinline__ Sym3 sym_exp(const Sym3& X, float x2) {
+    Sym3 t;
+    if (x2 < AEP_SHORT_E2) t = sym_axpi(1.0f / 3.0f, X, 1.0f);
+    else {
+        t = sym_axpi(0.2f, X, 1.0f);
+        t = sym_axpi(0.25f, sym_mul(X, t), 1.0f);
+        t = sym_axpi(1.0f / 3.0f, sym_mul(X, t), 1.0f);
+    }
     t = sym_axpi(0.5f, sym_mul(X, t), 1.0f);
     return sym_axpi(1.0f, sym_mul(X, t), 1.0f);
 }
@@ -267,8 +279,8 @@ __device__ __forceinline__ void mat_inv(const float (&A)[9], float (&Ai)[9]) {
         for (int c = 0; c < 3; ++c) Ai[3 * r + c] = cof[3 * c + r] * id;         // inverse = cof^T / det
 }
 // sand stress, small strain:  A = vol * tau * (FE Fhat^-1)^T,  tau = 2 mu H + lambda tr(H) I            HybridSolver.cpp:326-339
-__device__ __forceinline__ void sand_stress_small(const MatParams& mp, const Sym3& E, const float (&Fh)[9], const float (&FE)[9], float vol, float (&A)[9]) {
-    const Sym3 H = sym_half_log1p(E);
+__device__ __forceinline__ void sand_stress_small(const MatParams& mp, const Sym3& E, float e2, const float (&Fh)[9], const float (&FE)[9], float vol, float (&A)[9]) {
+    const Sym3 H = sym_half_log1p(E, e2);
     const float tr = H.xx + H.yy + H.zz;
     const Sym3 tau = sym_axpi(2.0f * mp.mu0 * vol, H, mp.lambda0 * tr * vol);
     float Fi[9], T[9], Tt[9];
@@ -280,9 +292,9 @@ __device__ __forceinline__ void sand_stress_small(const MatParams& mp, const Sym
     sym_mat_mul(tau, Tt, A);
 }
 // Drucker-Prager projection, small strain (HybridSolver.cpp:646-673): true when the particle yields; then F_E' = M Fhat
-__device__ __forceinline__ bool sand_project_small(const MatParams& mp, const Sym3& E, float& q, Sym3& M) {
+__device__ __forceinline__ bool sand_project_small(const MatParams& mp, const Sym3& E, float e2, float& q, Sym3& M) {
     const float PI_F = 3.14159265358979323846f;
-    const Sym3 H = sym_half_log1p(E);
+    const Sym3 H = sym_half_log1p(E, e2);
     const float phi = (mp.h0 + (mp.h1 * q - mp.h3) * expf(-mp.h2 * q)) * (PI_F / 180.0f);      // HybridSolver.cpp:646-647
     const float sp = sinf(phi);
     const float alpha = 0.81649658092772603f * 2.0f * sp / (3.0f - sp);                          // sqrt(2/3), :649-650
@@ -292,11 +304,12 @@ __device__ __forceinline__ bool sand_project_small(const MatParams& mp, const Sy
     const float dg = dn + mp.k_vol * tr * alpha;                                                 // :654-656
     if (dg <= 0.0f) return false;
     if (dn == 0.0f || tr > 0.0f) {                                                               // :662-666  ln s' = 0
-        q += sqrtf(sym_norm2(H));
-        M = sym_exp(sym_axpi(-1.0f, H, 0.0f));
+        const float h2 = sym_norm2(H);
+        q += sqrtf(h2);
+        M = sym_exp(sym_axpi(-1.0f, H, 0.0f), h2);
     } else {                                                                                     // :667-673  ln s' = ln s - (dg/dn) dev
         q += dg;
-        M = sym_exp(sym_axpi(-dg / dn, dev, 0.0f));
+        M = sym_exp(sym_axpi(-dg / dn, dev, 0.0f), dg * dg);                                  // |k dev H|_F = dg
     }
     return true;
 }
@@ -341,8 +354,8 @@ __device__ __forceinline__ void stress_times_FEt_svd(const MatParams& mp, const 
 // sand at small strain: no SVD (see above); snow and large strains: the SVD path
 __device__ __forceinline__ void stress_times_FEt(const MatParams& mp, const float (&Fh)[9], const float (&FE)[9],
                                                  float vol, float Jp, float (&A)[9]) {
-    Sym3 E;
-    if (mp.material != 0 && left_cauchy_green_minus_one(Fh, E) < AEP_SMALL_E2) sand_stress_small(mp, E, Fh, FE, vol, A);
+    Sym3 E; float e2 = 1.0f;
+    if (mp.material != 0 && (e2 = left_cauchy_green_minus_one(Fh, E)) < AEP_SMALL_E2) sand_stress_small(mp, E, e2, Fh, FE, vol, A);
     else stress_times_FEt_svd(mp, Fh, FE, vol, Jp, A);
 }
 
@@ -394,10 +407,10 @@ __device__ __forceinline__ void return_map_apply(const Svd3& sv, const float (&s
 }
 // both parts (in: Fh, FP, q; out: FE, FP, q)
 __device__ __forceinline__ void return_map(const MatParams& mp, const float (&Fh)[9], float (&FE)[9], float (&FP)[9], float& q) {
-    Sym3 E;
-    if (mp.material != 0 && left_cauchy_green_minus_one(Fh, E) < AEP_SMALL_E2) {
+    Sym3 E; float e2 = 1.0f;
+    if (mp.material != 0 && (e2 = left_cauchy_green_minus_one(Fh, E)) < AEP_SMALL_E2) {
         Sym3 M;
-        if (sand_project_small(mp, E, q, M)) sand_apply_small(M, Fh, FE, FP);
+        if (sand_project_small(mp, E, e2, q, M)) sand_apply_small(M, Fh, FE, FP);
         else {
 #pragma unroll
             for (int i = 0; i < 9; ++i) FE[i] = Fh[i];

@@ -533,9 +533,10 @@ __global__ void __launch_bounds__(G2G_NT, SCATTER ? G2G_MIN_CTAS : G2P_MIN_CTAS)
                         const float4 q0 = ldg4(P.a[PQ0] + p), q1 = ldg4(P.a[PQ1] + p), q2 = ldg4(P.a[PQ2] + p);
                         FP[0] = q0.x; FP[1] = q0.y; FP[2] = q0.z; FP[3] = q1.x; FP[4] = q1.y; FP[5] = q1.z; FP[6] = q2.x; FP[7] = q2.y; FP[8] = q2.z;
                     };
-                    if (mpar.material != 0 && left_cauchy_green_minus_one(Fh, E) < AEP_SMALL_E2) {     // sand, small strain: no SVD (aep_math.cuh)
+                    float e2 = 1.0f;
+                    if (mpar.material != 0 && (e2 = left_cauchy_green_minus_one(Fh, E)) < AEP_SMALL_E2) {     // sand, small strain: no SVD (aep_math.cuh)
                         Sym3 M;
-                        if (sand_project_small(mpar, E, qq, M) && live) { load_FP(); sand_apply_small(M, Fh, FE, FP); yields = true; }
+                        if (sand_project_small(mpar, E, e2, qq, M) && live) { load_FP(); sand_apply_small(M, Fh, FE, FP); yields = true; }
                     } else {
                         Svd3 sv; float sn[3];
                         if (return_map_project(mpar, Fh, sv, sn, qq) && live) { load_FP(); return_map_apply(sv, sn, Fh, FE, FP); yields = true; }

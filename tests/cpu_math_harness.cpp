@@ -48,8 +48,8 @@ void h_stress_svd(int material, double E, double nu, const float* Fh, const floa
     stress_times_FEt_svd(M, fh, fe, vol, Jp, a); std::memcpy(A, a, 36);
 }
 // matrix functions of the series path: in/out symmetric 3x3 as (xx, yy, zz, xy, xz, yz)
-void h_sym_half_log1p(const float* e, float* out) { Sym3 E{e[0], e[1], e[2], e[3], e[4], e[5]}; const Sym3 H = sym_half_log1p(E); out[0] = H.xx; out[1] = H.yy; out[2] = H.zz; out[3] = H.xy; out[4] = H.xz; out[5] = H.yz; }
-void h_sym_exp(const float* x, float* out) { Sym3 X{x[0], x[1], x[2], x[3], x[4], x[5]}; const Sym3 R = sym_exp(X); out[0] = R.xx; out[1] = R.yy; out[2] = R.zz; out[3] = R.xy; out[4] = R.xz; out[5] = R.yz; }
+void h_sym_half_log1p(const float* e, float* out) { Sym3 E{e[0], e[1], e[2], e[3], e[4], e[5]}; const Sym3 H = sym_half_log1p(E, sym_norm2(E)); out[0] = H.xx; out[1] = H.yy; out[2] = H.zz; out[3] = H.xy; out[4] = H.xz; out[5] = H.yz; }
+void h_sym_exp(const float* x, float* out) { Sym3 X{x[0], x[1], x[2], x[3], x[4], x[5]}; const Sym3 R = sym_exp(X, sym_norm2(X)); out[0] = R.xx; out[1] = R.yy; out[2] = R.zz; out[3] = R.xy; out[4] = R.xz; out[5] = R.yz; }
 void h_return_map_svd(int material, double E, double nu, double thetaC, double thetaS, const float* Fh, float* FE, float* FP, float* q) {
     MatParams M = mk(material, E, nu, thetaC, thetaS);
     float fh[9], fe[9], fp[9]; std::memcpy(fh, Fh, 36); std::memcpy(fp, FP, 36);

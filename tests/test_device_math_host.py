@@ -147,7 +147,7 @@ def test_series_matrix_functions_vs_scipy(H):
     (|E|_F < 0.05): the truncation (6 / 5 terms) stays below fp32 rounding of the result."""
     from scipy.linalg import expm, logm
     rng = np.random.default_rng(3)
-    for scale in (1e-4, 1e-3, 1e-2, 0.049):
+    for scale in (1e-4, 1e-3, 3.9e-3, 4.1e-3, 1e-2, 0.049):                    # 4e-3: where the short series hands over to the long one
         for _ in range(100):
             v = rng.standard_normal(6); M = _sym(v); M *= scale / np.linalg.norm(M)
             v32 = f32(np.array([M[0, 0], M[1, 1], M[2, 2], M[0, 1], M[0, 2], M[1, 2]])); M32 = _sym(v32.astype(np.float64))
