@@ -7,6 +7,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <nvtx3/nvToolsExt.h>          // header-only; ranges are emitted when AEP_NVTX=1 (a profiler that injects NVTX picks them up)
 #include <unistd.h>
 
 #include <algorithm>
@@ -127,6 +128,7 @@ struct aep_ctx {
     Comm comm;
 
     bool profile = false; Timers tm{};
+    bool nvtx = false;                          // AEP_NVTX=1: NVTX ranges per stage (host side of the launches) and per substep
     bool inited = false;
 };
 
@@ -153,10 +155,16 @@ cudaError_t dalloc(aep_ctx* c, T** p, size_t count) {
 
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
+const char* const STAGE_NAMES[AEP_NUM_STAGES] = { "aep:sort", "aep:p2g", "aep:forces(gather)", "aep:grid", "aep:g2p", "aep:mesh", "aep:halo", "aep:g2p2g(fused)",
+                                                  "aep:force_scatter", "aep:forces(list)", "aep:g2p(list)" };
 struct StageTimer {
     aep_ctx* c; int stage;
-    StageTimer(aep_ctx* c_, int s) : c(c_), stage(s) { if (c->profile) cudaEventRecord(c->tm.ev[0], c->stream); }
+    StageTimer(aep_ctx* c_, int s) : c(c_), stage(s) {
+        if (c->nvtx) nvtxRangePushA(STAGE_NAMES[s]);
+        if (c->profile) cudaEventRecord(c->tm.ev[0], c->stream);
+    }
     ~StageTimer() {
+        if (c->nvtx) nvtxRangePop();
         if (!c->profile) return;
         cudaEventRecord(c->tm.ev[1], c->stream); cudaEventSynchronize(c->tm.ev[1]);
         float ms = 0; cudaEventElapsedTime(&ms, c->tm.ev[0], c->tm.ev[1]);
@@ -534,6 +542,7 @@ int enqueue_substep(aep_ctx* c) {
 
 int do_substep(aep_ctx* c) {
     int r;
+    struct Range { bool on; explicit Range(bool o) : on(o) { if (on) nvtxRangePushA("aep:substep"); } ~Range() { if (on) nvtxRangePop(); } } range(c->nvtx);
     if (c->use_graph && !c->profile) {
         if (c->graph_dirty || !c->graph) {
             if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
@@ -652,6 +661,7 @@ int aep_create(aep_ctx** out, const aep_config* cfg) {
     ctx->cfg = *cfg; ctx->device = cfg->device; ctx->sm_count = prop.multiProcessorCount; ctx->mig.axis = -1;
     ctx->use_graph = cfg->use_graph != 0 && !getenv("AEP_NO_GRAPH");
     if (const char* f = getenv("AEP_FUSED")) ctx->fused = atoi(f) != 0;
+    if (const char* f = getenv("AEP_NVTX")) ctx->nvtx = atoi(f) != 0;
     if (const char* f = getenv("AEP_SPLIT_FORCES")) ctx->split_forces = atoi(f) != 0;
     c = ctx;
     auto bail = [&](int code) { std::string m = ctx->err; aep_destroy(ctx); g_create_error = m; return code; };
